@@ -1,0 +1,451 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//   out = act((A . B^T) * scale + bias + res),  A:[M,K] bf16 (or 5-D conv activation), B:[N,K] bf16
+// Roles per CTA (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 =
+// TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> global).  The fp32 accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Operands are staged by TMA with SWIZZLE_128B into a STAGES-deep ring of {A 128x64, B BNx64} tiles.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int GEMM_THREADS = 256;
+
+struct KParams {
+  int M, N, num_kb;
+  int tiles_m, tiles_n;
+  int a_mode;
+  int hw_shift, w_shift;
+  int cin_blocks;
+  int8_t tap_dw[12], tap_dh[12], tap_plane[12];
+  void* out;
+  long long ldo;
+  int out_f32;
+  __nv_bfloat16* out2;
+  long long ldo2;
+  const float* scale;
+  const float* bias;
+  const void* res;
+  long long ldr;
+  int res_f32;
+  int act;
+  int out_remap;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == RL_ACT_GELU) return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  if (act == RL_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == RL_ACT_TANH) return tanhf(x);
+  return x;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const KParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    rl::tma_prefetch_desc(&tmA);
+    rl::tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      rl::mbar_init(&full_bar[s], 1);
+      rl::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      rl::mbar_init(&tmem_full[s], 1);
+      rl::mbar_init(&tmem_empty[s], 128);
+    }
+    rl::fence_barrier_init();
+  }
+  if (warp == 2) rl::tmem_alloc(tmem_ptr, TMEM_COLS);
+  rl::tc_fence_before();
+  __syncthreads();
+  rl::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * BM;
+        const int n0 = n_blk * BN;
+        int img0 = 0, h0 = 0;
+        if (p.a_mode == 1) {
+          img0 = m0 >> p.hw_shift;
+          h0 = (m0 & ((1 << p.hw_shift) - 1)) >> p.w_shift;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          rl::mbar_wait(&empty_bar[stage], phase ^ 1);
+          rl::mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          if (p.a_mode == 0) {
+            rl::tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
+          } else {
+            const int t = kb / p.cin_blocks;
+            const int cb = kb - t * p.cin_blocks;
+            rl::tma_load_5d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], cb * BK,
+                            (int)p.tap_dw[t], h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
+          }
+          rl::tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = rl::make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        rl::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          rl::mbar_wait(&full_bar[stage], phase);
+          rl::tc_fence_after();
+          const uint32_t a_addr = rl::smem_u32(smem_a + stage * A_BYTES);
+          const uint32_t b_addr = rl::smem_u32(smem_b + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = rl::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = rl::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            rl::tc_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          rl::tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        rl::tc_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile - m_blk * p.tiles_n;
+      const int row = m_blk * BM + q * 32 + lane;
+      const int n0 = n_blk * BN;
+      const bool row_ok = row < p.M;
+      long long orow = row;
+      if (p.out_remap == 1) {
+        const int hw = 1 << p.hw_shift;
+        const int w = 1 << p.w_shift;
+        const int img = row >> p.hw_shift;
+        const int pix = row & (hw - 1);
+        const int oh = pix >> p.w_shift, ow = pix & (w - 1);
+        const int h2 = (hw >> p.w_shift) >> 1, w2 = w >> 1;
+        orow = (((long long)img * 4 + (oh & 1) * 2 + (ow & 1)) * h2 + (oh >> 1)) * w2 + (ow >> 1);
+      }
+      rl::mbar_wait(&tmem_full[acc], acc_phase);
+      rl::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        rl::tmem_ld_32x32(taddr + c * 32, v);
+        rl::tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (nb >= p.N) continue;  // warp-uniform
+        const bool full = (nb + 32 <= p.N);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (full) {
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + nb + j));
+              x[j] *= s.x; x[j + 1] *= s.y; x[j + 2] *= s.z; x[j + 3] *= s.w;
+            }
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              x[j] += s.x; x[j + 1] += s.y; x[j + 2] += s.z; x[j + 3] += s.w;
+            }
+          }
+          if (p.res && row_ok) {
+            if (p.res_f32) {
+              const float4* r = reinterpret_cast<const float4*>(
+                  reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 s = r[j];
+                x[4 * j] += s.x; x[4 * j + 1] += s.y; x[4 * j + 2] += s.z; x[4 * j + 3] += s.w;
+              }
+            } else {
+              const uint4* r = reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const __nv_bfloat16*>(p.res) + (long long)row * p.ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 s = r[j];
+                x[8 * j] += rl::bf16_lo(s.x); x[8 * j + 1] += rl::bf16_hi(s.x);
+                x[8 * j + 2] += rl::bf16_lo(s.y); x[8 * j + 3] += rl::bf16_hi(s.y);
+                x[8 * j + 4] += rl::bf16_lo(s.z); x[8 * j + 5] += rl::bf16_hi(s.z);
+                x[8 * j + 6] += rl::bf16_lo(s.w); x[8 * j + 7] += rl::bf16_hi(s.w);
+              }
+            }
+          }
+          if (p.act != RL_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
+          }
+          if (row_ok) {
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                    orow * p.ldo + nb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                o[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            } else {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                  orow * p.ldo + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]),
+                                  rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                  rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]),
+                                  rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            }
+            if (p.out2) {
+              uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]),
+                                  rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                  rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]),
+                                  rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            }
+          }
+        } else if (row_ok) {
+          // ragged N tail (e.g. vocab 21128): scalar path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n >= p.N) continue;
+            float y = x[j];
+            if (p.scale) y *= __ldg(p.scale + n);
+            if (p.bias) y += __ldg(p.bias + n);
+            if (p.res) {
+              y += p.res_f32
+                       ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + n]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                             p.res)[(long long)row * p.ldr + n]);
+            }
+            y = apply_act(y, p.act);
+            if (p.out_f32)
+              reinterpret_cast<float*>(p.out)[orow * p.ldo + n] = y;
+            else
+              reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + n] = __float2bfloat16(y);
+            if (p.out2) p.out2[orow * p.ldo2 + n] = __float2bfloat16(y);
+          }
+        }
+      }
+      rl::tc_fence_before();
+      rl::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  rl::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    rl::tc_fence_after();
+    rl::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int STAGES>
+constexpr int gemm_smem_bytes() {
+  return STAGES * (A_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+}
+
+template <int BN, int STAGES>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, cudaStream_t st) {
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < rl_num_sms() ? tiles : rl_num_sms();
+  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, p);
+  return rl_check_launch("rl_gemm_bf16");
+}
+
+int ilog2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return ((1 << s) == v) ? s : -1;
+}
+
+int g_force_bn = 0;
+
+}  // namespace
+
+extern "C" int rl_gemm_set_tile_n(int bn) {
+  g_force_bn = bn;
+  return 0;
+}
+
+extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
+  RL_REQUIRE(d != nullptr, RL_EINVAL, "rl_gemm_bf16: null descriptor");
+  RL_REQUIRE(d->a && d->b && d->out, RL_EINVAL, "rl_gemm_bf16: null operand pointer");
+  RL_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, RL_EINVAL, "rl_gemm_bf16: empty problem %lld x %lld x %lld",
+             (long long)d->M, (long long)d->N, (long long)d->K);
+  RL_REQUIRE(d->K % BK == 0, RL_EINVAL, "rl_gemm_bf16: K=%lld must be a multiple of %d", (long long)d->K, BK);
+  RL_REQUIRE(d->M < (1ll << 31) && d->N < (1ll << 31), RL_EINVAL, "rl_gemm_bf16: M/N too large");
+  RL_REQUIRE(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->b & 15) == 0, RL_EALIGN,
+             "rl_gemm_bf16: a/b must be 16-byte aligned");
+  RL_REQUIRE(d->ldb % 8 == 0, RL_EALIGN, "rl_gemm_bf16: ldb must be a multiple of 8 elements");
+  const int out_elt = d->out_dtype == RL_DT_F32 ? 4 : 2;
+  RL_REQUIRE(((uintptr_t)d->out & 15) == 0 && (d->ldo * out_elt) % 16 == 0, RL_EALIGN,
+             "rl_gemm_bf16: out / ldo must be 16-byte aligned");
+  if (d->out2)
+    RL_REQUIRE(((uintptr_t)d->out2 & 15) == 0 && d->ldo2 % 8 == 0, RL_EALIGN,
+               "rl_gemm_bf16: out2 / ldo2 must be 16-byte aligned");
+  if (d->res) {
+    const int res_elt = d->res_dtype == RL_DT_F32 ? 4 : 2;
+    RL_REQUIRE(((uintptr_t)d->res & 15) == 0 && (d->ldr * res_elt) % 16 == 0, RL_EALIGN,
+               "rl_gemm_bf16: res / ldr must be 16-byte aligned");
+  }
+  if (d->scale) RL_REQUIRE(((uintptr_t)d->scale & 15) == 0, RL_EALIGN, "rl_gemm_bf16: scale alignment");
+  if (d->bias) RL_REQUIRE(((uintptr_t)d->bias & 15) == 0, RL_EALIGN, "rl_gemm_bf16: bias alignment");
+
+  KParams p{};
+  p.M = (int)d->M;
+  p.N = (int)d->N;
+  p.num_kb = (int)(d->K / BK);
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.a_mode = d->a_mode;
+  p.out = d->out;
+  p.ldo = d->ldo;
+  p.out_f32 = d->out_dtype == RL_DT_F32;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(d->out2);
+  p.ldo2 = d->ldo2;
+  p.scale = d->scale;
+  p.bias = d->bias;
+  p.res = d->res;
+  p.ldr = d->ldr;
+  p.res_f32 = d->res_dtype == RL_DT_F32;
+  p.act = d->act;
+  p.out_remap = d->out_remap;
+
+  // choose the N tile: minimise waves * tile cost
+  int bn = 256;
+  {
+    const int sms = rl_num_sms();
+    long long t256 = (long long)p.tiles_m * ((p.N + 255) / 256);
+    long long t128 = (long long)p.tiles_m * ((p.N + 127) / 128);
+    long long c256 = ((t256 + sms - 1) / sms) * 256;
+    long long c128 = ((t128 + sms - 1) / sms) * 128;
+    if (c128 < c256) bn = 128;
+    if (p.N <= 128) bn = 128;
+    if (g_force_bn == 128 || g_force_bn == 256) bn = g_force_bn;
+  }
+  p.tiles_n = (p.N + bn - 1) / bn;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (d->a_mode == 0) {
+    RL_REQUIRE(d->lda % 8 == 0, RL_EALIGN, "rl_gemm_bf16: lda must be a multiple of 8 elements");
+    uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
+    uint64_t strides[1] = {(uint64_t)d->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    rc = rl_make_tmap_bf16(&tmA, d->a, 2, dims, strides, box);
+    if (rc) return rc;
+  } else if (d->a_mode == 1) {
+    const int C = d->conv_C, W = d->conv_W, H = d->conv_H, P = d->conv_P, NI = d->conv_NIMG;
+    RL_REQUIRE(C > 0 && C % BK == 0, RL_EINVAL, "rl_gemm_bf16(conv): C=%d must be a multiple of 64", C);
+    RL_REQUIRE(d->ntaps >= 1 && d->ntaps <= 12, RL_EINVAL, "rl_gemm_bf16(conv): ntaps=%d", d->ntaps);
+    RL_REQUIRE(d->K == (int64_t)d->ntaps * C, RL_EINVAL, "rl_gemm_bf16(conv): K != ntaps*C");
+    const int ws = ilog2_exact(W), hs = ilog2_exact(H);
+    RL_REQUIRE(ws >= 0 && hs >= 0 && W * H <= 256, RL_EINVAL,
+               "rl_gemm_bf16(conv): map %dx%d must be power-of-two with <= 256 pixels", W, H);
+    RL_REQUIRE(d->M == (int64_t)NI * W * H, RL_EINVAL, "rl_gemm_bf16(conv): M != NIMG*H*W");
+    RL_REQUIRE(P == 1 || P == 4, RL_EINVAL, "rl_gemm_bf16(conv): P must be 1 or 4");
+    p.hw_shift = ws + hs;
+    p.w_shift = ws;
+    p.cin_blocks = C / BK;
+    for (int t = 0; t < d->ntaps; ++t) {
+      p.tap_dw[t] = d->tap_dw[t];
+      p.tap_dh[t] = d->tap_dh[t];
+      p.tap_plane[t] = d->tap_plane[t];
+      RL_REQUIRE(d->tap_plane[t] >= 0 && d->tap_plane[t] < P, RL_EINVAL, "rl_gemm_bf16(conv): tap plane");
+    }
+    const int hw = W * H;
+    uint32_t box[5];
+    box[0] = BK;
+    box[1] = (uint32_t)W;
+    box[2] = (uint32_t)(hw >= BM ? BM / W : H);
+    box[3] = 1;
+    box[4] = (uint32_t)(hw >= BM ? 1 : BM / hw);
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)P, (uint64_t)NI};
+    uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)C * W * 2, (uint64_t)C * W * H * 2,
+                           (uint64_t)C * W * H * P * 2};
+    rc = rl_make_tmap_bf16(&tmA, d->a, 5, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    RL_REQUIRE(false, RL_EINVAL, "rl_gemm_bf16: unknown a_mode %d", d->a_mode);
+  }
+  if (d->out_remap == 1) {
+    RL_REQUIRE(d->a_mode == 1, RL_EINVAL, "rl_gemm_bf16: out_remap=1 needs conv geometry");
+    RL_REQUIRE(d->conv_W >= 2 && d->conv_H >= 2, RL_EINVAL, "rl_gemm_bf16: parity split needs >=2x2 map");
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+    uint64_t strides[1] = {(uint64_t)d->ldb * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    rc = rl_make_tmap_bf16(&tmB, d->b, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, p, st);
+  return launch_gemm<128, 6>(tmA, tmB, p, st);
+}

@@ -1,0 +1,93 @@
+"""Thin Python wrappers (torch tensors in, C-ABI calls out) around librealise_b200.so.
+
+torch is used only for device memory and the current stream; every arithmetic op on the hot path is
+a kernel in csrc/.  All wrappers raise if the tensors are not CUDA tensors of the expected dtype.
+"""
+import ctypes
+
+import torch
+
+from ._lib import GemmDesc, check, lib
+
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+_DT = {torch.bfloat16: 0, torch.float32: 1}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (realise_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None):
+    """out[M,N] = act((a[M,K] @ b[N,K]^T) * scale + bias + res).  a, b bf16; out bf16 or f32."""
+    _req(a, torch.bfloat16, "a")
+    _req(b, torch.bfloat16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and tuple(out.shape) == (M, N), (a.shape, b.shape, out.shape)
+    d = GemmDesc()
+    d.a, d.b = a.data_ptr(), b.data_ptr()
+    d.M, d.N, d.K = M, N, K
+    d.lda, d.ldb = a.stride(0), b.stride(0)
+    d.a_mode = 0
+    _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
+    check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16")
+    return out
+
+
+def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res=None,
+              act=ACT_NONE, out_remap=0):
+    """Implicit-GEMM convolution.  x: bf16 activation [nimg, planes, H, W, C] (contiguous);
+    w: bf16 [Cout, ntaps*C] tap-major; taps: list of (dw, dh, plane); output rows are (img, oh, ow)
+    over an H x W map; out_remap=1 writes rows parity-split for a following stride-2 conv."""
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    assert x.is_contiguous() and w.stride(1) == 1
+    C = x.shape[-1]
+    assert x.numel() == nimg * planes * H * W * C
+    M, N, K = nimg * H * W, w.shape[0], len(taps) * C
+    assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+    d = GemmDesc()
+    d.a, d.b = x.data_ptr(), w.data_ptr()
+    d.M, d.N, d.K = M, N, K
+    d.lda, d.ldb = C, w.stride(0)
+    d.a_mode = 1
+    d.conv_C, d.conv_W, d.conv_H, d.conv_P, d.conv_NIMG = C, W, H, planes, nimg
+    d.ntaps = len(taps)
+    for i, (dw, dh, pl) in enumerate(taps):
+        d.tap_dw[i], d.tap_dh[i], d.tap_plane[i] = dw, dh, pl
+    _fill_epilogue(d, out, scale, bias, res, act, None, out_remap)
+    check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16(conv)")
+    return out
+
+
+def _fill_epilogue(d, out, scale, bias, res, act, out2, out_remap):
+    if not out.is_cuda or out.dtype not in _DT:
+        raise RuntimeError("out must be a CUDA bf16/f32 tensor")
+    d.out, d.ldo, d.out_dtype = out.data_ptr(), out.stride(0), _DT[out.dtype]
+    if out2 is not None:
+        _req(out2, torch.bfloat16, "out2")
+        d.out2, d.ldo2 = out2.data_ptr(), out2.stride(0)
+    if scale is not None:
+        _req(scale, torch.float32, "scale")
+        d.scale = scale.data_ptr()
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+        d.bias = bias.data_ptr()
+    if res is not None:
+        assert res.is_cuda and res.dtype in _DT and res.stride(-1) == 1
+        d.res, d.ldr, d.res_dtype = res.data_ptr(), res.stride(0), _DT[res.dtype]
+    d.act = act
+    d.out_remap = out_remap
