@@ -74,5 +74,69 @@ typedef struct rl_gemm_desc {
 } rl_gemm_desc;
 
 RL_API int rl_gemm_bf16(const rl_gemm_desc* d, void* stream);
+/* tuning/debug: force the GEMM N tile (128 or 256; 0 = heuristic). */
+RL_API int rl_gemm_set_tile_n(int bn);
+
+/* ---- fused attention core -------------------------------------------------------------------
+ * ctx[b*L+q, h*64:(h+1)*64] = softmax(Q K^T / 8 + (1 - mask[b,:]) * -10000) V  per head.
+ * qkv: bf16 [B*L, 3*heads*64] = [Q | K | V] as written by the fused QKV projection GEMM;
+ * mask: int64 [B, L] (batch['masks']); ctx: bf16 [B*L, heads*64].  L <= 256, head_dim == 64.
+ * Replaces BertSelfAttention.forward score/softmax/context path (modeling_bert.py:234-260) and the
+ * extended-mask construction of BertModel.forward (:687, :696-697).  Dropout is identity (eval). */
+RL_API int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, int64_t B, int64_t L,
+                            int64_t heads, int64_t head_dim, void* stream);
+
+/* ---- LayerNorm (biased variance, eps inside sqrt) over rows of f32 [rows, H] ------------------
+ * Replaces BertLayerNorm in BertSelfOutput/BertOutput (modeling_bert.py:276, :342) and
+ * resnet_layernorm (src/models.py:838).  Writes f32 and/or bf16 (either may be NULL). */
+RL_API int rl_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32,
+                            void* out_bf16, int64_t rows, int64_t H, float eps, void* stream);
+
+/* ---- BertEmbeddings.forward (modeling_bert.py:169-193) ---------------------------------------
+ * out = LN(src + pos[position] + type[0]); src = word[ids[row]] when inputs_embeds is NULL else
+ * inputs_embeds[row].  pos_mode 0: position = row % L (default arange); 1: position 0 for every
+ * token (output_block, src/models.py:852-854). */
+RL_API int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds,
+                           const float* pos, const float* type0, const float* gamma, const float* beta,
+                           float* out_f32, void* out_bf16, int64_t rows, int64_t L, int64_t H,
+                           int32_t pos_mode, float eps, void* stream);
+
+/* ---- gated fusion (src/models.py:840-850; src/models_abla.py:243-279) -------------------------
+ * m0 = bert_hiddens, m1/m2 = the other present modalities in the reference's concat order, all
+ * f32 [B*L, H].  gate_w: f32 [G, (G+1)*H], gate_b: [G], G = num_modal.  sum_mode != 0 is
+ * fusion='sum'.  mean_dot_ws: f32 [B*3] scratch.  gates_out (optional): f32 [B*L, 3]. */
+RL_API int rl_gate_fuse_fwd(const float* m0, const float* m1, const float* m2, int32_t num_modal,
+                            int32_t sum_mode, const int64_t* mask, const float* gate_w,
+                            const float* gate_b, float* mean_dot_ws, float* out, float* gates_out,
+                            int64_t B, int64_t L, int64_t H, void* stream);
+
+/* ---- masked CrossEntropyLoss (src/models.py:862-868) -----------------------------------------
+ * loss = mean over rows with loss_mask == 1 of (logsumexp(logits[row]) - logits[row, tgt[row]]).
+ * logits f32 [rows, V] with row stride ld; row_loss_ws f32 [rows] scratch; loss f32 [1]. */
+RL_API int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask,
+                            float* row_loss_ws, float* loss, int64_t rows, int64_t V, int64_t ld,
+                            void* stream);
+
+/* ---- pinyin GRU (src/models.py:818-826: nn.Embedding -> pack_padded_sequence -> nn.GRU) -------
+ * rl_gru_input_table: table[v, :] = W_ih emb[v] + b_ih  (f32 [V=33, 3H]; gate order r,z,n).
+ * rl_gru_step_fwd: one time step t for every token row; gh = h_{t-1} W_hh^T + b_hh (f32 [rows,3H],
+ * produced by rl_gemm_bf16) or NULL with h_prev NULL at t = 0 (h_0 = 0).  Rows with lens[row] <= t
+ * keep their state, which reproduces the packed-sequence final hidden.  pho_idx int64 [rows, T]. */
+RL_API int rl_gru_input_table(const float* emb, const float* w_ih, const float* b_ih, float* table,
+                              int64_t V, int64_t H, void* stream);
+RL_API int rl_gru_step_fwd(const float* gh, const float* b_hh, const float* table,
+                           const int64_t* pho_idx, const int32_t* lens, const float* h_prev,
+                           float* h_out, void* h_out_bf16, int64_t rows, int64_t H, int64_t T,
+                           int64_t t, void* stream);
+
+/* ---- glyph stem (src/models.py:829-834 gather; src/char_cnn.py:15-29 for res_block1) ----------
+ * For every token: image = glyphs[ids[i]] (f32 [C,32,32]);  y1 = relu(bn1(conv3x3 s2 p1)),
+ * ysc = bn_sc(conv1x1 s2), both bf16 NHWC [n_img,16,16,64].  BatchNorm (eval) is passed folded:
+ * scale = gamma / sqrt(running_var + 1e-5), shift = beta - running_mean * scale.
+ * w1: f32 [64, C, 3, 3], wsc: f32 [64, C] (the reference weight layouts). */
+RL_API int rl_glyph_stem_fwd(const float* glyphs, const int64_t* ids, const float* w1, const float* wsc,
+                             const float* scale1, const float* shift1, const float* scale_sc,
+                             const float* shift_sc, void* y1, void* ysc, int64_t n_img, int32_t C,
+                             void* stream);
 
 #endif /* REALISE_B200_H */

@@ -1,0 +1,313 @@
+// Row-wise (HBM-bound) kernels of the ReaLiSe path: embedding-sum + LayerNorm, LayerNorm,
+// gated fusion, masked cross-entropy.  One warp per 768-wide row, 16-byte vector accesses.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_V4 = 8;  // per-lane float4 count: H <= 1024
+
+__device__ __forceinline__ void ln_row_store(const float4* x, int nv, float mean, float rstd,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             float* out_f32, __nv_bfloat16* out_bf16, int lane) {
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+      float4 y;
+      y.x = (x[i].x - mean) * rstd * g.x + b.x;
+      y.y = (x[i].y - mean) * rstd * g.y + b.y;
+      y.z = (x[i].z - mean) * rstd * g.z + b.z;
+      y.w = (x[i].w - mean) * rstd * g.w + b.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = y;
+      if (out_bf16)
+        *reinterpret_cast<uint2*>(out_bf16 + col) = make_uint2(rl::pack_bf16(y.x, y.y), rl::pack_bf16(y.z, y.w));
+    }
+  }
+}
+
+__device__ __forceinline__ void ln_stats(const float4* x, int nv, int H, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) s += x[i].x + x[i].y + x[i].z + x[i].w;
+  mean = rl::warp_sum(s) / (float)H;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+      v += a * a + b * b + c * c + d * d;
+    }
+  v = rl::warp_sum(v) / (float)H;
+  rstd = rsqrtf(v + eps);
+}
+
+// LayerNorm over the last dim (biased variance, eps inside the sqrt) — nn.LayerNorm /
+// BertLayerNorm.  x: f32 [rows, H]
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* out_f32,
+                                                        __nv_bfloat16* out_bf16, long long rows, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = H / 128;
+  float4 v[MAX_V4];
+  const float4* src = reinterpret_cast<const float4*>(x + row * H);
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) v[i] = src[i * 32 + lane];
+  float mean, rstd;
+  ln_stats(v, nv, H, eps, mean, rstd);
+  ln_row_store(v, nv, mean, rstd, gamma, beta, out_f32 ? out_f32 + row * H : nullptr,
+               out_bf16 ? out_bf16 + row * H : nullptr, lane);
+}
+
+// BertEmbeddings.forward: LN(word[ids] (or inputs_embeds) + pos[position] + type[0])
+// pos_mode 0: position = token index within the sentence (default arange), 1: position 0 for all.
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ inputs_embeds,
+                const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* out_f32, __nv_bfloat16* out_bf16, long long rows, int L,
+                int H, int pos_mode, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = H / 128;
+  const float4* src = inputs_embeds ? reinterpret_cast<const float4*>(inputs_embeds + row * H)
+                                    : reinterpret_cast<const float4*>(word + ids[row] * (long long)H);
+  const int position = pos_mode == 0 ? (int)(row % L) : 0;
+  const float4* ps = reinterpret_cast<const float4*>(pos + (long long)position * H);
+  const float4* ts = reinterpret_cast<const float4*>(type0);
+  float4 v[MAX_V4];
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) {
+      const float4 a = src[i * 32 + lane], b = __ldg(ps + i * 32 + lane), c = __ldg(ts + i * 32 + lane);
+      v[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+    }
+  float mean, rstd;
+  ln_stats(v, nv, H, eps, mean, rstd);
+  ln_row_store(v, nv, mean, rstd, gamma, beta, out_f32 ? out_f32 + row * H : nullptr,
+               out_bf16 ? out_bf16 + row * H : nullptr, lane);
+}
+
+// ---- gated fusion (src/models.py:840-850) ----
+// pass 1: per sentence, masked mean of bert_hiddens and its contribution to each gate logit
+__global__ void __launch_bounds__(256)
+gate_mean_kernel(const float* __restrict__ bert_h, const long long* __restrict__ mask, const float* __restrict__ gate_w,
+                 float* __restrict__ mean_dot, int L, int H, int G) {
+  extern __shared__ float s_mean[];  // [H]
+  __shared__ float s_red[8][4];
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int l = 0; l < L; ++l) cnt += (float)mask[(long long)b * L + l];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += bert_h[((long long)b * L + l) * H + c] * (float)mask[(long long)b * L + l];
+    s_mean[c] = s / cnt;
+  }
+  __syncthreads();
+  float d[3] = {0.f, 0.f, 0.f};
+  for (int c = threadIdx.x; c < H; c += blockDim.x)
+    for (int g = 0; g < G; ++g) d[g] += s_mean[c] * gate_w[(long long)g * (G + 1) * H + (long long)G * H + c];
+  for (int g = 0; g < G; ++g) {
+    d[g] = rl::warp_sum(d[g]);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][g] = d[g];
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float s = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += s_red[w][threadIdx.x];
+    mean_dot[b * 3 + threadIdx.x] = s;
+  }
+}
+
+// pass 2: per token, G dot products of length G*H, sigmoid, weighted sum of the modalities
+__global__ void __launch_bounds__(256)
+gate_fuse_kernel(const float* __restrict__ m0, const float* __restrict__ m1, const float* __restrict__ m2,
+                 const float* __restrict__ gate_w, const float* __restrict__ gate_b, const float* __restrict__ mean_dot,
+                 float* __restrict__ out, float* __restrict__ gates_out, long long rows, int L, int H, int G, int sum_mode) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = H / 128;
+  const float* mods[3] = {m0, m1, m2};
+  float4 x[3][MAX_V4];
+  float dots[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    if (m < G) {
+      const float4* src = reinterpret_cast<const float4*>(mods[m] + row * H);
+#pragma unroll
+      for (int i = 0; i < MAX_V4; ++i)
+        if (i < nv) x[m][i] = src[i * 32 + lane];
+    }
+  }
+  float g[3] = {1.f, 1.f, 1.f};
+  if (!sum_mode) {
+#pragma unroll
+    for (int gi = 0; gi < 3; ++gi) {
+      if (gi < G) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          if (m < G) {
+            const float4* w = reinterpret_cast<const float4*>(gate_w + (long long)gi * (G + 1) * H + (long long)m * H);
+#pragma unroll
+            for (int i = 0; i < MAX_V4; ++i)
+              if (i < nv) {
+                const float4 ww = __ldg(w + i * 32 + lane);
+                dots[gi] += x[m][i].x * ww.x + x[m][i].y * ww.y + x[m][i].z * ww.z + x[m][i].w * ww.w;
+              }
+          }
+        }
+        const float z = rl::warp_sum(dots[gi]) + mean_dot[(row / L) * 3 + gi] + gate_b[gi];
+        g[gi] = 1.0f / (1.0f + expf(-z));
+      }
+    }
+    if (gates_out && lane < G) gates_out[row * 3 + lane] = g[lane];
+  }
+  float4* dst = reinterpret_cast<float4*>(out + row * H);
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) {
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+        if (m < G) {
+          y.x += g[m] * x[m][i].x; y.y += g[m] * x[m][i].y; y.z += g[m] * x[m][i].z; y.w += g[m] * x[m][i].w;
+        }
+      dst[i * 32 + lane] = y;
+    }
+}
+
+// ---- masked cross entropy (src/models.py:862-868): mean over loss_mask==1 of lse - logit[tgt] ----
+__global__ void __launch_bounds__(256)
+ce_row_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
+              float* __restrict__ row_loss, long long rows, int V, long long ld) {
+  const long long row = blockIdx.x;
+  __shared__ float s_red[8];
+  __shared__ float s_bc;
+  if (loss_mask[row] != 1) {
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    return;
+  }
+  const float* x = logits + row * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
+  mx = rl::warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+    s_bc = m;
+  }
+  __syncthreads();
+  mx = s_bc;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - mx);
+  s = rl::warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    row_loss[row] = logf(t) + mx - x[tgt[row]];
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ loss_mask, float* __restrict__ loss,
+                 long long rows) {
+  __shared__ float s_sum[32], s_cnt[32];
+  float s = 0.f, c = 0.f;
+  for (long long i = threadIdx.x; i < rows; i += blockDim.x) {
+    s += row_loss[i];
+    c += loss_mask[i] == 1 ? 1.f : 0.f;
+  }
+  s = rl::warp_sum(s);
+  c = rl::warp_sum(c);
+  if ((threadIdx.x & 31) == 0) {
+    s_sum[threadIdx.x >> 5] = s;
+    s_cnt[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tc = 0.f;
+    for (int w = 0; w < 32; ++w) {
+      ts += s_sum[w];
+      tc += s_cnt[w];
+    }
+    loss[0] = ts / tc;
+  }
+}
+
+bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
+
+}  // namespace
+
+extern "C" int rl_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32,
+                                void* out_bf16, int64_t rows, int64_t H, float eps, void* stream) {
+  RL_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), RL_EINVAL, "rl_layernorm_fwd: null pointer");
+  RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_fwd: H=%lld must be a multiple of 128, <= 1024", (long long)H);
+  if (rows <= 0) return 0;
+  const int wpb = 8;
+  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows, (int)H, eps);
+  return rl_check_launch("rl_layernorm_fwd");
+}
+
+extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds, const float* pos,
+                               const float* type0, const float* gamma, const float* beta, float* out_f32,
+                               void* out_bf16, int64_t rows, int64_t L, int64_t H, int32_t pos_mode, float eps,
+                               void* stream) {
+  RL_REQUIRE((inputs_embeds || (ids && word)) && pos && type0 && gamma && beta && (out_f32 || out_bf16), RL_EINVAL,
+             "rl_embed_ln_fwd: null pointer");
+  RL_REQUIRE(h_ok(H) && L > 0, RL_EINVAL, "rl_embed_ln_fwd: bad H/L");
+  if (rows <= 0) return 0;
+  const int wpb = 8;
+  embed_ln_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      (const long long*)ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows,
+      (int)L, (int)H, pos_mode, eps);
+  return rl_check_launch("rl_embed_ln_fwd");
+}
+
+extern "C" int rl_gate_fuse_fwd(const float* m0, const float* m1, const float* m2, int32_t num_modal,
+                                int32_t sum_mode, const int64_t* mask, const float* gate_w, const float* gate_b,
+                                float* mean_dot_ws, float* out, float* gates_out, int64_t B, int64_t L, int64_t H,
+                                void* stream) {
+  RL_REQUIRE(m0 && out && num_modal >= 1 && num_modal <= 3, RL_EINVAL, "rl_gate_fuse_fwd: bad arguments");
+  RL_REQUIRE((num_modal < 2 || m1) && (num_modal < 3 || m2), RL_EINVAL, "rl_gate_fuse_fwd: missing modality");
+  RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_gate_fuse_fwd: bad H");
+  if (!sum_mode) RL_REQUIRE(mask && gate_w && gate_b && mean_dot_ws, RL_EINVAL, "rl_gate_fuse_fwd: gate needs mask/weights/ws");
+  if (B <= 0 || L <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!sum_mode) {
+    gate_mean_kernel<<<(unsigned)B, 256, (size_t)H * 4, st>>>(m0, (const long long*)mask, gate_w, mean_dot_ws, (int)L,
+                                                              (int)H, num_modal);
+    int rc = rl_check_launch("rl_gate_fuse_fwd(mean)");
+    if (rc) return rc;
+  }
+  const long long rows = B * L;
+  const int wpb = 8;
+  gate_fuse_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(m0, m1, m2, gate_w, gate_b, mean_dot_ws, out,
+                                                                           gates_out, rows, (int)L, (int)H, num_modal,
+                                                                           sum_mode);
+  return rl_check_launch("rl_gate_fuse_fwd");
+}
+
+extern "C" int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, float* row_loss_ws,
+                                float* loss, int64_t rows, int64_t V, int64_t ld, void* stream) {
+  RL_REQUIRE(logits && tgt && loss_mask && row_loss_ws && loss, RL_EINVAL, "rl_masked_ce_fwd: null pointer");
+  RL_REQUIRE(rows > 0 && V > 0 && ld >= V, RL_EINVAL, "rl_masked_ce_fwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  ce_row_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, (const long long*)tgt, (const long long*)loss_mask, row_loss_ws,
+                                                rows, (int)V, ld);
+  int rc = rl_check_launch("rl_masked_ce_fwd(rows)");
+  if (rc) return rc;
+  ce_reduce_kernel<<<1, 1024, 0, st>>>(row_loss_ws, (const long long*)loss_mask, loss, rows);
+  return rl_check_launch("rl_masked_ce_fwd");
+}

@@ -1,0 +1,495 @@
+"""SpellBertPho2ResArch3 / SpellBertPho2ResArch3Abla on librealise_b200.so.
+
+Drop-in for the reference model classes (src/models.py:652-870, src/models_abla.py:33-299): same
+constructor argument (a config object with the BertConfig attributes plus image_model_type /
+num_fonts / with_pho / with_res / fusion), identical state_dict keys and shapes, the same
+`forward(batch) -> tuple`, `tie_cls_weight`, `build_batch`, `save_pretrained` / `from_pretrained`.
+The nn.Modules below are parameter containers only: their forward() is never called — every
+arithmetic step of forward() is a kernel in csrc/ reached through realise_b200.ops.
+"""
+import json
+import os
+from copy import deepcopy
+
+import torch
+from torch import nn
+
+from . import ops
+from .synth import ArchConfig, PHO_VOCAB
+
+RES_CHANNELS = [None, 64, 128, 256, 512, 768]
+BN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers mirroring the reference module tree (names are part of the ckpt contract)
+# ------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the arithmetic lives in librealise_b200.so")
+
+
+class _BertEmbeddings(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(c.vocab_size, c.hidden_size, padding_idx=0)
+        self.position_embeddings = nn.Embedding(c.max_position_embeddings, c.hidden_size)
+        self.token_type_embeddings = nn.Embedding(c.type_vocab_size, c.hidden_size)
+        self.LayerNorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+
+
+class _SelfAttention(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.query = nn.Linear(c.hidden_size, c.hidden_size)
+        self.key = nn.Linear(c.hidden_size, c.hidden_size)
+        self.value = nn.Linear(c.hidden_size, c.hidden_size)
+
+
+class _DenseLN(_Holder):
+    def __init__(self, fin, fout, eps):
+        super().__init__()
+        self.dense = nn.Linear(fin, fout)
+        self.LayerNorm = nn.LayerNorm(fout, eps=eps)
+
+
+class _Dense(_Holder):
+    def __init__(self, fin, fout):
+        super().__init__()
+        self.dense = nn.Linear(fin, fout)
+
+
+class _Attention(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.self = _SelfAttention(c)
+        self.output = _DenseLN(c.hidden_size, c.hidden_size, c.layer_norm_eps)
+
+
+class _BertLayer(_Holder):
+    def __init__(self, c):
+        super().__init__()
+        self.attention = _Attention(c)
+        self.intermediate = _Dense(c.hidden_size, c.intermediate_size)
+        self.output = _DenseLN(c.intermediate_size, c.hidden_size, c.layer_norm_eps)
+
+
+class _Encoder(_Holder):
+    def __init__(self, c, n):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(c) for _ in range(n)])
+
+
+class _BertModel(_Holder):
+    """Mirror of transformers.BertModel (modeling_bert.py:586-745): embeddings, encoder, pooler."""
+
+    def __init__(self, c, n_layers):
+        super().__init__()
+        self.embeddings = _BertEmbeddings(c)
+        self.encoder = _Encoder(c, n_layers)
+        self.pooler = _Dense(c.hidden_size, c.hidden_size)  # kept for ckpt parity; output is never used
+
+
+class _BasicBlock(_Holder):
+    """Mirror of char_cnn.BasicBlock (src/char_cnn.py:9-32)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.residual_function = nn.Sequential(
+            nn.Conv2d(cin, cout, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+            nn.Conv2d(cout, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout))
+        self.shortcut = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=2, bias=False), nn.BatchNorm2d(cout))
+
+
+class _CharResNet(_Holder):
+    def __init__(self, in_channels):
+        super().__init__()
+        cin = in_channels
+        for b in range(1, 6):
+            setattr(self, f"res_block{b}", _BasicBlock(cin, RES_CHANNELS[b]))
+            cin = RES_CHANNELS[b]
+
+
+def _cfg_get(config, name, default=None):
+    return getattr(config, name, default)
+
+
+def normalize_config(config):
+    """Accepts an ArchConfig, a reference BertConfig (any object with the attributes) or a dict."""
+    if isinstance(config, ArchConfig):
+        return deepcopy(config)
+    get = (lambda k, d=None: config.get(k, d)) if isinstance(config, dict) else (lambda k, d=None: getattr(config, k, d))
+    base = ArchConfig()
+    out = ArchConfig()
+    for k in base.__dict__:
+        v = get(k, None)
+        if v is not None:
+            setattr(out, k, v)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+class SpellBertPho2ResArch3Abla(nn.Module):
+    """The shipped model (with_pho = with_res = 'yes', fusion = 'gate') and its ablations."""
+
+    def __init__(self, config):
+        super().__init__()
+        c = normalize_config(config)
+        self.config = c
+        if c.image_model_type != 0:
+            raise NotImplementedError("only image_model_type 0 (CharResNet) is on the hot path (train.sh:8)")
+        if c.hidden_size != 768 or c.hidden_size // c.num_attention_heads != 64:
+            raise NotImplementedError("kernels are built for hidden_size 768 / head_dim 64 (CharResNet emits 768)")
+        self.vocab_size = c.vocab_size
+        self.bert = _BertModel(c, c.num_hidden_layers)
+        if c.with_pho == "yes":
+            self.pho_embeddings = nn.Embedding(PHO_VOCAB, c.hidden_size, padding_idx=0)
+            self.pho_gru = nn.GRU(c.hidden_size, c.hidden_size, num_layers=1, batch_first=True)
+            self.pho_model = _BertModel(c, 4)
+        if c.with_res == "yes":
+            if c.num_fonts == 1:
+                self.char_images = nn.Embedding(c.vocab_size, 1024)
+                self.char_images.weight.requires_grad = False
+            else:
+                self.char_images_multifonts = nn.Parameter(torch.rand(21128, c.num_fonts, 32, 32), requires_grad=False)
+            self.resnet = _CharResNet(c.num_fonts)
+            self.resnet_layernorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        if c.fusion == "gate":
+            g = c.num_gates
+            self.gate_net = nn.Linear((g + 1) * c.hidden_size, g)
+        self.output_block = _BertModel(c, 3)
+        self.dropout = nn.Dropout(c.hidden_dropout_prob)
+        self.classifier = nn.Linear(c.hidden_size, c.vocab_size)
+        self.init_weights()
+        self._prepared = None
+        self._ws = {}
+        self.collect = None  # tests set this to a dict to receive clones of the sub-module outputs
+
+    def _keep(self, name, t):
+        if self.collect is not None:
+            self.collect[name] = t.detach().float().clone()
+
+    # ---- reference API -----------------------------------------------------------------------
+    def init_weights(self):
+        """BertPreTrainedModel._init_weights (modeling_bert.py:496-506): N(0, 0.02) for Linear and
+        Embedding weights, zero Linear bias, LayerNorm (1, 0); conv/BN/GRU keep torch defaults."""
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                m.weight.data.normal_(mean=0.0, std=0.02)
+            elif isinstance(m, nn.LayerNorm):
+                m.bias.data.zero_()
+                m.weight.data.fill_(1.0)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+    def tie_cls_weight(self):
+        self.classifier.weight = self.bert.embeddings.word_embeddings.weight
+        self._prepared = None
+
+    @staticmethod
+    def build_batch(batch, tokenizer, pho_convertor=None):
+        """src/models.py:797-804.  The pinyin convertor needs pypinyin (host-side, out of the
+        measured path); pass the reference's `pho2_convertor` or any object with .convert(chars)."""
+        if pho_convertor is None:
+            raise RuntimeError("build_batch needs a pinyin convertor (reference src/utils.py:Pinyin2)")
+        src_idx = batch["src_idx"].flatten().tolist()
+        chars = tokenizer.convert_ids_to_tokens(src_idx)
+        batch["pho_idx"], batch["pho_lens"] = pho_convertor.convert(chars)
+        return batch
+
+    def save_pretrained(self, save_directory):
+        """config.json + pytorch_model.bin, like PreTrainedModel.save_pretrained (modeling_utils.py:236-251)."""
+        os.makedirs(save_directory, exist_ok=True)
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(self.config.__dict__, f, indent=2, sort_keys=True)
+        torch.save(self.state_dict(), os.path.join(save_directory, "pytorch_model.bin"))
+
+    @classmethod
+    def from_pretrained(cls, path, config=None, **kw):
+        if config is None:
+            with open(os.path.join(path, "config.json")) as f:
+                config = json.load(f)
+        model = cls(config)
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        # old-checkpoint LayerNorm names (modeling_utils.py:429-444)
+        sd = {k.replace(".gamma", ".weight").replace(".beta", ".bias"): v for k, v in sd.items()}
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._prepared = None
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._prepared = None
+        self._ws = {}
+        return out
+
+    # ---- weight preparation (bf16 operand copies, fused / re-laid-out weights) -----------------
+    @torch.no_grad()
+    def prepare(self):
+        """(Re)build the device-side operand cache from the fp32 master parameters: bf16 GEMM
+        weights, fused QKV, tap-major conv weights, folded eval-mode BatchNorm, GRU input table."""
+        c = self.config
+        dev = self.classifier.bias.device
+        if dev.type != "cuda":
+            raise RuntimeError("realise_b200 runs on CUDA only: move the model with .to('cuda') first")
+        P = {}
+
+        def bert(prefix, mod):
+            e = mod.embeddings
+            P[prefix] = {
+                "word": e.word_embeddings.weight.detach().float().contiguous(),
+                "pos": e.position_embeddings.weight.detach().float().contiguous(),
+                "type0": e.token_type_embeddings.weight.detach()[0].float().contiguous(),
+                "ln_w": e.LayerNorm.weight.detach().float().contiguous(),
+                "ln_b": e.LayerNorm.bias.detach().float().contiguous(),
+                "layers": [],
+            }
+            for lyr in mod.encoder.layer:
+                s = lyr.attention.self
+                P[prefix]["layers"].append({
+                    "w_qkv": torch.cat([s.query.weight, s.key.weight, s.value.weight], 0).detach().bfloat16().contiguous(),
+                    "b_qkv": torch.cat([s.query.bias, s.key.bias, s.value.bias], 0).detach().float().contiguous(),
+                    "w_o": lyr.attention.output.dense.weight.detach().bfloat16().contiguous(),
+                    "b_o": lyr.attention.output.dense.bias.detach().float().contiguous(),
+                    "ln1_w": lyr.attention.output.LayerNorm.weight.detach().float().contiguous(),
+                    "ln1_b": lyr.attention.output.LayerNorm.bias.detach().float().contiguous(),
+                    "w_1": lyr.intermediate.dense.weight.detach().bfloat16().contiguous(),
+                    "b_1": lyr.intermediate.dense.bias.detach().float().contiguous(),
+                    "w_2": lyr.output.dense.weight.detach().bfloat16().contiguous(),
+                    "b_2": lyr.output.dense.bias.detach().float().contiguous(),
+                    "ln2_w": lyr.output.LayerNorm.weight.detach().float().contiguous(),
+                    "ln2_b": lyr.output.LayerNorm.bias.detach().float().contiguous(),
+                })
+
+        bert("bert", self.bert)
+        bert("output_block", self.output_block)
+        if c.with_pho == "yes":
+            bert("pho_model", self.pho_model)
+            g = self.pho_gru
+            table = torch.empty(PHO_VOCAB, 3 * c.hidden_size, device=dev, dtype=torch.float32)
+            ops.gru_input_table(self.pho_embeddings.weight.detach().float().contiguous(),
+                                g.weight_ih_l0.detach().float().contiguous(),
+                                g.bias_ih_l0.detach().float().contiguous(), table)
+            P["gru"] = {"table": table, "w_hh": g.weight_hh_l0.detach().bfloat16().contiguous(),
+                        "b_hh": g.bias_hh_l0.detach().float().contiguous()}
+        if c.with_res == "yes":
+            P["res"] = self._prepare_resnet()
+            P["res_ln_w"] = self.resnet_layernorm.weight.detach().float().contiguous()
+            P["res_ln_b"] = self.resnet_layernorm.bias.detach().float().contiguous()
+        if c.fusion == "gate":
+            P["gate_w"] = self.gate_net.weight.detach().float().contiguous()
+            P["gate_b"] = self.gate_net.bias.detach().float().contiguous()
+        P["cls_w"] = self.classifier.weight.detach().bfloat16().contiguous()
+        P["cls_b"] = self.classifier.bias.detach().float().contiguous()
+        torch.cuda.current_stream().synchronize()
+        self._prepared = P
+        return P
+
+    @staticmethod
+    def _fold_bn(bn):
+        scale = (bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + BN_EPS)).contiguous()
+        shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+        return scale, shift
+
+    def _prepare_resnet(self):
+        c = self.config
+        R = {"blocks": []}
+        if c.num_fonts == 1:
+            R["glyphs"] = self.char_images.weight.detach().float().contiguous()
+        else:
+            R["glyphs"] = self.char_images_multifonts.detach().float().contiguous()
+        for b in range(1, 6):
+            blk = getattr(self.resnet, f"res_block{b}")
+            conv1, bn1, _, conv2, bn2 = blk.residual_function
+            convs, bns = blk.shortcut
+            s1, t1 = self._fold_bn(bn1)
+            s2, t2 = self._fold_bn(bn2)
+            ss, ts = self._fold_bn(bns)
+            cout = RES_CHANNELS[b]
+            S = 32 >> b  # output map size of this block
+            e = {"s1": s1, "t1": t1, "s2": s2, "t2": t2, "ss": ss, "ts": ts, "S": S, "cout": cout}
+            w1 = conv1.weight.detach().float()
+            w2 = conv2.weight.detach().float()
+            wsc = convs.weight.detach().float()
+            if b == 1:
+                e["w1_f32"] = w1.contiguous()
+                e["wsc_f32"] = wsc.reshape(cout, -1).contiguous()
+            else:
+                # stride-2 3x3 over the parity-split input: tap (kh, kw) reads plane (ph, pw) at offset (dh, dw)
+                taps, cols = [], []
+                for kh in range(3):
+                    for kw in range(3):
+                        ph, dh = (0, 0) if kh == 1 else (1, -1 if kh == 0 else 0)
+                        pw, dw = (0, 0) if kw == 1 else (1, -1 if kw == 0 else 0)
+                        if S == 1 and (dh < 0 or dw < 0):
+                            continue  # 1x1 output map: those taps only ever see zero padding
+                        taps.append((dw, dh, ph * 2 + pw))
+                        cols.append(w1[:, :, kh, kw])
+                e["taps1"] = taps
+                e["w1"] = torch.cat(cols, 1).bfloat16().contiguous()          # [cout, ntaps*cin]
+                e["wsc"] = wsc.reshape(cout, -1).bfloat16().contiguous()      # [cout, cin], plane (0,0)
+            taps2, cols2 = [], []
+            for kh in range(3):
+                for kw in range(3):
+                    if S == 1 and (kh != 1 or kw != 1):
+                        continue  # 1x1 map: only the centre tap touches data
+                    taps2.append((kw - 1, kh - 1, 0))
+                    cols2.append(w2[:, :, kh, kw])
+            e["taps2"] = taps2
+            e["w2"] = torch.cat(cols2, 1).bfloat16().contiguous()
+            R["blocks"].append(e)
+        return R
+
+    # ---- workspace -----------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.classifier.bias.device, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    # ---- the hot path --------------------------------------------------------------------------
+    def _bert_stack(self, name, P, mask, B, L, ids=None, inputs_embeds=None, pos_mode=0):
+        """BertModel.forward minus the (discarded) pooler.  Returns (f32 [N,H], bf16 [N,H])."""
+        c = self.config
+        N, H, I = B * L, c.hidden_size, c.intermediate_size
+        f32, bf16 = torch.float32, torch.bfloat16
+        x = self._buf(name + ".x", (N, H), f32)
+        xb = self._buf(name + ".xb", (N, H), bf16)
+        y = self._buf("y", (N, H), f32)
+        x1 = self._buf("x1", (N, H), f32)
+        x1b = self._buf("x1b", (N, H), bf16)
+        qkv = self._buf("qkv", (N, 3 * H), bf16)
+        ctx = self._buf("ctx", (N, H), bf16)
+        hmid = self._buf("hmid", (N, I), bf16)
+        ops.embed_ln(ids, P["word"], inputs_embeds, P["pos"], P["type0"], P["ln_w"], P["ln_b"], x, xb, N, L, H,
+                     pos_mode, c.layer_norm_eps)
+        for lw in P["layers"]:
+            ops.gemm(xb, lw["w_qkv"], qkv, bias=lw["b_qkv"])
+            ops.attention(qkv, mask, ctx, B, L, c.num_attention_heads)
+            ops.gemm(ctx, lw["w_o"], y, bias=lw["b_o"], res=x)
+            ops.layernorm(y, lw["ln1_w"], lw["ln1_b"], x1, x1b, c.layer_norm_eps)
+            ops.gemm(x1b, lw["w_1"], hmid, bias=lw["b_1"], act=ops.ACT_GELU)
+            ops.gemm(hmid, lw["w_2"], y, bias=lw["b_2"], res=x1)
+            ops.layernorm(y, lw["ln2_w"], lw["ln2_b"], x, xb, c.layer_norm_eps)
+        return x, xb
+
+    def _gru(self, P, pho_idx, lens_dev, N):
+        c = self.config
+        H = c.hidden_size
+        T = pho_idx.shape[1]
+        h = [self._buf("gru.h0", (N, H), torch.float32), self._buf("gru.h1", (N, H), torch.float32)]
+        hb = self._buf("gru.hb", (N, H), torch.bfloat16)
+        gh = self._buf("gru.gh", (N, 3 * H), torch.float32)
+        G = P["gru"]
+        ops.gru_step(None, G["b_hh"], G["table"], pho_idx, lens_dev, None, h[0], hb, 0)
+        cur = 0
+        for t in range(1, T):
+            ops.gemm(hb, G["w_hh"], gh, bias=G["b_hh"])
+            ops.gru_step(gh, G["b_hh"], G["table"], pho_idx, lens_dev, h[cur], h[1 - cur], hb, t)
+            cur = 1 - cur
+        return h[cur]
+
+    def _resnet(self, P, ids_flat, N):
+        """CharResNet.forward in eval mode (BatchNorm folded): stem kernel + 13 implicit-GEMM convs."""
+        c = self.config
+        R = P["res"]
+        bf16 = torch.bfloat16
+        b1 = R["blocks"][0]
+        y1 = self._buf("res.y1", (N, 1, 16, 16, 64), bf16)
+        ysc = self._buf("res.ysc", (N * 256, 64), bf16)
+        ops.glyph_stem(R["glyphs"], ids_flat, b1["w1_f32"], b1["wsc_f32"], b1["s1"], b1["t1"], b1["ss"], b1["ts"],
+                       y1, ysc, N, c.num_fonts)
+        x = self._buf("res.x1", (N * 256, 64), bf16)  # block-1 output, parity-split rows
+        ops.conv_gemm(y1, b1["w2"], x, nimg=N, H=16, W=16, planes=1, taps=b1["taps2"], scale=b1["s2"], bias=b1["t2"],
+                      res=ysc, act=ops.ACT_RELU, out_remap=1)
+        self._keep("res_block1_split", x)
+        for bi in range(1, 5):
+            e = R["blocks"][bi]
+            S, cout = e["S"], e["cout"]
+            cin = RES_CHANNELS[bi]
+            xin = x.view(N, 4, S, S, cin)
+            sc = self._buf(f"res.sc{bi}", (N * S * S, cout), bf16)
+            ops.conv_gemm(xin, e["wsc"], sc, nimg=N, H=S, W=S, planes=4, taps=[(0, 0, 0)], scale=e["ss"], bias=e["ts"])
+            y = self._buf(f"res.y{bi}", (N * S * S, cout), bf16)
+            ops.conv_gemm(xin, e["w1"], y, nimg=N, H=S, W=S, planes=4, taps=e["taps1"], scale=e["s1"], bias=e["t1"],
+                          act=ops.ACT_RELU)
+            last = bi == 4
+            x = self._buf(f"res.x{bi + 1}", (N * S * S, cout), torch.float32 if last else bf16)
+            ops.conv_gemm(y.view(N, 1, S, S, cout), e["w2"], x, nimg=N, H=S, W=S, planes=1, taps=e["taps2"],
+                          scale=e["s2"], bias=e["t2"], res=sc, act=ops.ACT_RELU, out_remap=0 if last else 1)
+            self._keep(f"res_block{bi + 1}_split", x)
+        return x  # f32 [N, 768]
+
+    def forward(self, batch):
+        c = self.config
+        if self.training:
+            raise NotImplementedError("train-mode forward/backward kernels are not wired yet (round 2)")
+        input_ids = batch["src_idx"]
+        if not input_ids.is_cuda:
+            raise RuntimeError("realise_b200 has no CPU path: move the batch tensors to the model's CUDA device")
+        P = self._prepared or self.prepare()
+        mask = batch["masks"].contiguous()
+        B, L = input_ids.shape
+        N, H = B * L, c.hidden_size
+        ids_flat = input_ids.contiguous().view(-1)
+        f32 = torch.float32
+
+        bert_h, _ = self._bert_stack("bert", P["bert"], mask, B, L, ids=ids_flat)
+        self._keep("bert_hiddens", bert_h)
+        mods = [bert_h]
+        if c.with_pho == "yes":
+            lens = batch["pho_lens"]
+            lens_dev = lens.to(device=input_ids.device, dtype=torch.int32) if torch.is_tensor(lens) else \
+                torch.tensor(lens, dtype=torch.int32).to(input_ids.device, non_blocking=True)
+            pho_idx = batch["pho_idx"].contiguous()
+            pho_gru = self._gru(P, pho_idx, lens_dev, N)
+            self._keep("pho_gru", pho_gru)
+            pho_h, _ = self._bert_stack("pho", P["pho_model"], mask, B, L, inputs_embeds=pho_gru)
+            self._keep("pho_hiddens", pho_h)
+            mods.append(pho_h)
+        if c.with_res == "yes":
+            res_raw = self._resnet(P, ids_flat, N)
+            res_h = self._buf("res.h", (N, H), f32)
+            ops.layernorm(res_raw, P["res_ln_w"], P["res_ln_b"], res_h, None, c.layer_norm_eps)
+            self._keep("resnet", res_raw)
+            self._keep("res_hiddens", res_h)
+            mods.append(res_h)
+        fused = self._buf("fused", (N, H), f32)
+        if c.fusion == "gate":
+            ops.gate_fuse(mods, False, mask, P["gate_w"], P["gate_b"], self._buf("gate.ws", (B * 3,), f32), fused, None,
+                          B, L, H)
+        else:
+            ops.gate_fuse(mods, True, None, None, None, None, fused, None, B, L, H)
+        self._keep("fused", fused)
+        seq, seq_b = self._bert_stack("out", P["output_block"], mask, B, L, inputs_embeds=fused, pos_mode=1)
+        self._keep("sequence_output", seq)
+        logits = torch.empty(N, c.vocab_size, device=input_ids.device, dtype=f32)
+        ops.gemm(seq_b, P["cls_w"], logits, bias=P["cls_b"])
+        logits = logits.view(B, L, c.vocab_size)
+        if "tgt_idx" not in batch:
+            return (logits,)
+        loss = torch.empty(1, device=input_ids.device, dtype=f32)
+        ops.masked_ce(logits.view(N, -1), batch["tgt_idx"].contiguous().view(-1),
+                      batch["loss_masks"].contiguous().view(-1), self._buf("ce.rows", (N,), f32), loss)
+        return (loss[0], logits)
+
+
+class SpellBertPho2ResArch3(SpellBertPho2ResArch3Abla):
+    """src/models.py:652 — all three modalities, gate fusion."""
+
+    def __init__(self, config):
+        c = normalize_config(config)
+        c.with_pho, c.with_res, c.fusion = "yes", "yes", "gate"
+        super().__init__(c)
+
+
+MODEL_CLASSES = {  # the registry names of src/run.py:40-51 that this package serves
+    "bert-pho2-res-arch3": SpellBertPho2ResArch3,
+    "bert-pho2-res-arch3-abla": SpellBertPho2ResArch3Abla,
+}

@@ -91,3 +91,79 @@ def _fill_epilogue(d, out, scale, bias, res, act, out2, out_remap):
         d.res, d.ldr, d.res_dtype = res.data_ptr(), res.stride(0), _DT[res.dtype]
     d.act = act
     d.out_remap = out_remap
+
+
+_I64P = ctypes.POINTER(ctypes.c_int64)
+
+
+def _c(v):
+    return ctypes.c_int64(int(v))
+
+
+def attention(qkv, mask, ctx, B, L, heads):
+    """ctx = softmax(QK^T/8 + (1-mask)*-1e4) V per head; qkv bf16 [B*L, 3*heads*64], mask int64 [B, L]."""
+    _req(qkv, torch.bfloat16, "qkv")
+    _req(ctx, torch.bfloat16, "ctx")
+    _req(mask, torch.int64, "mask")
+    assert qkv.is_contiguous() and ctx.is_contiguous() and mask.is_contiguous()
+    check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _c(B), _c(L), _c(heads), _c(64), _stream()),
+          "rl_attention_fwd")
+    return ctx
+
+
+def layernorm(x, gamma, beta, out_f32, out_bf16, eps):
+    _req(x, torch.float32, "x")
+    rows, H = x.shape
+    check(lib().rl_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(H),
+                                 ctypes.c_float(eps), _stream()), "rl_layernorm_fwd")
+
+
+def embed_ln(ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, out_bf16, rows, L, H, pos_mode, eps):
+    if ids is not None:
+        _req(ids, torch.int64, "ids")
+    check(lib().rl_embed_ln_fwd(_ptr(ids), _ptr(word), _ptr(inputs_embeds), _ptr(pos), _ptr(type0), _ptr(gamma),
+                                _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(L), _c(H),
+                                ctypes.c_int32(pos_mode), ctypes.c_float(eps), _stream()), "rl_embed_ln_fwd")
+
+
+def gate_fuse(mods, sum_mode, mask, gate_w, gate_b, ws, out, gates_out, B, L, H):
+    m = list(mods) + [None] * (3 - len(mods))
+    for t in mods:
+        _req(t, torch.float32, "modality")
+    check(lib().rl_gate_fuse_fwd(_ptr(m[0]), _ptr(m[1]), _ptr(m[2]), ctypes.c_int32(len(mods)),
+                                 ctypes.c_int32(1 if sum_mode else 0), _ptr(mask), _ptr(gate_w), _ptr(gate_b),
+                                 _ptr(ws), _ptr(out), _ptr(gates_out), _c(B), _c(L), _c(H), _stream()),
+          "rl_gate_fuse_fwd")
+
+
+def masked_ce(logits, tgt, loss_mask, row_ws, loss):
+    _req(logits, torch.float32, "logits")
+    _req(tgt, torch.int64, "tgt")
+    _req(loss_mask, torch.int64, "loss_mask")
+    rows, V = logits.shape
+    check(lib().rl_masked_ce_fwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _c(rows), _c(V),
+                                 _c(logits.stride(0)), _stream()), "rl_masked_ce_fwd")
+
+
+def gru_input_table(emb, w_ih, b_ih, table):
+    V, H = emb.shape
+    check(lib().rl_gru_input_table(_ptr(emb), _ptr(w_ih), _ptr(b_ih), _ptr(table), _c(V), _c(H), _stream()),
+          "rl_gru_input_table")
+
+
+def gru_step(gh, b_hh, table, pho_idx, lens, h_prev, h_out, h_out_bf16, t):
+    _req(pho_idx, torch.int64, "pho_idx")
+    _req(lens, torch.int32, "lens")
+    rows, T = pho_idx.shape
+    H = h_out.shape[1]
+    check(lib().rl_gru_step_fwd(_ptr(gh), _ptr(b_hh), _ptr(table), _ptr(pho_idx), _ptr(lens), _ptr(h_prev),
+                                _ptr(h_out), _ptr(h_out_bf16), _c(rows), _c(H), _c(T), _c(t), _stream()),
+          "rl_gru_step_fwd")
+
+
+def glyph_stem(glyphs, ids, w1, wsc, scale1, shift1, scale_sc, shift_sc, y1, ysc, n_img, C):
+    _req(glyphs, torch.float32, "glyphs")
+    _req(ids, torch.int64, "ids")
+    check(lib().rl_glyph_stem_fwd(_ptr(glyphs), _ptr(ids), _ptr(w1), _ptr(wsc), _ptr(scale1), _ptr(shift1),
+                                  _ptr(scale_sc), _ptr(shift_sc), _ptr(y1), _ptr(ysc), _c(n_img), ctypes.c_int32(C),
+                                  _stream()), "rl_glyph_stem_fwd")
