@@ -117,6 +117,12 @@ RL_API int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64
                             float* row_loss_ws, float* loss, int64_t rows, int64_t V, int64_t ld,
                             void* stream);
 
+/* ---- row-wise argmax over the vocabulary (first maximum wins) --------------------------------
+ * Replaces the host-side `logits.detach().cpu().numpy()` + argmax of src/test.py:140-145 and
+ * src/run.py:262-263 so that only [B, L] int64 ids cross PCIe.  out: int64 [rows]. */
+RL_API int rl_argmax_rows(const float* logits, int64_t* out, int64_t rows, int64_t V, int64_t ld,
+                          void* stream);
+
 /* ---- pinyin GRU (src/models.py:818-826: nn.Embedding -> pack_padded_sequence -> nn.GRU) -------
  * rl_gru_input_table: table[v, :] = W_ih emb[v] + b_ih  (f32 [V=33, 3H]; gate order r,z,n).
  * rl_gru_step_fwd: one time step t for every token row; gh = h_{t-1} W_hh^T + b_hh (f32 [rows,3H],

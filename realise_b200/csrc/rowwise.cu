@@ -245,6 +245,47 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict
   }
 }
 
+// row-wise argmax (first maximum wins, like numpy/torch): the post-processing step of
+// src/test.py:140-145 / src/run.py:262-263 moved on-device so only [B, L] ids cross PCIe
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const float* __restrict__ logits, long long* __restrict__ out, int V, long long ld) {
+  const long long row = blockIdx.x;
+  const float* x = logits + row * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = x[i];
+    if (v > best) {
+      best = v;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  if ((threadIdx.x & 31) == 0) {
+    s_v[threadIdx.x >> 5] = best;
+    s_i[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) {
+        best = s_v[w];
+        bi = s_i[w];
+      }
+    out[row] = bi;
+  }
+}
+
 bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
 
 }  // namespace
@@ -310,4 +351,11 @@ extern "C" int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const i
   if (rc) return rc;
   ce_reduce_kernel<<<1, 1024, 0, st>>>(row_loss_ws, (const long long*)loss_mask, loss, rows);
   return rl_check_launch("rl_masked_ce_fwd");
+}
+
+extern "C" int rl_argmax_rows(const float* logits, int64_t* out, int64_t rows, int64_t V, int64_t ld, void* stream) {
+  RL_REQUIRE(logits && out && V > 0 && ld >= V, RL_EINVAL, "rl_argmax_rows: bad arguments");
+  if (rows <= 0) return 0;
+  argmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (long long*)out, (int)V, ld);
+  return rl_check_launch("rl_argmax_rows");
 }

@@ -163,6 +163,8 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         self.init_weights()
         self._prepared = None
         self._ws = {}
+        self._graphs = {}
+        self.use_cuda_graph = True
         self.collect = None  # tests set this to a dict to receive clones of the sub-module outputs
 
     def _keep(self, name, t):
@@ -225,6 +227,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         out = super()._apply(fn, *a, **k)
         self._prepared = None
         self._ws = {}
+        self._graphs = {}
         return out
 
     # ---- weight preparation (bf16 operand copies, fused / re-laid-out weights) -----------------
@@ -287,6 +290,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         P["cls_b"] = self.classifier.bias.detach().float().contiguous()
         torch.cuda.current_stream().synchronize()
         self._prepared = P
+        self._graphs = {}  # captured graphs hold pointers into the previous operand cache
         return P
 
     @staticmethod
@@ -427,28 +431,64 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         return x  # f32 [N, 768]
 
     def forward(self, batch):
+        """(loss, logits) when 'tgt_idx' is in the batch else (logits,) — src/models.py:806-870.
+        With `use_cuda_graph` (default) the launch sequence of one (B, L, T) shape is captured once
+        and replayed; the returned tensors are then static buffers that the next forward()
+        overwrites (the reference's callers consume them immediately: src/run.py:191,259,
+        src/test.py:138-140)."""
         c = self.config
         if self.training:
             raise NotImplementedError("train-mode forward/backward kernels are not wired yet (round 2)")
         input_ids = batch["src_idx"]
         if not input_ids.is_cuda:
             raise RuntimeError("realise_b200 has no CPU path: move the batch tensors to the model's CUDA device")
-        P = self._prepared or self.prepare()
-        mask = batch["masks"].contiguous()
+        if self._prepared is None:
+            self.prepare()
+        dev = input_ids.device
+        inputs = {"src_idx": input_ids.contiguous(), "masks": batch["masks"].contiguous()}
+        if "tgt_idx" in batch:
+            inputs["tgt_idx"] = batch["tgt_idx"].contiguous()
+            inputs["loss_masks"] = batch["loss_masks"].contiguous()
+        if c.with_pho == "yes":
+            lens = batch["pho_lens"]
+            if torch.is_tensor(lens):
+                inputs["pho_lens"] = lens.to(device=dev, dtype=torch.int32, non_blocking=True)
+            else:
+                inputs["pho_lens"] = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+            inputs["pho_idx"] = batch["pho_idx"].contiguous()
+        if not self.use_cuda_graph or self.collect is not None:
+            return self._run(inputs)
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static = {k: v.clone() for k, v in inputs.items()}
+            self._run(static)                      # eager warm-up: lazy init outside the capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._run(static)
+            entry = (graph, static, outs)
+            self._graphs[key] = entry
+        graph, static, outs = entry
+        for k, v in inputs.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return outs
+
+    def _run(self, inp):
+        c = self.config
+        P = self._prepared
+        input_ids, mask = inp["src_idx"], inp["masks"]
         B, L = input_ids.shape
         N, H = B * L, c.hidden_size
-        ids_flat = input_ids.contiguous().view(-1)
+        ids_flat = input_ids.view(-1)
         f32 = torch.float32
 
         bert_h, _ = self._bert_stack("bert", P["bert"], mask, B, L, ids=ids_flat)
         self._keep("bert_hiddens", bert_h)
         mods = [bert_h]
         if c.with_pho == "yes":
-            lens = batch["pho_lens"]
-            lens_dev = lens.to(device=input_ids.device, dtype=torch.int32) if torch.is_tensor(lens) else \
-                torch.tensor(lens, dtype=torch.int32).to(input_ids.device, non_blocking=True)
-            pho_idx = batch["pho_idx"].contiguous()
-            pho_gru = self._gru(P, pho_idx, lens_dev, N)
+            pho_gru = self._gru(P, inp["pho_idx"], inp["pho_lens"], N)
             self._keep("pho_gru", pho_gru)
             pho_h, _ = self._bert_stack("pho", P["pho_model"], mask, B, L, inputs_embeds=pho_gru)
             self._keep("pho_hiddens", pho_h)
@@ -472,11 +512,11 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         logits = torch.empty(N, c.vocab_size, device=input_ids.device, dtype=f32)
         ops.gemm(seq_b, P["cls_w"], logits, bias=P["cls_b"])
         logits = logits.view(B, L, c.vocab_size)
-        if "tgt_idx" not in batch:
+        if "tgt_idx" not in inp:
             return (logits,)
         loss = torch.empty(1, device=input_ids.device, dtype=f32)
-        ops.masked_ce(logits.view(N, -1), batch["tgt_idx"].contiguous().view(-1),
-                      batch["loss_masks"].contiguous().view(-1), self._buf("ce.rows", (N,), f32), loss)
+        ops.masked_ce(logits.view(N, -1), inp["tgt_idx"].view(-1), inp["loss_masks"].view(-1),
+                      self._buf("ce.rows", (N,), f32), loss)
         return (loss[0], logits)
 
 

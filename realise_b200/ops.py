@@ -10,6 +10,33 @@ import torch
 from ._lib import GemmDesc, check, lib
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+
+LAUNCHES = 0    # kernels launched through this module (each C-ABI call adds its kernel count)
+_prof = None    # bench.py sets this to a list to get (kind, work, start_event, end_event) per call
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Timed:
+    """CUDA-event bracket around one C-ABI call on the current stream (only when profiling)."""
+
+    def __init__(self, kind, work):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            self.e1.record()
+            _prof.append((self.kind, self.work, self.e0, self.e1))
+        return False
 _DT = {torch.bfloat16: 0, torch.float32: 1}
 
 
@@ -43,7 +70,9 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None)
     d.lda, d.ldb = a.stride(0), b.stride(0)
     d.a_mode = 0
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
-    check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16")
+    with _Timed("gemm", 2.0 * M * N * K):
+        check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16")
+    _count()
     return out
 
 
@@ -69,7 +98,9 @@ def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res
     for i, (dw, dh, pl) in enumerate(taps):
         d.tap_dw[i], d.tap_dh[i], d.tap_plane[i] = dw, dh, pl
     _fill_epilogue(d, out, scale, bias, res, act, None, out_remap)
-    check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16(conv)")
+    with _Timed("conv_gemm", 2.0 * M * N * K):
+        check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16(conv)")
+    _count()
     return out
 
 
@@ -106,34 +137,43 @@ def attention(qkv, mask, ctx, B, L, heads):
     _req(ctx, torch.bfloat16, "ctx")
     _req(mask, torch.int64, "mask")
     assert qkv.is_contiguous() and ctx.is_contiguous() and mask.is_contiguous()
-    check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _c(B), _c(L), _c(heads), _c(64), _stream()),
-          "rl_attention_fwd")
+    with _Timed("attention", 4.0 * B * heads * L * L * 64):
+        check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _c(B), _c(L), _c(heads), _c(64), _stream()),
+              "rl_attention_fwd")
+    _count()
     return ctx
 
 
 def layernorm(x, gamma, beta, out_f32, out_bf16, eps):
     _req(x, torch.float32, "x")
     rows, H = x.shape
-    check(lib().rl_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(H),
-                                 ctypes.c_float(eps), _stream()), "rl_layernorm_fwd")
+    nbytes = rows * H * (4 + (4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))
+    with _Timed("layernorm", nbytes):
+        check(lib().rl_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(H),
+                                     ctypes.c_float(eps), _stream()), "rl_layernorm_fwd")
+    _count()
 
 
 def embed_ln(ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, out_bf16, rows, L, H, pos_mode, eps):
     if ids is not None:
         _req(ids, torch.int64, "ids")
-    check(lib().rl_embed_ln_fwd(_ptr(ids), _ptr(word), _ptr(inputs_embeds), _ptr(pos), _ptr(type0), _ptr(gamma),
-                                _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(L), _c(H),
-                                ctypes.c_int32(pos_mode), ctypes.c_float(eps), _stream()), "rl_embed_ln_fwd")
+    with _Timed("embed_ln", rows * H * 10):
+        check(lib().rl_embed_ln_fwd(_ptr(ids), _ptr(word), _ptr(inputs_embeds), _ptr(pos), _ptr(type0), _ptr(gamma),
+                                    _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(L), _c(H),
+                                    ctypes.c_int32(pos_mode), ctypes.c_float(eps), _stream()), "rl_embed_ln_fwd")
+    _count()
 
 
 def gate_fuse(mods, sum_mode, mask, gate_w, gate_b, ws, out, gates_out, B, L, H):
     m = list(mods) + [None] * (3 - len(mods))
     for t in mods:
         _req(t, torch.float32, "modality")
-    check(lib().rl_gate_fuse_fwd(_ptr(m[0]), _ptr(m[1]), _ptr(m[2]), ctypes.c_int32(len(mods)),
-                                 ctypes.c_int32(1 if sum_mode else 0), _ptr(mask), _ptr(gate_w), _ptr(gate_b),
-                                 _ptr(ws), _ptr(out), _ptr(gates_out), _c(B), _c(L), _c(H), _stream()),
-          "rl_gate_fuse_fwd")
+    with _Timed("gate_fuse", B * L * H * 4 * (len(mods) + 1)):
+        check(lib().rl_gate_fuse_fwd(_ptr(m[0]), _ptr(m[1]), _ptr(m[2]), ctypes.c_int32(len(mods)),
+                                     ctypes.c_int32(1 if sum_mode else 0), _ptr(mask), _ptr(gate_w), _ptr(gate_b),
+                                     _ptr(ws), _ptr(out), _ptr(gates_out), _c(B), _c(L), _c(H), _stream()),
+              "rl_gate_fuse_fwd")
+    _count(1 if sum_mode else 2)
 
 
 def masked_ce(logits, tgt, loss_mask, row_ws, loss):
@@ -141,14 +181,17 @@ def masked_ce(logits, tgt, loss_mask, row_ws, loss):
     _req(tgt, torch.int64, "tgt")
     _req(loss_mask, torch.int64, "loss_mask")
     rows, V = logits.shape
-    check(lib().rl_masked_ce_fwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _c(rows), _c(V),
-                                 _c(logits.stride(0)), _stream()), "rl_masked_ce_fwd")
+    with _Timed("masked_ce", rows * V * 4):
+        check(lib().rl_masked_ce_fwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _c(rows),
+                                     _c(V), _c(logits.stride(0)), _stream()), "rl_masked_ce_fwd")
+    _count(2)
 
 
 def gru_input_table(emb, w_ih, b_ih, table):
     V, H = emb.shape
     check(lib().rl_gru_input_table(_ptr(emb), _ptr(w_ih), _ptr(b_ih), _ptr(table), _c(V), _c(H), _stream()),
           "rl_gru_input_table")
+    _count()
 
 
 def gru_step(gh, b_hh, table, pho_idx, lens, h_prev, h_out, h_out_bf16, t):
@@ -156,14 +199,30 @@ def gru_step(gh, b_hh, table, pho_idx, lens, h_prev, h_out, h_out_bf16, t):
     _req(lens, torch.int32, "lens")
     rows, T = pho_idx.shape
     H = h_out.shape[1]
-    check(lib().rl_gru_step_fwd(_ptr(gh), _ptr(b_hh), _ptr(table), _ptr(pho_idx), _ptr(lens), _ptr(h_prev),
-                                _ptr(h_out), _ptr(h_out_bf16), _c(rows), _c(H), _c(T), _c(t), _stream()),
-          "rl_gru_step_fwd")
+    with _Timed("gru_step", rows * H * (12 + 6 + 4 + 6)):
+        check(lib().rl_gru_step_fwd(_ptr(gh), _ptr(b_hh), _ptr(table), _ptr(pho_idx), _ptr(lens), _ptr(h_prev),
+                                    _ptr(h_out), _ptr(h_out_bf16), _c(rows), _c(H), _c(T), _c(t), _stream()),
+              "rl_gru_step_fwd")
+    _count()
 
 
 def glyph_stem(glyphs, ids, w1, wsc, scale1, shift1, scale_sc, shift_sc, y1, ysc, n_img, C):
     _req(glyphs, torch.float32, "glyphs")
     _req(ids, torch.int64, "ids")
-    check(lib().rl_glyph_stem_fwd(_ptr(glyphs), _ptr(ids), _ptr(w1), _ptr(wsc), _ptr(scale1), _ptr(shift1),
-                                  _ptr(scale_sc), _ptr(shift_sc), _ptr(y1), _ptr(ysc), _c(n_img), ctypes.c_int32(C),
-                                  _stream()), "rl_glyph_stem_fwd")
+    # algorithmic bytes per glyph: C*32*32*4 read + 2 * 16*16*64*2 written (conv1 out + shortcut out)
+    with _Timed("glyph_stem", n_img * (C * 4096 + 2 * 32768)):
+        check(lib().rl_glyph_stem_fwd(_ptr(glyphs), _ptr(ids), _ptr(w1), _ptr(wsc), _ptr(scale1), _ptr(shift1),
+                                      _ptr(scale_sc), _ptr(shift_sc), _ptr(y1), _ptr(ysc), _c(n_img),
+                                      ctypes.c_int32(C), _stream()), "rl_glyph_stem_fwd")
+    _count()
+
+
+def argmax_rows(logits, out):
+    _req(logits, torch.float32, "logits")
+    _req(out, torch.int64, "out")
+    rows, V = logits.shape
+    with _Timed("argmax", rows * V * 4):
+        check(lib().rl_argmax_rows(_ptr(logits), _ptr(out), _c(rows), _c(V), _c(logits.stride(0)), _stream()),
+              "rl_argmax_rows")
+    _count()
+    return out

@@ -1,0 +1,58 @@
+"""CPU: host-side contract of the drop-in model class (no compute)."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+from realise_b200.model import MODEL_CLASSES, SpellBertPho2ResArch3, SpellBertPho2ResArch3Abla
+from realise_b200.synth import ArchConfig, state_dict_spec, synth_batch
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = SpellBertPho2ResArch3(ArchConfig())
+    m.tie_cls_weight()
+    return m
+
+
+def test_state_dict_keys_and_shapes_match_reference(model):
+    ref = json.load(open(os.path.join(GOLDEN, "arch3_state_dict_keys.json")))
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k, _ in ref]
+    for k, shp in ref:
+        assert list(sd[k].shape) == shp, k
+    assert sorted((k, list(s)) for k, s in state_dict_spec(ArchConfig())) == sorted((k, s) for k, s in ref)
+
+
+def test_tied_classifier_and_frozen_glyphs(model):
+    assert model.classifier.weight is model.bert.embeddings.word_embeddings.weight
+    assert not model.char_images_multifonts.requires_grad
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert n_train == 204016523  # SURVEY.md §2.2 (probed on the reference)
+
+
+def test_no_cpu_fallback(model):
+    batch = synth_batch(2, 16)
+    model.eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(batch)
+
+
+def test_ablation_configs_build():
+    for wp, wr, fu, g in [("no", "no", "gate", 1), ("yes", "no", "gate", 2), ("no", "yes", "gate", 2)]:
+        m = SpellBertPho2ResArch3Abla(ArchConfig(with_pho=wp, with_res=wr, fusion=fu, num_hidden_layers=1))
+        assert tuple(m.gate_net.weight.shape) == (g, (g + 1) * 768)
+    assert set(MODEL_CLASSES) >= {"bert-pho2-res-arch3"}
+
+
+def test_synth_batch_shape_contract():
+    b = synth_batch(4, 32, seed=3)
+    assert b["src_idx"].shape == (4, 32) and b["pho_idx"].shape[0] == 128 and len(b["pho_lens"]) == 128
+    assert (b["src_idx"][:, 0] == 101).all()
+    lens = torch.tensor(b["pho_lens"])
+    assert lens.min() >= 1 and lens.max() <= 7
+    special = (b["src_idx"].view(-1) == 0) | (b["src_idx"].view(-1) == 101) | (b["src_idx"].view(-1) == 102)
+    assert (lens[special] == 1).all() and (b["pho_idx"][special, 0] == 32).all()
+    assert ((b["pho_idx"] != 0).sum(1) == lens).all()

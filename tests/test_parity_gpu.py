@@ -1,0 +1,142 @@
+"""GPU parity: the CUDA path (through the C ABI) against (a) the committed reference goldens,
+(b) the CPU oracle on fresh seeded inputs, (c) size-independent properties at the bench shape.
+
+Tolerances (BASELINE.json north_star): logits within 1e-2 absolute in bf16 compute vs the fp32
+reference; token argmax exact wherever the reference's own top-2 margin exceeds twice that
+tolerance (bf16 cannot order logits that the fp32 reference separates by less than the error).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cached_state_dict, load_golden
+from realise_b200.synth import ArchConfig, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1.5e-2     # bf16 operands / fp32 accumulate, 19 transformer layers + 15 convs deep
+HIDDEN_TOL = 3e-2      # post-LayerNorm hidden states (|x| up to ~6)
+
+
+def to_dev(batch):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def build(cfg, seed, cls=None):
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    m = (cls or SpellBertPho2ResArch3Abla)(cfg)
+    m.tie_cls_weight()
+    m.load_state_dict(cached_state_dict(cfg, seed), strict=True)
+    return m.eval().cuda()
+
+
+def unsplit(x, n, S, C):
+    h = S // 2
+    return x.view(n, 2, 2, h, h, C).permute(0, 5, 3, 1, 4, 2).reshape(n, C, S, S)
+
+
+GOLDENS = ["arch3_eval_B2_L16.npz", "arch3_eval_B3_L40.npz", "abla_pho-no_res-no_gate_B2_L16.npz",
+           "abla_pho-yes_res-no_gate_B2_L16.npz", "abla_pho-no_res-yes_gate_B2_L16.npz",
+           "abla_pho-yes_res-yes_sum_B2_L16.npz"]
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_cuda_path_matches_reference_golden(name):
+    g, meta = load_golden(name)
+    cfg = ArchConfig(**meta["cfg"])
+    model = build(cfg, meta["wseed"])
+    batch = to_dev(synth_batch(meta["B"], meta["L"], seed=meta["bseed"]))
+    model.collect = {}
+    with torch.no_grad():
+        loss, logits = model(batch)
+    torch.cuda.synchronize()
+    col = model.collect
+    n = meta["B"] * meta["L"]
+    for gk, ck in {"bert_hiddens": "bert_hiddens", "pho_hiddens": "pho_hiddens", "res_hiddens": "res_hiddens",
+                   "output_block": "sequence_output"}.items():
+        if gk in g.files:
+            err = np.abs(col[ck].cpu().numpy().reshape(g[gk].shape) - g[gk]).max()
+            assert err <= HIDDEN_TOL, (gk, err)
+    if "pho_gru" in g.files:
+        assert np.abs(col["pho_gru"].cpu().numpy() - g["pho_gru"]).max() <= 1e-3
+    if "res_block1" in g.files:
+        b1 = unsplit(col["res_block1_split"], n, 16, 64).cpu().numpy()[:8]
+        assert np.abs(b1 - g["res_block1"]).max() <= 2e-2
+        b2 = unsplit(col["res_block2_split"], n, 8, 128).cpu().numpy()[:8]
+        assert np.abs(b2 - g["res_block2"]).max() <= 2e-2
+        assert np.abs(col["resnet"].cpu().numpy() - g["resnet"]).max() <= 1e-2
+    flat = logits.reshape(n, -1).float().cpu()
+    err = np.abs(flat[torch.from_numpy(g["logits_rows"])].numpy() - g["logits_kept"]).max()
+    assert err <= LOGIT_TOL, err
+    assert np.abs(torch.logsumexp(flat, -1).numpy() - g["logits_lse"]).max() <= LOGIT_TOL
+    safe = g["logits_top2_gap"] > 2 * LOGIT_TOL
+    assert (flat.argmax(-1).numpy()[safe] == g["logits_argmax"][safe]).all()
+    assert abs(loss.item() - float(g["loss"])) <= 5e-3
+
+
+def test_cuda_path_matches_oracle_on_fresh_inputs():
+    """Different seeds / ragged lengths / L not a multiple of 16, checked against the CPU oracle."""
+    from oracle import realise_oracle as O
+    cfg = ArchConfig(num_hidden_layers=2)
+    sd = cached_state_dict(cfg, 5)
+    model = build(cfg, 5)
+    for (B, L, seed) in [(1, 8, 11), (5, 23, 12), (2, 130, 13)]:
+        batch = synth_batch(B, L, seed=seed)
+        with torch.no_grad():
+            rloss, rlogits = O.forward(sd, batch, cfg)
+            loss, logits = model(to_dev(batch))
+        err = (logits.float().cpu() - rlogits).abs().max().item()
+        assert err <= LOGIT_TOL, (B, L, err)
+        assert abs(loss.item() - rloss.item()) <= 5e-3
+        top2 = rlogits.reshape(B * L, -1).topk(2, -1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_TOL
+        assert (logits.reshape(B * L, -1).argmax(-1).cpu()[safe] == rlogits.reshape(B * L, -1).argmax(-1)[safe]).all()
+
+
+def test_single_font_glyph_table():
+    from oracle import realise_oracle as O
+    cfg = ArchConfig(num_hidden_layers=1, num_fonts=1, vocab_size=21128)
+    sd = cached_state_dict(cfg, 2)
+    model = build(cfg, 2)
+    batch = synth_batch(2, 16, seed=3)
+    with torch.no_grad():
+        _, rlogits = O.forward(sd, batch, cfg)
+        _, logits = model(to_dev(batch))
+    assert (logits.float().cpu() - rlogits).abs().max().item() <= LOGIT_TOL
+
+
+def test_bench_shape_properties():
+    """B=64, L=128 (BASELINE configs[1]): size-independent properties instead of a CPU re-run."""
+    cfg = ArchConfig(num_hidden_layers=2)
+    model = build(cfg, 5)
+    batch = synth_batch(64, 128, seed=21, ragged=True, with_labels=False)
+    db = to_dev(batch)
+    with torch.no_grad():
+        (logits,) = model(db)
+        logits = logits.clone()
+        # (1) sentences are independent: permuting the batch permutes the logits
+        perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
+        pb = {"src_idx": batch["src_idx"][perm], "masks": batch["masks"][perm], "loss_masks": batch["loss_masks"][perm],
+              "pho_idx": batch["pho_idx"].view(64, 128, -1)[perm].reshape(64 * 128, -1),
+              "pho_lens": torch.tensor(batch["pho_lens"]).view(64, 128)[perm].reshape(-1).tolist()}
+        (plogits,) = model(to_dev(pb))
+        assert torch.equal(plogits, logits[perm.cuda()])
+        # (2) a sentence alone gives the same logits as inside the batch (eval mode, padded to 128)
+        one = {"src_idx": batch["src_idx"][7:8], "masks": batch["masks"][7:8], "loss_masks": batch["loss_masks"][7:8],
+               "pho_idx": batch["pho_idx"].view(64, 128, -1)[7].reshape(128, -1),
+               "pho_lens": torch.tensor(batch["pho_lens"]).view(64, 128)[7].tolist()}
+        (ologits,) = model(to_dev(one))
+        assert (ologits[0] - logits[7]).abs().max().item() <= 1e-4
+        # (3) finite everywhere, including rows of padding tokens
+        assert torch.isfinite(logits).all()
+
+
+def test_error_paths():
+    from realise_b200 import ops
+    a = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(128, 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        ops.gemm(a, b, out)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.gemm(a.cpu(), b, out)
