@@ -83,6 +83,34 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed to run on (affinity / cgroup
+    quota), not the machine's core count — oversubscribing a shared host makes the baseline slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def pick_threads(fn, candidates):
+    """Calibrate: run fn() once per candidate thread count and keep the fastest (best for the CPU arm)."""
+    best, best_t = candidates[0], float("inf")
+    for n in candidates:
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_oracle_rate(batch_sentences, seq_len, budget_s, threads=None):
     """sentences/s of the CPU oracle (port of the reference forward) on a bounded sample."""
     from oracle import realise_oracle as O
@@ -95,6 +123,8 @@ def cpu_oracle_rate(batch_sentences, seq_len, budget_s, threads=None):
     batch = synth_batch(batch_sentences, seq_len, seed=1, ragged=False, with_labels=False)
     with torch.no_grad():
         O.forward(sd, batch, cfg)  # warm-up
+        maxt = threads or host_threads()
+        pick_threads(lambda: O.forward(sd, batch, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64, maxt)}))
         t0, n = time.perf_counter(), 0
         while True:
             O.forward(sd, batch, cfg)
@@ -110,15 +140,17 @@ def run_reference(args, rank, world):
         return
     from oracle import realise_oracle as O
     from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     O.FAST = True  # ATen fused CPU kernels, like the reference's nn.Modules
     cfg = ArchConfig()
     sd = synth_state_dict(cfg, seed=0)
     sample_b = 8  # bounded sample of the 64-sentence step
     batch = synth_batch(sample_b, SEQ_LEN, seed=1, ragged=False, with_labels=False)
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
+        maxt = host_threads()
+        torch.set_num_threads(maxt)
+        O.forward(sd, batch, cfg)
+        pick_threads(lambda: O.forward(sd, batch, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64, maxt)}))
+        for _ in range(max(0, min(args.warmup, 2) - 1)):
             O.forward(sd, batch, cfg)
         t0 = time.perf_counter()
         steps = 0
@@ -261,8 +293,7 @@ def run_ours(args, rank, world, local_rank):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        rate, reps, _, _ = cpu_oracle_rate(8, L, budget_s=15.0, threads=threads)
+        rate, reps, _, _ = cpu_oracle_rate(8, L, budget_s=15.0)
         cpu = {"value": rate, "unit": "sentences/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{reps} x eval forward of 8 sentences x {L} tokens (oracle/realise_oracle.py, fp32, all host threads)"}
     line = {

@@ -53,8 +53,8 @@ rl_tmap_encode_fn rl_get_tmap_encode() {
   return fn;
 }
 
-int rl_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box) {
+int rl_make_tmap(CUtensorMap* out, const void* base, int dtype, int swizzle_bytes, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box) {
   rl_tmap_encode_fn enc = rl_get_tmap_encode();
   RL_REQUIRE(enc != nullptr, RL_EDRIVER, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -67,8 +67,12 @@ int rl_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64
     estr[i] = 1;
     if (i < rank - 1) gstr[i] = strides_bytes[i];
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                   gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, dtype == RL_TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RL_REQUIRE(r == CUDA_SUCCESS, RL_EDRIVER,
              "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu %llu %llu, box %u %u %u)", (int)r,

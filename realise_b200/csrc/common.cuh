@@ -31,9 +31,14 @@ typedef CUresult (*rl_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 rl_tmap_encode_fn rl_get_tmap_encode();
 
-// Build a bf16 tiled tensor map, SWIZZLE_128B, dims fastest-first.  Returns 0 / error code.
-int rl_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box);
+// Build a tiled tensor map, dims fastest-first.  swizzle_bytes in {0, 32, 64, 128}.  Returns 0 / error code.
+enum { RL_TMAP_BF16 = 0, RL_TMAP_F32 = 1 };
+int rl_make_tmap(CUtensorMap* out, const void* base, int dtype, int swizzle_bytes, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box);
+inline int rl_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box) {
+  return rl_make_tmap(out, base, RL_TMAP_BF16, 128, rank, dims, strides_bytes, box);
+}
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------

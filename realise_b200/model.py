@@ -417,16 +417,26 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             e = R["blocks"][bi]
             S, cout = e["S"], e["cout"]
             cin = RES_CHANNELS[bi]
-            xin = x.view(N, 4, S, S, cin)
-            sc = self._buf(f"res.sc{bi}", (N * S * S, cout), bf16)
-            ops.conv_gemm(xin, e["wsc"], sc, nimg=N, H=S, W=S, planes=4, taps=[(0, 0, 0)], scale=e["ss"], bias=e["ts"])
-            y = self._buf(f"res.y{bi}", (N * S * S, cout), bf16)
-            ops.conv_gemm(xin, e["w1"], y, nimg=N, H=S, W=S, planes=4, taps=e["taps1"], scale=e["s1"], bias=e["t1"],
-                          act=ops.ACT_RELU)
             last = bi == 4
-            x = self._buf(f"res.x{bi + 1}", (N * S * S, cout), torch.float32 if last else bf16)
-            ops.conv_gemm(y.view(N, 1, S, S, cout), e["w2"], x, nimg=N, H=S, W=S, planes=1, taps=e["taps2"],
-                          scale=e["s2"], bias=e["t2"], res=sc, act=ops.ACT_RELU, out_remap=0 if last else 1)
+            sc = self._buf(f"res.sc{bi}", (N * S * S, cout), bf16)
+            y = self._buf(f"res.y{bi}", (N * S * S, cout), bf16)
+            xo = self._buf(f"res.x{bi + 1}", (N * S * S, cout), torch.float32 if last else bf16)
+            if S == 1:
+                # 1x1 output map: the parity-split input row IS the im2col row ([N, 4*cin], plane-major),
+                # the shortcut reads plane 0, conv2 is its centre tap -> three plain GEMMs
+                xin = x.view(N, 4 * cin)
+                ops.gemm(xin[:, :cin], e["wsc"], sc, scale=e["ss"], bias=e["ts"])
+                ops.gemm(xin, e["w1"], y, scale=e["s1"], bias=e["t1"], act=ops.ACT_RELU)
+                ops.gemm(y, e["w2"], xo, scale=e["s2"], bias=e["t2"], res=sc, act=ops.ACT_RELU)
+            else:
+                xin = x.view(N, 4, S, S, cin)
+                ops.conv_gemm(xin, e["wsc"], sc, nimg=N, H=S, W=S, planes=4, taps=[(0, 0, 0)], scale=e["ss"],
+                              bias=e["ts"])
+                ops.conv_gemm(xin, e["w1"], y, nimg=N, H=S, W=S, planes=4, taps=e["taps1"], scale=e["s1"],
+                              bias=e["t1"], act=ops.ACT_RELU)
+                ops.conv_gemm(y.view(N, 1, S, S, cout), e["w2"], xo, nimg=N, H=S, W=S, planes=1, taps=e["taps2"],
+                              scale=e["s2"], bias=e["t2"], res=sc, act=ops.ACT_RELU, out_remap=1)
+            x = xo
             self._keep(f"res_block{bi + 1}_split", x)
         return x  # f32 [N, 768]
 

@@ -76,28 +76,31 @@ def t_conv(nimg, Cin, Cout, S, stride):
     return report(f"conv nimg{nimg} {Cin}->{Cout} out{S}x{S} stride{stride}", out, ref, 5e-3)
 
 
-def perf(M, N, K, iters=20):
+def perf(M, N, K, iters=20, bias=False, act=0, res=None, out_dtype=torch.bfloat16):
     a = torch.randn(M, K, device=dev).bfloat16()
     b = torch.randn(N, K, device=dev).bfloat16()
-    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(M, N, device=dev, dtype=out_dtype)
+    bi = torch.randn(N, device=dev) if bias else None
+    r = torch.randn(M, N, device=dev).to(res) if res is not None else None
     for _ in range(3):
-        ops.gemm(a, b, out)
+        ops.gemm(a, b, out, bias=bi, act=act, res=r)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        ops.gemm(a, b, out)
+        ops.gemm(a, b, out, bias=bi, act=act, res=r)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     tf = 2.0 * M * N * K / ms / 1e9
+    out_b = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     e0.record()
     for _ in range(iters):
-        torch.matmul(a, b.t(), out=out)
+        torch.matmul(a, b.t(), out=out_b)
     e1.record()
     torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / iters
-    print(f"[perf] M{M} N{N} K{K}: ours {ms*1e3:.1f} us {tf:.0f} TF/s | cublas {ms2*1e3:.1f} us "
+    print(f"[perf] M{M} N{N} K{K} bias={bias} act={act} res={res} out={out_dtype}: ours {ms*1e3:.1f} us {tf:.0f} TF/s | cublas {ms2*1e3:.1f} us "
           f"{2.0*M*N*K/ms2/1e9:.0f} TF/s", flush=True)
 
 
@@ -113,6 +116,10 @@ if __name__ == "__main__":
     ok &= t_plain(300, 1000, 128, bias=True, out_dtype=torch.float32)
     ok &= t_plain(512, 21128, 768, bias=True, out_dtype=torch.float32)
     ok &= t_plain(512, 328, 192, scale=True, bias=True, act=2, res=torch.bfloat16)
+    ok &= t_plain(1000, 64, 576, scale=True, bias=True, act=2, res=torch.bfloat16)
+    ok &= t_plain(777, 200, 128, bias=True, res=torch.float32)
+    ok &= t_plain(640, 331, 64, bias=True, out_dtype=torch.float32)
+    ok &= t_plain(333, 776, 128, bias=True, act=1, res=torch.bfloat16)
     for args in [(4, 64, 64, 16, 1), (8, 128, 128, 8, 1), (16, 256, 256, 4, 1), (64, 512, 512, 2, 1),
                  (8, 64, 128, 8, 2), (16, 128, 256, 4, 2), (64, 256, 512, 2, 2), (200, 512, 768, 1, 2)]:
         try:
@@ -120,7 +127,13 @@ if __name__ == "__main__":
         except Exception as e:  # noqa: BLE001
             ok = False
             print(f"[FAIL] conv {args}: {e}", flush=True)
-    for shp in [(8192, 2304, 768), (8192, 768, 768), (8192, 3072, 768), (8192, 768, 3072), (8192, 21128, 768),
-                (16384, 3072, 768)]:
-        perf(*shp)
+    if "--quick" not in sys.argv:
+        for shp in [(8192, 2304, 768), (8192, 768, 768), (8192, 3072, 768), (8192, 768, 3072), (8192, 21128, 768),
+                    (16384, 3072, 768)]:
+            perf(*shp)
+    perf(8192, 2304, 768, bias=True)
+    perf(8192, 3072, 768, bias=True, act=1)
+    perf(8192, 768, 768, bias=True, res=torch.float32, out_dtype=torch.float32)
+    perf(8192, 768, 3072, bias=True, res=torch.float32, out_dtype=torch.float32)
+    perf(8192, 21128, 768, bias=True, out_dtype=torch.float32)
     print("ALL OK" if ok else "SOME FAILED", flush=True)
