@@ -22,20 +22,24 @@ template <int LKV_MAX>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const AttParams p) {
-  constexpr uint32_t TMEM_COLS = LKV_MAX <= 128 ? 256 : 512;
-  constexpr uint32_t O_COL = LKV_MAX <= 128 ? 128 : 256;
+  // O (64 fp32 columns) reuses the first S columns once every thread has consumed its S row, and for
+  // Lkv <= 128 the bf16 P tiles reuse the Q and K staging, so a CTA needs 128 TMEM columns and
+  // ~49 KB of shared memory: four CTAs are resident per SM and hide each other's TMA/MMA latency.
+  constexpr uint32_t TMEM_COLS = LKV_MAX <= 128 ? 128 : 256;
+  constexpr uint32_t O_COL = 0;
   constexpr int Q_BYTES = 128 * 128;
   constexpr int KV_BYTES = LKV_MAX * 128;
   constexpr int P_CHUNKS = LKV_MAX / 64;
+  constexpr bool P_ALIAS = LKV_MAX <= 128;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // pad to 1024 B by pointer arithmetic (keeps the shared address space visible to the compiler)
+  uint8_t* smem = smem_raw + ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + KV_BYTES;
-  uint8_t* sP = sV + KV_BYTES;  // P_CHUNKS tiles of [128 x 64] bf16, SW128 K-major
-  float* s_mask = reinterpret_cast<float*>(sP + P_CHUNKS * Q_BYTES);
+  uint8_t* sP = P_ALIAS ? sQ : sV + KV_BYTES;  // P_CHUNKS tiles of [128 x 64] bf16, SW128 K-major
+  float* s_mask = reinterpret_cast<float*>(sV + KV_BYTES + (P_ALIAS ? 0 : P_CHUNKS * Q_BYTES));
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + LKV_MAX);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
   uint64_t* bar_qk = &bars[0];
@@ -96,16 +100,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   rl::tc_fence_after();
   const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   const int nchunk = (lkv16 + 31) / 32;
+  const int nfull = L / 32;  // chunks whose 32 columns are all real keys
+  const float4* m4 = reinterpret_cast<const float4*>(s_mask);
   float mx = -INFINITY;
   for (int c = 0; c < nchunk; ++c) {
     uint32_t v[32];
     rl::tmem_ld_32x32(t_row + c * 32, v);
     rl::tmem_ld_wait();
+    if (c < nfull) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;  // columns >= L (tile padding / stale TMEM) never contribute
-      const float s = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
-      mx = fmaxf(mx, s);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 m = m4[c * 8 + (j >> 2)];
+        mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), p.scale_log2, m.x));
+        mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 1]), p.scale_log2, m.y));
+        mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 2]), p.scale_log2, m.z));
+        mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 3]), p.scale_log2, m.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;  // columns >= L (tile padding / stale TMEM) never contribute
+        const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+        mx = fmaxf(mx, sc);
+      }
     }
   }
   float sum = 0.0f;
@@ -115,13 +132,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     rl::tmem_ld_32x32(t_row + c * 32, v);
     rl::tmem_ld_wait();
     float e[32];
+    if (c < nfull) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      const float s = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
-      e[j] = exp2f(s - mx);
-      sum += e[j];
+      for (int j = 0; j < 32; j += 4) {
+        const float4 m = m4[c * 8 + (j >> 2)];
+        e[j] = rl::ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, m.x) - mx);
+        e[j + 1] = rl::ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, m.y) - mx);
+        e[j + 2] = rl::ex2(fmaf(__uint_as_float(v[j + 2]), p.scale_log2, m.z) - mx);
+        e[j + 3] = rl::ex2(fmaf(__uint_as_float(v[j + 3]), p.scale_log2, m.w) - mx);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+        e[j] = rl::ex2(sc - mx);
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) sum += (e[j] + e[j + 1]) + (e[j + 2] + e[j + 3]);
     // columns c*32 .. c*32+31 of P -> chunk tile (c/2), 16-byte pieces (c&1)*4 .. +3, swizzled by row
     uint8_t* tile = sP + (c >> 1) * Q_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
@@ -184,7 +213,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 template <int LKV_MAX>
 constexpr int att_smem_bytes() {
-  return 128 * 128 + 2 * LKV_MAX * 128 + (LKV_MAX / 64) * 128 * 128 + LKV_MAX * 4 + 4 * 8 + 16 + 1024;
+  return 128 * 128 + 2 * LKV_MAX * 128 + (LKV_MAX <= 128 ? 0 : (LKV_MAX / 64) * 128 * 128) + LKV_MAX * 4 + 4 * 8 + 16 +
+         1024;
 }
 
 template <int LKV_MAX>
