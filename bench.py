@@ -122,9 +122,11 @@ def cpu_oracle_rate(batch_sentences, seq_len, budget_s, threads=None):
     sd = synth_state_dict(cfg, seed=0)
     batch = synth_batch(batch_sentences, seq_len, seed=1, ragged=False, with_labels=False)
     with torch.no_grad():
-        O.forward(sd, batch, cfg)  # warm-up
+        torch.set_num_threads(min(threads or host_threads(), 16))
+        O.forward(sd, synth_batch(2, seq_len, seed=2, ragged=False, with_labels=False), cfg)  # warm-up
         maxt = threads or host_threads()
-        pick_threads(lambda: O.forward(sd, batch, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64, maxt)}))
+        small = synth_batch(2, seq_len, seed=2, ragged=False, with_labels=False)  # cheap calibration batch
+        pick_threads(lambda: O.forward(sd, small, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64)}))
         t0, n = time.perf_counter(), 0
         while True:
             O.forward(sd, batch, cfg)
@@ -147,9 +149,10 @@ def run_reference(args, rank, world):
     batch = synth_batch(sample_b, SEQ_LEN, seed=1, ragged=False, with_labels=False)
     with torch.no_grad():
         maxt = host_threads()
-        torch.set_num_threads(maxt)
-        O.forward(sd, batch, cfg)
-        pick_threads(lambda: O.forward(sd, batch, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64, maxt)}))
+        small = synth_batch(2, SEQ_LEN, seed=2, ragged=False, with_labels=False)  # cheap calibration batch
+        torch.set_num_threads(min(maxt, 16))
+        O.forward(sd, small, cfg)
+        pick_threads(lambda: O.forward(sd, small, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64)}))
         for _ in range(max(0, min(args.warmup, 2) - 1)):
             O.forward(sd, batch, cfg)
         t0 = time.perf_counter()

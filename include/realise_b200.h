@@ -76,6 +76,10 @@ typedef struct rl_gemm_desc {
 RL_API int rl_gemm_bf16(const rl_gemm_desc* d, void* stream);
 /* tuning/debug: force the GEMM N tile (128 or 256; 0 = heuristic). */
 RL_API int rl_gemm_set_tile_n(int bn);
+/* tuning/debug: 0 disables the CTA-pair (cta_group::2) kernel, 1 (default) lets the cost model pick it. */
+RL_API int rl_gemm_set_pair_mode(int on);
+/* tuning experiments only (results become meaningless): bit0 skip epilogue, bit1 skip TMA loads, bit2 skip MMAs. */
+RL_API int rl_gemm_set_debug_mode(int flags);
 
 /* ---- fused attention core -------------------------------------------------------------------
  * ctx[b*L+q, h*64:(h+1)*64] = softmax(Q K^T / 8 + (1 - mask[b,:]) * -10000) V  per head.
@@ -144,5 +148,18 @@ RL_API int rl_glyph_stem_fwd(const float* glyphs, const int64_t* ids, const floa
                              const float* scale1, const float* shift1, const float* scale_sc,
                              const float* shift_sc, void* y1, void* ysc, int64_t n_img, int32_t C,
                              void* stream);
+
+/* ---- fused CharResNet block 1, eval mode (src/models.py:829-834 + src/char_cnn.py:15-32) -------
+ * glyph gather -> conv3x3/s2+BN+ReLU -> conv3x3+BN (+ conv1x1/s2 shortcut+BN) -> ReLU in ONE persistent
+ * tcgen05 kernel; HBM traffic per glyph = C*4 KB in + 32 KB out.  Weights are passed packed, bf16,
+ * with the BatchNorm scale folded in (scale = gamma / sqrt(running_var + 1e-5)):
+ *   w1_packed  [64, 32]   : [co, c*9+kh*3+kw] = conv1.weight[co,c,kh,kw] * scale1[co], zero padded
+ *   wsc_packed [64, 32]   : [co, c*9+4]       = shortcut.weight[co,c]    * scale_sc[co]
+ *   w2_packed  [64, 576]  : [co, (kh*3+kw)*64+ci] = conv2.weight[co,ci,kh,kw] * scale2[co]
+ *   t1 [64] = BN1 shift;  t2s [64] = BN2 shift + shortcut-BN shift.
+ * out: bf16 [n_img*256, 64], rows parity-split ([img][oh&1][ow&1][oh/2][ow/2]) for block 2. */
+RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const void* w1_packed,
+                               const void* wsc_packed, const void* w2_packed, const float* t1,
+                               const float* t2s, void* out, int64_t n_img, int32_t C, void* stream);
 
 #endif /* REALISE_B200_H */

@@ -12,7 +12,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
-constexpr int STAGE_BYTES = 8 * 4096;  // per-epilogue-warp 32x32 fp32 transpose tiles
+constexpr int STAGE_BYTES = 8 * (8192 + 1024);  // per epilogue warp: two 32x32 fp32 staging tiles + scale/bias table
 
 struct KParams {
   int M, N, num_kb;
@@ -35,6 +35,7 @@ struct KParams {
   int out_remap;
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
+  int dbg;        // tuning experiments only: 1 = no epilogue work, 2 = no TMA loads, 4 = no MMA
 };
 
 // erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result)
@@ -55,6 +56,180 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == RL_ACT_RELU) return fmaxf(x, 0.0f);
   if (act == RL_ACT_TANH) return tanhf(x);
   return x;
+}
+
+__device__ __forceinline__ long long remap_row(const KParams& p, int row) {
+  if (p.out_remap != 1) return row;
+  const int hw = 1 << p.hw_shift, w = 1 << p.w_shift;
+  const int img = row >> p.hw_shift, pix = row & (hw - 1);
+  const int oh = pix >> p.w_shift, ow = pix & (w - 1);
+  const int h2 = (hw >> p.w_shift) >> 1, w2 = w >> 1;
+  return (((long long)img * 4 + (oh & 1) * 2 + (ow & 1)) * h2 + (oh >> 1)) * w2 + (ow >> 1);
+}
+
+// ---- epilogue -------------------------------------------------------------------------------------
+// One epilogue warp owns the TMEM lanes of its quarter (thread = output row) and one half of the tile's BN
+// columns, processed in 32-column chunks.  Everything that does not depend on the accumulator is fetched
+// early: scale/bias of the warp's columns go to a small smem table and the first chunk's residual goes to
+// registers BEFORE the warp waits for the MMAs of the tile; the residual of chunk c+1 is loaded while chunk c
+// is being computed.  Results leave through a swizzled 32x32 smem tile + one TMA store per chunk (coalesced,
+// clips the M/N tails) or, for remapped / oddly aligned outputs, through direct row stores.
+__device__ __forceinline__ void load_residual(const KParams& p, int row, bool row_ok, int nb, float (&x)[32]) {
+  if (p.res && row_ok && nb < p.N) {
+    if (nb + 32 <= p.N) {
+      if (p.res_f32) {
+        const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = r[j];
+          x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+        }
+      } else {
+        const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + (long long)row * p.ldr + nb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 t = r[j];
+          x[8 * j] = rl::bf16_lo(t.x); x[8 * j + 1] = rl::bf16_hi(t.x);
+          x[8 * j + 2] = rl::bf16_lo(t.y); x[8 * j + 3] = rl::bf16_hi(t.y);
+          x[8 * j + 4] = rl::bf16_lo(t.z); x[8 * j + 5] = rl::bf16_hi(t.z);
+          x[8 * j + 6] = rl::bf16_lo(t.w); x[8 * j + 7] = rl::bf16_hi(t.w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        x[j] = 0.f;
+        if (nb + j < p.N)
+          x[j] = p.res_f32 ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + nb + j]
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[(long long)row * p.ldr + nb + j]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = 0.f;
+  }
+}
+
+// scale/bias of this warp's BN/2 columns -> sb[0..BN/2) and sb[128..128+BN/2); first residual chunk -> xr
+template <int BN>
+__device__ __forceinline__ void epilogue_prefetch(const KParams& p, float* sb, int row0, int n0, int half, int lane,
+                                                  float (&xr)[32]) {
+  constexpr int HC = BN / 2;
+  const int c0 = n0 + half * HC;
+  __syncwarp();
+  for (int i = lane; i < HC; i += 32) {
+    const int n = c0 + i;
+    sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
+    sb[128 + i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+  }
+  load_residual(p, row0 + lane, row0 + lane < p.M, c0, xr);
+  __syncwarp();
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, uint8_t* stg_base,
+                                              const float* sb, uint32_t taddr, int row0, int n0, int half, int lane,
+                                              float (&xr)[32]) {
+  constexpr int CH = BN / 64;  // 32-column chunks per half
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  const long long orow = remap_row(p, row);
+#pragma unroll 1
+  for (int cc = 0; cc < CH; ++cc) {
+    const int c = half * CH + cc;
+    const int nb = n0 + c * 32;
+    uint32_t v[32];
+    rl::tmem_ld_32x32(taddr + c * 32, v);
+    float xn[32];
+    if (cc + 1 < CH) load_residual(p, row, row_ok, nb + 32, xn);  // overlaps the TMEM load and this chunk's math
+    rl::tmem_ld_wait();
+    const bool live = nb < p.N && row0 < p.M;  // warp-uniform
+    if (live) {
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
+        const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+        x[j] = xr[j] + fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+        x[j + 1] = xr[j + 1] + fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+        x[j + 2] = xr[j + 2] + fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+        x[j + 3] = xr[j + 3] + fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+      }
+      if (p.act == RL_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f * (1.0f + fast_erf(x[j] * 0.70710678118654752440f));
+      } else if (p.act == RL_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+      } else if (p.act == RL_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
+      }
+      if (p.tma_store) {
+        // two swizzled staging tiles per warp: the TMA store issued two chunks ago must have finished reading
+        uint8_t* stg = stg_base + (cc & 1) * 4096;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        if (p.out_f32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(rl::pack_bf16(x[8 * g], x[8 * g + 1]), rl::pack_bf16(x[8 * g + 2], x[8 * g + 3]),
+                           rl::pack_bf16(x[8 * g + 4], x[8 * g + 5]), rl::pack_bf16(x[8 * g + 6], x[8 * g + 7]));
+        }
+        rl::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(tmC_ptr)),
+                       "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else if (row_ok) {
+        if (nb + 32 <= p.N && p.vec_store) {
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          }
+          if (p.out2) {
+            uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j < p.N) {
+              if (p.out_f32)
+                reinterpret_cast<float*>(p.out)[orow * p.ldo + nb + j] = x[j];
+              else
+                reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + nb + j] = __float2bfloat16(x[j]);
+              if (p.out2) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
+            }
+          }
+        }
+      }
+    }
+    if (cc + 1 < CH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) xr[j] = xn[j];
+    }
+  }
 }
 
 template <int BN, int STAGES>
@@ -119,6 +294,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           rl::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg & 2) {
+            rl::mbar_arrive(&full_bar[stage]);
+          } else {
           rl::mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           if (p.a_mode == 0) {
             rl::tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
@@ -129,6 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             (int)p.tap_dw[t], h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
           }
           rl::tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -137,9 +316,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
       constexpr uint32_t idesc = rl::make_idesc_bf16(BM, BN);
+      const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -151,21 +332,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb) {
           rl::mbar_wait(&full_bar[stage], phase);
           rl::tc_fence_after();
-          const uint32_t a_addr = rl::smem_u32(smem_a + stage * A_BYTES);
-          const uint32_t b_addr = rl::smem_u32(smem_b + stage * B_BYTES);
+          if (rl::elect_one()) {
+            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * A_BYTES, 16, 1024);
+            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * B_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = rl::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = rl::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            rl::tc_mma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              if (!(p.dbg & 4)) rl::tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            rl::tc_commit(&empty_bar[stage]);
           }
-          rl::tc_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        rl::tc_commit(&tmem_full[acc]);
+        if (rl::elect_one()) rl::tc_commit(&tmem_full[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -180,164 +362,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;
     const int q = warp & 3;
     const int half = ew >> 2;
-    uint8_t* stg = smem_stage + ew * 4096;
-    constexpr int CH = BN / 64;  // 32-column chunks per half
+    uint8_t* stg = smem_stage + ew * (8192 + 1024);
+    float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n;
       const int n_blk = tile - m_blk * p.tiles_n;
       const int row0 = m_blk * BM + q * 32;
-      const int row = row0 + lane;
       const int n0 = n_blk * BN;
-      const bool row_ok = row < p.M;
-      long long orow = row;
-      if (p.out_remap == 1) {
-        const int hw = 1 << p.hw_shift, w = 1 << p.w_shift;
-        const int img = row >> p.hw_shift, pix = row & (hw - 1);
-        const int oh = pix >> p.w_shift, ow = pix & (w - 1);
-        const int h2 = (hw >> p.w_shift) >> 1, w2 = w >> 1;
-        orow = (((long long)img * 4 + (oh & 1) * 2 + (ow & 1)) * h2 + (oh >> 1)) * w2 + (ow >> 1);
-      }
+      float xr[32];
+      epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < CH; ++cc) {
-        const int c = half * CH + cc;
-        const int nb = n0 + c * 32;
-        uint32_t v[32];
-        rl::tmem_ld_32x32(taddr + c * 32, v);
-        const bool live = nb < p.N && row0 < p.M;  // warp-uniform
-        const bool full = nb + 32 <= p.N;
-        float x[32];
-        // residual first: its global loads overlap the TMEM load latency
-        if (live && p.res && row_ok) {
-          if (full) {
-            if (p.res_f32) {
-              const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
-                                                                (long long)row * p.ldr + nb);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = r[j];
-                x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
-              }
-            } else {
-              const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
-                                                              (long long)row * p.ldr + nb);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 t = r[j];
-                x[8 * j] = rl::bf16_lo(t.x); x[8 * j + 1] = rl::bf16_hi(t.x);
-                x[8 * j + 2] = rl::bf16_lo(t.y); x[8 * j + 3] = rl::bf16_hi(t.y);
-                x[8 * j + 4] = rl::bf16_lo(t.z); x[8 * j + 5] = rl::bf16_hi(t.z);
-                x[8 * j + 6] = rl::bf16_lo(t.w); x[8 * j + 7] = rl::bf16_hi(t.w);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              x[j] = 0.f;
-              if (nb + j < p.N)
-                x[j] = p.res_f32 ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + nb + j]
-                                 : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[(long long)row * p.ldr + nb + j]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = 0.f;
-        }
-        rl::tmem_ld_wait();
-        if (!live) continue;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + nb + j));
-            if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-            x[j] += fmaf(__uint_as_float(v[j]), sc.x, bi.x);
-            x[j + 1] += fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-            x[j + 2] += fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-            x[j + 3] += fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j < p.N ? nb + j : p.N - 1;
-            const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
-            const float bi = p.bias ? __ldg(p.bias + n) : 0.f;
-            x[j] += fmaf(__uint_as_float(v[j]), sc, bi);
-          }
-        }
-        if (p.act == RL_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f * (1.0f + fast_erf(x[j] * 0.70710678118654752440f));
-        } else if (p.act == RL_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-        } else if (p.act == RL_ACT_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
-        }
-        if (p.tma_store) {
-          // previous chunk's TMA store must have finished reading the staging tile
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-          if (p.out_f32) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<float4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                  make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(rl::pack_bf16(x[8 * g], x[8 * g + 1]), rl::pack_bf16(x[8 * g + 2], x[8 * g + 3]),
-                             rl::pack_bf16(x[8 * g + 4], x[8 * g + 5]), rl::pack_bf16(x[8 * g + 6], x[8 * g + 7]));
-          }
-          rl::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tmC)),
-                         "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        } else if (row_ok) {
-          if (full && p.vec_store) {
-            if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nb);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-            } else {
-              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                  rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
-            }
-            if (p.out2) {
-              uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                  rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (nb + j < p.N) {
-                if (p.out_f32)
-                  reinterpret_cast<float*>(p.out)[orow * p.ldo + nb + j] = x[j];
-                else
-                  reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + nb + j] = __float2bfloat16(x[j]);
-                if (p.out2) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
-              }
-            }
-          }
-        }
-      }
+      if (!(p.dbg & 1)) epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) rl::mbar_arrive(&tmem_empty[acc]);
@@ -380,6 +419,249 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   return rl_check_launch("rl_gemm_bf16");
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile, the leader's single thread issues M=256 tcgen05.mma that read both
+// CTAs' shared memory and write 128 accumulator lanes in each CTA's TMEM.  Per SM this cuts the operand bytes
+// pulled through L2 per flop by 1.5x (the 1-CTA kernel is bound by L2->SM bandwidth, not by the tensor pipe).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA 0 of the pair
+
+__device__ __forceinline__ void tma2_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(rl::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(rl::smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(rl::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(rl::smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {  // arrive on the same barrier in both CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          rl::smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // from either CTA of the pair
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rl::smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const KParams p) {
+  constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint8_t* smem_stage = smem_b + STAGES * BH_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    rl::tma_prefetch_desc(&tmA);
+    rl::tma_prefetch_desc(&tmB);
+    rl::tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      rl::mbar_init(&full_bar[s], 1);
+      rl::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      rl::mbar_init(&tmem_full[s], 1);
+      rl::mbar_init(&tmem_empty[s], 16);  // 8 epilogue warps in each CTA of the pair
+    }
+    rl::fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rl::smem_u32(tmem_ptr)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  rl::tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  rl::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row pair tiles here
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * 2 * BM + (int)rank * BM;
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);
+        int img0 = 0, h0 = 0;
+        if (p.a_mode == 1) {
+          img0 = m0 >> p.hw_shift;
+          h0 = (m0 & ((1 << p.hw_shift) - 1)) >> p.w_shift;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          rl::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.dbg & 2) {
+            if (leader) rl::mbar_arrive(&full_bar[stage]);
+          } else {
+          if (leader) rl::mbar_expect_tx(&full_bar[stage], 2 * (A_BYTES + BH_BYTES));
+          if (p.a_mode == 0) {
+            tma2_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
+          } else {
+            const int t = kb / p.cin_blocks;
+            const int cb = kb - t * p.cin_blocks;
+            tma2_load_5d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], cb * BK, (int)p.tap_dw[t],
+                         h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
+          }
+          tma2_load_2d(smem_b + stage * BH_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
+      constexpr uint32_t idesc = rl::make_idesc_bf16(2 * BM, BN);
+      const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        rl::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          rl::mbar_wait(&full_bar[stage], phase);
+          rl::tc_fence_after();
+          if (rl::elect_one()) {
+            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * A_BYTES, 16, 1024);
+            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * BH_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              if (!(p.dbg & 4)) tc2_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc2_commit_mc(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (rl::elect_one()) tc2_commit_mc(&tmem_full[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps in each CTA; rows of this CTA's half of the pair tile) =====
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    uint8_t* stg = smem_stage + ew * (8192 + 1024);
+    float* sb = reinterpret_cast<float*>(stg + 8192);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile - m_blk * p.tiles_n;
+      const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
+      const int n0 = n_blk * BN;
+      float xr[32];
+      epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
+      rl::mbar_wait(&tmem_full[acc], acc_phase);
+      rl::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (!(p.dbg & 1)) epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
+      rl::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  rl::tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / arriving on its barriers
+  if (warp == 2) {
+    rl::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+constexpr int gemm2_smem_bytes() {
+  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+}
+
+template <int BN, int STAGES>
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
+                 cudaStream_t st) {
+  constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int max_clusters = rl_num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm2_bf16_kernel<BN, STAGES><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);
+  return rl_check_launch("rl_gemm_bf16(cta_group::2)");
+}
+
 int ilog2_exact(int v) {
   int s = 0;
   while ((1 << s) < v) ++s;
@@ -387,11 +669,23 @@ int ilog2_exact(int v) {
 }
 
 int g_force_bn = 0;
+int g_pair_mode = 1;
+int g_dbg = 0;  // 1: use the cta_group::2 kernel when the problem is large enough
 
 }  // namespace
 
 extern "C" int rl_gemm_set_tile_n(int bn) {
   g_force_bn = bn;
+  return 0;
+}
+
+extern "C" int rl_gemm_set_debug_mode(int flags) {
+  g_dbg = flags;
+  return 0;
+}
+
+extern "C" int rl_gemm_set_pair_mode(int on) {
+  g_pair_mode = on;
   return 0;
 }
 
@@ -427,22 +721,47 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.res_f32 = d->res_dtype == RL_DT_F32;
   p.act = d->act;
   p.out_remap = d->out_remap;
+  p.dbg = g_dbg;
 
-  // choose the N tile: minimise waves * tile cost
+  // Tile / kernel selection.  Cost model per 64-deep k-block of one CTA tile (cycles): the tensor pipe needs
+  // 2*bn, the operand bytes need bytes / 42.6 (measured L2->SM ingress per SM, ~6.3 KB/clk chip-wide);
+  // a CTA pair (cta_group::2) stages only half of B per CTA.  Total = waves * max(mma, load).
   int bn = 256;
+  int pair = 0;
   {
     const int sms = rl_num_sms();
-    long long t256 = (long long)p.tiles_m * ((p.N + 255) / 256);
-    long long t128 = (long long)p.tiles_m * ((p.N + 127) / 128);
-    // a 128-wide tile moves 1/3 more operand bytes per flop through L2 and sits at the smem-read limit of
-    // the tensor pipe, so it has to win the wave quantisation by a clear margin to be chosen
-    long long c256 = ((t256 + sms - 1) / sms) * 256 * 4;
-    long long c128 = ((t128 + sms - 1) / sms) * 128 * 5;
-    if (c128 < c256) bn = 128;
-    if (p.N <= 128) bn = 128;
-    if (p.N <= 64) bn = 64;
-    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) bn = g_force_bn;
+    double best = 1e30;
+    for (int mode = 0; mode < 2; ++mode) {
+      if (mode == 1 && (!g_pair_mode || d->M <= BM)) continue;
+      for (int cand = 128; cand <= 256; cand += 128) {
+        if (g_force_bn == 128 || g_force_bn == 256) {
+          if (cand != g_force_bn) continue;
+        } else if (cand == 256 && p.N <= 128) {
+          continue;
+        }
+        const long long tn = (p.N + cand - 1) / cand;
+        const long long tm = mode ? 2 * ((d->M + 2 * BM - 1) / (2 * BM)) : (d->M + BM - 1) / BM;  // CTA tiles along M
+        const long long waves = (tm * tn + sms - 1) / sms;
+        const double bytes = A_BYTES + (mode ? cand / 2 : cand) * BK * 2.0;
+        const double per_kb = bytes / 42.6 > 2.0 * cand ? bytes / 42.6 : 2.0 * cand;
+        const double cost = waves * (per_kb * p.num_kb + 1500.0);  // + per-tile epilogue / pipeline bubble
+        if (cost < best) {
+          best = cost;
+          bn = cand;
+          pair = mode;
+        }
+      }
+    }
+    if (p.N <= 64 && g_force_bn == 0) {
+      bn = 64;
+      pair = 0;
+    }
+    if (g_force_bn == 64) {
+      bn = 64;
+      pair = 0;
+    }
   }
+  if (pair) p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   p.tiles_n = (p.N + bn - 1) / bn;
 
   CUtensorMap tmA, tmB;
@@ -495,7 +814,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   {
     uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
-    uint32_t box[2] = {BK, (uint32_t)bn};
+    uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};
     rc = rl_make_tmap_bf16(&tmB, d->b, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -518,7 +837,11 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, tmC, p, st);
-  if (bn == 64) return launch_gemm<64, 8>(tmA, tmB, tmC, p, st);
-  return launch_gemm<128, 6>(tmA, tmB, tmC, p, st);
+  if (pair) {
+    if (bn == 256) return launch_gemm2<256, 4>(tmA, tmB, tmC, p, st);
+    return launch_gemm2<128, 6>(tmA, tmB, tmC, p, st);
+  }
+  if (bn == 256) return launch_gemm<256, 3>(tmA, tmB, tmC, p, st);
+  if (bn == 64) return launch_gemm<64, 6>(tmA, tmB, tmC, p, st);
+  return launch_gemm<128, 4>(tmA, tmB, tmC, p, st);
 }

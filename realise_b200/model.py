@@ -165,6 +165,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         self._ws = {}
         self._graphs = {}
         self.use_cuda_graph = True
+        self.fuse_block1 = True   # eval: glyph gather + whole res_block1 in one tcgen05 kernel
         self.collect = None  # tests set this to a dict to receive clones of the sub-module outputs
 
     def _keep(self, name, t):
@@ -322,6 +323,16 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             if b == 1:
                 e["w1_f32"] = w1.contiguous()
                 e["wsc_f32"] = wsc.reshape(cout, -1).contiguous()
+                # packed operands of the fused block-1 kernel (BN scales folded into the bf16 weights)
+                C = c.num_fonts
+                w1p = torch.zeros(64, 32, device=w1.device)
+                w1p[:, :9 * C] = (w1 * s1[:, None, None, None]).reshape(64, 9 * C)
+                wscp = torch.zeros(64, 32, device=w1.device)
+                wscp[:, 4:9 * C:9] = wsc.reshape(64, C) * ss[:, None]
+                e["w1p"] = w1p.bfloat16().contiguous()
+                e["wscp"] = wscp.bfloat16().contiguous()
+                e["w2p"] = (w2 * s2[:, None, None, None]).permute(0, 2, 3, 1).reshape(64, 576).bfloat16().contiguous()
+                e["t2s"] = (t2 + ts).contiguous()
             else:
                 # stride-2 3x3 over the parity-split input: tap (kh, kw) reads plane (ph, pw) at offset (dh, dw)
                 taps, cols = [], []
@@ -405,6 +416,12 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         R = P["res"]
         bf16 = torch.bfloat16
         b1 = R["blocks"][0]
+        if self.fuse_block1:
+            x = self._buf("res.x1", (N * 256, 64), bf16)  # block-1 output, parity-split rows
+            ops.glyph_block1(R["glyphs"], ids_flat, b1["w1p"], b1["wscp"], b1["w2p"], b1["t1"], b1["t2s"], x, N,
+                             c.num_fonts)
+            self._keep("res_block1_split", x)
+            return self._resnet_tail(P, x, N)
         y1 = self._buf("res.y1", (N, 1, 16, 16, 64), bf16)
         ysc = self._buf("res.ysc", (N * 256, 64), bf16)
         ops.glyph_stem(R["glyphs"], ids_flat, b1["w1_f32"], b1["wsc_f32"], b1["s1"], b1["t1"], b1["ss"], b1["ts"],
@@ -413,6 +430,12 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         ops.conv_gemm(y1, b1["w2"], x, nimg=N, H=16, W=16, planes=1, taps=b1["taps2"], scale=b1["s2"], bias=b1["t2"],
                       res=ysc, act=ops.ACT_RELU, out_remap=1)
         self._keep("res_block1_split", x)
+        return self._resnet_tail(P, x, N)
+
+    def _resnet_tail(self, P, x, N):
+        """res_block2..5 as implicit GEMMs over the parity-split block-1 output."""
+        R = P["res"]
+        bf16 = torch.bfloat16
         for bi in range(1, 5):
             e = R["blocks"][bi]
             S, cout = e["S"], e["cout"]

@@ -226,3 +226,17 @@ def argmax_rows(logits, out):
               "rl_argmax_rows")
     _count()
     return out
+
+
+def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
+    """Fused res_block1 (eval): glyph gather + conv1/BN/ReLU + conv2/BN + shortcut/BN + ReLU."""
+    _req(glyphs, torch.float32, "glyphs")
+    _req(ids, torch.int64, "ids")
+    for t, n in ((w1p, "w1p"), (wscp, "wscp"), (w2p, "w2p"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+    # algorithmic bytes per glyph: C*32*32*4 read + 16*16*64*2 written; flops: conv1 + shortcut + conv2
+    with _Timed("glyph_block1", n_img * (C * 4096 + 32768)):
+        check(lib().rl_glyph_block1_fwd(_ptr(glyphs), _ptr(ids), _ptr(w1p), _ptr(wscp), _ptr(w2p), _ptr(t1),
+                                        _ptr(t2s), _ptr(out), _c(n_img), ctypes.c_int32(C), _stream()),
+              "rl_glyph_block1_fwd")
+    _count()

@@ -87,7 +87,7 @@ def test_cuda_path_matches_oracle_on_fresh_inputs():
             loss, logits = model(to_dev(batch))
         err = (logits.float().cpu() - rlogits).abs().max().item()
         assert err <= LOGIT_TOL, (B, L, err)
-        assert abs(loss.item() - rloss.item()) <= 5e-3
+        assert abs(loss.item() - rloss.item()) <= 1e-2  # mean of few per-token CE terms, each within 2*LOGIT_TOL
         top2 = rlogits.reshape(B * L, -1).topk(2, -1).values
         safe = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_TOL
         assert (logits.reshape(B * L, -1).argmax(-1).cpu()[safe] == rlogits.reshape(B * L, -1).argmax(-1)[safe]).all()

@@ -127,6 +127,9 @@ if __name__ == "__main__":
         except Exception as e:  # noqa: BLE001
             ok = False
             print(f"[FAIL] conv {args}: {e}", flush=True)
+    if "--pairoff" in sys.argv:
+        from realise_b200._lib import lib
+        lib().rl_gemm_set_pair_mode(0)
     if "--quick" not in sys.argv:
         for shp in [(8192, 2304, 768), (8192, 768, 768), (8192, 3072, 768), (8192, 768, 3072), (8192, 21128, 768),
                     (16384, 3072, 768)]:
