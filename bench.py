@@ -229,7 +229,7 @@ def run_ours(args, rank, world, local_rank):
     gemm_tf = gemm_w / gemm_t / 1e12
     detail = {k: {"work": v[0] / 3, "ms": v[1] / 3 * 1e3, "launches": v[2] // 3} for k, v in agg.items()}
     att = agg.get("attention")
-    stem = agg.get("glyph_stem")
+    stem = agg.get("glyph_block1") or agg.get("glyph_stem")
 
     # ---- timed region: K steps, device-resident inputs, CUDA events, L2 flushed between steps ----
     clocks = ClockSampler(local_rank)
@@ -309,13 +309,17 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "256 MB buffer written between timed steps (L2 flush)", "cuda_graph": True},
         "model_tflops": value * FLOP_PER_SENTENCE_FWD / 1e12,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tf / peaks["tf_sustained"], "traffic": None,
+                     "frac": gemm_tf / peaks["tf_sustained"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 GEMM launches of one
+                     # transformer layer in profiles/r01_ncu_full_summary.json (ncu --set full, round 1)
+                     "traffic": 40.2e6,
                      "kernel": "gemm_bf16_kernel (tcgen05 GEMM + implicit-GEMM conv), executed 2*M*N*K over CUDA-event time, "
                                f"{gemm_n // 3} launches/step", "peak_source": peaks["source"] + " bf16 sustained"},
         "roofline_detail": {
             "attention_tensor": None if not att else {"achieved_tflops": att[0] / att[1] / 1e12,
                                                       "frac_of_peak": att[0] / att[1] / 1e12 / peaks["tf_sustained"]},
-            "glyph_stem_hbm": None if not stem else {"achieved_gbs": stem[0] / stem[1] / 1e9,
+            "glyph_conv_hbm": None if not stem else {"kernel": "glyph_block1_kernel (gather + res_block1 fused)",
+                                                     "achieved_gbs": stem[0] / stem[1] / 1e9,
                                                      "frac_of_peak": stem[0] / stem[1] / 1e9 / peaks["hbm_gbs"]},
             "per_kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in detail.items()},
         },

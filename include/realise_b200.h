@@ -71,6 +71,10 @@ typedef struct rl_gemm_desc {
   int32_t act;
   int32_t out_remap; /* 0: row m -> m.  1: parity-split rows for a following stride-2 conv:
                         [img][oh&1][ow&1][oh/2][ow/2] */
+  int32_t a_major;   /* 0: A stored [M, K] (K-major).  1: A stored [K, M] with row stride lda (MN-major), e.g.
+                        A = dY^T for a weight gradient straight from dY [tokens, out] */
+  int32_t b_major;   /* 0: B stored [N, K].  1: B stored [K, N] with row stride ldb, e.g. B = W^T for a data
+                        gradient straight from W [out, in], or B = X^T for a weight gradient */
 } rl_gemm_desc;
 
 RL_API int rl_gemm_bf16(const rl_gemm_desc* d, void* stream);

@@ -26,6 +26,7 @@ class GemmDesc(ctypes.Structure):
         ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("res", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("res_dtype", ctypes.c_int32),
         ("act", ctypes.c_int32), ("out_remap", ctypes.c_int32),
+        ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32),
     ]
 
 

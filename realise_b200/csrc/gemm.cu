@@ -35,6 +35,7 @@ struct KParams {
   int out_remap;
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
+  int a_mn, b_mn; // operand stored MN-major: A as [K, M] (M contiguous), B as [K, N] (N contiguous)
   int dbg;        // tuning experiments only: 1 = no epilogue work, 2 = no TMA loads, 4 = no MMA
 };
 
@@ -298,7 +299,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             rl::mbar_arrive(&full_bar[stage]);
           } else {
           rl::mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-          if (p.a_mode == 0) {
+          if (p.a_mn) {
+            rl::tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], m0, kb * BK);
+            rl::tma_load_2d(smem_a + stage * A_BYTES + 8192, &tmA, &full_bar[stage], m0 + 64, kb * BK);
+          } else if (p.a_mode == 0) {
             rl::tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
           } else {
             const int t = kb / p.cin_blocks;
@@ -306,7 +310,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             rl::tma_load_5d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], cb * BK,
                             (int)p.tap_dw[t], h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
           }
-          rl::tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          if (p.b_mn) {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              rl::tma_load_2d(smem_b + stage * B_BYTES + b * 8192, &tmB, &full_bar[stage], n0 + b * 64, kb * BK);
+          } else {
+            rl::tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -319,8 +329,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       // ===================== MMA issuer =====================
       // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
-      constexpr uint32_t idesc = rl::make_idesc_bf16(BM, BN);
+      const uint32_t idesc = rl::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
+      // K-major: 128-byte rows, 8-row atoms 1024 B apart, a k-step of 16 is +32 B.  MN-major: 64-wide MN blocks
+      // 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), a k-step of 16 rows is +2048 B.
+      const uint32_t a_lbo = p.a_mn ? 8192 : 16, b_lbo = p.b_mn ? 8192 : 16;
+      const uint32_t a_kstep = p.a_mn ? 128 : 2, b_kstep = p.b_mn ? 128 : 2;  // in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -333,11 +347,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           rl::mbar_wait(&full_bar[stage], phase);
           rl::tc_fence_after();
           if (rl::elect_one()) {
-            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * A_BYTES, 16, 1024);
-            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * B_BYTES, 16, 1024);
+            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * A_BYTES, a_lbo, 1024);
+            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * B_BYTES, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              if (!(p.dbg & 4)) rl::tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (!(p.dbg & 4))
+                rl::tc_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
             rl::tc_commit(&empty_bar[stage]);
           }
           __syncwarp();
@@ -546,7 +561,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (leader) rl::mbar_arrive(&full_bar[stage]);
           } else {
           if (leader) rl::mbar_expect_tx(&full_bar[stage], 2 * (A_BYTES + BH_BYTES));
-          if (p.a_mode == 0) {
+          if (p.a_mn) {
+            tma2_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], m0, kb * BK);
+            tma2_load_2d(smem_a + stage * A_BYTES + 8192, &tmA, &full_bar[stage], m0 + 64, kb * BK);
+          } else if (p.a_mode == 0) {
             tma2_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
           } else {
             const int t = kb / p.cin_blocks;
@@ -554,7 +572,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma2_load_5d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], cb * BK, (int)p.tap_dw[t],
                          h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
           }
-          tma2_load_2d(smem_b + stage * BH_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          if (p.b_mn) {
+#pragma unroll
+            for (int b = 0; b < BN / 128; ++b)
+              tma2_load_2d(smem_b + stage * BH_BYTES + b * 8192, &tmB, &full_bar[stage], n0 + b * 64, kb * BK);
+          } else {
+            tma2_load_2d(smem_b + stage * BH_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -567,8 +591,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (leader) {
       // ===================== MMA issuer (leader CTA only) =====================
       // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
-      constexpr uint32_t idesc = rl::make_idesc_bf16(2 * BM, BN);
+      const uint32_t idesc = rl::make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn);
       const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
+      const uint32_t a_lbo = p.a_mn ? 8192 : 16, b_lbo = p.b_mn ? 8192 : 16;
+      const uint32_t a_kstep = p.a_mn ? 128 : 2, b_kstep = p.b_mn ? 128 : 2;  // in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -581,11 +607,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           rl::mbar_wait(&full_bar[stage], phase);
           rl::tc_fence_after();
           if (rl::elect_one()) {
-            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * A_BYTES, 16, 1024);
-            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * BH_BYTES, 16, 1024);
+            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * A_BYTES, a_lbo, 1024);
+            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * BH_BYTES, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              if (!(p.dbg & 4)) tc2_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (!(p.dbg & 4))
+                tc2_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
             tc2_commit_mc(&empty_bar[stage]);
           }
           __syncwarp();
@@ -694,7 +721,11 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   RL_REQUIRE(d->a && d->b && d->out, RL_EINVAL, "rl_gemm_bf16: null operand pointer");
   RL_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, RL_EINVAL, "rl_gemm_bf16: empty problem %lld x %lld x %lld",
              (long long)d->M, (long long)d->N, (long long)d->K);
-  RL_REQUIRE(d->K % BK == 0, RL_EINVAL, "rl_gemm_bf16: K=%lld must be a multiple of %d", (long long)d->K, BK);
+  RL_REQUIRE(d->K % 8 == 0, RL_EINVAL, "rl_gemm_bf16: K=%lld must be a multiple of 8 (16-byte rows; the K tail of a"
+             " 64-deep block is zero-filled by TMA)", (long long)d->K);
+  RL_REQUIRE((d->a_major == 0 || d->a_major == 1) && (d->b_major == 0 || d->b_major == 1), RL_EINVAL,
+             "rl_gemm_bf16: a_major / b_major must be 0 (K-major) or 1 (MN-major)");
+  RL_REQUIRE(!(d->a_major == 1 && d->a_mode != 0), RL_EINVAL, "rl_gemm_bf16: MN-major A needs a_mode 0");
   RL_REQUIRE(d->M < (1ll << 31) && d->N < (1ll << 31), RL_EINVAL, "rl_gemm_bf16: M/N too large");
   RL_REQUIRE(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->b & 15) == 0, RL_EALIGN,
              "rl_gemm_bf16: a/b must be 16-byte aligned");
@@ -706,7 +737,9 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   KParams p{};
   p.M = (int)d->M;
   p.N = (int)d->N;
-  p.num_kb = (int)(d->K / BK);
+  p.num_kb = (int)((d->K + BK - 1) / BK);
+  p.a_mn = d->a_major;
+  p.b_mn = d->b_major;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.a_mode = d->a_mode;
   p.out = d->out;
@@ -766,7 +799,14 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
 
   CUtensorMap tmA, tmB;
   int rc;
-  if (d->a_mode == 0) {
+  if (d->a_mode == 0 && d->a_major == 1) {
+    RL_REQUIRE(d->lda % 8 == 0, RL_EALIGN, "rl_gemm_bf16: lda must be a multiple of 8 elements");
+    uint64_t dims[2] = {(uint64_t)d->M, (uint64_t)d->K};  // stored [K, M], M contiguous
+    uint64_t strides[1] = {(uint64_t)d->lda * 2};
+    uint32_t box[2] = {64, BK};
+    rc = rl_make_tmap_bf16(&tmA, d->a, 2, dims, strides, box);
+    if (rc) return rc;
+  } else if (d->a_mode == 0) {
     RL_REQUIRE(d->lda % 8 == 0, RL_EALIGN, "rl_gemm_bf16: lda must be a multiple of 8 elements");
     uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
     uint64_t strides[1] = {(uint64_t)d->lda * 2};
@@ -811,7 +851,13 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     RL_REQUIRE(d->a_mode == 1, RL_EINVAL, "rl_gemm_bf16: out_remap=1 needs conv geometry");
     RL_REQUIRE(d->conv_W >= 2 && d->conv_H >= 2, RL_EINVAL, "rl_gemm_bf16: parity split needs >=2x2 map");
   }
-  {
+  if (d->b_major == 1) {
+    uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};  // stored [K, N], N contiguous
+    uint64_t strides[1] = {(uint64_t)d->ldb * 2};
+    uint32_t box[2] = {64, BK};
+    rc = rl_make_tmap_bf16(&tmB, d->b, 2, dims, strides, box);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
     uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};

@@ -55,19 +55,21 @@ def _req(t, dtype, name):
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
-def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None):
-    """out[M,N] = act((a[M,K] @ b[N,K]^T) * scale + bias + res).  a, b bf16; out bf16 or f32."""
+def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None, a_t=False, b_t=False):
+    """out[M,N] = act((A @ B^T) * scale + bias + res) with A = a [M,K] (or a^T when a_t: a is stored [K,M],
+    MN-major operand) and B = b [N,K] (or b^T when b_t: b is stored [K,N]).  a, b bf16; out bf16 or f32."""
     _req(a, torch.bfloat16, "a")
     _req(b, torch.bfloat16, "b")
     assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
-    M, K = a.shape
-    N = b.shape[0]
-    assert b.shape[1] == K and tuple(out.shape) == (M, N), (a.shape, b.shape, out.shape)
+    (K, M) = a.shape if a_t else a.shape[::-1]
+    (Kb, N) = b.shape if b_t else b.shape[::-1]
+    assert Kb == K and tuple(out.shape) == (M, N), (a.shape, b.shape, out.shape, a_t, b_t)
     d = GemmDesc()
     d.a, d.b = a.data_ptr(), b.data_ptr()
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldb = a.stride(0), b.stride(0)
+    d.a_major, d.b_major = int(a_t), int(b_t)
     d.a_mode = 0
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
     with _Timed("gemm", 2.0 * M * N * K):

@@ -46,6 +46,19 @@ def t_plain(M, N, K, bias=False, act=0, res=None, out_dtype=torch.bfloat16, scal
     return report(f"gemm M{M} N{N} K{K} bias={bias} act={act} res={res} out={out_dtype}", out, ref, tol)
 
 
+def t_trans(M, N, K, a_t, b_t, accumulate=False):
+    """MN-major operands (weight-gradient / data-gradient forms), optional in-place f32 accumulation."""
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+    a = A.t().contiguous() if a_t else A
+    b = B.t().contiguous() if b_t else B
+    out = torch.randn(M, N, device=dev) if accumulate else torch.empty(M, N, device=dev)
+    ref = A.float() @ B.float().t() + (out if accumulate else 0)
+    ops.gemm(a, b, out, a_t=a_t, b_t=b_t, res=out if accumulate else None)
+    torch.cuda.synchronize()
+    return report(f"gemm-T M{M} N{N} K{K} a_t={a_t} b_t={b_t} acc={accumulate}", out, ref, 2e-3)
+
+
 def t_conv(nimg, Cin, Cout, S, stride):
     """3x3 pad-1 conv (stride 1 or 2) as implicit GEMM vs F.conv2d.  S = OUTPUT map size."""
     if stride == 1:
@@ -120,6 +133,15 @@ if __name__ == "__main__":
     ok &= t_plain(777, 200, 128, bias=True, res=torch.float32)
     ok &= t_plain(640, 331, 64, bias=True, out_dtype=torch.float32)
     ok &= t_plain(333, 776, 128, bias=True, act=1, res=torch.bfloat16)
+    for args in [(128, 64, 64, True, False), (128, 64, 64, False, True), (128, 256, 128, True, True),
+                 (768, 768, 8192, True, True), (3072, 768, 4096, True, True), (8192, 768, 3072, False, True),
+                 (300, 200, 96, True, True), (1000, 21128, 768, False, True), (21128, 768, 1024, True, True, True),
+                 (768, 2304, 32, True, True)]:
+        try:
+            ok &= t_trans(*args)
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            print(f"[FAIL] gemm-T {args}: {e}", flush=True)
     for args in [(4, 64, 64, 16, 1), (8, 128, 128, 8, 1), (16, 256, 256, 4, 1), (64, 512, 512, 2, 1),
                  (8, 64, 128, 8, 2), (16, 128, 256, 4, 2), (64, 256, 512, 2, 2), (200, 512, 768, 1, 2)]:
         try:
