@@ -43,7 +43,11 @@ RL_API const char* rl_last_error(void);
  * (+ReLU, + residual add) of CharResNet blocks (src/char_cnn.py:15-32) as an im2col-free
  * implicit GEMM whose A tiles are fetched tap by tap with 5-D TMA boxes.
  */
-enum { RL_ACT_NONE = 0, RL_ACT_GELU = 1, RL_ACT_RELU = 2, RL_ACT_TANH = 3 };
+enum {
+  RL_ACT_NONE = 0, RL_ACT_GELU = 1, RL_ACT_RELU = 2, RL_ACT_TANH = 3,
+  RL_ACT_GELU_GRAD = 4, /* out = (acc*scale+bias) * gelu'(res): data gradient through GELU, res = saved pre-activation */
+  RL_ACT_GELU_SAVE = 5  /* out = gelu(pre), out2 = pre (bf16): training forward keeps the pre-activation */
+};
 enum { RL_DT_BF16 = 0, RL_DT_F32 = 1 };
 
 typedef struct rl_gemm_desc {
@@ -106,8 +110,8 @@ RL_API int rl_layernorm_fwd(const float* x, const float* gamma, const float* bet
  * token (output_block, src/models.py:852-854). */
 RL_API int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds,
                            const float* pos, const float* type0, const float* gamma, const float* beta,
-                           float* out_f32, void* out_bf16, int64_t rows, int64_t L, int64_t H,
-                           int32_t pos_mode, float eps, void* stream);
+                           float* out_f32, void* out_bf16, float* pre_ln_out /* optional: the summed embedding */,
+                           int64_t rows, int64_t L, int64_t H, int32_t pos_mode, float eps, void* stream);
 
 /* ---- gated fusion (src/models.py:840-850; src/models_abla.py:243-279) -------------------------
  * m0 = bert_hiddens, m1/m2 = the other present modalities in the reference's concat order, all
@@ -122,7 +126,8 @@ RL_API int rl_gate_fuse_fwd(const float* m0, const float* m1, const float* m2, i
  * loss = mean over rows with loss_mask == 1 of (logsumexp(logits[row]) - logits[row, tgt[row]]).
  * logits f32 [rows, V] with row stride ld; row_loss_ws f32 [rows] scratch; loss f32 [1]. */
 RL_API int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask,
-                            float* row_loss_ws, float* loss, int64_t rows, int64_t V, int64_t ld,
+                            float* row_loss_ws, float* loss, float* row_lse_out /* optional [rows] */,
+                            float* count_out /* optional [1] */, int64_t rows, int64_t V, int64_t ld,
                             void* stream);
 
 /* ---- row-wise argmax over the vocabulary (first maximum wins) --------------------------------
@@ -165,5 +170,50 @@ RL_API int rl_glyph_stem_fwd(const float* glyphs, const int64_t* ids, const floa
 RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const void* w1_packed,
                                const void* wsc_packed, const void* w2_packed, const float* t1,
                                const float* t2s, void* out, int64_t n_img, int32_t C, void* stream);
+
+/* ======================= training path (src/run.py:191-212) =========================================== */
+
+/* ---- attention backward (seq_len <= 128): dqkv = [dQ | dK | dV] from dctx, recomputing the probabilities ----
+ * Differentiates BertSelfAttention.forward (modeling_bert.py:234-260) with dropout = identity.
+ * ctx is the forward output (needed for delta = rowsum(dO o O)). */
+RL_API int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
+                            int64_t B, int64_t L, int64_t heads, int64_t head_dim, void* stream);
+
+/* ---- LayerNorm backward: x = LN input (f32), dy = grad of the LN output; dx (+= add_in) in f32 and/or bf16;
+ * dgamma/dbeta/dxsum (column sums of dy*xhat, dy, dx) are ACCUMULATED into (caller zeroes them per step). */
+RL_API int rl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* add_in, float* dx,
+                            void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int64_t H,
+                            float eps, void* stream);
+
+/* ---- out[c] += sum_r x[r, c] for a bf16 matrix (bias gradients of nn.Linear) ---- */
+RL_API int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream);
+
+/* ---- masked CE backward: dlogits (bf16 [rows, ldd], columns >= V zeroed) from the logits, the per-row
+ * logsumexp and the active-row count saved by rl_masked_ce_fwd; gscale = d(loss) (device scalar, may be NULL). */
+RL_API int rl_masked_ce_bwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, const float* row_lse,
+                            const float* count, const float* gscale, void* dlogits, int64_t rows, int64_t V,
+                            int64_t ld, int64_t ldd, void* stream);
+
+/* ---- BertEmbeddings backward: dword[ids[row]] += de[row], dpos[position(row)] += de[row] (vector atomics) ---- */
+RL_API int rl_embed_bwd(const float* de, const int64_t* ids, float* dword, float* dpos, int64_t rows, int64_t L,
+                        int64_t H, int32_t pos_mode, void* stream);
+
+/* ---- gated fusion backward (src/models.py:840-850).  gates = f32 [B*L, 3] saved by rl_gate_fuse_fwd.
+ * dm0..2 (f32 [B*L, H]) are written; dgate_w / dgate_b are accumulated.  ws: f32 scratch, B*L*3 + 2*B*H. */
+RL_API int rl_gate_fuse_bwd(const float* dhid, const float* m0, const float* m1, const float* m2, int32_t num_modal,
+                            const int64_t* mask, const float* gates, const float* gate_w, float* dm0, float* dm1,
+                            float* dm2, float* dgate_w, float* dgate_b, float* ws, int64_t B, int64_t L, int64_t H,
+                            void* stream);
+
+/* ---- multi-tensor grad-norm and fused clip + AdamW (src/run.py:207 clip_grad_norm_,
+ * transformers/optimization.py:113-169).  table: device array of {float* p; const float* g; float* m;
+ * float* v; bf16* shadow; float* shadow32; int64 n; float wd; int pad}; chunks: device array of int2 {tensor, chunk} covering
+ * every 4096-element block.  rl_mt_sumsq accumulates sum(g^2) into out (caller zeroes it);
+ * rl_mt_adamw applies g *= min(1, max_norm / (sqrt(sumsq)/grad_div + 1e-6)) / grad_div, then the AdamW update
+ * with bias corrections bias_corr1 = 1-beta1^t, bias_corr2 = 1-beta2^t, and refreshes the bf16 shadow copy. */
+RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, void* stream);
+RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
+                       float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
+                       float grad_div, void* stream);
 
 #endif /* REALISE_B200_H */

@@ -1,0 +1,269 @@
+// BertSelfAttention backward on tcgen05 (training path; seq_len <= 128, one CTA per (sentence, head)).
+//   given dO = d(ctx):   dV = P^T dO,   dP = dO V^T,   dS = P o (dP - delta),  delta_q = sum_d dO[q,d] O[q,d],
+//                        dQ = dS K / 8,  dK = dS^T Q / 8            (P = softmax(QK^T/8 + mask) is recomputed)
+// Seven small GEMMs per head, all on the tensor core: S and dP accumulate in TMEM (thread = query row does the
+// softmax algebra), P and dS are written as bf16 K-major smem tiles; the transposed products (P^T dO, dS^T Q)
+// read the same tiles through MN-major descriptors, so nothing is transposed in memory.
+// Reference math: transformers/modeling_bert.py:234-260 differentiated (dropout = identity, p = 0).
+#include "common.cuh"
+
+namespace {
+
+constexpr int ATT_THREADS = 128;
+constexpr int HEAD_DIM = 64;
+constexpr int T16K = 128 * 128;  // one [128 x 64] bf16 tile
+
+struct AttBwdParams {
+  const long long* mask;
+  const __nv_bfloat16* ctx;   // forward output O, [B*L, H]
+  const __nv_bfloat16* dctx;  // dO
+  __nv_bfloat16* dqkv;        // [B*L, 3H]
+  int L, H, lkv16;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                     const __grid_constant__ CUtensorMap tmDO, const AttBwdParams p) {
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + T16K;
+  uint8_t* sV = sK + T16K;
+  uint8_t* sDO = sV + T16K;
+  uint8_t* sP = sDO + T16K;        // two [128 q x 64 kv] tiles
+  uint8_t* sDS = sP + 2 * T16K;    // two tiles
+  float* s_mask = reinterpret_cast<float*>(sDS + 2 * T16K);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 128);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bar_ld = &bars[0];
+  uint64_t* bar_s = &bars[1];
+  uint64_t* bar_o = &bars[2];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int L = p.L, lkv16 = p.lkv16;
+  const int row0 = b * L;
+
+  if (tid == 0) {
+    rl::tma_prefetch_desc(&tmQ);
+    rl::tma_prefetch_desc(&tmKV);
+    rl::tma_prefetch_desc(&tmDO);
+    rl::mbar_init(bar_ld, 1);
+    rl::mbar_init(bar_s, 1);
+    rl::mbar_init(bar_o, 1);
+    rl::fence_barrier_init();
+  }
+  if (warp == 0) rl::tmem_alloc(tmem_ptr, 512);
+  for (int j = tid; j < 128; j += ATT_THREADS) {
+    float m = -INFINITY;
+    if (j < L) m = (1.0f - (float)p.mask[(long long)b * L + j]) * -10000.0f * 1.4426950408889634f;
+    s_mask[j] = m;
+  }
+  // zero the P / dS tiles once: chunk tiles or rows that are never written must not feed NaNs into the MMAs
+  for (int i = tid; i < 4 * T16K / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  rl::fence_proxy_async();
+  rl::tc_fence_before();
+  __syncthreads();
+  rl::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (tid == 0) {
+    rl::mbar_expect_tx(bar_ld, 2 * T16K + 2 * lkv16 * 128);
+    rl::tma_load_2d(sQ, &tmQ, bar_ld, head * HEAD_DIM, row0);
+    rl::tma_load_2d(sK, &tmKV, bar_ld, p.H + head * HEAD_DIM, row0);
+    rl::tma_load_2d(sV, &tmKV, bar_ld, 2 * p.H + head * HEAD_DIM, row0);
+    rl::tma_load_2d(sDO, &tmDO, bar_ld, head * HEAD_DIM, row0);
+    rl::mbar_wait(bar_ld, 0);
+    rl::tc_fence_after();
+    const uint32_t idesc = rl::make_idesc_bf16(128, lkv16);
+    const uint32_t qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK), va = rl::smem_u32(sV), da = rl::smem_u32(sDO);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // S = Q K^T
+      rl::tc_mma_f16(tmem_base + COL_S, rl::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                     rl::make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc, k != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // dP = dO V^T
+      rl::tc_mma_f16(tmem_base + COL_DP, rl::make_smem_desc_sw128(da + k * 32, 16, 1024),
+                     rl::make_smem_desc_sw128(va + k * 32, 16, 1024), idesc, k != 0);
+    rl::tc_commit(bar_s);
+  }
+
+  // delta = rowsum(dO o O) for this thread's query row (global reads overlap the loads / MMAs above)
+  const int r = tid;
+  float delta = 0.f;
+  if (r < L) {
+    const uint4* o = reinterpret_cast<const uint4*>(p.ctx + (long long)(row0 + r) * p.H + head * HEAD_DIM);
+    const uint4* g = reinterpret_cast<const uint4*>(p.dctx + (long long)(row0 + r) * p.H + head * HEAD_DIM);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 a = o[i], c = g[i];
+      delta += rl::bf16_lo(a.x) * rl::bf16_lo(c.x) + rl::bf16_hi(a.x) * rl::bf16_hi(c.x) +
+               rl::bf16_lo(a.y) * rl::bf16_lo(c.y) + rl::bf16_hi(a.y) * rl::bf16_hi(c.y) +
+               rl::bf16_lo(a.z) * rl::bf16_lo(c.z) + rl::bf16_hi(a.z) * rl::bf16_hi(c.z) +
+               rl::bf16_lo(a.w) * rl::bf16_lo(c.w) + rl::bf16_hi(a.w) * rl::bf16_hi(c.w);
+    }
+  }
+
+  rl::mbar_wait(bar_s, 0);
+  rl::tc_fence_after();
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int nchunk = (lkv16 + 31) / 32;
+  float mx = -INFINITY;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t v[32];
+    rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
+    rl::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+      mx = fmaxf(mx, sc);
+    }
+  }
+  float sum = 0.f;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t v[32];
+    rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
+    rl::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+      sum += rl::ex2(sc - mx);
+    }
+  }
+  const float inv = r < L ? 1.0f / sum : 0.0f;  // query rows beyond the sentence contribute nothing to dK / dV
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t v[32], w[32];
+    rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
+    rl::tmem_ld_32x32(t_row + COL_DP + c * 32, w);
+    rl::tmem_ld_wait();
+    float pr[32], ds[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+      pr[j] = rl::ex2(sc - mx) * inv;
+      ds[j] = col < L ? pr[j] * (__uint_as_float(w[j]) - delta) : 0.f;
+    }
+    uint8_t* tp = sP + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* td = sDS + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int piece = (((c & 1) * 4 + g) ^ (r & 7)) << 4;
+      *reinterpret_cast<uint4*>(tp + piece) =
+          make_uint4(rl::pack_bf16(pr[8 * g], pr[8 * g + 1]), rl::pack_bf16(pr[8 * g + 2], pr[8 * g + 3]),
+                     rl::pack_bf16(pr[8 * g + 4], pr[8 * g + 5]), rl::pack_bf16(pr[8 * g + 6], pr[8 * g + 7]));
+      *reinterpret_cast<uint4*>(td + piece) =
+          make_uint4(rl::pack_bf16(ds[8 * g], ds[8 * g + 1]), rl::pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
+                     rl::pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), rl::pack_bf16(ds[8 * g + 6], ds[8 * g + 7]));
+    }
+  }
+  rl::fence_proxy_async();
+  rl::tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    rl::tc_fence_after();
+    const uint32_t pa = rl::smem_u32(sP), dsa = rl::smem_u32(sDS), qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK),
+                   da = rl::smem_u32(sDO);
+    // dV[kv, d] = sum_q P[q, kv] dO[q, d] : A = P^T (MN-major: kv contiguous, 64-kv blocks one tile apart), B = dO^T
+    const uint32_t idesc_t = rl::make_idesc_bf16(128, HEAD_DIM, 1, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      rl::tc_mma_f16(tmem_base + COL_DV, rl::make_smem_desc_sw128(pa + k * 2048, T16K, 1024),
+                     rl::make_smem_desc_sw128(da + k * 2048, 1024, 1024), idesc_t, k != 0);
+    // dK[kv, d] = sum_q dS[q, kv] Q[q, d]
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      rl::tc_mma_f16(tmem_base + COL_DK, rl::make_smem_desc_sw128(dsa + k * 2048, T16K, 1024),
+                     rl::make_smem_desc_sw128(qa + k * 2048, 1024, 1024), idesc_t, k != 0);
+    // dQ[q, d] = sum_kv dS[q, kv] K[kv, d] : A = dS K-major over kv, B = K^T (MN-major)
+    const uint32_t idesc_q = rl::make_idesc_bf16(128, HEAD_DIM, 0, 1);
+    const int nk = lkv16 / 16;
+    for (int k = 0; k < nk; ++k)
+      rl::tc_mma_f16(tmem_base + COL_DQ, rl::make_smem_desc_sw128(dsa + (k >> 2) * T16K + (k & 3) * 32, 16, 1024),
+                     rl::make_smem_desc_sw128(ka + k * 2048, 1024, 1024), idesc_q, k != 0);
+    rl::tc_commit(bar_o);
+  }
+  rl::mbar_wait(bar_o, 0);
+  rl::tc_fence_after();
+  {
+    // tcgen05.ld is warp-collective: every lane loads, only rows inside the sentence store
+    __nv_bfloat16* base = p.dqkv + (long long)(row0 + r) * 3 * p.H + head * HEAD_DIM;
+    const uint32_t cols[3] = {COL_DQ, COL_DK, COL_DV};
+    const float scl[3] = {0.125f, 0.125f, 1.0f};
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        rl::tmem_ld_32x32(t_row + cols[t] + c * 32, v);
+        rl::tmem_ld_wait();
+        if (r < L) {
+          uint4* o = reinterpret_cast<uint4*>(base + t * p.H + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            o[g] = make_uint4(rl::pack_bf16(__uint_as_float(v[8 * g]) * scl[t], __uint_as_float(v[8 * g + 1]) * scl[t]),
+                              rl::pack_bf16(__uint_as_float(v[8 * g + 2]) * scl[t], __uint_as_float(v[8 * g + 3]) * scl[t]),
+                              rl::pack_bf16(__uint_as_float(v[8 * g + 4]) * scl[t], __uint_as_float(v[8 * g + 5]) * scl[t]),
+                              rl::pack_bf16(__uint_as_float(v[8 * g + 6]) * scl[t], __uint_as_float(v[8 * g + 7]) * scl[t]));
+        }
+      }
+    }
+  }
+  rl::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    rl::tc_fence_after();
+    rl::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr int ATT_BWD_SMEM = 8 * T16K + 128 * 4 + 3 * 8 + 16 + 1024;
+
+}  // namespace
+
+extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
+                                int64_t B, int64_t L, int64_t heads, int64_t head_dim, void* stream) {
+  RL_REQUIRE(qkv && mask && ctx && dctx && dqkv, RL_EINVAL, "rl_attention_bwd: null pointer");
+  RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_bwd: head_dim must be 64");
+  RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 128, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..128", (long long)L);
+  const int H = (int)(heads * head_dim);
+  const int lkv16 = (int)((L + 15) / 16 * 16);
+  CUtensorMap tq, tkv, tdo;
+  uint64_t dims[2] = {(uint64_t)(3 * H), (uint64_t)(B * L)};
+  uint64_t strides[1] = {(uint64_t)(3 * H) * 2};
+  uint32_t boxq[2] = {64, 128};
+  uint32_t boxkv[2] = {64, (uint32_t)lkv16};
+  int rc = rl_make_tmap_bf16(&tq, qkv, 2, dims, strides, boxq);
+  if (rc) return rc;
+  rc = rl_make_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv);
+  if (rc) return rc;
+  uint64_t dimso[2] = {(uint64_t)H, (uint64_t)(B * L)};
+  uint64_t strideso[1] = {(uint64_t)H * 2};
+  rc = rl_make_tmap_bf16(&tdo, dctx, 2, dimso, strideso, boxq);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
+    if (e != cudaSuccess) {
+      rl_set_error("rl_attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  AttBwdParams p;
+  p.mask = reinterpret_cast<const long long*>(mask);
+  p.ctx = reinterpret_cast<const __nv_bfloat16*>(ctx);
+  p.dctx = reinterpret_cast<const __nv_bfloat16*>(dctx);
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.L = (int)L;
+  p.H = H;
+  p.lkv16 = lkv16;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, p);
+  return rl_check_launch("rl_attention_bwd");
+}

@@ -1,0 +1,456 @@
+// Backward / training-step kernels that are not GEMMs: LayerNorm backward, bias (column) sums, masked-CE
+// backward, embedding scatter, gated-fusion backward, global grad-norm + fused clip/AdamW (multi-tensor).
+// Reference semantics: transformers/modeling_bert.py (BertLayerNorm, BertEmbeddings), src/models.py:840-868,
+// src/run.py:207 (clip_grad_norm_), transformers/optimization.py:113-169 (AdamW.step).
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_V4 = 8;
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm backward.  x = LN input (f32), dy = grad of LN output.  dx = rstd * (g - mean(g) - xhat*mean(g*xhat)),
+// g = dy*gamma.  Optionally dx += add_in (gradient arriving through the residual connection), a bf16 copy of dx
+// (operand of the following weight/data-gradient GEMMs), and the column sums dgamma += sum dy*xhat,
+// dbeta += sum dy, dxsum += sum dx (bias gradient of the linear layer that produced x / type-embedding grad).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LNB_ROWS = 64;  // rows per CTA (8 warps x 8 rows)
+
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ add_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int H,
+              float eps) {
+  extern __shared__ float s_part[];  // [3][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = H / 128;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  float4 pg[MAX_V4], pb[MAX_V4], px[MAX_V4];
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) pg[i] = pb[i] = px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long row_begin = (long long)blockIdx.x * LNB_ROWS;
+  for (int rr = warp; rr < LNB_ROWS; rr += 8) {
+    const long long row = row_begin + rr;
+    if (row >= rows) break;
+    float4 xv[MAX_V4], gv[MAX_V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+      if (i < nv) {
+        xv[i] = reinterpret_cast<const float4*>(x + row * H)[i * 32 + lane];
+        gv[i] = reinterpret_cast<const float4*>(dy + row * H)[i * 32 + lane];
+        s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+      }
+    const float mean = rl::warp_sum(s) / (float)H;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+      if (i < nv) {
+        xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+        var += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      }
+    const float rstd = rsqrtf(rl::warp_sum(var) / (float)H + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+      if (i < nv) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+        xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
+        pg[i].x += gv[i].x * xv[i].x; pg[i].y += gv[i].y * xv[i].y; pg[i].z += gv[i].z * xv[i].z; pg[i].w += gv[i].w * xv[i].w;
+        pb[i].x += gv[i].x; pb[i].y += gv[i].y; pb[i].z += gv[i].z; pb[i].w += gv[i].w;
+        gv[i].x *= gm.x; gv[i].y *= gm.y; gv[i].z *= gm.z; gv[i].w *= gm.w;  // g = dy * gamma
+        m1 += gv[i].x + gv[i].y + gv[i].z + gv[i].w;
+        m2 += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
+      }
+    m1 = rl::warp_sum(m1) / (float)H;
+    m2 = rl::warp_sum(m2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+      if (i < nv) {
+        float4 d;
+        d.x = rstd * (gv[i].x - m1 - xv[i].x * m2);
+        d.y = rstd * (gv[i].y - m1 - xv[i].y * m2);
+        d.z = rstd * (gv[i].z - m1 - xv[i].z * m2);
+        d.w = rstd * (gv[i].w - m1 - xv[i].w * m2);
+        px[i].x += d.x; px[i].y += d.y; px[i].z += d.z; px[i].w += d.w;
+        if (add_in) {
+          const float4 a = reinterpret_cast<const float4*>(add_in + row * H)[i * 32 + lane];
+          d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
+        }
+        if (dx) reinterpret_cast<float4*>(dx + row * H)[i * 32 + lane] = d;
+        if (dx_bf16)
+          reinterpret_cast<uint2*>(dx_bf16 + row * H)[i * 32 + lane] = make_uint2(rl::pack_bf16(d.x, d.y), rl::pack_bf16(d.z, d.w));
+      }
+  }
+  // CTA-level reduction of the column partials, then one atomic per column
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&s_part[c], pg[i].x); atomicAdd(&s_part[c + 1], pg[i].y); atomicAdd(&s_part[c + 2], pg[i].z); atomicAdd(&s_part[c + 3], pg[i].w);
+      atomicAdd(&s_part[H + c], pb[i].x); atomicAdd(&s_part[H + c + 1], pb[i].y); atomicAdd(&s_part[H + c + 2], pb[i].z); atomicAdd(&s_part[H + c + 3], pb[i].w);
+      atomicAdd(&s_part[2 * H + c], px[i].x); atomicAdd(&s_part[2 * H + c + 1], px[i].y); atomicAdd(&s_part[2 * H + c + 2], px[i].z); atomicAdd(&s_part[2 * H + c + 3], px[i].w);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + c, s_part[c]);
+    if (dbeta) atomicAdd(dbeta + c, s_part[H + c]);
+    if (dxsum) atomicAdd(dxsum + c, s_part[2 * H + c]);
+  }
+}
+
+// column sums of a bf16 [rows, cols] matrix (bias gradient): out[c] += sum_r x[r, c]
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols, long long ld) {
+  // block = 32 columns x 8 row-groups; grid = (cols/32 rounded up, row chunks)
+  __shared__ float s[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * 1024;
+  float acc = 0.f;
+  if (col < cols)
+    for (long long r = r0 + ry; r < r0 + 1024 && r < rows; r += 8) acc += __bfloat162float(x[r * ld + col]);
+  s[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][cx];
+    atomicAdd(out + col, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// masked CE backward: dlogits[r, j] = gscale * mask_r / count * (exp(logit_rj - lse_r) - [j == tgt_r]), bf16,
+// columns [V, ldd) zero (K padding of the following GEMMs).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
+              const float* __restrict__ row_lse, const float* __restrict__ count, const float* __restrict__ gscale,
+              __nv_bfloat16* __restrict__ dlogits, int V, long long ld, long long ldd) {
+  const long long row = blockIdx.x;
+  __nv_bfloat16* d = dlogits + row * ldd;
+  if (loss_mask[row] != 1) {
+    for (long long j = threadIdx.x * 8; j < ldd; j += blockDim.x * 8) *reinterpret_cast<uint4*>(d + j) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const float coef = (gscale ? gscale[0] : 1.0f) / count[0];
+  const float lse = row_lse[row];
+  const int t = (int)tgt[row];
+  const float* x = logits + row * ld;
+  for (int j = threadIdx.x; j < (int)ldd; j += blockDim.x) {
+    float v = 0.f;
+    if (j < V) v = coef * (expf(x[j] - lse) - (j == t ? 1.0f : 0.0f));
+    d[j] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// embedding backward: de [rows, H] f32 -> dword[ids[row]] += de, dpos[position] += de   (vector atomics)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const float* __restrict__ de, const long long* __restrict__ ids, float* __restrict__ dword,
+                 float* __restrict__ dpos, long long rows, int L, int H, int pos_mode) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = H / 128;
+  const int position = pos_mode == 0 ? (int)(row % L) : 0;
+  for (int i = 0; i < nv; ++i) {
+    const float4 g = reinterpret_cast<const float4*>(de + row * H)[i * 32 + lane];
+    if (dword) atomicAdd(reinterpret_cast<float4*>(dword + ids[row] * (long long)H) + i * 32 + lane, g);
+    if (dpos) atomicAdd(reinterpret_cast<float4*>(dpos + (long long)position * H) + i * 32 + lane, g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gated fusion backward (src/models.py:840-850).  Forward: z_i = W_i . [m_0..m_{G-1}, mean_b] + b_i, g = sigmoid(z),
+// hid = sum_i g_i m_i.  Given dhid: dz_i = (dhid . m_i) g_i (1-g_i);
+//   dm_j = g_j dhid + sum_i dz_i W[i, jH:(j+1)H];   dmean_b += sum_{l,i} dz_i W[i, GH:];   db_i = sum dz_i
+//   dbert_l += mask_l / cnt_b * dmean_b   (second kernel);  dW = dz^T . cat (third kernel).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_bwd_token_kernel(const float* __restrict__ dhid, const float* __restrict__ m0, const float* __restrict__ m1,
+                      const float* __restrict__ m2, const float* __restrict__ gates, const float* __restrict__ gate_w,
+                      float* __restrict__ dm0, float* __restrict__ dm1, float* __restrict__ dm2, float* __restrict__ dz_out,
+                      float* __restrict__ dmean, float* __restrict__ dgate_b, long long rows, int L, int H, int G) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = H / 128;
+  const float* mods[3] = {m0, m1, m2};
+  float* dms[3] = {dm0, dm1, dm2};
+  float4 dh[MAX_V4];
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) dh[i] = reinterpret_cast<const float4*>(dhid + row * H)[i * 32 + lane];
+  float g[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (j < G) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAX_V4; ++i)
+        if (i < nv) {
+          const float4 mv = reinterpret_cast<const float4*>(mods[j] + row * H)[i * 32 + lane];
+          dot += dh[i].x * mv.x + dh[i].y * mv.y + dh[i].z * mv.z + dh[i].w * mv.w;
+        }
+      dot = rl::warp_sum(dot);
+      g[j] = gates[row * 3 + j];
+      dz[j] = dot * g[j] * (1.0f - g[j]);
+    }
+  if (lane < G) {
+    dz_out[row * 3 + lane] = dz[lane];
+    atomicAdd(dgate_b + lane, dz[lane]);
+  }
+  const long long b = row / L;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv) {
+      const int c = (i * 32 + lane) * 4;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j < G) {
+          float4 o = make_float4(g[j] * dh[i].x, g[j] * dh[i].y, g[j] * dh[i].z, g[j] * dh[i].w);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < G) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(gate_w + (long long)k * (G + 1) * H + (long long)j * H + c));
+              o.x += dz[k] * w.x; o.y += dz[k] * w.y; o.z += dz[k] * w.z; o.w += dz[k] * w.w;
+            }
+          reinterpret_cast<float4*>(dms[j] + row * H)[i * 32 + lane] = o;
+        }
+      float4 dmn = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k < G) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(gate_w + (long long)k * (G + 1) * H + (long long)G * H + c));
+          dmn.x += dz[k] * w.x; dmn.y += dz[k] * w.y; dmn.z += dz[k] * w.z; dmn.w += dz[k] * w.w;
+        }
+      atomicAdd(reinterpret_cast<float4*>(dmean + b * H + c), dmn);
+    }
+}
+
+// dbert[row] += mask[row] / cnt_b * dmean_b
+__global__ void __launch_bounds__(256)
+gate_bwd_mean_kernel(float* __restrict__ dm0, const float* __restrict__ dmean, const long long* __restrict__ mask,
+                     long long rows, int L, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long b = row / L;
+  float cnt = 0.f;
+  for (int l = lane; l < L; l += 32) cnt += (float)mask[b * L + l];
+  cnt = rl::warp_sum(cnt);
+  const float w = (float)mask[row] / cnt;
+  if (w == 0.f) return;
+  for (int i = 0; i < H / 128; ++i) {
+    float4* p = reinterpret_cast<float4*>(dm0 + row * H) + i * 32 + lane;
+    const float4 d = reinterpret_cast<const float4*>(dmean + b * H)[i * 32 + lane];
+    float4 o = *p;
+    o.x += w * d.x; o.y += w * d.y; o.z += w * d.z; o.w += w * d.w;
+    *p = o;
+  }
+}
+
+// dW[k, j*H + c] += sum_rows dz[row, k] * cat_j[row, c]  (cat_j = modality j, or the broadcast masked mean for j == G)
+__global__ void __launch_bounds__(256)
+gate_bwd_weight_kernel(const float* __restrict__ dz, const float* __restrict__ src, const float* __restrict__ mean_src,
+                       float* __restrict__ dgate_w, long long rows, int L, int H, int G, int j) {
+  // grid: (H/32, row chunks of 2048); block: 32 columns x 8 row lanes
+  __shared__ float s[3][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * 2048;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (long long r = r0 + ry; r < r0 + 2048 && r < rows; r += 8) {
+    const float v = mean_src ? mean_src[(r / L) * H + col] : src[r * H + col];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (k < G) acc[k] += dz[r * 3 + k] * v;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s[k][ry][cx] = acc[k];
+  __syncthreads();
+  if (ry < G) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[ry][i][cx];
+    atomicAdd(dgate_w + (long long)ry * (G + 1) * H + (long long)j * H + col, t);
+  }
+}
+
+// masked mean of bert_hiddens per sentence (needed again for dW of the mean block)
+__global__ void __launch_bounds__(256)
+masked_mean_kernel(const float* __restrict__ x, const long long* __restrict__ mask, float* __restrict__ mean, int L, int H) {
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int l = 0; l < L; ++l) cnt += (float)mask[(long long)b * L + l];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += x[((long long)b * L + l) * H + c] * (float)mask[(long long)b * L + l];
+    mean[(long long)b * H + c] = s / cnt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-tensor grad-norm + clip + AdamW.  A device table describes every parameter; the grid runs over 4096-
+// element chunks listed in a chunk table.  The step is two launches: sum of squares, then the update which
+// reads the clip coefficient min(1, max_norm / (norm + 1e-6)) computed on device (no host sync).
+// ---------------------------------------------------------------------------------------------------------
+struct TensorEntry {   // mirrored by realise_b200/optim.py (ctypes) — keep in sync
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  __nv_bfloat16* shadow;  // optional bf16 operand copy refreshed in the same pass
+  float* shadow32;        // optional f32 copy (e.g. the slice of a fused QKV bias vector)
+  long long n;
+  float wd;
+  int pad;
+};
+constexpr int OPT_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256)
+mt_sumsq_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ chunks, float* __restrict__ out) {
+  const int2 ck = chunks[blockIdx.x];
+  const TensorEntry e = tab[ck.x];
+  const long long base = (long long)ck.y * OPT_CHUNK;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
+    const long long idx = base + i;
+    if (idx < e.n) {
+      const float g = e.g[idx];
+      s += g * g;
+    }
+  }
+  s = rl::warp_sum(s);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mt_adamw_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ chunks, const float* __restrict__ sumsq,
+                float max_norm, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_div) {
+  const int2 ck = chunks[blockIdx.x];
+  const TensorEntry e = tab[ck.x];
+  const long long base = (long long)ck.y * OPT_CHUNK;
+  float coef = 1.0f / grad_div;
+  if (max_norm > 0.f) {
+    const float norm = sqrtf(sumsq[0]) / grad_div;
+    const float c = max_norm / (norm + 1e-6f);
+    if (c < 1.0f) coef *= c;
+  }
+  const float step_size = lr * sqrtf(bc2) / bc1;
+  for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
+    const long long idx = base + i;
+    if (idx < e.n) {
+      const float g = e.g[idx] * coef;
+      const float m = beta1 * e.m[idx] + (1.0f - beta1) * g;
+      const float v = beta2 * e.v[idx] + (1.0f - beta2) * g * g;
+      float pv = e.p[idx];
+      pv -= step_size * m / (sqrtf(v) + eps);
+      if (e.wd > 0.f) pv -= lr * e.wd * pv;
+      e.m[idx] = m;
+      e.v[idx] = v;
+      e.p[idx] = pv;
+      if (e.shadow) e.shadow[idx] = __float2bfloat16(pv);
+      if (e.shadow32) e.shadow32[idx] = pv;
+    }
+  }
+}
+
+bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
+
+}  // namespace
+
+extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* add_in, float* dx,
+                                void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int64_t H,
+                                float eps, void* stream) {
+  RL_REQUIRE(dy && x && gamma && (dx || dx_bf16), RL_EINVAL, "rl_layernorm_bwd: null pointer");
+  RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_bwd: bad H");
+  if (rows <= 0) return 0;
+  ln_bwd_kernel<<<(unsigned)((rows + LNB_ROWS - 1) / LNB_ROWS), 256, 3 * H * sizeof(float), (cudaStream_t)stream>>>(
+      dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps);
+  return rl_check_launch("rl_layernorm_bwd");
+}
+
+extern "C" int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream) {
+  RL_REQUIRE(x && out && cols > 0 && ld >= cols, RL_EINVAL, "rl_colsum_bf16: bad arguments");
+  if (rows <= 0) return 0;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 1023) / 1024));
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, (int)cols, ld);
+  return rl_check_launch("rl_colsum_bf16");
+}
+
+extern "C" int rl_masked_ce_bwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, const float* row_lse,
+                                const float* count, const float* gscale, void* dlogits, int64_t rows, int64_t V,
+                                int64_t ld, int64_t ldd, void* stream) {
+  RL_REQUIRE(logits && tgt && loss_mask && row_lse && count && dlogits, RL_EINVAL, "rl_masked_ce_bwd: null pointer");
+  RL_REQUIRE(ldd >= V && ldd % 8 == 0 && ((uintptr_t)dlogits & 15) == 0, RL_EALIGN, "rl_masked_ce_bwd: ldd must be >= V, %%8");
+  if (rows <= 0) return 0;
+  ce_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)tgt, (const long long*)loss_mask,
+                                                                 row_lse, count, gscale, (__nv_bfloat16*)dlogits, (int)V, ld, ldd);
+  return rl_check_launch("rl_masked_ce_bwd");
+}
+
+extern "C" int rl_embed_bwd(const float* de, const int64_t* ids, float* dword, float* dpos, int64_t rows, int64_t L,
+                            int64_t H, int32_t pos_mode, void* stream) {
+  RL_REQUIRE(de && (dword == nullptr || ids) && h_ok(H) && L > 0, RL_EINVAL, "rl_embed_bwd: bad arguments");
+  if (rows <= 0) return 0;
+  embed_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(de, (const long long*)ids, dword, dpos, rows,
+                                                                               (int)L, (int)H, pos_mode);
+  return rl_check_launch("rl_embed_bwd");
+}
+
+extern "C" int rl_gate_fuse_bwd(const float* dhid, const float* m0, const float* m1, const float* m2, int32_t num_modal,
+                                const int64_t* mask, const float* gates, const float* gate_w, float* dm0, float* dm1,
+                                float* dm2, float* dgate_w, float* dgate_b, float* ws, int64_t B, int64_t L, int64_t H,
+                                void* stream) {
+  // ws: f32 scratch of size B*L*3 (dz) + 2*B*H (dmean, mean)
+  RL_REQUIRE(dhid && m0 && dm0 && gates && gate_w && dgate_w && dgate_b && ws && mask, RL_EINVAL, "rl_gate_fuse_bwd: null pointer");
+  RL_REQUIRE(num_modal >= 1 && num_modal <= 3 && h_ok(H), RL_EINVAL, "rl_gate_fuse_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = B * L;
+  float* dz = ws;
+  float* dmean = ws + rows * 3;
+  float* mean = dmean + B * H;
+  cudaMemsetAsync(dmean, 0, (size_t)B * H * sizeof(float), st);
+  gate_bwd_token_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dhid, m0, m1, m2, gates, gate_w, dm0, dm1, dm2, dz, dmean,
+                                                                  dgate_b, rows, (int)L, (int)H, num_modal);
+  int rc = rl_check_launch("rl_gate_fuse_bwd(token)");
+  if (rc) return rc;
+  gate_bwd_mean_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dm0, dmean, (const long long*)mask, rows, (int)L, (int)H);
+  masked_mean_kernel<<<(unsigned)B, 256, 0, st>>>(m0, (const long long*)mask, mean, (int)L, (int)H);
+  const float* srcs[3] = {m0, m1, m2};
+  dim3 grid((unsigned)(H / 32), (unsigned)((rows + 2047) / 2048));
+  for (int j = 0; j <= num_modal; ++j)
+    gate_bwd_weight_kernel<<<grid, 256, 0, st>>>(dz, j < num_modal ? srcs[j] : nullptr, j < num_modal ? nullptr : mean, dgate_w,
+                                                rows, (int)L, (int)H, num_modal, j);
+  return rl_check_launch("rl_gate_fuse_bwd");
+}
+
+extern "C" int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, void* stream) {
+  RL_REQUIRE(table && chunks && out, RL_EINVAL, "rl_mt_sumsq: null pointer");
+  if (num_chunks <= 0) return 0;
+  mt_sumsq_kernel<<<(unsigned)num_chunks, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, out);
+  return rl_check_launch("rl_mt_sumsq");
+}
+
+extern "C" int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
+                           float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
+                           float grad_div, void* stream) {
+  RL_REQUIRE(table && chunks && sumsq, RL_EINVAL, "rl_mt_adamw: null pointer");
+  if (num_chunks <= 0) return 0;
+  mt_adamw_kernel<<<(unsigned)num_chunks, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, sumsq,
+                                                                        max_norm, lr, beta1, beta2, eps, bias_corr1,
+                                                                        bias_corr2, grad_div);
+  return rl_check_launch("rl_mt_adamw");
+}

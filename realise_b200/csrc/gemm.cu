@@ -52,6 +52,13 @@ __device__ __forceinline__ float fast_erf(float x) {
   return copysignf(y, x);
 }
 
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + fast_erf(u * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  return fmaf(u, pdf, cdf);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == RL_ACT_GELU) return x * 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f));
   if (act == RL_ACT_RELU) return fmaxf(x, 0.0f);
@@ -147,16 +154,43 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
     const bool live = nb < p.N && row0 < p.M;  // warp-uniform
     if (live) {
       float x[32];
+      if (p.act == RL_ACT_GELU_GRAD) {
+        // data gradient through GELU: the `res` operand carries the saved pre-activation u
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
-        const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
-        x[j] = xr[j] + fmaf(__uint_as_float(v[j]), sc.x, bi.x);
-        x[j + 1] = xr[j + 1] + fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-        x[j + 2] = xr[j + 2] + fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-        x[j + 3] = xr[j + 3] + fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
+          const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+          x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x) * gelu_grad(xr[j]);
+          x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y) * gelu_grad(xr[j + 1]);
+          x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z) * gelu_grad(xr[j + 2]);
+          x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w) * gelu_grad(xr[j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
+          const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+          x[j] = xr[j] + fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+          x[j + 1] = xr[j + 1] + fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+          x[j + 2] = xr[j + 2] + fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+          x[j + 3] = xr[j + 3] + fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+        }
       }
-      if (p.act == RL_ACT_GELU) {
+      if (p.act == RL_ACT_GELU_SAVE && row_ok && p.out2) {
+        // training forward: keep the pre-activation (bf16) for the backward pass, then activate
+        if (nb + 32 <= p.N && p.vec_store) {
+          uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                              rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
+        }
+      }
+      if (p.act == RL_ACT_GELU || p.act == RL_ACT_GELU_SAVE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f * (1.0f + fast_erf(x[j] * 0.70710678118654752440f));
       } else if (p.act == RL_ACT_RELU) {
@@ -205,7 +239,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
               o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
                                 rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
           }
-          if (p.out2) {
+          if (p.out2 && p.act != RL_ACT_GELU_SAVE) {
             uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -220,7 +254,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
                 reinterpret_cast<float*>(p.out)[orow * p.ldo + nb + j] = x[j];
               else
                 reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + nb + j] = __float2bfloat16(x[j]);
-              if (p.out2) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
+              if (p.out2 && p.act != RL_ACT_GELU_SAVE) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
             }
           }
         }

@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256)
 embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ inputs_embeds,
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float* out_f32, __nv_bfloat16* out_bf16, long long rows, int L,
-                int H, int pos_mode, float eps) {
+                const float* __restrict__ beta, float* out_f32, __nv_bfloat16* out_bf16, float* pre_out, long long rows,
+                int L, int H, int pos_mode, float eps) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -86,6 +86,7 @@ embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ wor
     if (i < nv) {
       const float4 a = src[i * 32 + lane], b = __ldg(ps + i * 32 + lane), c = __ldg(ts + i * 32 + lane);
       v[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+      if (pre_out) reinterpret_cast<float4*>(pre_out + row * H)[i * 32 + lane] = v[i];
     }
   float mean, rstd;
   ln_stats(v, nv, H, eps, mean, rstd);
@@ -185,7 +186,7 @@ gate_fuse_kernel(const float* __restrict__ m0, const float* __restrict__ m1, con
 // ---- masked cross entropy (src/models.py:862-868): mean over loss_mask==1 of lse - logit[tgt] ----
 __global__ void __launch_bounds__(256)
 ce_row_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
-              float* __restrict__ row_loss, long long rows, int V, long long ld) {
+              float* __restrict__ row_loss, float* __restrict__ row_lse, long long rows, int V, long long ld) {
   const long long row = blockIdx.x;
   __shared__ float s_red[8];
   __shared__ float s_bc;
@@ -215,13 +216,15 @@ ce_row_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += s_red[w];
-    row_loss[row] = logf(t) + mx - x[tgt[row]];
+    const float lse = logf(t) + mx;
+    if (row_lse) row_lse[row] = lse;
+    row_loss[row] = lse - x[tgt[row]];
   }
 }
 
 __global__ void __launch_bounds__(1024)
 ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ loss_mask, float* __restrict__ loss,
-                 long long rows) {
+                 float* __restrict__ count_out, long long rows) {
   __shared__ float s_sum[32], s_cnt[32];
   float s = 0.f, c = 0.f;
   for (long long i = threadIdx.x; i < rows; i += blockDim.x) {
@@ -242,6 +245,7 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict
       tc += s_cnt[w];
     }
     loss[0] = ts / tc;
+    if (count_out) count_out[0] = tc;
   }
 }
 
@@ -303,16 +307,16 @@ extern "C" int rl_layernorm_fwd(const float* x, const float* gamma, const float*
 
 extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds, const float* pos,
                                const float* type0, const float* gamma, const float* beta, float* out_f32,
-                               void* out_bf16, int64_t rows, int64_t L, int64_t H, int32_t pos_mode, float eps,
-                               void* stream) {
+                               void* out_bf16, float* pre_ln_out, int64_t rows, int64_t L, int64_t H, int32_t pos_mode,
+                               float eps, void* stream) {
   RL_REQUIRE((inputs_embeds || (ids && word)) && pos && type0 && gamma && beta && (out_f32 || out_bf16), RL_EINVAL,
              "rl_embed_ln_fwd: null pointer");
   RL_REQUIRE(h_ok(H) && L > 0, RL_EINVAL, "rl_embed_ln_fwd: bad H/L");
   if (rows <= 0) return 0;
   const int wpb = 8;
   embed_ln_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      (const long long*)ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows,
-      (int)L, (int)H, pos_mode, eps);
+      (const long long*)ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, pre_ln_out,
+      rows, (int)L, (int)H, pos_mode, eps);
   return rl_check_launch("rl_embed_ln_fwd");
 }
 
@@ -341,15 +345,16 @@ extern "C" int rl_gate_fuse_fwd(const float* m0, const float* m1, const float* m
 }
 
 extern "C" int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, float* row_loss_ws,
-                                float* loss, int64_t rows, int64_t V, int64_t ld, void* stream) {
+                                float* loss, float* row_lse_out, float* count_out, int64_t rows, int64_t V, int64_t ld,
+                                void* stream) {
   RL_REQUIRE(logits && tgt && loss_mask && row_loss_ws && loss, RL_EINVAL, "rl_masked_ce_fwd: null pointer");
   RL_REQUIRE(rows > 0 && V > 0 && ld >= V, RL_EINVAL, "rl_masked_ce_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   ce_row_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, (const long long*)tgt, (const long long*)loss_mask, row_loss_ws,
-                                                rows, (int)V, ld);
+                                                row_lse_out, rows, (int)V, ld);
   int rc = rl_check_launch("rl_masked_ce_fwd(rows)");
   if (rc) return rc;
-  ce_reduce_kernel<<<1, 1024, 0, st>>>(row_loss_ws, (const long long*)loss_mask, loss, rows);
+  ce_reduce_kernel<<<1, 1024, 0, st>>>(row_loss_ws, (const long long*)loss_mask, loss, count_out, rows);
   return rl_check_launch("rl_masked_ce_fwd");
 }
 

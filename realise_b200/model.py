@@ -165,6 +165,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         self._ws = {}
         self._graphs = {}
         self.use_cuda_graph = True
+        self._engine = None       # realise_b200.train.TrainEngine, built on the first train-mode forward
         self.fuse_block1 = True   # eval: glyph gather + whole res_block1 in one tcgen05 kernel
         self.collect = None  # tests set this to a dict to receive clones of the sub-module outputs
 
@@ -241,6 +242,13 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("realise_b200 runs on CUDA only: move the model with .to('cuda') first")
         P = {}
+        # operand copies that the fused optimizer refreshes in place: id(param) -> tensor view of equal numel
+        sh16, sh32 = {}, {}
+
+        def bf(p):
+            t = p.detach().bfloat16().contiguous()
+            sh16[id(p)] = t
+            return t
 
         def bert(prefix, mod):
             e = mod.embeddings
@@ -254,16 +262,22 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             }
             for lyr in mod.encoder.layer:
                 s = lyr.attention.self
+                w_qkv = torch.cat([s.query.weight, s.key.weight, s.value.weight], 0).detach().bfloat16().contiguous()
+                b_qkv = torch.cat([s.query.bias, s.key.bias, s.value.bias], 0).detach().float().contiguous()
+                Hh = c.hidden_size
+                for k, lin in enumerate((s.query, s.key, s.value)):
+                    sh16[id(lin.weight)] = w_qkv[k * Hh:(k + 1) * Hh]
+                    sh32[id(lin.bias)] = b_qkv[k * Hh:(k + 1) * Hh]
                 P[prefix]["layers"].append({
-                    "w_qkv": torch.cat([s.query.weight, s.key.weight, s.value.weight], 0).detach().bfloat16().contiguous(),
-                    "b_qkv": torch.cat([s.query.bias, s.key.bias, s.value.bias], 0).detach().float().contiguous(),
-                    "w_o": lyr.attention.output.dense.weight.detach().bfloat16().contiguous(),
+                    "w_qkv": w_qkv,
+                    "b_qkv": b_qkv,
+                    "w_o": bf(lyr.attention.output.dense.weight),
                     "b_o": lyr.attention.output.dense.bias.detach().float().contiguous(),
                     "ln1_w": lyr.attention.output.LayerNorm.weight.detach().float().contiguous(),
                     "ln1_b": lyr.attention.output.LayerNorm.bias.detach().float().contiguous(),
-                    "w_1": lyr.intermediate.dense.weight.detach().bfloat16().contiguous(),
+                    "w_1": bf(lyr.intermediate.dense.weight),
                     "b_1": lyr.intermediate.dense.bias.detach().float().contiguous(),
-                    "w_2": lyr.output.dense.weight.detach().bfloat16().contiguous(),
+                    "w_2": bf(lyr.output.dense.weight),
                     "b_2": lyr.output.dense.bias.detach().float().contiguous(),
                     "ln2_w": lyr.output.LayerNorm.weight.detach().float().contiguous(),
                     "ln2_b": lyr.output.LayerNorm.bias.detach().float().contiguous(),
@@ -287,10 +301,11 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         if c.fusion == "gate":
             P["gate_w"] = self.gate_net.weight.detach().float().contiguous()
             P["gate_b"] = self.gate_net.bias.detach().float().contiguous()
-        P["cls_w"] = self.classifier.weight.detach().bfloat16().contiguous()
+        P["cls_w"] = bf(self.classifier.weight)
         P["cls_b"] = self.classifier.bias.detach().float().contiguous()
         torch.cuda.current_stream().synchronize()
         self._prepared = P
+        self._shadow_bf16, self._shadow_f32 = sh16, sh32
         self._graphs = {}  # captured graphs hold pointers into the previous operand cache
         return P
 
@@ -470,8 +485,6 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         overwrites (the reference's callers consume them immediately: src/run.py:191,259,
         src/test.py:138-140)."""
         c = self.config
-        if self.training:
-            raise NotImplementedError("train-mode forward/backward kernels are not wired yet (round 2)")
         input_ids = batch["src_idx"]
         if not input_ids.is_cuda:
             raise RuntimeError("realise_b200 has no CPU path: move the batch tensors to the model's CUDA device")
@@ -489,6 +502,13 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             else:
                 inputs["pho_lens"] = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
             inputs["pho_idx"] = batch["pho_idx"].contiguous()
+        if self.training:
+            if "tgt_idx" not in batch:
+                raise RuntimeError("train-mode forward needs 'tgt_idx' / 'loss_masks' (src/models.py:861-869)")
+            if self._engine is None:
+                from .train import TrainEngine
+                self._engine = TrainEngine(self)
+            return self._engine.run(inputs)
         if not self.use_cuda_graph or self.collect is not None:
             return self._run(inputs)
         key = tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items()))

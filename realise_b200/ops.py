@@ -9,7 +9,7 @@ import torch
 
 from ._lib import GemmDesc, check, lib
 
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_GELU_GRAD, ACT_GELU_SAVE = 0, 1, 2, 3, 4, 5
 
 LAUNCHES = 0    # kernels launched through this module (each C-ABI call adds its kernel count)
 _prof = None    # bench.py sets this to a list to get (kind, work, start_event, end_event) per call
@@ -156,12 +156,13 @@ def layernorm(x, gamma, beta, out_f32, out_bf16, eps):
     _count()
 
 
-def embed_ln(ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, out_bf16, rows, L, H, pos_mode, eps):
+def embed_ln(ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, out_bf16, rows, L, H, pos_mode, eps,
+             pre_out=None):
     if ids is not None:
         _req(ids, torch.int64, "ids")
     with _Timed("embed_ln", rows * H * 10):
         check(lib().rl_embed_ln_fwd(_ptr(ids), _ptr(word), _ptr(inputs_embeds), _ptr(pos), _ptr(type0), _ptr(gamma),
-                                    _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(L), _c(H),
+                                    _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _ptr(pre_out), _c(rows), _c(L), _c(H),
                                     ctypes.c_int32(pos_mode), ctypes.c_float(eps), _stream()), "rl_embed_ln_fwd")
     _count()
 
@@ -178,14 +179,14 @@ def gate_fuse(mods, sum_mode, mask, gate_w, gate_b, ws, out, gates_out, B, L, H)
     _count(1 if sum_mode else 2)
 
 
-def masked_ce(logits, tgt, loss_mask, row_ws, loss):
+def masked_ce(logits, tgt, loss_mask, row_ws, loss, row_lse=None, count=None):
     _req(logits, torch.float32, "logits")
     _req(tgt, torch.int64, "tgt")
     _req(loss_mask, torch.int64, "loss_mask")
     rows, V = logits.shape
     with _Timed("masked_ce", rows * V * 4):
-        check(lib().rl_masked_ce_fwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _c(rows),
-                                     _c(V), _c(logits.stride(0)), _stream()), "rl_masked_ce_fwd")
+        check(lib().rl_masked_ce_fwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _ptr(row_lse),
+                                     _ptr(count), _c(rows), _c(V), _c(logits.stride(0)), _stream()), "rl_masked_ce_fwd")
     _count(2)
 
 
@@ -242,3 +243,58 @@ def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
                                         _ptr(t2s), _ptr(out), _c(n_img), ctypes.c_int32(C), _stream()),
               "rl_glyph_block1_fwd")
     _count()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training path
+# ---------------------------------------------------------------------------------------------------------
+def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads):
+    for t, n in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
+        _req(t, torch.bfloat16, n)
+    with _Timed("attention_bwd", 14.0 * B * heads * L * L * 64):
+        check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _c(B), _c(L), _c(heads),
+                                     _c(64), _stream()), "rl_attention_bwd")
+    _count()
+
+
+def layernorm_bwd(dy, x, gamma, add_in, dx, dx_bf16, dgamma, dbeta, dxsum, eps):
+    _req(dy, torch.float32, "dy")
+    _req(x, torch.float32, "x")
+    rows, H = x.shape
+    with _Timed("layernorm_bwd", rows * H * 18):
+        check(lib().rl_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(add_in), _ptr(dx), _ptr(dx_bf16), _ptr(dgamma),
+                                     _ptr(dbeta), _ptr(dxsum), _c(rows), _c(H), ctypes.c_float(eps), _stream()),
+              "rl_layernorm_bwd")
+    _count()
+
+
+def colsum_bf16(x, out):
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.float32, "out")
+    rows, cols = x.shape
+    check(lib().rl_colsum_bf16(_ptr(x), _ptr(out), _c(rows), _c(cols), _c(x.stride(0)), _stream()), "rl_colsum_bf16")
+    _count()
+
+
+def masked_ce_bwd(logits, tgt, loss_mask, row_lse, count, gscale, dlogits):
+    rows, V = logits.shape
+    _req(dlogits, torch.bfloat16, "dlogits")
+    check(lib().rl_masked_ce_bwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_lse), _ptr(count), _ptr(gscale),
+                                 _ptr(dlogits), _c(rows), _c(V), _c(logits.stride(0)), _c(dlogits.stride(0)), _stream()),
+          "rl_masked_ce_bwd")
+    _count()
+
+
+def embed_bwd(de, ids, dword, dpos, rows, L, H, pos_mode):
+    check(lib().rl_embed_bwd(_ptr(de), _ptr(ids), _ptr(dword), _ptr(dpos), _c(rows), _c(L), _c(H),
+                             ctypes.c_int32(pos_mode), _stream()), "rl_embed_bwd")
+    _count()
+
+
+def gate_fuse_bwd(dhid, mods, mask, gates, gate_w, dmods, dgate_w, dgate_b, ws, B, L, H):
+    m = list(mods) + [None] * (3 - len(mods))
+    dm = list(dmods) + [None] * (3 - len(dmods))
+    check(lib().rl_gate_fuse_bwd(_ptr(dhid), _ptr(m[0]), _ptr(m[1]), _ptr(m[2]), ctypes.c_int32(len(mods)), _ptr(mask),
+                                 _ptr(gates), _ptr(gate_w), _ptr(dm[0]), _ptr(dm[1]), _ptr(dm[2]), _ptr(dgate_w),
+                                 _ptr(dgate_b), _ptr(ws), _c(B), _c(L), _c(H), _stream()), "rl_gate_fuse_bwd")
+    _count(4 + len(mods))

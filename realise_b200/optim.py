@@ -1,0 +1,90 @@
+"""Fused multi-tensor clip_grad_norm_ + AdamW on librealise_b200.so.
+
+Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)` (src/run.py:207) followed by the
+vendored `AdamW.step()` (transformers/optimization.py:113-169: bias-corrected Adam, decoupled weight decay applied
+after the update) with two kernel launches over every parameter: sum of squared gradients, then the update which
+reads the clip coefficient on device.  The same pass refreshes the bf16 operand copies the GEMMs consume.
+"""
+import ctypes
+
+import torch
+
+from ._lib import check, lib
+
+
+class _Entry(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("shadow", ctypes.c_void_p), ("shadow32", ctypes.c_void_p), ("n", ctypes.c_int64), ("wd", ctypes.c_float),
+                ("pad", ctypes.c_int32)]
+
+
+CHUNK = 4096
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
+                 correct_bias=True, model=None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = max_grad_norm
+        self.correct_bias = correct_bias
+        self.model = model                # realise_b200 model: its bf16 / f32 operand copies are refreshed by the update
+        self._step = 0
+        self._sig = None
+        self._sumsq = None
+
+    def _build(self):
+        entries, sig = [], []
+        sh16, sh32 = ({}, {})
+        if self.model is not None:
+            if self.model._prepared is None:
+                self.model.prepare()
+            sh16, sh32 = self.model._shadow_bf16, self.model._shadow_f32
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["exp_avg"] = torch.zeros_like(p, dtype=torch.float32)
+                    st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32)
+                assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                sh, s32 = sh16.get(id(p)), sh32.get(id(p))
+                entries.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                sh.data_ptr() if sh is not None else 0, s32.data_ptr() if s32 is not None else 0,
+                                p.numel(), float(group["weight_decay"]), gi))
+                sig.append((p.data_ptr(), p.grad.data_ptr(), entries[-1][4], entries[-1][5]))
+        if sig == self._sig:
+            return
+        self._sig = sig
+        dev = self.param_groups[0]["params"][0].device
+        arr = (_Entry * len(entries))()
+        chunks = []
+        for i, (pp, g, m, v, sh, s32, n, wd, gi) in enumerate(entries):
+            arr[i] = _Entry(pp, g, m, v, sh or None, s32 or None, n, wd, 0)
+            chunks += [(i, c) for c in range((n + CHUNK - 1) // CHUNK)]
+        self._table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self._chunks = torch.tensor(chunks, dtype=torch.int32).to(dev).contiguous()
+        self._nchunks = len(chunks)
+        self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_div=1.0):
+        self._build()
+        self._step += 1
+        g0 = self.param_groups[0]
+        b1, b2 = g0["betas"]
+        bc1 = 1.0 - b1 ** self._step if self.correct_bias else 1.0
+        bc2 = 1.0 - b2 ** self._step if self.correct_bias else 1.0
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        tab, ck = ctypes.c_void_p(self._table.data_ptr()), ctypes.c_void_p(self._chunks.data_ptr())
+        self._sumsq.zero_()
+        ss = ctypes.c_void_p(self._sumsq.data_ptr())
+        f = ctypes.c_float
+        check(lib().rl_mt_sumsq(tab, ck, ctypes.c_int64(self._nchunks), ss, st), "rl_mt_sumsq")
+        check(lib().rl_mt_adamw(tab, ck, ctypes.c_int64(self._nchunks), ss, f(self.max_grad_norm or 0.0), f(g0["lr"]),
+                                f(b1), f(b2), f(g0["eps"]), f(bc1), f(bc2), f(grad_div), st), "rl_mt_adamw")
+
+    def grad_norm(self):
+        """Global L2 norm of the last step's gradients (device scalar -> host)."""
+        return float(self._sumsq.sqrt().item())
