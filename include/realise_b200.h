@@ -77,6 +77,9 @@ typedef struct rl_gemm_desc {
                         [img][oh&1][ow&1][oh/2][ow/2] */
   int32_t a_major;   /* 0: A stored [M, K] (K-major).  1: A stored [K, M] with row stride lda (MN-major), e.g.
                         A = dY^T for a weight gradient straight from dY [tokens, out] */
+  float drop_p;        /* training: dropout on (acc*scale+bias) BEFORE the residual add (BertSelfOutput/BertOutput, */
+  uint32_t drop_site;  /* modeling_bert.py:275,341); the mask is the pure function keep(seed, site, m*N+n) also used */
+  uint64_t drop_seed;  /* by the backward kernels.  drop_p = 0 disables it. */
   int32_t b_major;   /* 0: B stored [N, K].  1: B stored [K, N] with row stride ldb, e.g. B = W^T for a data
                         gradient straight from W [out, in], or B = X^T for a weight gradient */
 } rl_gemm_desc;
@@ -96,13 +99,15 @@ RL_API int rl_gemm_set_debug_mode(int flags);
  * Replaces BertSelfAttention.forward score/softmax/context path (modeling_bert.py:234-260) and the
  * extended-mask construction of BertModel.forward (:687, :696-697).  Dropout is identity (eval). */
 RL_API int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, int64_t B, int64_t L,
-                            int64_t heads, int64_t head_dim, void* stream);
+                            int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                            void* stream);
 
 /* ---- LayerNorm (biased variance, eps inside sqrt) over rows of f32 [rows, H] ------------------
  * Replaces BertLayerNorm in BertSelfOutput/BertOutput (modeling_bert.py:276, :342) and
  * resnet_layernorm (src/models.py:838).  Writes f32 and/or bf16 (either may be NULL). */
 RL_API int rl_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32,
-                            void* out_bf16, int64_t rows, int64_t H, float eps, void* stream);
+                            void* out_bf16, int64_t rows, int64_t H, float eps, float drop_p, uint64_t drop_seed,
+                            uint32_t drop_site, int32_t drop_f32 /* mask the f32 output too */, void* stream);
 
 /* ---- BertEmbeddings.forward (modeling_bert.py:169-193) ---------------------------------------
  * out = LN(src + pos[position] + type[0]); src = word[ids[row]] when inputs_embeds is NULL else
@@ -111,7 +116,8 @@ RL_API int rl_layernorm_fwd(const float* x, const float* gamma, const float* bet
 RL_API int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds,
                            const float* pos, const float* type0, const float* gamma, const float* beta,
                            float* out_f32, void* out_bf16, float* pre_ln_out /* optional: the summed embedding */,
-                           int64_t rows, int64_t L, int64_t H, int32_t pos_mode, float eps, void* stream);
+                           int64_t rows, int64_t L, int64_t H, int32_t pos_mode, float eps, float drop_p,
+                           uint64_t drop_seed, uint32_t drop_site, void* stream);
 
 /* ---- gated fusion (src/models.py:840-850; src/models_abla.py:243-279) -------------------------
  * m0 = bert_hiddens, m1/m2 = the other present modalities in the reference's concat order, all
@@ -177,13 +183,18 @@ RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const vo
  * Differentiates BertSelfAttention.forward (modeling_bert.py:234-260) with dropout = identity.
  * ctx is the forward output (needed for delta = rowsum(dO o O)). */
 RL_API int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                            int64_t B, int64_t L, int64_t heads, int64_t head_dim, void* stream);
+                            int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed,
+                            uint32_t drop_site, void* stream);
 
 /* ---- LayerNorm backward: x = LN input (f32), dy = grad of the LN output; dx (+= add_in) in f32 and/or bf16;
  * dgamma/dbeta/dxsum (column sums of dy*xhat, dy, dx) are ACCUMULATED into (caller zeroes them per step). */
 RL_API int rl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* add_in, float* dx,
                             void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int64_t H,
-                            float eps, void* stream);
+                            float eps, float drop_p, uint64_t drop_seed, uint32_t site_in /* 0 = none: dy is masked */,
+                            uint32_t site_out /* 0 = none: dx_bf16 and dxsum are masked */, void* stream);
+
+/* ---- keep mask of a dropout site as bytes (tests feed the kernel's masks to the CPU oracle) ---- */
+RL_API int rl_dropout_mask(uint8_t* out, int64_t n, float drop_p, uint64_t drop_seed, uint32_t drop_site, void* stream);
 
 /* ---- out[c] += sum_r x[r, c] for a bf16 matrix (bias gradients of nn.Linear) ---- */
 RL_API int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream);

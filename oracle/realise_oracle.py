@@ -49,10 +49,29 @@ def gelu_erf(x):
     return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def dropout(x, p, train, gen=None):
+# Dropout masks: torch's RNG stream cannot be reproduced by the CUDA kernels, so for train-mode parity the tests
+# install MASK_FN(site_id, shape) -> keep mask (the kernels' own counter-based masks, exported with
+# rl_dropout_mask) and both sides apply identical masks.  Site ids (realise_b200/train.py): stack * 1000 +
+# layer * 10 + k, stack in {bert 1, pho_model 2, output_block 3}, k in {1 attention probs, 2 attention-output
+# dense, 3 FFN-output dense, 9 embeddings}; 9999 = the dropout before the classifier.
+MASK_FN = None
+STACK_ID = {"bert": 1, "pho_model": 2, "output_block": 3}
+SITE_FINAL = 9999
+
+
+def site_id(path, k):
+    parts = path.split(".")
+    layer = int(parts[3]) if len(parts) > 3 else 0
+    return STACK_ID[parts[0]] * 1000 + layer * 10 + k
+
+
+def dropout(x, p, train, site=None, gen=None):
     if not train or p == 0.0:
         return x
-    keep = (torch.rand(x.shape, generator=gen) >= p).to(x.dtype)
+    if MASK_FN is not None and site is not None:
+        keep = MASK_FN(site, tuple(x.shape)).to(x.dtype)
+    else:
+        keep = (torch.rand(x.shape, generator=gen) >= p).to(x.dtype)
     return x * keep / (1.0 - p)
 
 
@@ -68,7 +87,7 @@ def embeddings(sd, prefix, cfg, input_ids=None, inputs_embeds=None, position_ids
     x = inputs_embeds + pos + typ
     x = layer_norm(x, sd[f"{prefix}.embeddings.LayerNorm.weight"], sd[f"{prefix}.embeddings.LayerNorm.bias"],
                    cfg.layer_norm_eps)
-    return dropout(x, cfg.hidden_dropout_prob, train)
+    return dropout(x, cfg.hidden_dropout_prob, train, site=site_id(prefix, 9))
 
 
 def self_attention(sd, p, cfg, x, ext_mask, train=False):
@@ -82,7 +101,7 @@ def self_attention(sd, p, cfg, x, ext_mask, train=False):
 
     q, k, v = proj("query"), proj("key"), proj("value")
     scores = q @ k.transpose(-1, -2) / math.sqrt(d) + ext_mask
-    probs = dropout(torch.softmax(scores, dim=-1), cfg.attention_probs_dropout_prob, train)
+    probs = dropout(torch.softmax(scores, dim=-1), cfg.attention_probs_dropout_prob, train, site=site_id(p, 1))
     ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, L, H)
     return ctx
 
@@ -90,12 +109,12 @@ def self_attention(sd, p, cfg, x, ext_mask, train=False):
 def bert_layer(sd, p, cfg, x, ext_mask, train=False):
     ctx = self_attention(sd, p, cfg, x, ext_mask, train)
     y = F.linear(ctx, sd[f"{p}.attention.output.dense.weight"], sd[f"{p}.attention.output.dense.bias"])
-    y = dropout(y, cfg.hidden_dropout_prob, train)
+    y = dropout(y, cfg.hidden_dropout_prob, train, site=site_id(p, 2))
     x = layer_norm(y + x, sd[f"{p}.attention.output.LayerNorm.weight"],
                    sd[f"{p}.attention.output.LayerNorm.bias"], cfg.layer_norm_eps)
     h = gelu_erf(F.linear(x, sd[f"{p}.intermediate.dense.weight"], sd[f"{p}.intermediate.dense.bias"]))
     y = F.linear(h, sd[f"{p}.output.dense.weight"], sd[f"{p}.output.dense.bias"])
-    y = dropout(y, cfg.hidden_dropout_prob, train)
+    y = dropout(y, cfg.hidden_dropout_prob, train, site=site_id(p, 3))
     return layer_norm(y + x, sd[f"{p}.output.LayerNorm.weight"], sd[f"{p}.output.LayerNorm.bias"],
                       cfg.layer_norm_eps)
 
@@ -219,7 +238,7 @@ def forward(sd, batch, cfg, train=False, collect=None, bn_stats=None):
     seq = bert_model(sd, "output_block", 3, cfg, attention_mask, inputs_embeds=hid,
                      position_ids=torch.zeros(B, L, dtype=torch.long), train=train)
     c["sequence_output"] = seq
-    seq = dropout(seq, cfg.hidden_dropout_prob, train)
+    seq = dropout(seq, cfg.hidden_dropout_prob, train, site=SITE_FINAL)
     logits = F.linear(seq, sd["classifier.weight"], sd["classifier.bias"])
     c["logits"] = logits
     if "tgt_idx" not in batch:

@@ -16,6 +16,8 @@ struct AttParams {
   __nv_bfloat16* ctx;     // [B*L, H]
   int L, H, lkv16;
   float scale_log2;       // (1/sqrt(d)) * log2(e)
+  int heads;
+  rl::DropSpec drop;      // dropout on the attention probabilities (modeling_bert.py:250)
 };
 
 template <int LKV_MAX>
@@ -151,6 +153,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) sum += (e[j] + e[j + 1]) + (e[j + 2] + e[j + 3]);
+    if (p.drop.thresh) {  // the row sum stays that of the undropped probabilities (softmax, then dropout)
+      const unsigned long long e0 = (((unsigned long long)b * p.heads + head) * L + (q0 + r)) * L + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) e[j] = rl::drop_apply(p.drop, e0 + j, e[j]);
+    }
     // columns c*32 .. c*32+31 of P -> chunk tile (c/2), 16-byte pieces (c&1)*4 .. +3, swizzled by row
     uint8_t* tile = sP + (c >> 1) * Q_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
@@ -236,7 +243,8 @@ int launch_att(const CUtensorMap& tq, const CUtensorMap& tkv, const AttParams& p
 }  // namespace
 
 extern "C" int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, int64_t B, int64_t L,
-                                int64_t heads, int64_t head_dim, void* stream) {
+                                int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                                void* stream) {
   RL_REQUIRE(qkv && mask && ctx, RL_EINVAL, "rl_attention_fwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_fwd: head_dim must be 64, got %lld", (long long)head_dim);
   RL_REQUIRE(B > 0 && heads > 0 && L > 0, RL_EINVAL, "rl_attention_fwd: empty problem");
@@ -260,6 +268,8 @@ extern "C" int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx,
   p.H = H;
   p.lkv16 = lkv16;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.heads = (int)heads;
+  p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)heads, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (lkv16 <= 128) return launch_att<128>(tq, tkv, p, grid, st);

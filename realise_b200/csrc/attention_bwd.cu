@@ -20,6 +20,8 @@ struct AttBwdParams {
   __nv_bfloat16* dqkv;        // [B*L, 3H]
   int L, H, lkv16;
   float scale_log2;
+  int heads;
+  rl::DropSpec drop;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -146,7 +148,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int col = c * 32 + j;
       const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
       pr[j] = rl::ex2(sc - mx) * inv;
-      ds[j] = col < L ? pr[j] * (__uint_as_float(w[j]) - delta) : 0.f;
+      float dp = __uint_as_float(w[j]);  // gradient wrt the (dropped-out) probabilities
+      if (p.drop.thresh) {
+        const unsigned long long e = (((unsigned long long)b * p.heads + head) * L + r) * L + col;
+        const bool keep = rl::drop_keep(p.drop.seed, p.drop.site, e, p.drop.thresh);
+        dp = keep ? dp * p.drop.scale : 0.f;
+        ds[j] = col < L ? pr[j] * (dp - delta) : 0.f;
+        pr[j] = keep ? pr[j] * p.drop.scale : 0.f;  // the tile used for dV = P_drop^T dO
+      } else {
+        ds[j] = col < L ? pr[j] * (dp - delta) : 0.f;
+      }
     }
     uint8_t* tp = sP + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* td = sDS + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
@@ -227,7 +238,8 @@ constexpr int ATT_BWD_SMEM = 8 * T16K + 128 * 4 + 3 * 8 + 16 + 1024;
 }  // namespace
 
 extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                                int64_t B, int64_t L, int64_t heads, int64_t head_dim, void* stream) {
+                                int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed,
+                                uint32_t drop_site, void* stream) {
   RL_REQUIRE(qkv && mask && ctx && dctx && dqkv, RL_EINVAL, "rl_attention_bwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_bwd: head_dim must be 64");
   RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 128, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..128", (long long)L);
@@ -264,6 +276,8 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
   p.H = H;
   p.lkv16 = lkv16;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.heads = (int)heads;
+  p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
   attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, p);
   return rl_check_launch("rl_attention_bwd");
 }

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ add_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int H,
-              float eps) {
+              float eps, rl::DropSpec drop_in, rl::DropSpec drop_out) {
   extern __shared__ float s_part[];  // [3][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = H / 128;
@@ -40,6 +40,11 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
       if (i < nv) {
         xv[i] = reinterpret_cast<const float4*>(x + row * H)[i * 32 + lane];
         gv[i] = reinterpret_cast<const float4*>(dy + row * H)[i * 32 + lane];
+        if (drop_in.thresh) {  // the LN output went through dropout in the forward: dy_eff = dy * keep / (1-p)
+          const long long e0 = row * H + (i * 32 + lane) * 4;
+          gv[i].x = rl::drop_apply(drop_in, e0, gv[i].x); gv[i].y = rl::drop_apply(drop_in, e0 + 1, gv[i].y);
+          gv[i].z = rl::drop_apply(drop_in, e0 + 2, gv[i].z); gv[i].w = rl::drop_apply(drop_in, e0 + 3, gv[i].w);
+        }
         s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
       }
     const float mean = rl::warp_sum(s) / (float)H;
@@ -73,14 +78,20 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
         d.y = rstd * (gv[i].y - m1 - xv[i].y * m2);
         d.z = rstd * (gv[i].z - m1 - xv[i].z * m2);
         d.w = rstd * (gv[i].w - m1 - xv[i].w * m2);
-        px[i].x += d.x; px[i].y += d.y; px[i].z += d.z; px[i].w += d.w;
+        float4 dm = d;  // gradient of the producing linear layer's output: masked when that output was dropped out
+        if (drop_out.thresh) {
+          const long long e0 = row * H + (i * 32 + lane) * 4;
+          dm.x = rl::drop_apply(drop_out, e0, d.x); dm.y = rl::drop_apply(drop_out, e0 + 1, d.y);
+          dm.z = rl::drop_apply(drop_out, e0 + 2, d.z); dm.w = rl::drop_apply(drop_out, e0 + 3, d.w);
+        }
+        px[i].x += dm.x; px[i].y += dm.y; px[i].z += dm.z; px[i].w += dm.w;
+        if (dx_bf16)
+          reinterpret_cast<uint2*>(dx_bf16 + row * H)[i * 32 + lane] = make_uint2(rl::pack_bf16(dm.x, dm.y), rl::pack_bf16(dm.z, dm.w));
         if (add_in) {
           const float4 a = reinterpret_cast<const float4*>(add_in + row * H)[i * 32 + lane];
           d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
         }
         if (dx) reinterpret_cast<float4*>(dx + row * H)[i * 32 + lane] = d;
-        if (dx_bf16)
-          reinterpret_cast<uint2*>(dx_bf16 + row * H)[i * 32 + lane] = make_uint2(rl::pack_bf16(d.x, d.y), rl::pack_bf16(d.z, d.w));
       }
   }
   // CTA-level reduction of the column partials, then one atomic per column
@@ -373,12 +384,14 @@ bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
 
 extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* add_in, float* dx,
                                 void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int64_t H,
-                                float eps, void* stream) {
+                                float eps, float drop_p, uint64_t drop_seed, uint32_t site_in, uint32_t site_out,
+                                void* stream) {
   RL_REQUIRE(dy && x && gamma && (dx || dx_bf16), RL_EINVAL, "rl_layernorm_bwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_bwd: bad H");
   if (rows <= 0) return 0;
   ln_bwd_kernel<<<(unsigned)((rows + LNB_ROWS - 1) / LNB_ROWS), 256, 3 * H * sizeof(float), (cudaStream_t)stream>>>(
-      dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps);
+      dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps,
+      rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in), rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out));
   return rl_check_launch("rl_layernorm_bwd");
 }
 

@@ -241,6 +241,36 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Counter-based dropout mask: keep(seed, site, idx) is a pure function, so the backward kernels regenerate
+// exactly the mask the forward used.  splitmix64 finalizer over (seed, site, element index); an element is
+// dropped when the low 32 bits fall below thresh = p * 2^32.
+__host__ __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned int site, unsigned long long idx,
+                                                   unsigned int thresh) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)site + 1ull) + idx * 0xD1342543DE82EF95ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (unsigned int)z >= thresh;
+}
+struct DropSpec {   // passed by value to kernels; thresh == 0 means "no dropout"
+  unsigned long long seed;
+  unsigned int site;
+  unsigned int thresh;
+  float scale;      // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ DropSpec make_drop(float p, unsigned long long seed, unsigned int site) {
+  DropSpec d;
+  d.seed = seed;
+  d.site = site;
+  d.thresh = p > 0.f ? (unsigned int)(p * 4294967296.0) : 0u;
+  d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+__device__ __forceinline__ float drop_apply(const DropSpec& d, unsigned long long idx, float x) {
+  if (d.thresh == 0u) return x;
+  return drop_keep(d.seed, d.site, idx, d.thresh) ? x * d.scale : 0.0f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

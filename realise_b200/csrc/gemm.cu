@@ -35,6 +35,7 @@ struct KParams {
   int out_remap;
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
+  rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
   int a_mn, b_mn; // operand stored MN-major: A as [K, M] (M contiguous), B as [K, N] (N contiguous)
   int dbg;        // tuning experiments only: 1 = no epilogue work, 2 = no TMA loads, 4 = no MMA
 };
@@ -170,11 +171,18 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         for (int j = 0; j < 32; j += 4) {
           const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
           const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
-          x[j] = xr[j] + fmaf(__uint_as_float(v[j]), sc.x, bi.x);
-          x[j + 1] = xr[j + 1] + fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-          x[j + 2] = xr[j + 2] + fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-          x[j + 3] = xr[j + 3] + fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+          x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+          x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+          x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+          x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
         }
+        if (p.drop.thresh) {
+          const unsigned long long e0 = (unsigned long long)row * p.N + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = rl::drop_apply(p.drop, e0 + j, x[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] += xr[j];
       }
       if (p.act == RL_ACT_GELU_SAVE && row_ok && p.out2) {
         // training forward: keep the pre-activation (bf16) for the backward pass, then activate
@@ -789,6 +797,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.act = d->act;
   p.out_remap = d->out_remap;
   p.dbg = g_dbg;
+  p.drop = rl::make_drop(d->drop_p, d->drop_seed, d->drop_site);
 
   // Tile / kernel selection.  Cost model per 64-deep k-block of one CTA tile (cycles): the tensor pipe needs
   // 2*bn, the operand bytes need bytes / 42.6 (measured L2->SM ingress per SM, ~6.3 KB/clk chip-wide);

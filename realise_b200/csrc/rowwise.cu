@@ -8,7 +8,8 @@ constexpr int MAX_V4 = 8;  // per-lane float4 count: H <= 1024
 
 __device__ __forceinline__ void ln_row_store(const float4* x, int nv, float mean, float rstd,
                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             float* out_f32, __nv_bfloat16* out_bf16, int lane) {
+                                             float* out_f32, __nv_bfloat16* out_bf16, int lane,
+                                             const rl::DropSpec& drop, bool drop_f32, long long elem0) {
 #pragma unroll
   for (int i = 0; i < MAX_V4; ++i) {
     if (i < nv) {
@@ -20,9 +21,14 @@ __device__ __forceinline__ void ln_row_store(const float4* x, int nv, float mean
       y.y = (x[i].y - mean) * rstd * g.y + b.y;
       y.z = (x[i].z - mean) * rstd * g.z + b.z;
       y.w = (x[i].w - mean) * rstd * g.w + b.w;
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = y;
+      float4 yd = y;
+      if (drop.thresh) {  // dropout after the LayerNorm (BertEmbeddings.forward :192, src/models.py:858)
+        yd.x = rl::drop_apply(drop, elem0 + col, y.x); yd.y = rl::drop_apply(drop, elem0 + col + 1, y.y);
+        yd.z = rl::drop_apply(drop, elem0 + col + 2, y.z); yd.w = rl::drop_apply(drop, elem0 + col + 3, y.w);
+      }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = drop_f32 ? yd : y;
       if (out_bf16)
-        *reinterpret_cast<uint2*>(out_bf16 + col) = make_uint2(rl::pack_bf16(y.x, y.y), rl::pack_bf16(y.z, y.w));
+        *reinterpret_cast<uint2*>(out_bf16 + col) = make_uint2(rl::pack_bf16(yd.x, yd.y), rl::pack_bf16(yd.z, yd.w));
     }
   }
 }
@@ -48,7 +54,8 @@ __device__ __forceinline__ void ln_stats(const float4* x, int nv, int H, float e
 // BertLayerNorm.  x: f32 [rows, H]
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* out_f32,
-                                                        __nv_bfloat16* out_bf16, long long rows, int H, float eps) {
+                                                        __nv_bfloat16* out_bf16, long long rows, int H, float eps,
+                                                        rl::DropSpec drop, int drop_f32) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float mean, rstd;
   ln_stats(v, nv, H, eps, mean, rstd);
   ln_row_store(v, nv, mean, rstd, gamma, beta, out_f32 ? out_f32 + row * H : nullptr,
-               out_bf16 ? out_bf16 + row * H : nullptr, lane);
+               out_bf16 ? out_bf16 + row * H : nullptr, lane, drop, drop_f32 != 0, row * H);
 }
 
 // BertEmbeddings.forward: LN(word[ids] (or inputs_embeds) + pos[position] + type[0])
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ inputs_embeds,
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* out_f32, __nv_bfloat16* out_bf16, float* pre_out, long long rows,
-                int L, int H, int pos_mode, float eps) {
+                int L, int H, int pos_mode, float eps, rl::DropSpec drop) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -91,7 +98,7 @@ embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ wor
   float mean, rstd;
   ln_stats(v, nv, H, eps, mean, rstd);
   ln_row_store(v, nv, mean, rstd, gamma, beta, out_f32 ? out_f32 + row * H : nullptr,
-               out_bf16 ? out_bf16 + row * H : nullptr, lane);
+               out_bf16 ? out_bf16 + row * H : nullptr, lane, drop, true, row * H);
 }
 
 // ---- gated fusion (src/models.py:840-850) ----
@@ -290,25 +297,32 @@ argmax_rows_kernel(const float* __restrict__ logits, long long* __restrict__ out
   }
 }
 
+__global__ void __launch_bounds__(256) dropout_mask_kernel(unsigned char* out, long long n, rl::DropSpec d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (d.thresh == 0u || rl::drop_keep(d.seed, d.site, (unsigned long long)i, d.thresh)) ? 1 : 0;
+}
+
 bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
 
 }  // namespace
 
 extern "C" int rl_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32,
-                                void* out_bf16, int64_t rows, int64_t H, float eps, void* stream) {
+                                void* out_bf16, int64_t rows, int64_t H, float eps, float drop_p, uint64_t drop_seed,
+                                uint32_t drop_site, int32_t drop_f32, void* stream) {
   RL_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), RL_EINVAL, "rl_layernorm_fwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_fwd: H=%lld must be a multiple of 128, <= 1024", (long long)H);
   if (rows <= 0) return 0;
   const int wpb = 8;
   layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows, (int)H, eps);
+      x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows, (int)H, eps, rl::make_drop(drop_p, drop_seed, drop_site),
+      drop_f32);
   return rl_check_launch("rl_layernorm_fwd");
 }
 
 extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds, const float* pos,
                                const float* type0, const float* gamma, const float* beta, float* out_f32,
                                void* out_bf16, float* pre_ln_out, int64_t rows, int64_t L, int64_t H, int32_t pos_mode,
-                               float eps, void* stream) {
+                               float eps, float drop_p, uint64_t drop_seed, uint32_t drop_site, void* stream) {
   RL_REQUIRE((inputs_embeds || (ids && word)) && pos && type0 && gamma && beta && (out_f32 || out_bf16), RL_EINVAL,
              "rl_embed_ln_fwd: null pointer");
   RL_REQUIRE(h_ok(H) && L > 0, RL_EINVAL, "rl_embed_ln_fwd: bad H/L");
@@ -316,7 +330,7 @@ extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const floa
   const int wpb = 8;
   embed_ln_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       (const long long*)ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, pre_ln_out,
-      rows, (int)L, (int)H, pos_mode, eps);
+      rows, (int)L, (int)H, pos_mode, eps, rl::make_drop(drop_p, drop_seed, drop_site));
   return rl_check_launch("rl_embed_ln_fwd");
 }
 
@@ -363,4 +377,11 @@ extern "C" int rl_argmax_rows(const float* logits, int64_t* out, int64_t rows, i
   if (rows <= 0) return 0;
   argmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (long long*)out, (int)V, ld);
   return rl_check_launch("rl_argmax_rows");
+}
+
+extern "C" int rl_dropout_mask(uint8_t* out, int64_t n, float drop_p, uint64_t drop_seed, uint32_t drop_site, void* stream) {
+  RL_REQUIRE(out && n >= 0, RL_EINVAL, "rl_dropout_mask: bad arguments");
+  if (n == 0) return 0;
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, rl::make_drop(drop_p, drop_seed, drop_site));
+  return rl_check_launch("rl_dropout_mask");
 }

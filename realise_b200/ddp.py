@@ -1,0 +1,50 @@
+"""Data parallelism for the training step: batch sharding + ONE gradient all-reduce over the flat buffer.
+
+Reference behaviour (src/run.py:131-137, :165-167, :200): every rank keeps examples r, r+W, ... (tail dropped so all
+ranks see the same count), the model is wrapped in DistributedDataParallel, and `loss.backward()` all-reduces
+(sum / W) the gradients in 25 MB buckets.  Here the gradients of a rank already live in one contiguous fp32 buffer
+(realise_b200.train.TrainEngine.flat), so the exchange is a single NCCL all-reduce(sum) on it — over NVLink 5 /
+NVSwitch on the 8xB200 box — and the division by W is folded into the fused clip+AdamW kernel (grad_div).
+BatchNorm statistics stay per-rank (plain BatchNorm2d in the reference, no SyncBN).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_examples(examples, rank, world_size):
+    """src/run.py:131-137: rank-strided shard, tail dropped so every rank has len(examples) // world_size items."""
+    n = len(examples) // world_size
+    return examples[rank::world_size][:n]
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place sum over ranks of a flat gradient buffer (NCCL for CUDA tensors, gloo for the CPU tests)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 1
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return dist.get_world_size(group)
+
+
+class DataParallel:
+    """Attach to a realise_b200 model: after every backward the flat gradient buffer is all-reduced and the
+    optimizer divides by the world size.  Usage mirrors the reference loop:
+
+        dp = DataParallel(model)                       # instead of DistributedDataParallel(model, ...)
+        loss = model(batch)[0]; loss.backward()        # gradients are summed across ranks here
+        optimizer.step()                               # FusedAdamW(model=model) reads model.grad_div
+    """
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+        model.grad_div = float(dist.get_world_size(group)) if dist.is_initialized() else 1.0
+        model._post_backward = self.sync
+
+    def sync(self, engine):
+        allreduce_sum_(engine.flat, self.group)
+
+    def broadcast_parameters(self, src=0):
+        """DDP broadcasts rank-0 parameters/buffers at construction; do the same once."""
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+            self.model._prepared = None

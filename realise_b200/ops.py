@@ -55,7 +55,7 @@ def _req(t, dtype, name):
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
-def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None, a_t=False, b_t=False):
+def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None, a_t=False, b_t=False, drop=None):
     """out[M,N] = act((A @ B^T) * scale + bias + res) with A = a [M,K] (or a^T when a_t: a is stored [K,M],
     MN-major operand) and B = b [N,K] (or b^T when b_t: b is stored [K,N]).  a, b bf16; out bf16 or f32."""
     _req(a, torch.bfloat16, "a")
@@ -70,6 +70,8 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldb = a.stride(0), b.stride(0)
     d.a_major, d.b_major = int(a_t), int(b_t)
+    if drop:
+        d.drop_p, d.drop_seed, d.drop_site = drop
     d.a_mode = 0
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
     with _Timed("gemm", 2.0 * M * N * K):
@@ -133,37 +135,45 @@ def _c(v):
     return ctypes.c_int64(int(v))
 
 
-def attention(qkv, mask, ctx, B, L, heads):
+def _drop(drop):
+    """drop = None or (p, seed, site) -> ctypes (float, uint64, uint32)."""
+    p, seed, site = drop if drop else (0.0, 0, 0)
+    return ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_uint32(site)
+
+
+def attention(qkv, mask, ctx, B, L, heads, drop=None):
     """ctx = softmax(QK^T/8 + (1-mask)*-1e4) V per head; qkv bf16 [B*L, 3*heads*64], mask int64 [B, L]."""
     _req(qkv, torch.bfloat16, "qkv")
     _req(ctx, torch.bfloat16, "ctx")
     _req(mask, torch.int64, "mask")
     assert qkv.is_contiguous() and ctx.is_contiguous() and mask.is_contiguous()
     with _Timed("attention", 4.0 * B * heads * L * L * 64):
-        check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _c(B), _c(L), _c(heads), _c(64), _stream()),
-              "rl_attention_fwd")
+        check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _c(B), _c(L), _c(heads), _c(64), *_drop(drop),
+                                     _stream()), "rl_attention_fwd")
     _count()
     return ctx
 
 
-def layernorm(x, gamma, beta, out_f32, out_bf16, eps):
+def layernorm(x, gamma, beta, out_f32, out_bf16, eps, drop=None, drop_f32=False):
     _req(x, torch.float32, "x")
     rows, H = x.shape
     nbytes = rows * H * (4 + (4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))
     with _Timed("layernorm", nbytes):
         check(lib().rl_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(H),
-                                     ctypes.c_float(eps), _stream()), "rl_layernorm_fwd")
+                                     ctypes.c_float(eps), *_drop(drop), ctypes.c_int32(int(drop_f32)), _stream()),
+              "rl_layernorm_fwd")
     _count()
 
 
 def embed_ln(ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, out_bf16, rows, L, H, pos_mode, eps,
-             pre_out=None):
+             pre_out=None, drop=None):
     if ids is not None:
         _req(ids, torch.int64, "ids")
     with _Timed("embed_ln", rows * H * 10):
         check(lib().rl_embed_ln_fwd(_ptr(ids), _ptr(word), _ptr(inputs_embeds), _ptr(pos), _ptr(type0), _ptr(gamma),
                                     _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _ptr(pre_out), _c(rows), _c(L), _c(H),
-                                    ctypes.c_int32(pos_mode), ctypes.c_float(eps), _stream()), "rl_embed_ln_fwd")
+                                    ctypes.c_int32(pos_mode), ctypes.c_float(eps), *_drop(drop), _stream()),
+              "rl_embed_ln_fwd")
     _count()
 
 
@@ -248,23 +258,27 @@ def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
 # ---------------------------------------------------------------------------------------------------------
 # training path
 # ---------------------------------------------------------------------------------------------------------
-def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads):
+def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None):
     for t, n in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, n)
     with _Timed("attention_bwd", 14.0 * B * heads * L * L * 64):
         check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _c(B), _c(L), _c(heads),
-                                     _c(64), _stream()), "rl_attention_bwd")
+                                     _c(64), *_drop(drop), _stream()), "rl_attention_bwd")
     _count()
 
 
-def layernorm_bwd(dy, x, gamma, add_in, dx, dx_bf16, dgamma, dbeta, dxsum, eps):
+def layernorm_bwd(dy, x, gamma, add_in, dx, dx_bf16, dgamma, dbeta, dxsum, eps, drop_p=0.0, drop_seed=0, site_in=0,
+                  site_out=0):
+    """site_in: dropout site applied to the LN OUTPUT in the forward (dy is masked); site_out: dropout site applied
+    to the linear output that fed the LN input (dx_bf16 / dxsum are masked).  0 = no dropout there."""
     _req(dy, torch.float32, "dy")
     _req(x, torch.float32, "x")
     rows, H = x.shape
     with _Timed("layernorm_bwd", rows * H * 18):
         check(lib().rl_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(add_in), _ptr(dx), _ptr(dx_bf16), _ptr(dgamma),
-                                     _ptr(dbeta), _ptr(dxsum), _c(rows), _c(H), ctypes.c_float(eps), _stream()),
-              "rl_layernorm_bwd")
+                                     _ptr(dbeta), _ptr(dxsum), _c(rows), _c(H), ctypes.c_float(eps), ctypes.c_float(drop_p),
+                                     ctypes.c_uint64(drop_seed), ctypes.c_uint32(site_in), ctypes.c_uint32(site_out),
+                                     _stream()), "rl_layernorm_bwd")
     _count()
 
 
@@ -298,3 +312,11 @@ def gate_fuse_bwd(dhid, mods, mask, gates, gate_w, dmods, dgate_w, dgate_b, ws, 
                                  _ptr(gates), _ptr(gate_w), _ptr(dm[0]), _ptr(dm[1]), _ptr(dm[2]), _ptr(dgate_w),
                                  _ptr(dgate_b), _ptr(ws), _c(B), _c(L), _c(H), _stream()), "rl_gate_fuse_bwd")
     _count(4 + len(mods))
+
+
+def dropout_mask(n, p, seed, site, device="cuda"):
+    """uint8 keep mask of a dropout site (what the kernels compute on the fly) — for tests."""
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    check(lib().rl_dropout_mask(_ptr(out), _c(n), ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_uint32(site),
+                                _stream()), "rl_dropout_mask")
+    return out

@@ -69,7 +69,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
 
     @torch.no_grad()
-    def step(self, closure=None, grad_div=1.0):
+    def step(self, closure=None, grad_div=None):
+        if grad_div is None:  # data parallel: gradients were summed over ranks (realise_b200.ddp.DataParallel)
+            grad_div = float(getattr(self.model, "grad_div", 1.0)) if self.model is not None else 1.0
         self._build()
         self._step += 1
         g0 = self.param_groups[0]

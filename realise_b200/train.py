@@ -31,6 +31,9 @@ class _StepFn(torch.autograd.Function):
     def backward(ctx, gloss, _glogits):
         eng = ctx.engine
         eng.backward(gloss)
+        hook = getattr(eng.m, "_post_backward", None)   # realise_b200.ddp.DataParallel: one all-reduce of eng.flat
+        if hook is not None:
+            hook(eng)
         # gradients live in persistent buffers (stable pointers for the fused optimizer); they are attached to the
         # parameters directly instead of being handed to autograd, which would copy or alias them
         for p, g in zip(eng.params, eng.grads):
@@ -46,19 +49,85 @@ class TrainEngine:
         if c.with_pho == "yes" or c.with_res == "yes":
             raise NotImplementedError("training kernels cover the semantic path only in this round: GRU BPTT and "
                                       "CharResNet/BatchNorm backward are not written yet (use with_pho='no', with_res='no')")
-        if c.hidden_dropout_prob != 0.0 or c.attention_probs_dropout_prob != 0.0:
-            raise NotImplementedError("train mode needs hidden_dropout_prob = attention_probs_dropout_prob = 0 in this "
-                                      "round (Philox dropout kernels not written yet)")
         self.saved = None
+        self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
         # trainable parameters in a fixed order
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.index = {id(p): i for i, p in enumerate(self.params)}
-        self.grads = [None] * len(self.params)   # persistent fp32 gradient buffers (allocated on first use)
-        self.zero_list = []                       # buffers that kernels accumulate into: zeroed every step
+        self._layout()
+
+    def _layout(self):
+        """All gradients live in ONE flat fp32 buffer (stable pointers for the fused optimizer, one NCCL all-reduce
+        for data parallelism): [ accumulated-into region (zeroed every step) | overwritten-by-GEMM region ].
+        The q/k/v weights (biases) of a layer are adjacent so that the fused [3H, H] wgrad GEMM ([3H] column sum)
+        writes them in one go.  Parameters that never receive a gradient (poolers, the unused word embeddings of
+        pho_model / output_block) are left out, like autograd leaves their .grad at None in the reference."""
+        m = self.m
+        H = m.config.hidden_size
+        dev = m.classifier.bias.device
+        no_grad = set()
+        for stack in [m.bert, m.output_block] + ([m.pho_model] if hasattr(m, "pho_model") else []):
+            no_grad.update(id(p) for p in stack.pooler.parameters())
+            if stack is not m.bert:
+                no_grad.add(id(stack.embeddings.word_embeddings.weight))
+        tied = m.classifier.weight is m.bert.embeddings.word_embeddings.weight
+        over_ids, order_zero, order_over, seen = set(), [], [], set()
         self._fused = {}
+        stacks = [m.bert, m.output_block] + ([m.pho_model] if hasattr(m, "pho_model") else [])
+        for stack in stacks:
+            for lyr in stack.encoder.layer:
+                sa = lyr.attention.self
+                order_over.append(("qkv_w", lyr.attention, [sa.query.weight, sa.key.weight, sa.value.weight]))
+                order_zero.append(("qkv_b", lyr.attention, [sa.query.bias, sa.key.bias, sa.value.bias]))
+                for p in (sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias):
+                    seen.add(id(p))
+                for lin in (lyr.attention.output.dense, lyr.intermediate.dense, lyr.output.dense):
+                    over_ids.add(id(lin.weight))
+        over_ids.add(id(m.classifier.weight))
+        for p in self.params:
+            if id(p) in seen or id(p) in no_grad:
+                continue
+            (order_over if id(p) in over_ids else order_zero).append(("p", None, [p]))
+        n_zero = sum(p.numel() for _, _, ps in order_zero for p in ps)
+        n_over = sum(p.numel() for _, _, ps in order_over for p in ps)
+        self.flat = torch.zeros(n_zero + n_over, device=dev, dtype=F32)
+        self.flat_zero = self.flat[:n_zero]
+        self.grads = [None] * len(self.params)
+        off = 0
+        for kind, att, ps in order_zero + order_over:
+            start = off
+            for p in ps:
+                self.grads[self.index[id(p)]] = self.flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            if kind == "qkv_w":
+                self._fused.setdefault(id(att), {})["w"] = self.flat[start:off].view(3 * H, H)
+            elif kind == "qkv_b":
+                self._fused.setdefault(id(att), {})["b"] = self.flat[start:off]
+        self.tied = tied
 
     def run(self, inputs):
         return _StepFn.apply(self, inputs, *self.params)
+
+    def set_seed(self, seed):
+        self.seed = int(seed)
+
+    # dropout sites: stack s in {bert: 1, pho_model: 2, output_block: 3}; the masks are pure functions of
+    # (seed, site, element index), regenerated by the backward kernels
+    STACK_ID = {"bert": 1, "pho": 2, "out": 3}
+
+    def site(self, stack, layer, k):
+        """k: 1 attention probs, 2 attention-output dense, 3 FFN-output dense, 9 embeddings (layer ignored)."""
+        return self.STACK_ID[stack] * 1000 + layer * 10 + k
+
+    SITE_FINAL = 9999
+
+    def hdrop(self, site):
+        p = self.m.config.hidden_dropout_prob
+        return (p, self.step_seed, site) if p > 0 else None
+
+    def adrop(self, site):
+        p = self.m.config.attention_probs_dropout_prob
+        return (p, self.step_seed, site) if p > 0 else None
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _new(self, shape, dtype, zero=False):
@@ -66,51 +135,44 @@ class TrainEngine:
         return torch.zeros(shape, device=dev, dtype=dtype) if zero else torch.empty(shape, device=dev, dtype=dtype)
 
     def _grad(self, p, zero=False):
-        """Persistent fp32 gradient buffer of parameter p (registered for per-step zeroing when accumulated into)."""
-        i = self.index[id(p)]
-        if self.grads[i] is None:
-            self.grads[i] = self._new(tuple(p.shape), F32, zero=zero)
-            if zero:
-                self.zero_list.append(self.grads[i])
-        return self.grads[i]
+        """Persistent fp32 gradient view of parameter p inside the flat buffer."""
+        return self.grads[self.index[id(p)]]
 
     def _qkv_grads(self, att, H):
-        """Fused [3H, H] weight / [3H] bias gradient of a layer's query/key/value; the parameters get row views."""
-        key = id(att)
-        if key not in self._fused:
-            dw, db = self._new((3 * H, H), F32), self._new((3 * H,), F32, zero=True)
-            self.zero_list.append(db)
-            for k, lin in enumerate((att.self.query, att.self.key, att.self.value)):
-                self.grads[self.index[id(lin.weight)]] = dw[k * H:(k + 1) * H]
-                self.grads[self.index[id(lin.bias)]] = db[k * H:(k + 1) * H]
-            self._fused[key] = (dw, db)
-        return self._fused[key]
+        """Fused [3H, H] weight / [3H] bias gradient of a layer's query/key/value (views of the flat buffer)."""
+        f = self._fused[id(att)]
+        return f["w"], f["b"]
 
     # ---- forward -----------------------------------------------------------------------------------
-    def _stack_fwd(self, name, mod, P, mask, B, L, ids=None, inputs_embeds=None, pos_mode=0):
+    def _stack_fwd(self, name, mod, P, mask, B, L, ids=None, inputs_embeds=None, pos_mode=0, last_drop=False):
         c = self.m.config
         N, H, I = B * L, c.hidden_size, c.intermediate_size
-        sv = {"layers": [], "ids": ids, "pos_mode": pos_mode, "mod": mod, "P": P, "from_embeds": inputs_embeds is not None}
+        sv = {"layers": [], "ids": ids, "pos_mode": pos_mode, "mod": mod, "P": P, "from_embeds": inputs_embeds is not None,
+              "name": name, "last_drop": last_drop}
         x, xb = self._new((N, H), F32), self._new((N, H), BF16)
         sv["e_pre"] = self._new((N, H), F32)
         ops.embed_ln(ids, P["word"], inputs_embeds, P["pos"], P["type0"], P["ln_w"], P["ln_b"], x, xb, N, L, H, pos_mode,
-                     c.layer_norm_eps, pre_out=sv["e_pre"])
-        for lw in P["layers"]:
+                     c.layer_norm_eps, pre_out=sv["e_pre"], drop=self.hdrop(self.site(name, 0, 9)))
+        nl = len(P["layers"])
+        for li, lw in enumerate(P["layers"]):
             s = {"xb": xb}
             s["qkv"] = self._new((N, 3 * H), BF16)
             ops.gemm(xb, lw["w_qkv"], s["qkv"], bias=lw["b_qkv"])
             s["ctx"] = self._new((N, H), BF16)
-            ops.attention(s["qkv"], mask, s["ctx"], B, L, c.num_attention_heads)
+            ops.attention(s["qkv"], mask, s["ctx"], B, L, c.num_attention_heads, drop=self.adrop(self.site(name, li, 1)))
             s["y1"] = self._new((N, H), F32)
-            ops.gemm(s["ctx"], lw["w_o"], s["y1"], bias=lw["b_o"], res=x)
+            ops.gemm(s["ctx"], lw["w_o"], s["y1"], bias=lw["b_o"], res=x, drop=self.hdrop(self.site(name, li, 2)))
             x1, s["x1b"] = self._new((N, H), F32), self._new((N, H), BF16)
             ops.layernorm(s["y1"], lw["ln1_w"], lw["ln1_b"], x1, s["x1b"], c.layer_norm_eps)
             s["u"], s["h"] = self._new((N, I), BF16), self._new((N, I), BF16)
             ops.gemm(s["x1b"], lw["w_1"], s["h"], bias=lw["b_1"], act=ops.ACT_GELU_SAVE, out2=s["u"])
             s["y2"] = self._new((N, H), F32)
-            ops.gemm(s["h"], lw["w_2"], s["y2"], bias=lw["b_2"], res=x1)
+            ops.gemm(s["h"], lw["w_2"], s["y2"], bias=lw["b_2"], res=x1, drop=self.hdrop(self.site(name, li, 3)))
             x, xb = self._new((N, H), F32), self._new((N, H), BF16)
-            ops.layernorm(s["y2"], lw["ln2_w"], lw["ln2_b"], x, xb, c.layer_norm_eps)
+            # the classifier consumes dropout(sequence_output) (src/models.py:858): only the bf16 operand copy of
+            # the last LayerNorm of output_block is masked
+            fin = self.hdrop(self.SITE_FINAL) if (last_drop and li == nl - 1) else None
+            ops.layernorm(s["y2"], lw["ln2_w"], lw["ln2_b"], x, xb, c.layer_norm_eps, drop=fin, drop_f32=False)
             sv["layers"].append(s)
         return x, xb, sv
 
@@ -124,7 +186,9 @@ class TrainEngine:
         N, H, V = B * L, c.hidden_size, c.vocab_size
         if L > 128:
             raise NotImplementedError("attention backward kernel supports seq_len <= 128")
-        sv = {"B": B, "L": L, "mask": mask, "inp": inp}
+        self.step_seed = self.seed
+        self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        sv = {"B": B, "L": L, "mask": mask, "inp": inp, "seed": self.step_seed}
         bert_h, _, sv["bert"] = self._stack_fwd("bert", m.bert, P["bert"], mask, B, L, ids=input_ids.view(-1))
         mods = [bert_h]
         sv["mods"] = mods
@@ -135,7 +199,7 @@ class TrainEngine:
         else:
             ops.gate_fuse(mods, True, None, None, None, None, fused, None, B, L, H)
         _, seq_b, sv["out"] = self._stack_fwd("out", m.output_block, P["output_block"], mask, B, L, inputs_embeds=fused,
-                                              pos_mode=1)
+                                              pos_mode=1, last_drop=True)
         sv["seq_b"] = seq_b
         logits = self._new((N, V), F32)
         ops.gemm(seq_b, P["cls_w"], logits, bias=P["cls_b"])
@@ -152,14 +216,20 @@ class TrainEngine:
         """dx: f32 [N,H] gradient of the stack output.  Returns the gradient wrt inputs_embeds (or None)."""
         c = self.m.config
         N, H, I = B * L, c.hidden_size, c.intermediate_size
-        mod, P = sv["mod"], sv["P"]
-        for li in range(len(sv["layers"]) - 1, -1, -1):
+        mod, P, name = sv["mod"], sv["P"], sv["name"]
+        hp, seed = c.hidden_dropout_prob, self.step_seed
+        nl = len(sv["layers"])
+        for li in range(nl - 1, -1, -1):
             s, lw, lyr = sv["layers"][li], P["layers"][li], mod.encoder.layer[li]
             att, out = lyr.attention, lyr.output
             # x = LN2(y2),  y2 = h W2^T + b2 + x1
             dy2, dy2b = self._new((N, H), F32), self._new((N, H), BF16)
+            # dx arrives through dropout only for the last LayerNorm of output_block (final dropout, site_in)
             ops.layernorm_bwd(dx, s["y2"], lw["ln2_w"], None, dy2, dy2b, self._grad(out.LayerNorm.weight, True),
-                              self._grad(out.LayerNorm.bias, True), self._grad(out.dense.bias, True), c.layer_norm_eps)
+                              self._grad(out.LayerNorm.bias, True), self._grad(out.dense.bias, True), c.layer_norm_eps,
+                              drop_p=hp, drop_seed=seed,
+                              site_in=self.SITE_FINAL if (hp > 0 and sv["last_drop"] and li == nl - 1) else 0,
+                              site_out=self.site(name, li, 3) if hp > 0 else 0)
             ops.gemm(dy2b, s["h"], self._grad(out.dense.weight), a_t=True, b_t=True)              # dW2 = dy2^T h
             du = self._new((N, I), BF16)
             ops.gemm(dy2b, lw["w_2"], du, b_t=True, res=s["u"], act=ops.ACT_GELU_GRAD)              # du = (dy2 W2) gelu'(u)
@@ -171,12 +241,13 @@ class TrainEngine:
             dy1, dy1b = self._new((N, H), F32), self._new((N, H), BF16)
             ops.layernorm_bwd(dx1, s["y1"], lw["ln1_w"], None, dy1, dy1b, self._grad(att.output.LayerNorm.weight, True),
                               self._grad(att.output.LayerNorm.bias, True), self._grad(att.output.dense.bias, True),
-                              c.layer_norm_eps)
+                              c.layer_norm_eps, drop_p=hp, drop_seed=seed, site_out=self.site(name, li, 2) if hp > 0 else 0)
             ops.gemm(dy1b, s["ctx"], self._grad(att.output.dense.weight), a_t=True, b_t=True)      # dWo = dy1^T ctx
             dctx = self._new((N, H), BF16)
             ops.gemm(dy1b, lw["w_o"], dctx, b_t=True)
             dqkv = self._new((N, 3 * H), BF16)
-            ops.attention_bwd(s["qkv"], mask, s["ctx"], dctx, dqkv, B, L, c.num_attention_heads)
+            ops.attention_bwd(s["qkv"], mask, s["ctx"], dctx, dqkv, B, L, c.num_attention_heads,
+                              drop=self.adrop(self.site(name, li, 1)))
             dw, db = self._qkv_grads(att, H)
             ops.colsum_bf16(dqkv, db)
             ops.gemm(dqkv, s["xb"], dw, a_t=True, b_t=True)                                         # dWqkv = dqkv^T x
@@ -188,7 +259,8 @@ class TrainEngine:
         de = self._new((N, H), F32)
         dtype_sum = self._new((H,), F32, zero=True)
         ops.layernorm_bwd(dx, sv["e_pre"], P["ln_w"], None, de, None, self._grad(e.LayerNorm.weight, True),
-                          self._grad(e.LayerNorm.bias, True), dtype_sum, c.layer_norm_eps)
+                          self._grad(e.LayerNorm.bias, True), dtype_sum, c.layer_norm_eps, drop_p=hp, drop_seed=seed,
+                          site_in=self.site(name, 0, 9) if hp > 0 else 0)
         gtype = self._grad(e.token_type_embeddings.weight, True)
         gtype[0].copy_(dtype_sum)
         dpos = self._grad(e.position_embeddings.weight, True)
@@ -203,8 +275,8 @@ class TrainEngine:
         P = m._prepared
         B, L, mask = sv["B"], sv["L"], sv["mask"]
         N, H, V = B * L, c.hidden_size, c.vocab_size
-        if self.zero_list:
-            torch._foreach_zero_(self.zero_list)
+        self.step_seed = sv["seed"]
+        self.flat_zero.zero_()
         inp = sv["inp"]
         # classifier + masked CE:  logits = seq E^T + b
         dlogits = self._new((N, V), BF16)
@@ -212,7 +284,6 @@ class TrainEngine:
         ops.masked_ce_bwd(sv["logits"], inp["tgt_idx"].view(-1), inp["loss_masks"].view(-1), sv["lse"], sv["count"], gscale,
                           dlogits)
         ops.colsum_bf16(dlogits, self._grad(m.classifier.bias, True))
-        tied = m.classifier.weight is m.bert.embeddings.word_embeddings.weight
         gE = self._grad(m.classifier.weight, zero=False)
         ops.gemm(dlogits, sv["seq_b"], gE, a_t=True, b_t=True)                                      # dE = dlogits^T seq
         dseq = self._new((N, H), F32)
@@ -226,8 +297,6 @@ class TrainEngine:
                               self._grad(m.gate_net.bias, True), ws, B, L, H)
         else:
             dm0 = dfused
-        if not tied:
-            self._grad(m.bert.embeddings.word_embeddings.weight, True)
         self._stack_bwd(sv["bert"], dm0, mask, B, L)   # scatter-adds the embedding rows into the (tied) dE buffer
         self.saved = None
         # parameters that never receive a gradient (poolers, unused word embeddings of output_block) -> None

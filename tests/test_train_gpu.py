@@ -112,3 +112,75 @@ def test_train_mode_guards():
     db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
     with pytest.raises(NotImplementedError):
         m(db)
+
+
+def test_dropout_training_parity_with_exported_masks():
+    """p = 0.1 everywhere (the reference config): the kernels' counter-based masks are exported with
+    rl_dropout_mask and installed in the oracle, so both sides drop exactly the same elements."""
+    from oracle import realise_oracle as O
+    from realise_b200 import ops
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    from realise_b200.train import TrainEngine
+    cfg = ArchConfig(num_hidden_layers=2, with_pho="no", with_res="no")
+    assert cfg.hidden_dropout_prob == 0.1 and cfg.attention_probs_dropout_prob == 0.1
+    sd = cached_state_dict(ArchConfig(num_hidden_layers=2, with_pho="no", with_res="no", hidden_dropout_prob=0.0,
+                                      attention_probs_dropout_prob=0.0), 11)
+    model = SpellBertPho2ResArch3Abla(cfg)
+    model.tie_cls_weight()
+    model.load_state_dict(sd, strict=True)
+    model.train().cuda()
+    model._engine = TrainEngine(model)
+    model._engine.set_seed(4242)
+    batch = synth_batch(3, 40, seed=6)
+    db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    loss, logits = model(db)
+    loss.backward()
+
+    def mask_fn(site, shape):
+        n = int(torch.tensor(shape).prod().item())
+        p = 0.1
+        return ops.dropout_mask(n, p, 4242, site).cpu().reshape(shape).float()
+
+    O.MASK_FN = mask_fn
+    try:
+        rloss, rlogits, leaves = _oracle_grads(sd, batch, cfg)
+    finally:
+        O.MASK_FN = None
+    assert abs(loss.item() - rloss.item()) <= 1e-2
+    keep = ops.dropout_mask(1 << 20, 0.1, 4242, 1012).float().mean().item()
+    assert abs(keep - 0.9) < 2e-3
+    gmax = max(v.grad.abs().max().item() for v in leaves.values() if v.grad is not None)
+    for name, p in model.named_parameters():
+        if name == "classifier.weight" or p.grad is None:
+            continue
+        rg = leaves[name].grad
+        if rg.norm().item() < 1e-6 * gmax:
+            continue
+        rel = (p.grad.float().cpu() - rg).norm().item() / rg.norm().item()
+        assert rel <= 2e-2, (name, rel)
+    # a different seed gives different masks (the loss moves), the same seed reproduces the loss bit for bit
+    model._engine.set_seed(4242)
+    l_same, _ = model(db)
+    model._engine.set_seed(7)
+    l_other, _ = model(db)
+    assert l_same.item() == loss.item() and l_other.item() != loss.item()
+
+
+def test_flat_gradient_buffer_layout():
+    cfg, sd, model = _setup(layers=1)
+    batch = synth_batch(2, 16, seed=5)
+    db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    loss, _ = model(db)
+    loss.backward()
+    eng = model._engine
+    lo, hi = eng.flat.data_ptr(), eng.flat.data_ptr() + eng.flat.numel() * 4
+    n = 0
+    for p in model.parameters():
+        if p.grad is not None:
+            assert lo <= p.grad.data_ptr() < hi          # every gradient is a view of the one flat buffer
+            n += p.grad.numel()
+    assert n == eng.flat.numel()
+    no_grad = [name for name, p in model.named_parameters() if p.grad is None]
+    assert sorted(no_grad) == sorted(["bert.pooler.dense.weight", "bert.pooler.dense.bias",
+                                      "output_block.pooler.dense.weight", "output_block.pooler.dense.bias",
+                                      "output_block.embeddings.word_embeddings.weight"])

@@ -64,6 +64,56 @@ for (B, L, seed) in [(2, 16, 5), (3, 40, 6)]:
         print(f"  rel_err {rel:.3e}  |g|={n:.3e}  {name}")
     print(f"  median rel_err {sorted(w[0] for w in worst)[len(worst)//2]:.3e} over {len(worst)} tensors")
 
+# ---- dropout ON: feed the kernels' own masks to the oracle ----
+from realise_b200 import ops  # noqa: E402
+cfg_d = ArchConfig(num_hidden_layers=2, with_pho="no", with_res="no")   # p = 0.1 / 0.1 as in the reference config
+md = SpellBertPho2ResArch3Abla(cfg_d)
+md.tie_cls_weight()
+md.load_state_dict(sd, strict=True)
+md.train().cuda()
+B, L = 3, 40
+batch = synth_batch(B, L, seed=6)
+db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+from realise_b200.train import TrainEngine  # noqa: E402
+md._engine = TrainEngine(md)
+md._engine.set_seed(4242)
+loss, logits = md(db)
+loss.backward()
+torch.cuda.synchronize()
+
+
+def mask_fn(site, shape):
+    n = 1
+    for d in shape:
+        n *= d
+    p = cfg_d.attention_probs_dropout_prob if site % 10 == 1 and site != 9999 else cfg_d.hidden_dropout_prob
+    return ops.dropout_mask(n, p, 4242, site).cpu().reshape(shape).float()
+
+
+O.MASK_FN = mask_fn
+rsd = {k: v.clone() for k, v in sd.items()}
+rsd["classifier.weight"] = rsd["bert.embeddings.word_embeddings.weight"]
+leaves = {}
+for k, v in rsd.items():
+    if v.dtype.is_floating_point:
+        v.requires_grad_(True)
+        leaves[k] = v
+rloss, rlogits = O.forward(rsd, batch, cfg_d, train=True)
+rloss.backward()
+O.MASK_FN = None
+print(f"dropout 0.1: loss {loss.item():.5f} vs {rloss.item():.5f}; logits err {(logits.float().cpu()-rlogits).abs().max().item():.3e}")
+keep = ops.dropout_mask(1 << 20, 0.1, 4242, 1012).float().mean().item()
+print(f"  keep rate {keep:.4f}")
+worst = []
+for name, p in md.named_parameters():
+    if name == "classifier.weight" or p.grad is None:
+        continue
+    rg = leaves[name].grad
+    worst.append(((p.grad.float().cpu() - rg).norm().item() / (rg.norm().item() + 1e-12), name, rg.norm().item()))
+worst.sort(reverse=True)
+for rel, name, n in worst[:8]:
+    print(f"  rel_err {rel:.3e}  |g|={n:.3e}  {name}")
+
 # optimizer parity on the last gradients
 params = [p for p in model.parameters() if p.requires_grad and p.grad is not None]
 no_decay = [p for n, p in model.named_parameters() if p.grad is not None and ("bias" in n or "LayerNorm.weight" in n)]
