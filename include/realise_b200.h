@@ -216,6 +216,18 @@ RL_API int rl_gate_fuse_bwd(const float* dhid, const float* m0, const float* m1,
                             float* dm2, float* dgate_w, float* dgate_b, float* ws, int64_t B, int64_t L, int64_t H,
                             void* stream);
 
+/* ---- pinyin GRU backward through time (nn.GRU over packed sequences, src/models.py:818-826) ----
+ * One step t: gates are recomputed from gh (saved forward recurrent pre-activations; NULL with h_prev NULL at
+ * t = 0), dh_prev = dh * z (the dgh W_hh term is added by a following rl_gemm_bf16 with res = dh_prev), dgi / dgh
+ * bf16 [rows, 3H] and the bf16 one-hot [rows, 64] of the step's symbol are GEMM operands for
+ * dW_hh += dgh^T h_prev, dtable += onehot^T dgi.  rl_gru_table_bwd turns dtable [V, 3H] into db_ih, dW_ih, demb
+ * (accumulating). */
+RL_API int rl_gru_step_bwd(const float* dh, const float* gh, const float* b_hh, const float* table,
+                           const int64_t* pho_idx, const int32_t* lens, const float* h_prev, float* dh_prev, void* dgi,
+                           void* dgh, void* onehot, int64_t rows, int64_t H, int64_t T, int64_t t, void* stream);
+RL_API int rl_gru_table_bwd(const float* dtable, const float* emb, const float* w_ih, float* dw_ih, float* db_ih,
+                            float* demb, int64_t V, int64_t H, void* stream);
+
 /* ---- multi-tensor grad-norm and fused clip + AdamW (src/run.py:207 clip_grad_norm_,
  * transformers/optimization.py:113-169).  table: device array of {float* p; const float* g; float* m;
  * float* v; bf16* shadow; float* shadow32; int64 n; float wd; int pad}; chunks: device array of int2 {tensor, chunk} covering

@@ -14,18 +14,16 @@ constexpr int MAX_V4 = 8;
 // (operand of the following weight/data-gradient GEMMs), and the column sums dgamma += sum dy*xhat,
 // dbeta += sum dy, dxsum += sum dx (bias gradient of the linear layer that produced x / type-embedding grad).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LNB_ROWS = 64;  // rows per CTA (8 warps x 8 rows)
+constexpr int LNB_ROWS = 32;  // rows per CTA (8 warps x 4 rows)
 
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ add_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int H,
               float eps, rl::DropSpec drop_in, rl::DropSpec drop_out) {
-  extern __shared__ float s_part[];  // [3][H]
+  extern __shared__ float s_part[];  // [8 warps][3][H]: per-warp column partials, no atomics
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = H / 128;
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) s_part[i] = 0.f;
-  __syncthreads();
   float4 pg[MAX_V4], pb[MAX_V4], px[MAX_V4];
 #pragma unroll
   for (int i = 0; i < MAX_V4; ++i) pg[i] = pb[i] = px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -94,20 +92,25 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
         if (dx) reinterpret_cast<float4*>(dx + row * H)[i * 32 + lane] = d;
       }
   }
-  // CTA-level reduction of the column partials, then one atomic per column
+  // CTA-level reduction of the column partials (each warp owns a slice), then one global atomic per column
+  {
+    float* mine = s_part + (size_t)warp * 3 * H;
 #pragma unroll
-  for (int i = 0; i < MAX_V4; ++i)
-    if (i < nv) {
-      const int c = (i * 32 + lane) * 4;
-      atomicAdd(&s_part[c], pg[i].x); atomicAdd(&s_part[c + 1], pg[i].y); atomicAdd(&s_part[c + 2], pg[i].z); atomicAdd(&s_part[c + 3], pg[i].w);
-      atomicAdd(&s_part[H + c], pb[i].x); atomicAdd(&s_part[H + c + 1], pb[i].y); atomicAdd(&s_part[H + c + 2], pb[i].z); atomicAdd(&s_part[H + c + 3], pb[i].w);
-      atomicAdd(&s_part[2 * H + c], px[i].x); atomicAdd(&s_part[2 * H + c + 1], px[i].y); atomicAdd(&s_part[2 * H + c + 2], px[i].z); atomicAdd(&s_part[2 * H + c + 3], px[i].w);
-    }
+    for (int i = 0; i < MAX_V4; ++i)
+      if (i < nv) {
+        const int c = (i * 32 + lane) * 4;
+        *reinterpret_cast<float4*>(mine + c) = pg[i];
+        *reinterpret_cast<float4*>(mine + H + c) = pb[i];
+        *reinterpret_cast<float4*>(mine + 2 * H + c) = px[i];
+      }
+  }
   __syncthreads();
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + c, s_part[c]);
-    if (dbeta) atomicAdd(dbeta + c, s_part[H + c]);
-    if (dxsum) atomicAdd(dxsum + c, s_part[2 * H + c]);
+  for (int c = threadIdx.x; c < 3 * H; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[(size_t)w * 3 * H + c];
+    float* dst = c < H ? dgamma : (c < 2 * H ? dbeta : dxsum);
+    if (dst) atomicAdd(dst + (c % H), t);
   }
 }
 
@@ -389,7 +392,12 @@ extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* ga
   RL_REQUIRE(dy && x && gamma && (dx || dx_bf16), RL_EINVAL, "rl_layernorm_bwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_bwd: bad H");
   if (rows <= 0) return 0;
-  ln_bwd_kernel<<<(unsigned)((rows + LNB_ROWS - 1) / LNB_ROWS), 256, 3 * H * sizeof(float), (cudaStream_t)stream>>>(
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * (int)sizeof(float));
+    configured = true;
+  }
+  ln_bwd_kernel<<<(unsigned)((rows + LNB_ROWS - 1) / LNB_ROWS), 256, 8 * 3 * H * sizeof(float), (cudaStream_t)stream>>>(
       dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps,
       rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in), rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out));
   return rl_check_launch("rl_layernorm_bwd");

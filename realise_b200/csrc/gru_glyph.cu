@@ -175,6 +175,141 @@ glyph_stem_kernel(const float* __restrict__ glyphs, const long long* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// GRU backward through time (one step).  Recomputes the gates from the saved gh_t (or b_hh at t = 0) and the
+// input table, then for active rows:
+//   dn = dh (1-z), dz = dh (h_prev - n), dh_prev = dh z, dn_pre = dn (1-n^2), dr_pre = dn_pre gh_n r (1-r),
+//   dz_pre = dz z (1-z);   dgi = [dr_pre, dz_pre, dn_pre],  dgh = [dr_pre, dz_pre, dn_pre r]
+// Rows whose sequence already ended pass dh through unchanged.  dgi / dgh are written as bf16 GEMM operands
+// (data gradient dgh W_hh, weight gradient dgh^T h_prev, table gradient onehot^T dgi), together with the bf16
+// one-hot row of the step's pinyin symbol.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gru_step_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ gh, const float* __restrict__ b_hh,
+                    const float* __restrict__ table, const long long* __restrict__ pho_idx, const int* __restrict__ lens,
+                    const float* __restrict__ h_prev, float* __restrict__ dh_prev, __nv_bfloat16* __restrict__ dgi,
+                    __nv_bfloat16* __restrict__ dgh, __nv_bfloat16* __restrict__ onehot, long long rows, int H, int T, int t) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bool active = lens[row] > t;
+  const int nv = H / 128;
+  const long long sym = active ? pho_idx[row * T + t] : -1;
+  // one-hot [64] bf16: two lanes-worth of uint32 pairs
+  reinterpret_cast<uint32_t*>(onehot + row * 64)[lane] =
+      (sym == 2 * lane ? 0x3F80u : 0u) | (sym == 2 * lane + 1 ? 0x3F800000u : 0u);
+  const float* gi = table + (active ? sym : 0) * 3 * H;
+  for (int i = 0; i < nv; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 d = *reinterpret_cast<const float4*>(dh + row * H + c);
+    uint2 z2 = make_uint2(0u, 0u);
+    if (!active) {
+      *reinterpret_cast<float4*>(dh_prev + row * H + c) = d;
+      *reinterpret_cast<uint2*>(dgi + row * 3 * H + c) = z2;
+      *reinterpret_cast<uint2*>(dgi + row * 3 * H + H + c) = z2;
+      *reinterpret_cast<uint2*>(dgi + row * 3 * H + 2 * H + c) = z2;
+      *reinterpret_cast<uint2*>(dgh + row * 3 * H + c) = z2;
+      *reinterpret_cast<uint2*>(dgh + row * 3 * H + H + c) = z2;
+      *reinterpret_cast<uint2*>(dgh + row * 3 * H + 2 * H + c) = z2;
+      continue;
+    }
+    const float4 ir = __ldg(reinterpret_cast<const float4*>(gi + c));
+    const float4 iz = __ldg(reinterpret_cast<const float4*>(gi + H + c));
+    const float4 in = __ldg(reinterpret_cast<const float4*>(gi + 2 * H + c));
+    float4 hr, hz, hn, hp;
+    if (gh) {
+      hr = *reinterpret_cast<const float4*>(gh + row * 3 * H + c);
+      hz = *reinterpret_cast<const float4*>(gh + row * 3 * H + H + c);
+      hn = *reinterpret_cast<const float4*>(gh + row * 3 * H + 2 * H + c);
+      hp = *reinterpret_cast<const float4*>(h_prev + row * H + c);
+    } else {
+      hr = __ldg(reinterpret_cast<const float4*>(b_hh + c));
+      hz = __ldg(reinterpret_cast<const float4*>(b_hh + H + c));
+      hn = __ldg(reinterpret_cast<const float4*>(b_hh + 2 * H + c));
+      hp = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 o_prev, g_r, g_z, g_n, g_nr;
+#define RL_GRU_BWD(f)                                              \
+  {                                                                \
+    const float r = 1.0f / (1.0f + expf(-(ir.f + hr.f)));          \
+    const float z = 1.0f / (1.0f + expf(-(iz.f + hz.f)));          \
+    const float n = tanhf(in.f + r * hn.f);                        \
+    const float dn_pre = d.f * (1.0f - z) * (1.0f - n * n);        \
+    const float dz_pre = d.f * (hp.f - n) * z * (1.0f - z);        \
+    const float dr_pre = dn_pre * hn.f * r * (1.0f - r);           \
+    o_prev.f = d.f * z;                                            \
+    g_r.f = dr_pre; g_z.f = dz_pre; g_n.f = dn_pre; g_nr.f = dn_pre * r; \
+  }
+    RL_GRU_BWD(x) RL_GRU_BWD(y) RL_GRU_BWD(z) RL_GRU_BWD(w)
+#undef RL_GRU_BWD
+    *reinterpret_cast<float4*>(dh_prev + row * H + c) = o_prev;
+    const uint2 pr = make_uint2(rl::pack_bf16(g_r.x, g_r.y), rl::pack_bf16(g_r.z, g_r.w));
+    const uint2 pz = make_uint2(rl::pack_bf16(g_z.x, g_z.y), rl::pack_bf16(g_z.z, g_z.w));
+    *reinterpret_cast<uint2*>(dgi + row * 3 * H + c) = pr;
+    *reinterpret_cast<uint2*>(dgi + row * 3 * H + H + c) = pz;
+    *reinterpret_cast<uint2*>(dgi + row * 3 * H + 2 * H + c) = make_uint2(rl::pack_bf16(g_n.x, g_n.y), rl::pack_bf16(g_n.z, g_n.w));
+    *reinterpret_cast<uint2*>(dgh + row * 3 * H + c) = pr;
+    *reinterpret_cast<uint2*>(dgh + row * 3 * H + H + c) = pz;
+    *reinterpret_cast<uint2*>(dgh + row * 3 * H + 2 * H + c) = make_uint2(rl::pack_bf16(g_nr.x, g_nr.y), rl::pack_bf16(g_nr.z, g_nr.w));
+  }
+}
+
+// table[v] = W_ih emb[v] + b_ih  =>  db_ih = sum_v dT[v],  dW_ih[j, :] = sum_v dT[v, j] emb[v, :],  demb = dT W_ih
+__global__ void __launch_bounds__(256)
+gru_table_bwd_w_kernel(const float* __restrict__ dT, const float* __restrict__ emb, float* __restrict__ dw_ih,
+                       float* __restrict__ db_ih, int V, int H) {
+  const int j = blockIdx.x;  // row of W_ih, in [0, 3H)
+  __shared__ float s_d[64];
+  if (threadIdx.x < V) s_d[threadIdx.x] = dT[(long long)threadIdx.x * 3 * H + j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int v = 0; v < V; ++v) b += s_d[v];
+    db_ih[j] += b;
+  }
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc = 0.f;
+    for (int v = 0; v < V; ++v) acc += s_d[v] * __ldg(emb + (long long)v * H + c);
+    dw_ih[(long long)j * H + c] += acc;
+  }
+}
+__global__ void __launch_bounds__(256)
+gru_table_bwd_e_kernel(const float* __restrict__ dT, const float* __restrict__ w_ih, float* __restrict__ demb, int V, int H) {
+  const int v = blockIdx.x;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < 3 * H; ++j) acc += dT[(long long)v * 3 * H + j] * __ldg(w_ih + (long long)j * H + c);
+    demb[(long long)v * H + c] += acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int rl_gru_step_bwd(const float* dh, const float* gh, const float* b_hh, const float* table,
+                               const int64_t* pho_idx, const int32_t* lens, const float* h_prev, float* dh_prev, void* dgi,
+                               void* dgh, void* onehot, int64_t rows, int64_t H, int64_t T, int64_t t, void* stream) {
+  RL_REQUIRE(dh && b_hh && table && pho_idx && lens && dh_prev && dgi && dgh && onehot, RL_EINVAL, "rl_gru_step_bwd: null pointer");
+  RL_REQUIRE((gh == nullptr) == (h_prev == nullptr), RL_EINVAL, "rl_gru_step_bwd: gh and h_prev go together");
+  RL_REQUIRE(H % 128 == 0 && t >= 0 && t < T, RL_EINVAL, "rl_gru_step_bwd: bad shape");
+  if (rows <= 0) return 0;
+  gru_step_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      dh, gh, b_hh, table, (const long long*)pho_idx, lens, h_prev, dh_prev, (__nv_bfloat16*)dgi, (__nv_bfloat16*)dgh,
+      (__nv_bfloat16*)onehot, rows, (int)H, (int)T, (int)t);
+  return rl_check_launch("rl_gru_step_bwd");
+}
+
+extern "C" int rl_gru_table_bwd(const float* dtable, const float* emb, const float* w_ih, float* dw_ih, float* db_ih,
+                                float* demb, int64_t V, int64_t H, void* stream) {
+  RL_REQUIRE(dtable && emb && w_ih && dw_ih && db_ih && demb && V > 0 && V <= 64, RL_EINVAL, "rl_gru_table_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  gru_table_bwd_w_kernel<<<(unsigned)(3 * H), 256, 0, st>>>(dtable, emb, dw_ih, db_ih, (int)V, (int)H);
+  gru_table_bwd_e_kernel<<<(unsigned)V, 256, 0, st>>>(dtable, w_ih, demb, (int)V, (int)H);
+  return rl_check_launch("rl_gru_table_bwd");
+}
+
+namespace {
+
 }  // namespace
 
 extern "C" int rl_gru_input_table(const float* emb, const float* w_ih, const float* b_ih, float* table, int64_t V,

@@ -292,8 +292,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             ops.gru_input_table(self.pho_embeddings.weight.detach().float().contiguous(),
                                 g.weight_ih_l0.detach().float().contiguous(),
                                 g.bias_ih_l0.detach().float().contiguous(), table)
-            P["gru"] = {"table": table, "w_hh": g.weight_hh_l0.detach().bfloat16().contiguous(),
-                        "b_hh": g.bias_hh_l0.detach().float().contiguous()}
+            P["gru"] = {"table": table, "w_hh": bf(g.weight_hh_l0), "b_hh": g.bias_hh_l0.detach().float().contiguous()}
         if c.with_res == "yes":
             P["res"] = self._prepare_resnet()
             P["res_ln_w"] = self.resnet_layernorm.weight.detach().float().contiguous()

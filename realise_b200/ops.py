@@ -320,3 +320,19 @@ def dropout_mask(n, p, seed, site, device="cuda"):
     check(lib().rl_dropout_mask(_ptr(out), _c(n), ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_uint32(site),
                                 _stream()), "rl_dropout_mask")
     return out
+
+
+def gru_step_bwd(dh, gh, b_hh, table, pho_idx, lens, h_prev, dh_prev, dgi, dgh, onehot, t):
+    rows, T = pho_idx.shape
+    H = dh.shape[1]
+    check(lib().rl_gru_step_bwd(_ptr(dh), _ptr(gh), _ptr(b_hh), _ptr(table), _ptr(pho_idx), _ptr(lens), _ptr(h_prev),
+                                _ptr(dh_prev), _ptr(dgi), _ptr(dgh), _ptr(onehot), _c(rows), _c(H), _c(T), _c(t), _stream()),
+          "rl_gru_step_bwd")
+    _count()
+
+
+def gru_table_bwd(dtable, emb, w_ih, dw_ih, db_ih, demb):
+    V, H = emb.shape
+    check(lib().rl_gru_table_bwd(_ptr(dtable), _ptr(emb), _ptr(w_ih), _ptr(dw_ih), _ptr(db_ih), _ptr(demb), _c(V), _c(H),
+                                 _stream()), "rl_gru_table_bwd")
+    _count(2)

@@ -46,9 +46,9 @@ class TrainEngine:
     def __init__(self, model):
         self.m = model
         c = model.config
-        if c.with_pho == "yes" or c.with_res == "yes":
-            raise NotImplementedError("training kernels cover the semantic path only in this round: GRU BPTT and "
-                                      "CharResNet/BatchNorm backward are not written yet (use with_pho='no', with_res='no')")
+        if c.with_res == "yes":
+            raise NotImplementedError("training kernels cover the semantic and pinyin paths in this round: CharResNet "
+                                      "conv / batch-stat BatchNorm backward is not written yet (use with_res='no')")
         self.saved = None
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
         # trainable parameters in a fixed order
@@ -88,14 +88,17 @@ class TrainEngine:
             if id(p) in seen or id(p) in no_grad:
                 continue
             (order_over if id(p) in over_ids else order_zero).append(("p", None, [p]))
-        n_zero = sum(p.numel() for _, _, ps in order_zero for p in ps)
-        n_over = sum(p.numel() for _, _, ps in order_over for p in ps)
+        def padded(n):  # every block starts 256-byte aligned (float4 atomics, TMA stores, vector loads)
+            return (n + 63) // 64 * 64
+
+        n_zero = sum(padded(sum(p.numel() for p in ps)) for _, _, ps in order_zero)
+        n_over = sum(padded(sum(p.numel() for p in ps)) for _, _, ps in order_over)
         self.flat = torch.zeros(n_zero + n_over, device=dev, dtype=F32)
         self.flat_zero = self.flat[:n_zero]
         self.grads = [None] * len(self.params)
         off = 0
         for kind, att, ps in order_zero + order_over:
-            start = off
+            start = off = padded(off)
             for p in ps:
                 self.grads[self.index[id(p)]] = self.flat[off:off + p.numel()].view(p.shape)
                 off += p.numel()
@@ -176,6 +179,54 @@ class TrainEngine:
             sv["layers"].append(s)
         return x, xb, sv
 
+    # ---- pinyin GRU (train): every step's state is kept for the backward-through-time ---------------
+    def _gru_fwd(self, P, pho_idx, lens_dev, N, sv):
+        H = self.m.config.hidden_size
+        T = pho_idx.shape[1]
+        G = P["gru"]
+        m = self.m
+        # the input-projection table depends on trainable weights: rebuild it every training step
+        ops.gru_input_table(m.pho_embeddings.weight.detach(), m.pho_gru.weight_ih_l0.detach(), m.pho_gru.bias_ih_l0.detach(),
+                            G["table"])
+        hs, hbs, ghs = [], [], [None]
+        h, hb = self._new((N, H), F32), self._new((N, H), BF16)
+        ops.gru_step(None, G["b_hh"], G["table"], pho_idx, lens_dev, None, h, hb, 0)
+        hs.append(h)
+        hbs.append(hb)
+        for t in range(1, T):
+            gh = self._new((N, 3 * H), F32)
+            ops.gemm(hbs[-1], G["w_hh"], gh, bias=G["b_hh"])
+            h, hb = self._new((N, H), F32), self._new((N, H), BF16)
+            ops.gru_step(gh, G["b_hh"], G["table"], pho_idx, lens_dev, hs[-1], h, hb, t)
+            hs.append(h)
+            hbs.append(hb)
+            ghs.append(gh)
+        sv["gru"] = {"hs": hs, "hbs": hbs, "ghs": ghs, "pho_idx": pho_idx, "lens": lens_dev, "T": T}
+        return hs[-1]
+
+    def _gru_bwd(self, P, sv, dh, N):
+        m = self.m
+        H = m.config.hidden_size
+        g, G = sv["gru"], P["gru"]
+        gru = m.pho_gru
+        dW_hh, db_hh = self._grad(gru.weight_hh_l0), self._grad(gru.bias_hh_l0)
+        dtable = self._new((64, 3 * H), F32, zero=True)
+        for t in range(g["T"] - 1, -1, -1):
+            dh_prev = self._new((N, H), F32)
+            dgi, dgh = self._new((N, 3 * H), BF16), self._new((N, 3 * H), BF16)
+            onehot = self._new((N, 64), BF16)
+            ops.gru_step_bwd(dh, g["ghs"][t], G["b_hh"], G["table"], g["pho_idx"], g["lens"],
+                             g["hs"][t - 1] if t > 0 else None, dh_prev, dgi, dgh, onehot, t)
+            ops.colsum_bf16(dgh, db_hh)
+            ops.gemm(onehot, dgi, dtable, a_t=True, b_t=True, res=dtable)                 # dtable += onehot^T dgi
+            if t > 0:
+                ops.gemm(dgh, g["hbs"][t - 1], dW_hh, a_t=True, b_t=True, res=dW_hh)      # dW_hh += dgh^T h_{t-1}
+                dh_next = self._new((N, H), F32)
+                ops.gemm(dgh, G["w_hh"], dh_next, b_t=True, res=dh_prev)                 # dh_{t-1} = dh z + dgh W_hh
+                dh = dh_next
+        ops.gru_table_bwd(dtable, m.pho_embeddings.weight.detach(), gru.weight_ih_l0.detach(),
+                          self._grad(gru.weight_ih_l0), self._grad(gru.bias_ih_l0), self._grad(m.pho_embeddings.weight))
+
     def forward(self, inp):
         m, c = self.m, self.m.config
         if m._prepared is None:
@@ -191,6 +242,10 @@ class TrainEngine:
         sv = {"B": B, "L": L, "mask": mask, "inp": inp, "seed": self.step_seed}
         bert_h, _, sv["bert"] = self._stack_fwd("bert", m.bert, P["bert"], mask, B, L, ids=input_ids.view(-1))
         mods = [bert_h]
+        if c.with_pho == "yes":
+            pho_gru = self._gru_fwd(P, inp["pho_idx"], inp["pho_lens"], N, sv)
+            pho_h, _, sv["pho"] = self._stack_fwd("pho", m.pho_model, P["pho_model"], mask, B, L, inputs_embeds=pho_gru)
+            mods.append(pho_h)
         sv["mods"] = mods
         fused = self._new((N, H), F32)
         if c.fusion == "gate":
@@ -290,13 +345,18 @@ class TrainEngine:
         ops.gemm(dlogits, P["cls_w"], dseq, b_t=True)                                               # dseq = dlogits E
         dfused = self._stack_bwd(sv["out"], dseq, mask, B, L)
         # gated fusion
-        dm0 = self._new((N, H), F32)
+        nm = len(sv["mods"])
         if c.fusion == "gate":
+            dms = [self._new((N, H), F32) for _ in range(nm)]
             ws = self._new((N * 3 + 2 * B * H,), F32)
-            ops.gate_fuse_bwd(dfused, sv["mods"], mask, sv["gates"], P["gate_w"], [dm0], self._grad(m.gate_net.weight, True),
+            ops.gate_fuse_bwd(dfused, sv["mods"], mask, sv["gates"], P["gate_w"], dms, self._grad(m.gate_net.weight, True),
                               self._grad(m.gate_net.bias, True), ws, B, L, H)
         else:
-            dm0 = dfused
+            dms = [dfused] * nm
+        dm0 = dms[0]
+        if c.with_pho == "yes":
+            dgru = self._stack_bwd(sv["pho"], dms[1], mask, B, L)
+            self._gru_bwd(P, sv, dgru, N)
         self._stack_bwd(sv["bert"], dm0, mask, B, L)   # scatter-adds the embedding rows into the (tied) dE buffer
         self.saved = None
         # parameters that never receive a gradient (poolers, unused word embeddings of output_block) -> None

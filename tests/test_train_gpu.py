@@ -70,6 +70,37 @@ def test_backward_matches_oracle_autograd(B, L, seed):
     assert checked >= 90
 
 
+def test_pinyin_branch_backward_matches_oracle_autograd():
+    """with_pho='yes': GRU backward-through-time (table, W_hh, biases, pho_embeddings) + pho_model stack."""
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    cfg = ArchConfig(num_hidden_layers=1, with_pho="yes", with_res="no", hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0)
+    sd = cached_state_dict(cfg, 12)
+    model = SpellBertPho2ResArch3Abla(cfg)
+    model.tie_cls_weight()
+    model.load_state_dict(sd, strict=True)
+    model.train().cuda()
+    batch = synth_batch(3, 24, seed=8)
+    db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    loss, _ = model(db)
+    loss.backward()
+    rloss, _, leaves = _oracle_grads(sd, batch, cfg)
+    assert abs(loss.item() - rloss.item()) <= 1e-2
+    gmax = max(v.grad.abs().max().item() for v in leaves.values() if v.grad is not None)
+    seen = set()
+    for name, p in model.named_parameters():
+        if name == "classifier.weight" or p.grad is None:
+            continue
+        rg = leaves[name].grad
+        if rg.norm().item() < 1e-6 * gmax:
+            continue
+        rel = (p.grad.float().cpu() - rg).norm().item() / rg.norm().item()
+        assert rel <= 2e-2, (name, rel)
+        seen.add(name)
+    assert {"pho_gru.weight_ih_l0", "pho_gru.weight_hh_l0", "pho_gru.bias_ih_l0", "pho_gru.bias_hh_l0",
+            "pho_embeddings.weight"} <= seen
+
+
 def test_fused_adamw_step_matches_reference_formula():
     from realise_b200.optim import FusedAdamW
     cfg, sd, model = _setup(layers=1)
@@ -179,7 +210,7 @@ def test_flat_gradient_buffer_layout():
         if p.grad is not None:
             assert lo <= p.grad.data_ptr() < hi          # every gradient is a view of the one flat buffer
             n += p.grad.numel()
-    assert n == eng.flat.numel()
+    assert n <= eng.flat.numel() <= n + 64 * sum(p.grad is not None for p in model.parameters())   # 256-byte padding
     no_grad = [name for name, p in model.named_parameters() if p.grad is None]
     assert sorted(no_grad) == sorted(["bert.pooler.dense.weight", "bert.pooler.dense.bias",
                                       "output_block.pooler.dense.weight", "output_block.pooler.dense.bias",

@@ -64,6 +64,45 @@ for (B, L, seed) in [(2, 16, 5), (3, 40, 6)]:
         print(f"  rel_err {rel:.3e}  |g|={n:.3e}  {name}")
     print(f"  median rel_err {sorted(w[0] for w in worst)[len(worst)//2]:.3e} over {len(worst)} tensors")
 
+# ---- pinyin branch (GRU BPTT + pho_model) ----
+cfg_p = ArchConfig(num_hidden_layers=1, with_pho="yes", with_res="no", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+sd_p = synth_state_dict(cfg_p, 12)
+mp_ = SpellBertPho2ResArch3Abla(cfg_p)
+mp_.tie_cls_weight()
+mp_.load_state_dict(sd_p, strict=True)
+mp_.train().cuda()
+batch = synth_batch(3, 24, seed=8)
+db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+loss, logits = mp_(db)
+loss.backward()
+torch.cuda.synchronize()
+rsd = {k: v.clone() for k, v in sd_p.items()}
+rsd["classifier.weight"] = rsd["bert.embeddings.word_embeddings.weight"]
+leaves = {}
+for k, v in rsd.items():
+    if v.dtype.is_floating_point:
+        v.requires_grad_(True)
+        leaves[k] = v
+rloss, rlogits = O.forward(rsd, batch, cfg_p, train=True)
+rloss.backward()
+print(f"with_pho: loss {loss.item():.5f} vs {rloss.item():.5f}")
+worst = []
+for name, p in mp_.named_parameters():
+    if name == "classifier.weight":
+        continue
+    rg = leaves[name].grad
+    if p.grad is None:
+        if rg is not None and rg.abs().max() > 0:
+            print("  MISSING grad", name, rg.norm().item())
+        continue
+    worst.append(((p.grad.float().cpu() - rg).norm().item() / (rg.norm().item() + 1e-12), name, rg.norm().item()))
+worst.sort(reverse=True)
+for rel, name, n in worst[:14]:
+    print(f"  rel_err {rel:.3e}  |g|={n:.3e}  {name}")
+for name in ["pho_gru.weight_ih_l0", "pho_gru.weight_hh_l0", "pho_gru.bias_ih_l0", "pho_gru.bias_hh_l0", "pho_embeddings.weight"]:
+    r = [w for w in worst if w[1] == name]
+    print("  ", name, r[0][0] if r else "n/a")
+
 # ---- dropout ON: feed the kernels' own masks to the oracle ----
 from realise_b200 import ops  # noqa: E402
 cfg_d = ArchConfig(num_hidden_layers=2, with_pho="no", with_res="no")   # p = 0.1 / 0.1 as in the reference config
