@@ -178,6 +178,64 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_train(dev, rank, world, dist, steps):
+    """Secondary line: one optimizer step (fwd + bwd + gradient all-reduce + clip + AdamW) of the full
+    SpellBertPho2ResArch3 (all three encoders), batch 128/GPU x seq_len 128, dropout 0.1, batch-stat BatchNorm —
+    BASELINE configs[2] (1 GPU) / configs[3] (N GPUs, weak scaling)."""
+    from realise_b200.ddp import DataParallel
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    from realise_b200.optim import FusedAdamW
+    from realise_b200.synth import ArchConfig, synth_batch
+    B, L = 128, SEQ_LEN
+    cfg = ArchConfig(with_pho="yes", with_res="yes")
+    torch.manual_seed(0)
+    model = SpellBertPho2ResArch3Abla(cfg)
+    model.tie_cls_weight()
+    model.train().to(dev)
+    if world > 1:
+        dp = DataParallel(model)
+        dp.broadcast_parameters()
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    nd = [p for n, p in named if "bias" in n or "LayerNorm.weight" in n]
+    dc = [p for n, p in named if not ("bias" in n or "LayerNorm.weight" in n)]
+    opt = FusedAdamW([{"params": dc, "weight_decay": 0.0}, {"params": nd, "weight_decay": 0.0}], lr=5e-5, eps=1e-8,
+                     max_grad_norm=1.0, model=model)
+    host = synth_batch(B, L, seed=4321 + rank, ragged=False, with_labels=True)
+    db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    db["pho_lens"] = torch.tensor(host["pho_lens"], dtype=torch.int32, device=dev)
+
+    def step():
+        loss = model(db)[0]
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    out = {"value": world * B / ms * 1e3, "unit": "sentences/s", "ms_per_step": ms, "steps": steps,
+           "config": {"workload": "BASELINE configs[2]: train step fwd+bwd+clip+AdamW of the full SpellBertPho2ResArch3 "
+                                  "(BERT 12L + pinyin GRU/4L + glyph CharResNet + gate + 3L output block + classifier)",
+                      "global_batch": world * B, "seq_len": L, "dropout": 0.1, "trainable_params": sum(p.numel() for _, p in named),
+                      "grad_allreduce": "one NCCL all-reduce over the flat fp32 gradient buffer" if world > 1 else "none (1 GPU)"},
+           "final_loss": float(loss.item()), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     from realise_b200 import ops
     from realise_b200.model import SpellBertPho2ResArch3
@@ -290,6 +348,14 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / t.item()
 
+    train = None
+    if not args.no_train:
+        try:
+            del model
+            torch.cuda.empty_cache()
+            train = measure_train(dev, rank, world, dist, steps=max(3, min(args.steps, 10)))
+        except Exception as e:  # noqa: BLE001 — the secondary line must never take the headline down
+            train = {"error": repr(e)[:300]}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -325,6 +391,7 @@ def run_ours(args, rank, world, local_rank):
         },
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "train_step": train,
         "gpu_launches": (launches_per_step) * args.steps,
         "clocks": clk,
     }
@@ -340,6 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -75,6 +75,9 @@ typedef struct rl_gemm_desc {
   int32_t act;
   int32_t out_remap; /* 0: row m -> m.  1: parity-split rows for a following stride-2 conv:
                         [img][oh&1][ow&1][oh/2][ow/2] */
+  int32_t remap_plane; /* out_remap 2: GEMM row (img, h, w) -> row ((img*4 + remap_plane)*H + h)*W + w: one parity plane of
+                          the data gradient of a stride-2 conv */
+  int32_t conv_Cuse;   /* conv mode: channels [0, conv_Cuse) of every tap are the GEMM's K (0 = all conv_C) */
   int32_t a_major;   /* 0: A stored [M, K] (K-major).  1: A stored [K, M] with row stride lda (MN-major), e.g.
                         A = dY^T for a weight gradient straight from dY [tokens, out] */
   float drop_p;        /* training: dropout on (acc*scale+bias) BEFORE the residual add (BertSelfOutput/BertOutput, */
@@ -227,6 +230,32 @@ RL_API int rl_gru_step_bwd(const float* dh, const float* gh, const float* b_hh, 
                            void* dgh, void* onehot, int64_t rows, int64_t H, int64_t T, int64_t t, void* stream);
 RL_API int rl_gru_table_bwd(const float* dtable, const float* emb, const float* w_ih, float* dw_ih, float* db_ih,
                             float* demb, int64_t V, int64_t H, void* stream);
+
+/* ---- CharResNet training pieces (src/char_cnn.py:9-55 with nn.BatchNorm2d in batch-statistics mode) -------------
+ * rl_bn_stats: sums[0:C] += sum_m x, sums[C:2C] += sum_m x^2 over a raw conv output [M, C] (f32 in training; caller zeroes sums).
+ * rl_bn_finalize: mean, biased var -> scale = gamma*rstd, shift = beta - mean*scale, mean/rstd saved for the backward;
+ *   running_mean/var updated with `momentum` (unbiased var) and num_batches_tracked += 1, as nn.BatchNorm2d does.
+ * rl_bn_apply: out = [relu](x1*scale1 + shift1 [+ x2*scale2 + shift2]); remap = 1 writes parity-split rows.
+ * rl_bn_bwd: BatchNorm backward for dy (f32/bf16; rows parity-split when remap) optionally masked by the ReLU that
+ *   followed (act_out > 0); dbeta/dgamma accumulated, dx written as bf16 with row stride ldx.
+ * rl_im2col_bf16: col[m, ci*T + t] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] so that a conv weight gradient in the
+ *   reference's [Cout, Cin, kh, kw] layout is ONE rl_gemm_bf16 (A = dY MN-major, B = col MN-major).
+ * rl_glyph_im2col: the same for res_block1 straight from the glyph table: col1 [n*256, 32] (27 used), colsc [n*256, 8]. */
+RL_API int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t M, int64_t C, int64_t ld, void* stream);
+RL_API int rl_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* mean_out,
+                          float* rstd_out, int64_t M, int64_t C, float momentum, float eps, void* stream);
+RL_API int rl_bn_apply(const void* x1, const float* scale1, const float* shift1, const void* x2, const float* scale2,
+                       const float* shift2, int32_t x_dtype, void* out, int32_t out_dtype, int32_t relu, int64_t M,
+                       int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream);
+RL_API int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const void* x,
+                     int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
+                     int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream);
+RL_API int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C, int32_t W, int32_t H, int32_t P,
+                          int32_t ntaps, const int8_t* tap_dw, const int8_t* tap_dh, const int8_t* tap_plane,
+                          void* stream);
+RL_API int rl_glyph_im2col(const float* glyphs, const int64_t* ids, void* col1, void* colsc, int64_t n_img, int32_t C,
+                           void* stream);
 
 /* ---- multi-tensor grad-norm and fused clip + AdamW (src/run.py:207 clip_grad_norm_,
  * transformers/optimization.py:113-169).  table: device array of {float* p; const float* g; float* m;

@@ -176,14 +176,27 @@ def batch_norm(sd, p, x, train, stats=None):
     return (x - mean[None, :, None, None]) * (inv * w)[None, :, None, None] + b[None, :, None, None]
 
 
+# ReLU gates: a reduced-precision forward flips the sign of a few pre-activations that sit within its error of
+# zero, and every flipped gate moves a whole gradient element.  To check the BACKWARD kernels tightly the
+# train-mode parity test installs RELU_MASK_FN(site, shape) -> {0,1} gates taken from the CUDA forward, so both
+# sides differentiate through identical gates (same idea as MASK_FN for dropout).  Sites: "<block>.a1", "<block>.out".
+RELU_MASK_FN = None
+
+
+def relu_gate(x, site):
+    if RELU_MASK_FN is None:
+        return torch.relu(x)
+    return x * RELU_MASK_FN(site, tuple(x.shape)).to(x.dtype)
+
+
 def basic_block(sd, p, x, train, stats=None):
     y = F.conv2d(x, sd[f"{p}.residual_function.0.weight"], stride=2, padding=1)
-    y = torch.relu(batch_norm(sd, f"{p}.residual_function.1", y, train, stats))
+    y = relu_gate(batch_norm(sd, f"{p}.residual_function.1", y, train, stats), f"{p}.a1")
     y = F.conv2d(y, sd[f"{p}.residual_function.3.weight"], stride=1, padding=1)
     y = batch_norm(sd, f"{p}.residual_function.4", y, train, stats)
     s = F.conv2d(x, sd[f"{p}.shortcut.0.weight"], stride=2)
     s = batch_norm(sd, f"{p}.shortcut.1", s, train, stats)
-    return torch.relu(y + s)
+    return relu_gate(y + s, f"{p}.out")
 
 
 def char_resnet(sd, images, train=False, stats=None, collect=None):

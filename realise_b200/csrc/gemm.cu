@@ -33,6 +33,7 @@ struct KParams {
   int res_f32;
   int act;
   int out_remap;
+  int remap_plane;  // out_remap == 2: rows (img, h, w) of the GEMM go to plane `remap_plane` of a parity-split tensor
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
   rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
@@ -68,6 +69,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 __device__ __forceinline__ long long remap_row(const KParams& p, int row) {
+  if (p.out_remap == 2) {  // data gradient of a stride-2 conv: this GEMM produces one parity plane of dX
+    const int hw = 1 << p.hw_shift;
+    const long long img = row >> p.hw_shift;
+    return (img * 4 + p.remap_plane) * hw + (row & (hw - 1));
+  }
   if (p.out_remap != 1) return row;
   const int hw = 1 << p.hw_shift, w = 1 << p.w_shift;
   const int img = row >> p.hw_shift, pix = row & (hw - 1);
@@ -796,6 +802,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.res_f32 = d->res_dtype == RL_DT_F32;
   p.act = d->act;
   p.out_remap = d->out_remap;
+  p.remap_plane = d->remap_plane;
   p.dbg = g_dbg;
   p.drop = rl::make_drop(d->drop_p, d->drop_seed, d->drop_site);
 
@@ -858,9 +865,11 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     if (rc) return rc;
   } else if (d->a_mode == 1) {
     const int C = d->conv_C, W = d->conv_W, H = d->conv_H, P = d->conv_P, NI = d->conv_NIMG;
-    RL_REQUIRE(C > 0 && C % BK == 0, RL_EINVAL, "rl_gemm_bf16(conv): C=%d must be a multiple of 64", C);
+    const int Cuse = d->conv_Cuse > 0 ? d->conv_Cuse : C;  // channels [0, Cuse) of each tap feed the GEMM
+    RL_REQUIRE(C > 0 && C % 8 == 0 && Cuse % BK == 0 && Cuse <= C, RL_EINVAL,
+               "rl_gemm_bf16(conv): C=%d / used channels %d (must be a multiple of 64)", C, Cuse);
     RL_REQUIRE(d->ntaps >= 1 && d->ntaps <= 12, RL_EINVAL, "rl_gemm_bf16(conv): ntaps=%d", d->ntaps);
-    RL_REQUIRE(d->K == (int64_t)d->ntaps * C, RL_EINVAL, "rl_gemm_bf16(conv): K != ntaps*C");
+    RL_REQUIRE(d->K == (int64_t)d->ntaps * Cuse, RL_EINVAL, "rl_gemm_bf16(conv): K != ntaps*C");
     const int ws = ilog2_exact(W), hs = ilog2_exact(H);
     RL_REQUIRE(ws >= 0 && hs >= 0 && W * H <= 256, RL_EINVAL,
                "rl_gemm_bf16(conv): map %dx%d must be power-of-two with <= 256 pixels", W, H);
@@ -868,7 +877,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     RL_REQUIRE(P == 1 || P == 4, RL_EINVAL, "rl_gemm_bf16(conv): P must be 1 or 4");
     p.hw_shift = ws + hs;
     p.w_shift = ws;
-    p.cin_blocks = C / BK;
+    p.cin_blocks = Cuse / BK;
     for (int t = 0; t < d->ntaps; ++t) {
       p.tap_dw[t] = d->tap_dw[t];
       p.tap_dh[t] = d->tap_dh[t];
@@ -894,6 +903,9 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     RL_REQUIRE(d->a_mode == 1, RL_EINVAL, "rl_gemm_bf16: out_remap=1 needs conv geometry");
     RL_REQUIRE(d->conv_W >= 2 && d->conv_H >= 2, RL_EINVAL, "rl_gemm_bf16: parity split needs >=2x2 map");
   }
+  if (d->out_remap == 2)
+    RL_REQUIRE(d->a_mode == 1 && d->remap_plane >= 0 && d->remap_plane < 4, RL_EINVAL,
+               "rl_gemm_bf16: out_remap=2 needs conv geometry and a plane in 0..3");
   if (d->b_major == 1) {
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};  // stored [K, N], N contiguous
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
@@ -910,7 +922,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   // output path: TMA store for plain row-major outputs with 16-byte aligned rows
   const int oelt = p.out_f32 ? 4 : 2;
   const bool aligned16 = ((uintptr_t)d->out & 15) == 0 && (d->ldo * oelt) % 16 == 0;
-  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16) ? 1 : 0;
+  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16) ? 1 : 0;  // remapped rows: direct stores
   p.vec_store = (aligned16 && (d->out2 == nullptr || (((uintptr_t)d->out2 & 15) == 0 && d->ldo2 % 8 == 0))) ? 1 : 0;
   if (d->res) {
     const int relt = p.res_f32 ? 4 : 2;

@@ -1,0 +1,363 @@
+// Training-mode pieces of CharResNet (src/char_cnn.py:9-55): BatchNorm2d with batch statistics (forward and
+// backward), the im2col gathers that turn conv weight gradients into plain tcgen05 GEMMs, and the raw
+// (pre-BatchNorm) glyph stem.  Convolutions themselves (forward, data gradients) run through rl_gemm_bf16.
+//
+// Layouts: activations are NHWC bf16.  "plain" rows are (img, h, w); "parity-split" rows are
+// [img][h&1][w&1][h/2][w/2] (the input layout of a stride-2 conv).  Raw conv outputs are always plain.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ long long split_row(long long row, int hw_shift, int w_shift) {
+  const int hw = 1 << hw_shift, w = 1 << w_shift;
+  const long long img = row >> hw_shift;
+  const int pix = (int)(row & (hw - 1));
+  const int oh = pix >> w_shift, ow = pix & (w - 1);
+  const int h2 = (hw >> w_shift) >> 1, w2 = w >> 1;
+  return ((img * 4 + (oh & 1) * 2 + (ow & 1)) * h2 + (oh >> 1)) * w2 + (ow >> 1);
+}
+
+__device__ __forceinline__ float load_raw(const void* x, int x_f32, long long i) {
+  return x_f32 ? reinterpret_cast<const float*>(x)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
+}
+__device__ __forceinline__ void load_raw8(const void* x, int x_f32, long long i, float (&v)[8]) {
+  if (x_f32) {
+    const float4 a = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i)[0];
+    const float4 b = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + i);
+    v[0] = rl::bf16_lo(a.x); v[1] = rl::bf16_hi(a.x); v[2] = rl::bf16_lo(a.y); v[3] = rl::bf16_hi(a.y);
+    v[4] = rl::bf16_lo(a.z); v[5] = rl::bf16_hi(a.z); v[6] = rl::bf16_lo(a.w); v[7] = rl::bf16_hi(a.w);
+  }
+}
+
+// ---- BatchNorm forward: per-channel sum / sum of squares of a raw conv output [M, C] (f32 or bf16) ----------
+// (raw conv outputs are kept in f32 in training: batch statistics over few samples cancel catastrophically in bf16)
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const void* __restrict__ x, int x_f32, float* __restrict__ sums, long long M, int C, long long ld) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * 2048;
+  float a = 0.f, b = 0.f;
+  if (col < C)
+    for (long long r = r0 + ry; r < r0 + 2048 && r < M; r += 8) {
+      const float v = load_raw(x, x_f32, r * ld + col);
+      a += v;
+      b += v * v;
+    }
+  s1[ry][cx] = a;
+  s2[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && col < C) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      t1 += s1[i][cx];
+      t2 += s2[i][cx];
+    }
+    atomicAdd(sums + col, t1);
+    atomicAdd(sums + C + col, t2);
+  }
+}
+
+// mean / biased var -> scale = gamma*rstd, shift = beta - mean*scale; running stats with momentum (unbiased var)
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, long long M, int C, float momentum, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
+  if (c >= C) return;
+  const float mean = sums[c] / (float)M;
+  float var = sums[C + c] / (float)M - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * ((float)M / (float)(M > 1 ? M - 1 : 1));
+  }
+}
+
+// out = act(x1*scale1 + shift1 [+ x2*scale2 + shift2]); 8 channels per thread; optional parity-split row remap
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const void* __restrict__ x1, const float* __restrict__ sc1, const float* __restrict__ sh1,
+                const void* __restrict__ x2, const float* __restrict__ sc2, const float* __restrict__ sh2, int x_f32,
+                void* __restrict__ out, int out_f32, int relu, long long M, int C, int remap, int hw_shift, int w_shift) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over M * C/8
+  const int c8 = C >> 3;
+  if (idx >= M * c8) return;
+  const long long row = idx / c8;
+  const int c = (int)(idx - row * c8) * 8;
+  float v[8];
+  load_raw8(x1, x_f32, row * C + c, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], __ldg(sc1 + c + j), __ldg(sh1 + c + j));
+  if (x2) {
+    float w[8];
+    load_raw8(x2, x_f32, row * C + c, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += fmaf(w[j], __ldg(sc2 + c + j), __ldg(sh2 + c + j));
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  const long long orow = remap ? split_row(row, hw_shift, w_shift) : row;
+  if (out_f32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow * C + c);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * C + c) =
+        make_uint4(rl::pack_bf16(v[0], v[1]), rl::pack_bf16(v[2], v[3]), rl::pack_bf16(v[4], v[5]), rl::pack_bf16(v[6], v[7]));
+  }
+}
+
+// ---- BatchNorm backward -----------------------------------------------------------------------------------
+// dy (f32 or bf16, rows possibly parity-split) masked by the ReLU that followed (act_out > 0, same rows as dy);
+// x = raw conv output (plain rows).  reduce: dbeta += sum dy, dgamma += sum dy*xhat.
+// apply: dx = gamma*rstd*(dy - dbeta/M - xhat*dgamma/M) as bf16, written at column offset into a wider matrix.
+__device__ __forceinline__ float load_dy(const void* dy, int dy_f32, long long i) {
+  return dy_f32 ? reinterpret_cast<const float*>(dy)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[i]);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32,
+                     const void* __restrict__ x, int x_f32, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ dbeta, float* __restrict__ dgamma, long long M, int C, int remap, int hw_shift,
+                     int w_shift) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * 2048;
+  float a = 0.f, b = 0.f;
+  if (col < C) {
+    const float mu = mean[col], rs = rstd[col];
+    for (long long r = r0 + ry; r < r0 + 2048 && r < M; r += 8) {
+      const long long dr = remap ? split_row(r, hw_shift, w_shift) : r;
+      float g = load_dy(dy, dy_f32, dr * C + col);
+      if (act_out && !(load_dy(act_out, act_f32, dr * C + col) > 0.f)) g = 0.f;
+      const float xh = (load_raw(x, x_f32, r * C + col) - mu) * rs;
+      a += g;
+      b += g * xh;
+    }
+  }
+  s1[ry][cx] = a;
+  s2[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && col < C) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      t1 += s1[i][cx];
+      t2 += s2[i][cx];
+    }
+    atomicAdd(dbeta + col, t1);
+    atomicAdd(dgamma + col, t2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32,
+                    const void* __restrict__ x, int x_f32, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                    __nv_bfloat16* __restrict__ dx, long long ldx, long long M, int C, int remap, int hw_shift, int w_shift) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over M * C/8
+  const int c8 = C >> 3;
+  if (idx >= M * c8) return;
+  const long long row = idx / c8;
+  const int c = (int)(idx - row * c8) * 8;
+  const long long dr = remap ? split_row(row, hw_shift, w_shift) : row;
+  float xv[8];
+  load_raw8(x, x_f32, row * C + c, xv);
+  const float invM = 1.0f / (float)M;
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float g = load_dy(dy, dy_f32, dr * C + c + j);
+    if (act_out && !(load_dy(act_out, act_f32, dr * C + c + j) > 0.f)) g = 0.f;
+    const float rs = __ldg(rstd + c + j);
+    const float xh = (xv[j] - __ldg(mean + c + j)) * rs;
+    o[j] = __ldg(gamma + c + j) * rs * (g - __ldg(dbeta + c + j) * invM - xh * __ldg(dgamma + c + j) * invM);
+  }
+  *reinterpret_cast<uint4*>(dx + row * ldx + c) =
+      make_uint4(rl::pack_bf16(o[0], o[1]), rl::pack_bf16(o[2], o[3]), rl::pack_bf16(o[4], o[5]), rl::pack_bf16(o[6], o[7]));
+}
+
+// ---- im2col for weight gradients: col[m, ci*T + t] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] (0 outside) ------
+// so that dW[co, ci, kh, kw] (the reference layout) = sum_m dY[m, co] * col[m, ci*T + t] is one plain GEMM.
+struct TapTable {
+  int n;
+  signed char dw[12], dh[12], plane[12];
+};
+
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, long long M, int C, int W, int H, int P,
+              int hw_shift, int w_shift, TapTable taps) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over M * C/8
+  const int c8 = C >> 3;
+  if (idx >= M * c8) return;
+  const long long row = idx / c8;
+  const int c = (int)(idx - row * c8) * 8;
+  const long long img = row >> hw_shift;
+  const int pix = (int)(row & ((1 << hw_shift) - 1));
+  const int oh = pix >> w_shift, ow = pix & ((1 << w_shift) - 1);
+  const int T = taps.n;
+  __nv_bfloat16* dst = col + row * (long long)(C * T) + (long long)c * T;
+  for (int t = 0; t < T; ++t) {
+    const int ih = oh + taps.dh[t], iw = ow + taps.dw[t];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+      v = *reinterpret_cast<const uint4*>(x + ((((img * P + taps.plane[t]) * H + ih) * W + iw) * (long long)C + c));
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j * T + t] = e[j];
+  }
+}
+
+// glyph patches for the block-1 weight gradients: col1[m, c*9 + kh*3 + kw] (32 columns, 27 used) and the
+// centre pixel colsc[m, c] (8 columns, C used); m = (img, oh, ow) over the 16x16 output map
+template <int C>
+__global__ void __launch_bounds__(256)
+glyph_im2col_kernel(const float* __restrict__ glyphs, const long long* __restrict__ ids, __nv_bfloat16* __restrict__ col1,
+                    __nv_bfloat16* __restrict__ colsc) {
+  __shared__ float s_img[C * 1024];
+  const int tid = threadIdx.x;
+  const long long img = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(glyphs + ids[img] * (long long)(C * 1024));
+  for (int i = tid; i < C * 256; i += 256) reinterpret_cast<float4*>(s_img)[i] = __ldg(src + i);
+  __syncthreads();
+  const int oh = tid >> 4, ow = tid & 15;
+  float a[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = 2 * oh + kh - 1, iw = 2 * ow + kw - 1;
+        if (ih >= 0 && iw >= 0) a[c * 9 + kh * 3 + kw] = s_img[c * 1024 + ih * 32 + iw];
+      }
+  uint4* d1 = reinterpret_cast<uint4*>(col1 + (img * 256 + tid) * 32);
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    d1[g] = make_uint4(rl::pack_bf16(a[8 * g], a[8 * g + 1]), rl::pack_bf16(a[8 * g + 2], a[8 * g + 3]),
+                       rl::pack_bf16(a[8 * g + 4], a[8 * g + 5]), rl::pack_bf16(a[8 * g + 6], a[8 * g + 7]));
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = k < C ? s_img[k * 1024 + (2 * oh) * 32 + 2 * ow] : 0.f;
+  *reinterpret_cast<uint4*>(colsc + (img * 256 + tid) * 8) =
+      make_uint4(rl::pack_bf16(s[0], s[1]), rl::pack_bf16(s[2], s[3]), rl::pack_bf16(s[4], s[5]), rl::pack_bf16(s[6], s[7]));
+}
+
+int ilog2x(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return ((1 << s) == v) ? s : -1;
+}
+
+}  // namespace
+
+extern "C" int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t M, int64_t C, int64_t ld, void* stream) {
+  RL_REQUIRE(x && sums && M > 0 && C > 0 && ld >= C, RL_EINVAL, "rl_bn_stats: bad arguments");
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
+  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == RL_DT_F32, sums, M, (int)C, ld);
+  return rl_check_launch("rl_bn_stats");
+}
+
+extern "C" int rl_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* mean_out,
+                              float* rstd_out, int64_t M, int64_t C, float momentum, float eps, void* stream) {
+  RL_REQUIRE(sums && gamma && beta && scale && shift && mean_out && rstd_out && M > 0 && C > 0, RL_EINVAL,
+             "rl_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(unsigned)((C + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      sums, gamma, beta, running_mean, running_var, (long long*)num_batches_tracked, scale, shift, mean_out, rstd_out, M, (int)C,
+      momentum, eps);
+  return rl_check_launch("rl_bn_finalize");
+}
+
+extern "C" int rl_bn_apply(const void* x1, const float* scale1, const float* shift1, const void* x2, const float* scale2,
+                           const float* shift2, int32_t x_dtype, void* out, int32_t out_dtype, int32_t relu, int64_t M,
+                           int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream) {
+  RL_REQUIRE(x1 && scale1 && shift1 && out && M > 0 && C > 0 && C % 8 == 0, RL_EINVAL, "rl_bn_apply: bad arguments");
+  RL_REQUIRE(!x2 || (scale2 && shift2), RL_EINVAL, "rl_bn_apply: second operand needs scale/shift");
+  int hs = 0, ws = 0;
+  if (remap) {
+    hs = ilog2x(map_h);
+    ws = ilog2x(map_w);
+    RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_apply: parity split needs a power-of-two map >= 2x2");
+  }
+  const long long n = M * (C / 8);
+  bn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x1, scale1, shift1, x2, scale2, shift2, x_dtype == RL_DT_F32, out, out_dtype == RL_DT_F32, relu, M, (int)C, remap, hs + ws,
+      ws);
+  return rl_check_launch("rl_bn_apply");
+}
+
+extern "C" int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const void* x,
+                         int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
+                         int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream) {
+  RL_REQUIRE(dy && x && mean && rstd && gamma && dbeta && dgamma && dx && M > 0 && C > 0 && C % 8 == 0 && ldx >= C, RL_EINVAL,
+             "rl_bn_bwd: bad arguments");
+  int hs = 0, ws = 0;
+  if (remap) {
+    hs = ilog2x(map_h);
+    ws = ilog2x(map_w);
+    RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_bwd: parity split needs a power-of-two map >= 2x2");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, dy_dtype == RL_DT_F32, act_out, act_dtype == RL_DT_F32, x, x_dtype == RL_DT_F32,
+                                             mean, rstd, dbeta, dgamma, M, (int)C, remap, hs + ws, ws);
+  int rc = rl_check_launch("rl_bn_bwd(reduce)");
+  if (rc) return rc;
+  const long long n = M * (C / 8);
+  bn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, dy_dtype == RL_DT_F32, act_out, act_dtype == RL_DT_F32,
+                                                                  x, x_dtype == RL_DT_F32, mean, rstd, gamma, dbeta, dgamma,
+                                                                  (__nv_bfloat16*)dx, ldx, M, (int)C, remap, hs + ws, ws);
+  return rl_check_launch("rl_bn_bwd");
+}
+
+extern "C" int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C, int32_t W, int32_t H, int32_t P,
+                              int32_t ntaps, const int8_t* tap_dw, const int8_t* tap_dh, const int8_t* tap_plane,
+                              void* stream) {
+  RL_REQUIRE(x && col && tap_dw && tap_dh && tap_plane && ntaps >= 1 && ntaps <= 12 && C % 8 == 0, RL_EINVAL,
+             "rl_im2col_bf16: bad arguments");
+  const int ws = ilog2x(W), hs = ilog2x(H);
+  RL_REQUIRE(ws >= 0 && hs >= 0, RL_EINVAL, "rl_im2col_bf16: map must be power-of-two");
+  TapTable t;
+  t.n = ntaps;
+  for (int i = 0; i < ntaps; ++i) {
+    t.dw[i] = tap_dw[i];
+    t.dh[i] = tap_dh[i];
+    t.plane[i] = tap_plane[i];
+  }
+  const long long M = n_img * W * H;
+  const long long n = M * (C / 8);
+  if (n == 0) return 0;
+  im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, M, C,
+                                                                              W, H, P, ws + hs, ws, t);
+  return rl_check_launch("rl_im2col_bf16");
+}
+
+extern "C" int rl_glyph_im2col(const float* glyphs, const int64_t* ids, void* col1, void* colsc, int64_t n_img, int32_t C,
+                               void* stream) {
+  RL_REQUIRE(glyphs && ids && col1 && colsc && (C == 1 || C == 3), RL_EINVAL, "rl_glyph_im2col: bad arguments");
+  if (n_img <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 3)
+    glyph_im2col_kernel<3><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, (__nv_bfloat16*)col1, (__nv_bfloat16*)colsc);
+  else
+    glyph_im2col_kernel<1><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, (__nv_bfloat16*)col1, (__nv_bfloat16*)colsc);
+  return rl_check_launch("rl_glyph_im2col");
+}

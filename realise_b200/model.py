@@ -220,6 +220,13 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         model.load_state_dict(sd, strict=False)
         return model
 
+    def train(self, mode=True):
+        # leaving train mode: the eval operand cache (folded BatchNorm, conv layouts) must be rebuilt from the
+        # parameters / running statistics the training steps have changed
+        if not mode and self.training:
+            self._prepared = None
+        return super().train(mode)
+
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
         self._prepared = None

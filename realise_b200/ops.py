@@ -81,7 +81,7 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
 
 
 def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res=None,
-              act=ACT_NONE, out_remap=0):
+              act=ACT_NONE, out_remap=0, remap_plane=0, c_use=0):
     """Implicit-GEMM convolution.  x: bf16 activation [nimg, planes, H, W, C] (contiguous);
     w: bf16 [Cout, ntaps*C] tap-major; taps: list of (dw, dh, plane); output rows are (img, oh, ow)
     over an H x W map; out_remap=1 writes rows parity-split for a following stride-2 conv."""
@@ -90,8 +90,8 @@ def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res
     assert x.is_contiguous() and w.stride(1) == 1
     C = x.shape[-1]
     assert x.numel() == nimg * planes * H * W * C
-    M, N, K = nimg * H * W, w.shape[0], len(taps) * C
-    assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+    M, N, K = nimg * H * W, w.shape[0], len(taps) * (c_use or C)
+    assert w.shape[1] == K and out.shape[0] == (4 * M if out_remap == 2 else M) and out.shape[1] == N
     d = GemmDesc()
     d.a, d.b = x.data_ptr(), w.data_ptr()
     d.M, d.N, d.K = M, N, K
@@ -99,6 +99,8 @@ def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res
     d.a_mode = 1
     d.conv_C, d.conv_W, d.conv_H, d.conv_P, d.conv_NIMG = C, W, H, planes, nimg
     d.ntaps = len(taps)
+    d.conv_Cuse = c_use
+    d.remap_plane = remap_plane
     for i, (dw, dh, pl) in enumerate(taps):
         d.tap_dw[i], d.tap_dh[i], d.tap_plane[i] = dw, dh, pl
     _fill_epilogue(d, out, scale, bias, res, act, None, out_remap)
@@ -336,3 +338,53 @@ def gru_table_bwd(dtable, emb, w_ih, dw_ih, db_ih, demb):
     check(lib().rl_gru_table_bwd(_ptr(dtable), _ptr(emb), _ptr(w_ih), _ptr(dw_ih), _ptr(db_ih), _ptr(demb), _c(V), _c(H),
                                  _stream()), "rl_gru_table_bwd")
     _count(2)
+
+
+# ---- CharResNet training pieces ----
+def bn_stats(x, sums):
+    M, C = x.shape
+    check(lib().rl_bn_stats(_ptr(x), ctypes.c_int32(_DT[x.dtype]), _ptr(sums), _c(M), _c(C), _c(x.stride(0)), _stream()),
+          "rl_bn_stats")
+    _count()
+
+
+def bn_finalize(sums, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, rstd, M, momentum=0.1, eps=1e-5):
+    C = gamma.numel()
+    check(lib().rl_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(nbt),
+                               _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _c(M), _c(C), ctypes.c_float(momentum),
+                               ctypes.c_float(eps), _stream()), "rl_bn_finalize")
+    _count()
+
+
+def bn_apply(x1, sc1, sh1, x2, sc2, sh2, out, relu, remap=False, map_hw=(1, 1)):
+    M, C = x1.shape
+    check(lib().rl_bn_apply(_ptr(x1), _ptr(sc1), _ptr(sh1), _ptr(x2), _ptr(sc2), _ptr(sh2), ctypes.c_int32(_DT[x1.dtype]),
+                            _ptr(out), ctypes.c_int32(_DT[out.dtype]), ctypes.c_int32(int(relu)), _c(M), _c(C), ctypes.c_int32(int(remap)),
+                            ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), _stream()), "rl_bn_apply")
+    _count()
+
+
+def bn_bwd(dy, act_out, x, mean, rstd, gamma, dbeta, dgamma, dx, remap=False, map_hw=(1, 1)):
+    M, C = x.shape
+    check(lib().rl_bn_bwd(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out),
+                          ctypes.c_int32(_DT[act_out.dtype] if act_out is not None else 0), _ptr(x),
+                          ctypes.c_int32(_DT[x.dtype]), _ptr(mean), _ptr(rstd),
+                          _ptr(gamma), _ptr(dbeta), _ptr(dgamma), _ptr(dx), _c(dx.stride(0)), _c(M), _c(C),
+                          ctypes.c_int32(int(remap)), ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), _stream()),
+          "rl_bn_bwd")
+    _count(2)
+
+
+def im2col(x, col, nimg, C, W, H, P, taps):
+    n = len(taps)
+    arr = ctypes.c_int8 * n
+    dw, dh, pl = arr(*[t[0] for t in taps]), arr(*[t[1] for t in taps]), arr(*[t[2] for t in taps])
+    check(lib().rl_im2col_bf16(_ptr(x), _ptr(col), _c(nimg), ctypes.c_int32(C), ctypes.c_int32(W), ctypes.c_int32(H),
+                               ctypes.c_int32(P), ctypes.c_int32(n), dw, dh, pl, _stream()), "rl_im2col_bf16")
+    _count()
+
+
+def glyph_im2col(glyphs, ids, col1, colsc, n_img, C):
+    check(lib().rl_glyph_im2col(_ptr(glyphs), _ptr(ids), _ptr(col1), _ptr(colsc), _c(n_img), ctypes.c_int32(C), _stream()),
+          "rl_glyph_im2col")
+    _count()

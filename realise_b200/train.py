@@ -46,10 +46,10 @@ class TrainEngine:
     def __init__(self, model):
         self.m = model
         c = model.config
-        if c.with_res == "yes":
-            raise NotImplementedError("training kernels cover the semantic and pinyin paths in this round: CharResNet "
-                                      "conv / batch-stat BatchNorm backward is not written yet (use with_res='no')")
+        if c.with_res == "yes" and c.num_fonts not in (1, 3):
+            raise NotImplementedError("glyph kernels are built for 1 or 3 fonts")
         self.saved = None
+        self.debug = None             # tests set a dict to receive intermediate gradients
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
         # trainable parameters in a fixed order
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -179,6 +179,210 @@ class TrainEngine:
             sv["layers"].append(s)
         return x, xb, sv
 
+    # ---- CharResNet (train): batch-statistics BatchNorm, every conv as a tcgen05 GEMM -------------------------
+    RES_CH = [None, 64, 128, 256, 512, 768]
+
+    @staticmethod
+    def _s2_taps(S):
+        """taps of a 3x3 stride-2 pad-1 conv over the parity-split input: (dw, dh, plane, kh, kw)."""
+        taps = []
+        for kh in range(3):
+            for kw in range(3):
+                ph, dh = (0, 0) if kh == 1 else (1, -1 if kh == 0 else 0)
+                pw, dw = (0, 0) if kw == 1 else (1, -1 if kw == 0 else 0)
+                if S == 1 and (dh < 0 or dw < 0):
+                    continue
+                taps.append((dw, dh, ph * 2 + pw, kh, kw))
+        return taps
+
+    @staticmethod
+    def _s1_taps(S):
+        return [(kw - 1, kh - 1, 0, kh, kw) for kh in range(3) for kw in range(3) if not (S == 1 and (kh != 1 or kw != 1))]
+
+    def _resnet_weights(self):
+        """bf16 operand layouts of the current conv weights (re-derived every step: pure layout + cast)."""
+        m, c = self.m, self.m.config
+        W = []
+        cin = c.num_fonts
+        for b in range(1, 6):
+            blk = getattr(m.resnet, f"res_block{b}")
+            conv1, bn1, _, conv2, bn2 = blk.residual_function
+            convs, bns = blk.shortcut
+            cout, S = self.RES_CH[b], 32 >> b
+            w1, w2, wsc = conv1.weight.detach(), conv2.weight.detach(), convs.weight.detach().reshape(cout, cin)
+            e = {"S": S, "cin": cin, "cout": cout, "conv1": conv1, "conv2": conv2, "convs": convs, "bn1": bn1, "bn2": bn2,
+                 "bns": bns}
+            t2 = self._s1_taps(S)
+            e["taps2"] = t2
+            e["w2f"] = torch.cat([w2[:, :, kh, kw] for (_, _, _, kh, kw) in t2], 1).bfloat16().contiguous()
+            # data gradient of conv2: da1[h, w] = sum_taps dc2[h - dh, w - dw] W2[:, :, kh, kw]^T
+            e["w2t"] = torch.cat([w2[:, :, kh, kw].t() for (_, _, _, kh, kw) in t2], 1).bfloat16().contiguous()
+            e["taps2t"] = [(-dw, -dh, 0) for (dw, dh, _, _, _) in t2]
+            if b == 1:
+                w1g = torch.zeros(cout, 32, device=w1.device)
+                w1g[:, :9 * cin] = w1.reshape(cout, 9 * cin)
+                wsg = torch.zeros(cout, 8, device=w1.device)
+                wsg[:, :cin] = wsc
+                e["w1g"], e["wscg"] = w1g.bfloat16().contiguous(), wsg.bfloat16().contiguous()
+            else:
+                t1 = self._s2_taps(S)
+                e["taps1"] = t1
+                e["w1f"] = torch.cat([w1[:, :, kh, kw] for (_, _, _, kh, kw) in t1], 1).bfloat16().contiguous()
+                e["wscf"] = wsc.bfloat16().contiguous()
+                if S == 1:
+                    # dx_in [N, 4*cin] = [dc1 | dcs] . Wbig^T, Wbig[p*cin+ci] = [W1[:, ci, 1+ph, 1+pw] | (p == 0) Wsc[:, ci]]
+                    rows = []
+                    for pl in range(4):
+                        a = w1[:, :, 1 + pl // 2, 1 + pl % 2].t()
+                        bsc = wsc.t() if pl == 0 else torch.zeros_like(wsc.t())
+                        rows.append(torch.cat([a, bsc], 1))
+                    e["wbig"] = torch.cat(rows, 0).bfloat16().contiguous()          # [4*cin, 2*cout]
+                else:
+                    e["dgrad"] = []
+                    for pl in range(4):
+                        ph, pw = pl // 2, pl % 2
+                        khs, kws = ([1] if ph == 0 else [0, 2]), ([1] if pw == 0 else [0, 2])
+                        taps, cols = [], []
+                        for kh in khs:
+                            for kw in kws:
+                                dh = -1 if kh == 0 else 0
+                                dw = -1 if kw == 0 else 0
+                                taps.append((-dw, -dh, 0))
+                                cols.append(w1[:, :, kh, kw].t())                    # [cin, cout]
+                        if pl == 0:
+                            cols.append(wsc.t())                                     # the shortcut rides on tap (0, 0)
+                        e["dgrad"].append((taps, torch.cat(cols, 1).bfloat16().contiguous()))
+            W.append(e)
+            cin = cout
+        return W
+
+    def _bn_train(self, raw, bn, M):
+        """Batch statistics of a raw conv output -> (scale, shift, mean, rstd); updates the running stats."""
+        C = raw.shape[1]
+        sums = self._new((2 * C,), F32, zero=True)
+        ops.bn_stats(raw, sums)
+        sc, sh, mu, rs = (self._new((C,), F32) for _ in range(4))
+        ops.bn_finalize(sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked, sc, sh, mu, rs, M)
+        return sc, sh, mu, rs
+
+    def _resnet_fwd(self, P, ids_flat, N, sv):
+        c = self.m.config
+        Ws = self._resnet_weights()
+        glyphs = P["res"]["glyphs"]
+        blocks = []
+        x = None
+        for bi, e in enumerate(Ws):
+            S, cin, cout = e["S"], e["cin"], e["cout"]
+            M = N * S * S
+            s = {"e": e, "x_in": x}
+            c1, cs = self._new((M, cout), F32), self._new((M, cout), F32)   # raw conv outputs stay f32 (batch stats)
+            if bi == 0:
+                s["col1"], s["colsc"] = self._new((M, 32), BF16), self._new((M, 8), BF16)
+                ops.glyph_im2col(glyphs, ids_flat, s["col1"], s["colsc"], N, c.num_fonts)
+                ops.gemm(s["col1"], e["w1g"], c1)
+                ops.gemm(s["colsc"], e["wscg"], cs)
+            elif S == 1:
+                xin = x.view(N, 4 * cin)
+                ops.gemm(xin, e["w1f"], c1)
+                ops.gemm(xin[:, :cin], e["wscf"], cs)
+            else:
+                xin = x.view(N, 4, S, S, cin)
+                ops.conv_gemm(xin, e["w1f"], c1, nimg=N, H=S, W=S, planes=4, taps=[t[:3] for t in e["taps1"]])
+                ops.conv_gemm(xin, e["wscf"], cs, nimg=N, H=S, W=S, planes=4, taps=[(0, 0, 0)])
+            s["bn1"] = self._bn_train(c1, e["bn1"], M)
+            a1 = self._new((M, cout), BF16)
+            ops.bn_apply(c1, s["bn1"][0], s["bn1"][1], None, None, None, a1, relu=True)
+            c2 = self._new((M, cout), F32)
+            if S == 1:
+                ops.gemm(a1, e["w2f"], c2)
+            else:
+                ops.conv_gemm(a1.view(N, 1, S, S, cout), e["w2f"], c2, nimg=N, H=S, W=S, planes=1,
+                              taps=[t[:3] for t in e["taps2"]])
+            s["bn2"] = self._bn_train(c2, e["bn2"], M)
+            s["bns"] = self._bn_train(cs, e["bns"], M)
+            last = bi == 4
+            out = self._new((M, cout), F32 if last else BF16)
+            ops.bn_apply(c2, s["bn2"][0], s["bn2"][1], cs, s["bns"][0], s["bns"][1], out, relu=True, remap=S >= 2, map_hw=(S, S))
+            s.update({"c1": c1, "cs": cs, "a1": a1, "c2": c2, "out": out})
+            blocks.append(s)
+            x = out
+        sv["res"] = blocks
+        return x   # f32 [N, 768]
+
+    def _resnet_bwd(self, sv, dout, N):
+        for bi in range(4, -1, -1):
+            s = sv["res"][bi]
+            if self.debug is not None:
+                self.debug[f"dout{bi + 1}"] = dout.clone()
+                self.debug[f"out{bi + 1}"] = s["out"].clone()
+                self.debug[f"a1_{bi + 1}"] = s["a1"].clone()
+            e = s["e"]
+            S, cin, cout = e["S"], e["cin"], e["cout"]
+            M = N * S * S
+            remap = S >= 2
+            g = self._grad
+            dcat = self._new((M, 2 * cout), BF16)
+            dc2 = self._new((M, cout), BF16)
+            # out = relu(bn2(c2) + bns(cs))
+            ops.bn_bwd(dout, s["out"], s["c2"], s["bn2"][2], s["bn2"][3], e["bn2"].weight.detach(), g(e["bn2"].bias),
+                       g(e["bn2"].weight), dc2, remap=remap, map_hw=(S, S))
+            ops.bn_bwd(dout, s["out"], s["cs"], s["bns"][2], s["bns"][3], e["bns"].weight.detach(), g(e["bns"].bias),
+                       g(e["bns"].weight), dcat[:, cout:], remap=remap, map_hw=(S, S))
+            # conv2 weight gradient (reference layout [cout, cin, kh, kw]) and data gradient
+            T2 = len(e["taps2"])
+            gw2 = g(e["conv2"].weight)
+            if T2 == 9:
+                col = self._new((M, cout * 9), BF16)
+                ops.im2col(s["a1"], col, N, cout, S, S, 1, [t[:3] for t in e["taps2"]])
+                ops.gemm(dc2, col, gw2.view(cout, cout * 9), a_t=True, b_t=True)
+                da1 = self._new((M, cout), BF16)
+                ops.conv_gemm(dc2.view(N, 1, S, S, cout), e["w2t"], da1, nimg=N, H=S, W=S, planes=1, taps=e["taps2t"])
+            else:  # 1x1 map: only the centre tap touched data
+                tmp = self._new((cout, cout), F32)
+                ops.gemm(dc2, s["a1"], tmp, a_t=True, b_t=True)
+                gw2[:, :, 1, 1].copy_(tmp)
+                da1 = self._new((M, cout), BF16)
+                ops.gemm(dc2, e["w2f"], da1, b_t=True)
+            # a1 = relu(bn1(c1))
+            ops.bn_bwd(da1, s["a1"], s["c1"], s["bn1"][2], s["bn1"][3], e["bn1"].weight.detach(), g(e["bn1"].bias),
+                       g(e["bn1"].weight), dcat[:, :cout])
+            dc1, dcs = dcat[:, :cout], dcat[:, cout:]
+            gw1, gws = g(e["conv1"].weight), g(e["convs"].weight)
+            if bi == 0:
+                tmp = self._new((cout, 32), F32)
+                ops.gemm(dc1, s["col1"], tmp, a_t=True, b_t=True)
+                gw1.view(cout, 9 * cin).copy_(tmp[:, :9 * cin])
+                tmp2 = self._new((cout, 8), F32)
+                ops.gemm(dcs, s["colsc"], tmp2, a_t=True, b_t=True)
+                gws.view(cout, cin).copy_(tmp2[:, :cin])
+                return
+            x_in = s["x_in"]
+            t1 = e["taps1"]
+            col = self._new((M, cin * len(t1)), BF16)
+            ops.im2col(x_in, col, N, cin, S, S, 4, [t[:3] for t in t1])
+            if len(t1) == 9:
+                ops.gemm(dc1, col, gw1.view(cout, cin * 9), a_t=True, b_t=True)
+            else:
+                tmp = self._new((cout, cin * len(t1)), F32)
+                ops.gemm(dc1, col, tmp, a_t=True, b_t=True)
+                idx = torch.tensor([kh * 3 + kw for (_, _, _, kh, kw) in t1], device=tmp.device)
+                gw1.view(cout, cin, 9)[:, :, idx] = tmp.view(cout, cin, len(t1))
+            colsc = self._new((M, cin), BF16)
+            ops.im2col(x_in, colsc, N, cin, S, S, 4, [(0, 0, 0)])
+            ops.gemm(dcs, colsc, gws.view(cout, cin), a_t=True, b_t=True)
+            # data gradient wrt the block input (parity-split rows = the previous block's output layout)
+            dx = self._new((N * 4 * S * S, cin), BF16)
+            if S == 1:
+                ops.gemm(dcat, e["wbig"], dx.view(N, 4 * cin))
+            else:
+                dview = dcat.view(N, 1, S, S, 2 * cout)
+                for pl, (taps, wp) in enumerate(e["dgrad"]):
+                    cu = 2 * cout if pl == 0 else cout
+                    ops.conv_gemm(dview, wp, dx, nimg=N, H=S, W=S, planes=1, taps=taps, out_remap=2, remap_plane=pl,
+                                  c_use=cu)
+            dout = dx
+
     # ---- pinyin GRU (train): every step's state is kept for the backward-through-time ---------------
     def _gru_fwd(self, P, pho_idx, lens_dev, N, sv):
         H = self.m.config.hidden_size
@@ -246,6 +450,12 @@ class TrainEngine:
             pho_gru = self._gru_fwd(P, inp["pho_idx"], inp["pho_lens"], N, sv)
             pho_h, _, sv["pho"] = self._stack_fwd("pho", m.pho_model, P["pho_model"], mask, B, L, inputs_embeds=pho_gru)
             mods.append(pho_h)
+        if c.with_res == "yes":
+            res_raw = self._resnet_fwd(P, input_ids.view(-1), N, sv)
+            sv["res_raw"] = res_raw
+            res_h = self._new((N, H), F32)
+            ops.layernorm(res_raw, P["res_ln_w"], P["res_ln_b"], res_h, None, c.layer_norm_eps)
+            mods.append(res_h)
         sv["mods"] = mods
         fused = self._new((N, H), F32)
         if c.fusion == "gate":
@@ -357,6 +567,13 @@ class TrainEngine:
         if c.with_pho == "yes":
             dgru = self._stack_bwd(sv["pho"], dms[1], mask, B, L)
             self._gru_bwd(P, sv, dgru, N)
+        if c.with_res == "yes":
+            dres = self._new((N, H), F32)
+            ops.layernorm_bwd(dms[-1], sv["res_raw"], P["res_ln_w"], None, dres, None, self._grad(m.resnet_layernorm.weight),
+                              self._grad(m.resnet_layernorm.bias), None, c.layer_norm_eps)
+            if self.debug is not None:
+                self.debug["dres"] = dres.clone()
+            self._resnet_bwd(sv, dres, N)
         self._stack_bwd(sv["bert"], dm0, mask, B, L)   # scatter-adds the embedding rows into the (tied) dE buffer
         self.saved = None
         # parameters that never receive a gradient (poolers, unused word embeddings of output_block) -> None

@@ -101,6 +101,82 @@ def test_pinyin_branch_backward_matches_oracle_autograd():
             "pho_embeddings.weight"} <= seen
 
 
+def _unsplit(x, n, S, C):
+    h = S // 2
+    return x.view(n, 2, 2, h, h, C).permute(0, 5, 3, 1, 4, 2).reshape(n, C, S, S)
+
+
+@pytest.mark.parametrize("with_pho,B,L", [("no", 2, 16), ("yes", 3, 24)])
+def test_glyph_branch_and_full_arch3_backward(with_pho, B, L):
+    """CharResNet with batch-statistics BatchNorm (+ the full three-encoder model).  The bf16-operand forward flips
+    the sign of a few ReLU pre-activations that lie within its error of zero; each flip moves a whole gradient
+    element, so the oracle differentiates through the CUDA forward's ReLU gates (exported via engine.debug), exactly
+    as it is handed the kernels' dropout masks.  Without shared gates the CNN gradients differ by ~20 % in norm while
+    every non-CNN gradient still agrees to 1 % — see DESIGN.md."""
+    from oracle import realise_oracle as O
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    from realise_b200.train import TrainEngine
+    cfg = ArchConfig(num_hidden_layers=1, with_pho=with_pho, with_res="yes", hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0)
+    sd = cached_state_dict(cfg, 13)
+    model = SpellBertPho2ResArch3Abla(cfg)
+    model.tie_cls_weight()
+    model.load_state_dict(sd, strict=True)
+    model.train().cuda()
+    model._engine = TrainEngine(model)
+    model._engine.debug = dbg = {}
+    batch = synth_batch(B, L, seed=9)
+    db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    loss, _ = model(db)
+    loss.backward()
+    n = B * L
+
+    def gates(site, shape):
+        b = int(site.split("res_block")[1][0])
+        S, C = shape[-1], shape[1]
+        if site.endswith(".a1"):
+            t = dbg[f"a1_{b}"].float().cpu().view(n, S, S, C).permute(0, 3, 1, 2)
+        else:
+            t = dbg[f"out{b}"].float().cpu()
+            t = _unsplit(t, n, S, C) if S >= 2 else t.view(n, C, 1, 1)
+        return (t > 0).float()
+
+    rsd = {k: v.clone() for k, v in sd.items()}
+    rsd["classifier.weight"] = rsd["bert.embeddings.word_embeddings.weight"]
+    leaves = {}
+    for k, v in rsd.items():
+        if v.dtype.is_floating_point and "running" not in k and not k.startswith("char_images"):
+            v.requires_grad_(True)
+            leaves[k] = v
+    stats = {}
+    O.RELU_MASK_FN = gates
+    try:
+        rloss, _ = O.forward(rsd, batch, cfg, train=True, bn_stats=stats)
+        rloss.backward()
+    finally:
+        O.RELU_MASK_FN = None
+    assert abs(loss.item() - rloss.item()) <= 1e-2
+    gmax = max(v.grad.abs().max().item() for v in leaves.values() if v.grad is not None)
+    n_res = 0
+    for name, p in model.named_parameters():
+        if name == "classifier.weight" or name.startswith("char_images") or p.grad is None:
+            continue
+        rg = leaves[name].grad
+        if rg.norm().item() < 1e-6 * gmax:
+            continue
+        rel = (p.grad.float().cpu() - rg).norm().item() / rg.norm().item()
+        assert rel <= (4e-2 if name.startswith("resnet") else 2e-2), (name, rel)
+        n_res += name.startswith("resnet")
+    assert n_res == 47   # 15 convs + 15 BatchNorm (weight, bias) + resnet_layernorm (weight, bias)
+    # BatchNorm running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance, counter)
+    for b in (1, 3, 5):
+        bn = getattr(model.resnet, f"res_block{b}").residual_function[1]
+        key = f"resnet.res_block{b}.residual_function.1"
+        assert (bn.running_mean.cpu() - stats[key + ".running_mean"]).abs().max().item() <= 2e-3
+        assert (bn.running_var.cpu() - stats[key + ".running_var"]).abs().max().item() <= 2e-3
+        assert bn.num_batches_tracked.item() == 1
+
+
 def test_fused_adamw_step_matches_reference_formula():
     from realise_b200.optim import FusedAdamW
     cfg, sd, model = _setup(layers=1)
@@ -139,10 +215,13 @@ def test_fused_adamw_step_matches_reference_formula():
 def test_train_mode_guards():
     from realise_b200.model import SpellBertPho2ResArch3
     m = SpellBertPho2ResArch3(ArchConfig(num_hidden_layers=1)).train().cuda()
-    batch = synth_batch(2, 16, seed=1)
+    batch = synth_batch(2, 16, seed=1, with_labels=False)
     db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="tgt_idx"):
         m(db)
+    long = synth_batch(1, 160, seed=1)
+    with pytest.raises(NotImplementedError, match="seq_len"):
+        m({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in long.items()})
 
 
 def test_dropout_training_parity_with_exported_masks():

@@ -103,6 +103,50 @@ for name in ["pho_gru.weight_ih_l0", "pho_gru.weight_hh_l0", "pho_gru.bias_ih_l0
     r = [w for w in worst if w[1] == name]
     print("  ", name, r[0][0] if r else "n/a")
 
+# ---- glyph branch (CharResNet with batch-stat BatchNorm) and the full Arch3 ----
+for (wp, tag, B_, L_) in [("no", "with_res", 2, 16), ("yes", "full arch3", 3, 24)]:
+    cfg_r = ArchConfig(num_hidden_layers=1, with_pho=wp, with_res="yes", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd_r = synth_state_dict(cfg_r, 13)
+    mr = SpellBertPho2ResArch3Abla(cfg_r)
+    mr.tie_cls_weight()
+    mr.load_state_dict(sd_r, strict=True)
+    mr.train().cuda()
+    batch = synth_batch(B_, L_, seed=9)
+    db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    loss, logits = mr(db)
+    loss.backward()
+    torch.cuda.synchronize()
+    rsd = {k: v.clone() for k, v in sd_r.items()}
+    rsd["classifier.weight"] = rsd["bert.embeddings.word_embeddings.weight"]
+    leaves = {}
+    for k, v in rsd.items():
+        if v.dtype.is_floating_point and "running" not in k and not k.startswith("char_images"):
+            v.requires_grad_(True)
+            leaves[k] = v
+    stats = {}
+    rloss, rlogits = O.forward(rsd, batch, cfg_r, train=True, bn_stats=stats)
+    rloss.backward()
+    print(f"{tag}: loss {loss.item():.5f} vs {rloss.item():.5f}")
+    worst = []
+    for name, p in mr.named_parameters():
+        if name == "classifier.weight" or name.startswith("char_images"):
+            continue
+        rg = leaves[name].grad
+        if p.grad is None:
+            if rg is not None and rg.abs().max() > 0:
+                print("  MISSING grad", name, rg.norm().item())
+            continue
+        worst.append(((p.grad.float().cpu() - rg).norm().item() / (rg.norm().item() + 1e-12), name, rg.norm().item()))
+    worst.sort(reverse=True)
+    for rel, name, n in [w for w in worst if "key.bias" not in w[1]][:10]:
+        print(f"  rel_err {rel:.3e}  |g|={n:.3e}  {name}")
+    resn = [w for w in worst if w[1].startswith("resnet")]
+    print(f"  resnet tensors: {len(resn)}, max rel {max(w[0] for w in resn):.3e}, median {sorted(w[0] for w in resn)[len(resn)//2]:.3e}")
+    bn = mr.resnet.res_block2.residual_function[1]
+    print("  running_mean err", (bn.running_mean.cpu() - stats["resnet.res_block2.residual_function.1.running_mean"]).abs().max().item(),
+          "running_var err", (bn.running_var.cpu() - stats["resnet.res_block2.residual_function.1.running_var"]).abs().max().item(),
+          "nbt", bn.num_batches_tracked.item())
+
 # ---- dropout ON: feed the kernels' own masks to the oracle ----
 from realise_b200 import ops  # noqa: E402
 cfg_d = ArchConfig(num_hidden_layers=2, with_pho="no", with_res="no")   # p = 0.1 / 0.1 as in the reference config
