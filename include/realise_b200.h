@@ -78,6 +78,10 @@ typedef struct rl_gemm_desc {
   int32_t remap_plane; /* out_remap 2: GEMM row (img, h, w) -> row ((img*4 + remap_plane)*H + h)*W + w: one parity plane of
                           the data gradient of a stride-2 conv */
   int32_t conv_Cuse;   /* conv mode: channels [0, conv_Cuse) of every tap are the GEMM's K (0 = all conv_C) */
+  int32_t split_k;     /* 0: off.  > 0: that many K ranges, -1: auto.  out (f32, no epilogue operands) is ACCUMULATED
+                          INTO: out += A*B, partial sums of the K ranges meeting through f32 atomics, so the caller
+                          zero-initialises it once per step (weight gradients: few output tiles, K = tokens or
+                          pixels; also sums a gradient over time steps / shared weights for free) */
   int32_t a_major;   /* 0: A stored [M, K] (K-major).  1: A stored [K, M] with row stride lda (MN-major), e.g.
                         A = dY^T for a weight gradient straight from dY [tokens, out] */
   float drop_p;        /* training: dropout on (acc*scale+bias) BEFORE the residual add (BertSelfOutput/BertOutput, */
@@ -238,8 +242,8 @@ RL_API int rl_gru_table_bwd(const float* dtable, const float* emb, const float* 
  * rl_bn_apply: out = [relu](x1*scale1 + shift1 [+ x2*scale2 + shift2]); remap = 1 writes parity-split rows.
  * rl_bn_bwd: BatchNorm backward for dy (f32/bf16; rows parity-split when remap) optionally masked by the ReLU that
  *   followed (act_out > 0); dbeta/dgamma accumulated, dx written as bf16 with row stride ldx.
- * rl_im2col_bf16: col[m, ci*T + t] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] so that a conv weight gradient in the
- *   reference's [Cout, Cin, kh, kw] layout is ONE rl_gemm_bf16 (A = dY MN-major, B = col MN-major).
+ * rl_im2col_bf16: col[m, t*C + ci] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] so that a conv weight gradient
+ *   dW[co, t, ci] is ONE split-K rl_gemm_bf16 (A = dY MN-major, B = col MN-major).
  * rl_glyph_im2col: the same for res_block1 straight from the glyph table: col1 [n*256, 32] (27 used), colsc [n*256, 8]. */
 RL_API int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t M, int64_t C, int64_t ld, void* stream);
 RL_API int rl_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,

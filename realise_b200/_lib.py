@@ -26,7 +26,7 @@ class GemmDesc(ctypes.Structure):
         ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("res", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("res_dtype", ctypes.c_int32),
         ("act", ctypes.c_int32), ("out_remap", ctypes.c_int32),
-        ("remap_plane", ctypes.c_int32), ("conv_Cuse", ctypes.c_int32),
+        ("remap_plane", ctypes.c_int32), ("conv_Cuse", ctypes.c_int32), ("split_k", ctypes.c_int32),
         ("a_major", ctypes.c_int32),
         ("drop_p", ctypes.c_float), ("drop_site", ctypes.c_uint32), ("drop_seed", ctypes.c_uint64),
         ("b_major", ctypes.c_int32),

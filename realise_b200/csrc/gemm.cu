@@ -16,6 +16,8 @@ constexpr int STAGE_BYTES = 8 * (8192 + 1024);  // per epilogue warp: two 32x32 
 
 struct KParams {
   int M, N, num_kb;
+  int k_splits, kb_per_split;  // split-K: tile index = (m, n, split); splits accumulate with f32 atomics
+  int atomic_out;              // split_k requested: out += A*B through atomics even when one split suffices
   int tiles_m, tiles_n;
   int a_mode;
   int hw_shift, w_shift;
@@ -240,6 +242,20 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      } else if (p.atomic_out) {
+        // split-K: partial sums of the different K ranges meet in the (zero-initialised) f32 output
+        if (row_ok) {
+          float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + nb;
+          if (nb + 32 <= p.N && p.vec_store) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) atomicAdd(o + j, x[j]);
+          }
+        }
       } else if (row_ok) {
         if (nb + 32 <= p.N && p.vec_store) {
           if (p.out_f32) {
@@ -324,7 +340,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   rl::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -332,8 +348,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n;
-        const int n_blk = tile - m_blk * p.tiles_n;
+        const int mn = tile / p.k_splits, ks = tile - mn * p.k_splits;
+        const int m_blk = mn / p.tiles_n;
+        const int n_blk = mn - m_blk * p.tiles_n;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int m0 = m_blk * BM;
         const int n0 = n_blk * BN;
         int img0 = 0, h0 = 0;
@@ -341,7 +359,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           img0 = m0 >> p.hw_shift;
           h0 = (m0 & ((1 << p.hw_shift) - 1)) >> p.w_shift;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           rl::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.dbg & 2) {
             rl::mbar_arrive(&full_bar[stage]);
@@ -388,10 +406,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile % p.k_splits;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         rl::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           rl::mbar_wait(&full_bar[stage], phase);
           rl::tc_fence_after();
           if (rl::elect_one()) {
@@ -400,7 +420,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               if (!(p.dbg & 4))
-                rl::tc_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                rl::tc_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             rl::tc_commit(&empty_bar[stage]);
           }
           __syncwarp();
@@ -430,8 +450,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n;
-      const int n_blk = tile - m_blk * p.tiles_n;
+      const int mn = tile / p.k_splits;
+      const int m_blk = mn / p.tiles_n;
+      const int n_blk = mn - m_blk * p.tiles_n;
       const int row0 = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
@@ -476,7 +497,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     }
     configured = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = tiles < rl_num_sms() ? tiles : rl_num_sms();
   gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);
   return rl_check_launch("rl_gemm_bf16");
@@ -584,7 +605,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   rl::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row pair tiles here
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;  // tiles_m counts 256-row pair tiles here
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
@@ -594,8 +615,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / p.tiles_n;
-        const int n_blk = tile - m_blk * p.tiles_n;
+        const int mn = tile / p.k_splits, ks = tile - mn * p.k_splits;
+        const int m_blk = mn / p.tiles_n;
+        const int n_blk = mn - m_blk * p.tiles_n;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int m0 = m_blk * 2 * BM + (int)rank * BM;
         const int n0 = n_blk * BN + (int)rank * (BN / 2);
         int img0 = 0, h0 = 0;
@@ -603,7 +626,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           img0 = m0 >> p.hw_shift;
           h0 = (m0 & ((1 << p.hw_shift) - 1)) >> p.w_shift;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           rl::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.dbg & 2) {
             if (leader) rl::mbar_arrive(&full_bar[stage]);
@@ -648,10 +671,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int ks = tile % p.k_splits;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         rl::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           rl::mbar_wait(&full_bar[stage], phase);
           rl::tc_fence_after();
           if (rl::elect_one()) {
@@ -660,7 +685,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               if (!(p.dbg & 4))
-                tc2_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                tc2_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             tc2_commit_mc(&empty_bar[stage]);
           }
           __syncwarp();
@@ -685,8 +710,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile / p.tiles_n;
-      const int n_blk = tile - m_blk * p.tiles_n;
+      const int mn = tile / p.k_splits;
+      const int m_blk = mn / p.tiles_n;
+      const int n_blk = mn - m_blk * p.tiles_n;
       const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
@@ -730,7 +756,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     }
     configured = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int max_clusters = rl_num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   gemm2_bf16_kernel<BN, STAGES><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);
@@ -846,6 +872,22 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   }
   if (pair) p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   p.tiles_n = (p.N + bn - 1) / bn;
+  // split-K (weight gradients: few output tiles, K = tokens / pixels): ~2 CTAs per SM worth of tiles, >= 8 k-blocks each
+  p.k_splits = 1;
+  p.kb_per_split = p.num_kb;
+  p.atomic_out = d->split_k != 0;
+  if (d->split_k != 0) {
+    RL_REQUIRE(d->out_dtype == RL_DT_F32 && !d->res && !d->bias && !d->scale && d->act == RL_ACT_NONE && !d->out2 &&
+                   d->out_remap == 0 && d->drop_p == 0.f,
+               RL_EINVAL, "rl_gemm_bf16: split_k needs a plain f32 accumulate-into output (no epilogue operands)");
+    const long long ctas = (long long)p.tiles_m * p.tiles_n * (pair ? 2 : 1);
+    int want = d->split_k > 0 ? d->split_k : (int)((2LL * rl_num_sms() + ctas - 1) / ctas);
+    int maxs = p.num_kb / 8;
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    p.kb_per_split = (p.num_kb + want - 1) / want;
+    p.k_splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  }
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -922,7 +964,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   // output path: TMA store for plain row-major outputs with 16-byte aligned rows
   const int oelt = p.out_f32 ? 4 : 2;
   const bool aligned16 = ((uintptr_t)d->out & 15) == 0 && (d->ldo * oelt) % 16 == 0;
-  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16) ? 1 : 0;  // remapped rows: direct stores
+  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16 && !p.atomic_out) ? 1 : 0;  // else direct stores
   p.vec_store = (aligned16 && (d->out2 == nullptr || (((uintptr_t)d->out2 & 15) == 0 && d->ldo2 % 8 == 0))) ? 1 : 0;
   if (d->res) {
     const int relt = p.res_f32 ? 4 : 2;

@@ -192,8 +192,9 @@ bn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32, const void* __restr
       make_uint4(rl::pack_bf16(o[0], o[1]), rl::pack_bf16(o[2], o[3]), rl::pack_bf16(o[4], o[5]), rl::pack_bf16(o[6], o[7]));
 }
 
-// ---- im2col for weight gradients: col[m, ci*T + t] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] (0 outside) ------
-// so that dW[co, ci, kh, kw] (the reference layout) = sum_m dY[m, co] * col[m, ci*T + t] is one plain GEMM.
+// ---- im2col for weight gradients: col[m, t*C + ci] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] (0 outside) ------
+// so that dW[co, t, ci] = sum_m dY[m, co] * col[m, t*C + ci] is one plain (split-K) GEMM; the small result is
+// permuted to the reference's [co, ci, kh, kw] layout afterwards.
 struct TapTable {
   int n;
   signed char dw[12], dh[12], plane[12];
@@ -211,15 +212,13 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ c
   const int pix = (int)(row & ((1 << hw_shift) - 1));
   const int oh = pix >> w_shift, ow = pix & ((1 << w_shift) - 1);
   const int T = taps.n;
-  __nv_bfloat16* dst = col + row * (long long)(C * T) + (long long)c * T;
+  __nv_bfloat16* dst = col + row * (long long)(C * T) + c;   // tap-major columns: col[m, t*C + ci], 16-byte copies
   for (int t = 0; t < T; ++t) {
     const int ih = oh + taps.dh[t], iw = ow + taps.dw[t];
     uint4 v = make_uint4(0, 0, 0, 0);
     if (ih >= 0 && ih < H && iw >= 0 && iw < W)
       v = *reinterpret_cast<const uint4*>(x + ((((img * P + taps.plane[t]) * H + ih) * W + iw) * (long long)C + c));
-    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j * T + t] = e[j];
+    *reinterpret_cast<uint4*>(dst + (long long)t * C) = v;
   }
 }
 

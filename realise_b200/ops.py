@@ -55,7 +55,8 @@ def _req(t, dtype, name):
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
-def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None, a_t=False, b_t=False, drop=None):
+def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None, a_t=False, b_t=False, drop=None,
+         split_k=0):
     """out[M,N] = act((A @ B^T) * scale + bias + res) with A = a [M,K] (or a^T when a_t: a is stored [K,M],
     MN-major operand) and B = b [N,K] (or b^T when b_t: b is stored [K,N]).  a, b bf16; out bf16 or f32."""
     _req(a, torch.bfloat16, "a")
@@ -72,6 +73,7 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
     d.a_major, d.b_major = int(a_t), int(b_t)
     if drop:
         d.drop_p, d.drop_seed, d.drop_site = drop
+    d.split_k = split_k
     d.a_mode = 0
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
     with _Timed("gemm", 2.0 * M * N * K):

@@ -310,6 +310,18 @@ class TrainEngine:
         sv["res"] = blocks
         return x   # f32 [N, 768]
 
+    def _conv_wgrad(self, dy, col, weight, taps, cout, cin):
+        """dW[co, t, ci] = dy^T col (split-K GEMM, tap-major) -> the parameter's [co, ci, kh, kw] gradient view."""
+        T = len(taps)
+        tmp = self._new((cout, T * cin), F32, zero=True)
+        ops.gemm(dy, col, tmp, a_t=True, b_t=True, split_k=-1)
+        gw = self._grad(weight).view(cout, cin, 9)
+        if T == 9:
+            gw.copy_(tmp.view(cout, 9, cin).permute(0, 2, 1))
+        else:
+            idx = torch.tensor([kh * 3 + kw for (_, _, _, kh, kw) in taps], device=tmp.device)
+            gw[:, :, idx] = tmp.view(cout, T, cin).permute(0, 2, 1)
+
     def _resnet_bwd(self, sv, dout, N):
         for bi in range(4, -1, -1):
             s = sv["res"][bi]
@@ -331,17 +343,14 @@ class TrainEngine:
                        g(e["bns"].weight), dcat[:, cout:], remap=remap, map_hw=(S, S))
             # conv2 weight gradient (reference layout [cout, cin, kh, kw]) and data gradient
             T2 = len(e["taps2"])
-            gw2 = g(e["conv2"].weight)
             if T2 == 9:
                 col = self._new((M, cout * 9), BF16)
                 ops.im2col(s["a1"], col, N, cout, S, S, 1, [t[:3] for t in e["taps2"]])
-                ops.gemm(dc2, col, gw2.view(cout, cout * 9), a_t=True, b_t=True)
+                self._conv_wgrad(dc2, col, e["conv2"].weight, e["taps2"], cout, cout)
                 da1 = self._new((M, cout), BF16)
                 ops.conv_gemm(dc2.view(N, 1, S, S, cout), e["w2t"], da1, nimg=N, H=S, W=S, planes=1, taps=e["taps2t"])
             else:  # 1x1 map: only the centre tap touched data
-                tmp = self._new((cout, cout), F32)
-                ops.gemm(dc2, s["a1"], tmp, a_t=True, b_t=True)
-                gw2[:, :, 1, 1].copy_(tmp)
+                self._conv_wgrad(dc2, s["a1"], e["conv2"].weight, e["taps2"], cout, cout)
                 da1 = self._new((M, cout), BF16)
                 ops.gemm(dc2, e["w2f"], da1, b_t=True)
             # a1 = relu(bn1(c1))
@@ -350,27 +359,21 @@ class TrainEngine:
             dc1, dcs = dcat[:, :cout], dcat[:, cout:]
             gw1, gws = g(e["conv1"].weight), g(e["convs"].weight)
             if bi == 0:
-                tmp = self._new((cout, 32), F32)
-                ops.gemm(dc1, s["col1"], tmp, a_t=True, b_t=True)
+                tmp = self._new((cout, 32), F32, zero=True)
+                ops.gemm(dc1, s["col1"], tmp, a_t=True, b_t=True, split_k=-1)
                 gw1.view(cout, 9 * cin).copy_(tmp[:, :9 * cin])
-                tmp2 = self._new((cout, 8), F32)
-                ops.gemm(dcs, s["colsc"], tmp2, a_t=True, b_t=True)
+                tmp2 = self._new((cout, 8), F32, zero=True)
+                ops.gemm(dcs, s["colsc"], tmp2, a_t=True, b_t=True, split_k=-1)
                 gws.view(cout, cin).copy_(tmp2[:, :cin])
                 return
             x_in = s["x_in"]
             t1 = e["taps1"]
             col = self._new((M, cin * len(t1)), BF16)
             ops.im2col(x_in, col, N, cin, S, S, 4, [t[:3] for t in t1])
-            if len(t1) == 9:
-                ops.gemm(dc1, col, gw1.view(cout, cin * 9), a_t=True, b_t=True)
-            else:
-                tmp = self._new((cout, cin * len(t1)), F32)
-                ops.gemm(dc1, col, tmp, a_t=True, b_t=True)
-                idx = torch.tensor([kh * 3 + kw for (_, _, _, kh, kw) in t1], device=tmp.device)
-                gw1.view(cout, cin, 9)[:, :, idx] = tmp.view(cout, cin, len(t1))
+            self._conv_wgrad(dc1, col, e["conv1"].weight, t1, cout, cin)
             colsc = self._new((M, cin), BF16)
             ops.im2col(x_in, colsc, N, cin, S, S, 4, [(0, 0, 0)])
-            ops.gemm(dcs, colsc, gws.view(cout, cin), a_t=True, b_t=True)
+            ops.gemm(dcs, colsc, gws.view(cout, cin), a_t=True, b_t=True, split_k=-1)
             # data gradient wrt the block input (parity-split rows = the previous block's output layout)
             dx = self._new((N * 4 * S * S, cin), BF16)
             if S == 1:
@@ -422,9 +425,9 @@ class TrainEngine:
             ops.gru_step_bwd(dh, g["ghs"][t], G["b_hh"], G["table"], g["pho_idx"], g["lens"],
                              g["hs"][t - 1] if t > 0 else None, dh_prev, dgi, dgh, onehot, t)
             ops.colsum_bf16(dgh, db_hh)
-            ops.gemm(onehot, dgi, dtable, a_t=True, b_t=True, res=dtable)                 # dtable += onehot^T dgi
+            ops.gemm(onehot, dgi, dtable, a_t=True, b_t=True, split_k=-1)                 # dtable += onehot^T dgi
             if t > 0:
-                ops.gemm(dgh, g["hbs"][t - 1], dW_hh, a_t=True, b_t=True, res=dW_hh)      # dW_hh += dgh^T h_{t-1}
+                ops.gemm(dgh, g["hbs"][t - 1], dW_hh, a_t=True, b_t=True, split_k=-1)      # dW_hh += dgh^T h_{t-1}
                 dh_next = self._new((N, H), F32)
                 ops.gemm(dgh, G["w_hh"], dh_next, b_t=True, res=dh_prev)                 # dh_{t-1} = dh z + dgh W_hh
                 dh = dh_next
@@ -495,11 +498,11 @@ class TrainEngine:
                               drop_p=hp, drop_seed=seed,
                               site_in=self.SITE_FINAL if (hp > 0 and sv["last_drop"] and li == nl - 1) else 0,
                               site_out=self.site(name, li, 3) if hp > 0 else 0)
-            ops.gemm(dy2b, s["h"], self._grad(out.dense.weight), a_t=True, b_t=True)              # dW2 = dy2^T h
+            ops.gemm(dy2b, s["h"], self._grad(out.dense.weight), a_t=True, b_t=True, split_k=-1)              # dW2 = dy2^T h
             du = self._new((N, I), BF16)
             ops.gemm(dy2b, lw["w_2"], du, b_t=True, res=s["u"], act=ops.ACT_GELU_GRAD)              # du = (dy2 W2) gelu'(u)
             ops.colsum_bf16(du, self._grad(lyr.intermediate.dense.bias, True))
-            ops.gemm(du, s["x1b"], self._grad(lyr.intermediate.dense.weight), a_t=True, b_t=True)  # dW1 = du^T x1
+            ops.gemm(du, s["x1b"], self._grad(lyr.intermediate.dense.weight), a_t=True, b_t=True, split_k=-1)  # dW1 = du^T x1
             dx1 = self._new((N, H), F32)
             ops.gemm(du, lw["w_1"], dx1, b_t=True, res=dy2)                                         # dx1 = du W1 + dy2
             # x1 = LN1(y1),  y1 = ctx Wo^T + bo + x
@@ -507,7 +510,7 @@ class TrainEngine:
             ops.layernorm_bwd(dx1, s["y1"], lw["ln1_w"], None, dy1, dy1b, self._grad(att.output.LayerNorm.weight, True),
                               self._grad(att.output.LayerNorm.bias, True), self._grad(att.output.dense.bias, True),
                               c.layer_norm_eps, drop_p=hp, drop_seed=seed, site_out=self.site(name, li, 2) if hp > 0 else 0)
-            ops.gemm(dy1b, s["ctx"], self._grad(att.output.dense.weight), a_t=True, b_t=True)      # dWo = dy1^T ctx
+            ops.gemm(dy1b, s["ctx"], self._grad(att.output.dense.weight), a_t=True, b_t=True, split_k=-1)      # dWo = dy1^T ctx
             dctx = self._new((N, H), BF16)
             ops.gemm(dy1b, lw["w_o"], dctx, b_t=True)
             dqkv = self._new((N, 3 * H), BF16)
@@ -515,7 +518,7 @@ class TrainEngine:
                               drop=self.adrop(self.site(name, li, 1)))
             dw, db = self._qkv_grads(att, H)
             ops.colsum_bf16(dqkv, db)
-            ops.gemm(dqkv, s["xb"], dw, a_t=True, b_t=True)                                         # dWqkv = dqkv^T x
+            ops.gemm(dqkv, s["xb"], dw, a_t=True, b_t=True, split_k=-1)                                         # dWqkv = dqkv^T x
             dxin = self._new((N, H), F32)
             ops.gemm(dqkv, lw["w_qkv"], dxin, b_t=True, res=dy1)                                    # dx = dqkv Wqkv + dy1
             dx = dxin
@@ -541,7 +544,7 @@ class TrainEngine:
         B, L, mask = sv["B"], sv["L"], sv["mask"]
         N, H, V = B * L, c.hidden_size, c.vocab_size
         self.step_seed = sv["seed"]
-        self.flat_zero.zero_()
+        self.flat.zero_()   # every gradient is accumulated into (split-K GEMMs use f32 atomics)
         inp = sv["inp"]
         # classifier + masked CE:  logits = seq E^T + b
         dlogits = self._new((N, V), BF16)
@@ -550,7 +553,7 @@ class TrainEngine:
                           dlogits)
         ops.colsum_bf16(dlogits, self._grad(m.classifier.bias, True))
         gE = self._grad(m.classifier.weight, zero=False)
-        ops.gemm(dlogits, sv["seq_b"], gE, a_t=True, b_t=True)                                      # dE = dlogits^T seq
+        ops.gemm(dlogits, sv["seq_b"], gE, a_t=True, b_t=True, split_k=-1)                                      # dE = dlogits^T seq
         dseq = self._new((N, H), F32)
         ops.gemm(dlogits, P["cls_w"], dseq, b_t=True)                                               # dseq = dlogits E
         dfused = self._stack_bwd(sv["out"], dseq, mask, B, L)

@@ -136,7 +136,7 @@ def test_error_paths():
     a = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
     b = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
     out = torch.zeros(128, 128, device="cuda", dtype=torch.bfloat16)
-    with pytest.raises(RuntimeError, match="multiple of 64"):
+    with pytest.raises(RuntimeError, match="multiple of 8"):
         ops.gemm(a, b, out)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.gemm(a.cpu(), b, out)
