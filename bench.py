@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — sentences/s of the ReaLiSe multimodal hot path (SpellBertPho2ResArch3.forward).
+"""bench.py — sentences/s of the ReaLiSe multimodal hot path, forward + backward + optimizer.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): 1 GPU = forward-only eval step, batch 64 x seq_len 128, all
-three encoders + fusion + classifier, bf16 operands / fp32 accumulate, synthetic batch
-(realise_b200.synth) and seeded random weights of the full architecture (21128 vocab, 12+4+3
-transformer layers, 3-font glyph table).  N GPUs: one process per GPU, each its own batch of 64
-(sentences are independent: no data-path collective), whole-job value = N*64*K / max-rank time.
-One JSON line on stdout (rank 0).  `--impl reference` times the CPU oracle port of the reference
-on the host cores for the same metric/config on a bounded sample per step.
+Headline workload = the configuration BASELINE.json's metric ("sentences/sec fwd+bwd seq_len=128") is quoted
+on: configs[2] at N=1 (one optimizer step = train-mode forward with dropout 0.1 and batch-statistics BatchNorm,
+backward, clip_grad_norm_(1.0), AdamW; batch 128 x seq_len 128; all three encoders + gate + output block +
+21128-way classifier; bf16 operands / fp32 accumulate, fp32 master weights and moments) and configs[3] at N>1
+(128 sentences per GPU, ONE NCCL all-reduce of the flat fp32 gradient buffer per step, weak scaling).
+Synthetic batch (realise_b200.synth) and random-init weights of the full architecture.
+`value` = device-resident inputs, CUDA events around the K steps, max over ranks.  `e2e` = the reference's
+training-loop body (src/run.py:186-212) through the public API with a pinned HOST batch: H2D of the batch,
+model(batch) -> loss.backward() -> optimizer.step() -> loss.item() (D2H).  The forward-only configs[1] number
+(B=64, eval, CUDA graph) is reported as the secondary `forward_only` object.
+`--impl reference` / `cpu_baseline` time the CPU oracle port of the same train step (autograd + clip + AdamW
+as transformers/optimization.py:113-169) on the host cores on a bounded sample.  One JSON line (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -25,9 +31,10 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-B_PER_GPU, SEQ_LEN = 64, 128
-METRIC = "sentences/sec fwd seq_len=128 (BASELINE configs[1]: forward-only B=64 L=128, all encoders + fusion)"
-FLOP_PER_SENTENCE_FWD = 59.39e9  # SURVEY.md §8(d), nominal, L=128
+B_TRAIN, B_FWD, SEQ_LEN = 128, 64, 128
+METRIC = "sentences/sec fwd+bwd seq_len=128 (BASELINE configs[2]/[3]: train step fwd+bwd+clip+AdamW, B=128/GPU)"
+FLOP_PER_SENTENCE_FWD = 59.39e9      # SURVEY.md §8(d), nominal, L=128
+FLOP_PER_SENTENCE_TRAIN = 178.2e9    # 3 x forward
 
 
 def load_peaks():
@@ -111,83 +118,116 @@ def pick_threads(fn, candidates):
     return best
 
 
-def cpu_oracle_rate(batch_sentences, seq_len, budget_s, threads=None):
-    """sentences/s of the CPU oracle (port of the reference forward) on a bounded sample."""
-    from oracle import realise_oracle as O
-    from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
-    O.FAST = True  # ATen fused CPU kernels, like the reference's nn.Modules
-    if threads:
-        torch.set_num_threads(threads)
-    cfg = ArchConfig()
-    sd = synth_state_dict(cfg, seed=0)
-    batch = synth_batch(batch_sentences, seq_len, seed=1, ragged=False, with_labels=False)
-    with torch.no_grad():
-        torch.set_num_threads(min(threads or host_threads(), 16))
-        O.forward(sd, synth_batch(2, seq_len, seed=2, ragged=False, with_labels=False), cfg)  # warm-up
-        maxt = threads or host_threads()
-        small = synth_batch(2, seq_len, seed=2, ragged=False, with_labels=False)  # cheap calibration batch
-        pick_threads(lambda: O.forward(sd, small, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64)}))
-        t0, n = time.perf_counter(), 0
-        while True:
-            O.forward(sd, batch, cfg)
-            n += 1
-            if time.perf_counter() - t0 >= budget_s or n >= 50:
-                break
-        dt = time.perf_counter() - t0
-    return n * batch_sentences / dt, n, sd, cfg
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference train step (the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------------
+class CpuTrainStep:
+    """fwd (train mode, dropout 0.1, batch-stat BN) + autograd bwd + clip_grad_norm_(1.0) + AdamW with the
+    vendored optimizer's semantics (transformers/optimization.py:113-169) on the oracle's state_dict."""
+
+    def __init__(self, batch_sentences, seq_len):
+        from oracle import realise_oracle as O
+        from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
+        O.FAST = True  # ATen fused CPU kernels, like the reference's nn.Modules
+        self.O, self.cfg = O, ArchConfig()
+        sd = synth_state_dict(self.cfg, seed=0)
+        sd["classifier.weight"] = sd["bert.embeddings.word_embeddings.weight"]   # tie_cls_weight (src/models.py:700)
+        frozen = ("char_images", "num_batches_tracked", "running_")
+        self.leaves = []
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and not any(f in k for f in frozen) and k != "classifier.weight":
+                v.requires_grad_(True)
+                self.leaves.append(v)
+        self.sd = sd
+        self.m = [torch.zeros_like(p) for p in self.leaves]
+        self.v = [torch.zeros_like(p) for p in self.leaves]
+        self.t = 0
+        self.B = batch_sentences
+        self.batch = synth_batch(batch_sentences, seq_len, seed=1, ragged=False, with_labels=True)
+
+    def __call__(self):
+        loss = self.O.forward(self.sd, self.batch, self.cfg, train=True)[0]
+        loss.backward()
+        ps = [p for p in self.leaves if p.grad is not None]
+        gs = [p.grad for p in ps]
+        with torch.no_grad():
+            torch.nn.utils.clip_grad_norm_(ps, 1.0)
+            self.t += 1
+            ms = [m for m, p in zip(self.m, self.leaves) if p.grad is not None]
+            vs = [v for v, p in zip(self.v, self.leaves) if p.grad is not None]
+            torch._foreach_mul_(ms, 0.9)
+            torch._foreach_add_(ms, gs, alpha=0.1)
+            torch._foreach_mul_(vs, 0.999)
+            torch._foreach_addcmul_(vs, gs, gs, value=0.001)
+            step = 5e-5 * math.sqrt(1.0 - 0.999 ** self.t) / (1.0 - 0.9 ** self.t)
+            den = torch._foreach_sqrt(vs)
+            torch._foreach_add_(den, 1e-8)
+            torch._foreach_addcdiv_(ps, ms, den, value=-step)
+            for p in ps:
+                p.grad = None
+        return float(loss)
+
+
+def cpu_train_rate(budget_s, max_steps, sample_b=4, warmup=1):
+    """sentences/s of the CPU train step on a bounded sample; returns (rate, steps, threads, sample text)."""
+    maxt = host_threads()
+    torch.set_num_threads(min(maxt, 16))
+    small = CpuTrainStep(1, SEQ_LEN)
+    small()                                                        # page in, warm the allocator
+    pick_threads(small, sorted({min(maxt, c) for c in (8, 16, 32, 64)}))
+    del small
+    st = CpuTrainStep(sample_b, SEQ_LEN)
+    for _ in range(warmup):
+        st()
+    t0, n = time.perf_counter(), 0
+    while n < max_steps:
+        st()
+        n += 1
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    sample = (f"{n} x train step (fwd+bwd+clip+AdamW, dropout 0.1) of {sample_b} sentences x {SEQ_LEN} tokens, "
+              f"oracle/realise_oracle.py FAST mode (ATen CPU kernels), fp32")
+    return n * sample_b / dt, n, torch.get_num_threads(), sample, dt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import realise_oracle as O
-    from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
-    O.FAST = True  # ATen fused CPU kernels, like the reference's nn.Modules
-    cfg = ArchConfig()
-    sd = synth_state_dict(cfg, seed=0)
-    sample_b = 8  # bounded sample of the 64-sentence step
-    batch = synth_batch(sample_b, SEQ_LEN, seed=1, ragged=False, with_labels=False)
-    with torch.no_grad():
-        maxt = host_threads()
-        small = synth_batch(2, SEQ_LEN, seed=2, ragged=False, with_labels=False)  # cheap calibration batch
-        torch.set_num_threads(min(maxt, 16))
-        O.forward(sd, small, cfg)
-        pick_threads(lambda: O.forward(sd, small, cfg), sorted({min(maxt, c) for c in (8, 16, 32, 64)}))
-        for _ in range(max(0, min(args.warmup, 2) - 1)):
-            O.forward(sd, batch, cfg)
-        t0 = time.perf_counter()
-        steps = 0
-        for _ in range(args.steps):
-            O.forward(sd, batch, cfg)
-            steps += 1
-            if time.perf_counter() - t0 > 150:
-                break
-        dt = time.perf_counter() - t0
-    value = steps * sample_b / dt
+    value, steps, threads, sample, dt = cpu_train_rate(budget_s=150.0, max_steps=args.steps, warmup=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "sentences/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] forward-only B=64 L=128; each step = bounded sample of 8 sentences on CPU",
-                   "global_batch": sample_b, "seq_len": SEQ_LEN},
-        "cpu_baseline": {"value": value, "unit": "sentences/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{steps} x forward of {sample_b} sentences x {SEQ_LEN} tokens, oracle/realise_oracle.py"},
+        "config": {"workload": "BASELINE configs[2]: train step fwd+bwd+clip+AdamW of the full SpellBertPho2ResArch3, "
+                               "seq_len 128; each step = bounded sample of 4 sentences on the host CPU",
+                   "global_batch": 4, "seq_len": SEQ_LEN},
+        "cpu_baseline": {"value": value, "unit": "sentences/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def measure_train(dev, rank, world, dist, steps):
-    """Secondary line: one optimizer step (fwd + bwd + gradient all-reduce + clip + AdamW) of the full
-    SpellBertPho2ResArch3 (all three encoders), batch 128/GPU x seq_len 128, dropout 0.1, batch-stat BatchNorm —
-    BASELINE configs[2] (1 GPU) / configs[3] (N GPUs, weak scaling)."""
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def _agg(prof):
+    agg = {}
+    for kind, work, e0, e1 in prof:
+        a = agg.setdefault(kind, [0.0, 0.0, 0])
+        a[0] += work
+        a[1] += e0.elapsed_time(e1) * 1e-3
+        a[2] += 1
+    return agg
+
+
+def build_train(dev, rank, world):
     from realise_b200.ddp import DataParallel
     from realise_b200.model import SpellBertPho2ResArch3Abla
     from realise_b200.optim import FusedAdamW
-    from realise_b200.synth import ArchConfig, synth_batch
-    B, L = 128, SEQ_LEN
-    cfg = ArchConfig(with_pho="yes", with_res="yes")
+    from realise_b200.synth import ArchConfig
+    cfg = ArchConfig(with_pho="yes", with_res="yes")       # == SpellBertPho2ResArch3 (src/models.py:652)
     torch.manual_seed(0)
     model = SpellBertPho2ResArch3Abla(cfg)
     model.tie_cls_weight()
@@ -196,50 +236,190 @@ def measure_train(dev, rank, world, dist, steps):
         dp = DataParallel(model)
         dp.broadcast_parameters()
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-    nd = [p for n, p in named if "bias" in n or "LayerNorm.weight" in n]
+    nd = [p for n, p in named if "bias" in n or "LayerNorm.weight" in n]                 # src/run.py:146-151
     dc = [p for n, p in named if not ("bias" in n or "LayerNorm.weight" in n)]
     opt = FusedAdamW([{"params": dc, "weight_decay": 0.0}, {"params": nd, "weight_decay": 0.0}], lr=5e-5, eps=1e-8,
                      max_grad_norm=1.0, model=model)
+    return model, opt, sum(p.numel() for _, p in named)
+
+
+def measure_train(args, dev, rank, world, dist, peaks):
+    from realise_b200 import ops
+    from realise_b200.synth import synth_batch
+    B, L = B_TRAIN, SEQ_LEN
+    model, opt, n_params = build_train(dev, rank, world)
     host = synth_batch(B, L, seed=4321 + rank, ragged=False, with_labels=True)
     db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
     db["pho_lens"] = torch.tensor(host["pho_lens"], dtype=torch.int32, device=dev)
 
-    def step():
-        loss = model(db)[0]
+    def step(b=db):
+        loss = model(b)[0]
         loss.backward()
         opt.step()
         return loss
 
-    for _ in range(3):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         step()
     torch.cuda.synchronize()
+    # ---- launches per step + per-kernel roofline pass (CUDA events around every C-ABI call, eager) ----
+    n0 = ops.LAUNCHES
+    step()
+    launches_per_step = ops.LAUNCHES - n0
+    ops._prof = []
+    step()
+    torch.cuda.synchronize()
+    prof, ops._prof = ops._prof, None
+    agg = _agg(prof)
+    gw = agg.get("gemm", [0, 0, 0])[0] + agg.get("conv_gemm", [0, 0, 0])[0]
+    gt = agg.get("gemm", [0, 1e-9, 0])[1] + agg.get("conv_gemm", [0, 0, 0])[1]
+    gn = agg.get("gemm", [0, 0, 0])[2] + agg.get("conv_gemm", [0, 0, 0])[2]
+    gemm_tf = gw / gt / 1e12
+
+    # ---- timed region: K optimizer steps, device-resident batch, CUDA events, max over ranks ----
+    clocks = ClockSampler(dev.index)
     if dist:
         dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
+    for _ in range(args.steps):
         loss = step()
     e1.record()
     torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clk = clocks.stop()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item() / steps
-    out = {"value": world * B / ms * 1e3, "unit": "sentences/s", "ms_per_step": ms, "steps": steps,
-           "config": {"workload": "BASELINE configs[2]: train step fwd+bwd+clip+AdamW of the full SpellBertPho2ResArch3 "
-                                  "(BERT 12L + pinyin GRU/4L + glyph CharResNet + gate + 3L output block + classifier)",
-                      "global_batch": world * B, "seq_len": L, "dropout": 0.1, "trainable_params": sum(p.numel() for _, p in named),
-                      "grad_allreduce": "one NCCL all-reduce over the flat fp32 gradient buffer" if world > 1 else "none (1 GPU)"},
-           "final_loss": float(loss.item()), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    total_ms = t.item()
+    value = world * B * args.steps / (total_ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- e2e: pinned host batch -> H2D -> forward/backward/optimizer through the public API -> loss.item() ----
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values() if torch.is_tensor(v)) + 4 * len(host["pho_lens"])
+
+    def e2e_step():
+        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in pinned.items()}
+        return step(b).item()                     # pho_lens stays a Python list (src/run.py:189); .item() = D2H + sync
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / t.item()
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 1e9
+    att, attb = agg.get("attention"), agg.get("attention_bwd")
+    out = {
+        "value": value, "ms_per_step": total_ms / args.steps, "warmup": W, "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * args.steps,
+        "model_tflops": value * FLOP_PER_SENTENCE_TRAIN / 1e12 / world,
+        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tf / peaks["tf_sustained"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch: mean over the 4 forward GEMM launches of
+                     # one transformer layer (B=64) in profiles/r01_ncu_full_summary.json (ncu --set full, round 1)
+                     "traffic": 40.2e6,
+                     "kernel": "gemm_bf16_kernel / gemm2_bf16_kernel (tcgen05 GEMM, implicit-GEMM conv, split-K wgrad): "
+                               f"executed 2*M*N*K over CUDA-event time of its {gn} launches in one train step",
+                     "peak_source": peaks["source"] + " bf16 sustained"},
+        "roofline_detail": {
+            "gemm_ms_per_step": gt * 1e3,
+            "attention_fwd_tflops": None if not att else att[0] / att[1] / 1e12,
+            "attention_bwd_tflops": None if not attb else attb[0] / attb[1] / 1e12,
+            "per_kernel_ms_per_step": {k: round(v[1] * 1e3, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+            "timed_kernels_ms": round(sum(v[1] for v in agg.values()) * 1e3, 3),
+        },
+        "config": {"workload": "BASELINE configs[2] (N=1) / configs[3] (N>1): one optimizer step of the full "
+                               "SpellBertPho2ResArch3 (BERT 12L + pinyin GRU/4L + glyph CharResNet + gate + 3L output "
+                               "block + tied classifier): train-mode fwd (dropout 0.1, batch-stat BN) + bwd + clip(1.0) "
+                               "+ AdamW; random-init full-size weights",
+                   "global_batch": world * B, "seq_len": L, "parallelism": f"dp{world} (batch-sharded, "
+                   + ("one NCCL all-reduce of the flat fp32 gradient buffer per step)" if world > 1 else "no collective)"),
+                   "trainable_params": n_params,
+                   "l2": f"no explicit flush: a step streams {peak_mem:.1f} GB of activations/gradients/optimizer state "
+                         "(>> 126 MB L2) between any two uses of the same data",
+                   "cuda_graph": False},
+        "final_loss": final_loss, "peak_mem_gb": peak_mem,
+    }
     del model, opt
     torch.cuda.empty_cache()
     return out
 
 
-def run_ours(args, rank, world, local_rank):
+def measure_forward(args, dev, rank, world, dist, peaks):
+    """Secondary object: BASELINE configs[1], forward-only eval, B=64 x L=128 per GPU, CUDA graph, L2 flushed."""
     from realise_b200 import ops
     from realise_b200.model import SpellBertPho2ResArch3
     from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
+    cfg = ArchConfig()
+    model = SpellBertPho2ResArch3(cfg)
+    model.tie_cls_weight()
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    model.eval().to(dev)
+    B, L = B_FWD, SEQ_LEN
+    host = synth_batch(B, L, seed=1234 + rank, ragged=False, with_labels=True)
+    dbatch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    dbatch["pho_lens"] = torch.tensor(host["pho_lens"], dtype=torch.int32, device=dev)
+    fwd_batch = {k: v for k, v in dbatch.items() if k not in ("tgt_idx", "loss_masks")}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    steps = min(args.steps, 20)
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        model(fwd_batch)
+        ops._prof = []
+        model(fwd_batch)
+        torch.cuda.synchronize()
+        prof, ops._prof = ops._prof, None
+        model.use_cuda_graph = True
+        for _ in range(3):
+            model(fwd_batch)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(fwd_batch)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value = world * B * steps / (t.item() * 1e-3)
+    agg = _agg(prof)
+    gw = agg.get("gemm", [0, 0, 0])[0] + agg.get("conv_gemm", [0, 0, 0])[0]
+    gt = agg.get("gemm", [0, 1e-9, 0])[1] + agg.get("conv_gemm", [0, 0, 0])[1]
+    att = agg.get("attention")
+    stem = agg.get("glyph_block1") or agg.get("glyph_stem")
+    out = {"value": value, "unit": "sentences/s", "ms_per_step": t.item() / steps, "steps": steps,
+           "workload": "BASELINE configs[1]: forward-only eval, batch 64/GPU x seq_len 128, CUDA graph, 256 MB L2 flush "
+                       "between steps", "model_tflops": value * FLOP_PER_SENTENCE_FWD / 1e12 / world,
+           "gemm_tflops": gw / gt / 1e12, "gemm_frac_of_peak": gw / gt / 1e12 / peaks["tf_sustained"],
+           "attention_tflops": None if not att else att[0] / att[1] / 1e12,
+           "glyph_block1_gbs": None if not stem else stem[0] / stem[1] / 1e9,
+           "glyph_block1_frac_of_hbm_peak": None if not stem else stem[0] / stem[1] / 1e9 / peaks["hbm_gbs"],
+           "per_kernel_ms_per_step": {k: round(v[1] * 1e3, 3) for k, v in agg.items()}}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -248,156 +428,32 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    cfg = ArchConfig()
-    sd = synth_state_dict(cfg, seed=0)
-    model = SpellBertPho2ResArch3(cfg)
-    model.tie_cls_weight()
-    model.load_state_dict(sd, strict=True)
-    model.eval().to(dev)
-    B, L = B_PER_GPU, SEQ_LEN
-    host = synth_batch(B, L, seed=1234 + rank, ragged=False, with_labels=True)
-    dbatch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
-    dbatch["pho_lens"] = torch.tensor(host["pho_lens"], dtype=torch.int32, device=dev)
-    fwd_batch = {k: v for k, v in dbatch.items() if k not in ("tgt_idx", "loss_masks")}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    # ---- launches per step (eager pass) + per-kernel roofline pass (CUDA events per launch) ----
-    with torch.no_grad():
-        model.use_cuda_graph = False
-        model(fwd_batch)
-        torch.cuda.synchronize()
-        n0 = ops.LAUNCHES
-        model(fwd_batch)
-        launches_per_step = ops.LAUNCHES - n0
-        ops._prof = []
-        for _ in range(3):
-            model(fwd_batch)
-        torch.cuda.synchronize()
-        prof, ops._prof = ops._prof, None
-        model.use_cuda_graph = True
-    agg = {}
-    for kind, work, e0, e1 in prof:
-        a = agg.setdefault(kind, [0.0, 0.0, 0])
-        a[0] += work
-        a[1] += e0.elapsed_time(e1) * 1e-3
-        a[2] += 1
-    gemm_w = agg.get("gemm", [0, 0, 0])[0] + agg.get("conv_gemm", [0, 0, 0])[0]
-    gemm_t = agg.get("gemm", [0, 1e-9, 0])[1] + agg.get("conv_gemm", [0, 0, 0])[1]
-    gemm_n = agg.get("gemm", [0, 0, 0])[2] + agg.get("conv_gemm", [0, 0, 0])[2]
-    gemm_tf = gemm_w / gemm_t / 1e12
-    detail = {k: {"work": v[0] / 3, "ms": v[1] / 3 * 1e3, "launches": v[2] // 3} for k, v in agg.items()}
-    att = agg.get("attention")
-    stem = agg.get("glyph_block1") or agg.get("glyph_stem")
-
-    # ---- timed region: K steps, device-resident inputs, CUDA events, L2 flushed between steps ----
-    clocks = ClockSampler(local_rank)
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            model(fwd_batch)
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-        clocks.start()
-        evs = []
-        for _ in range(args.steps):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            model(fwd_batch)
-            e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        clk = clocks.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([total_ms], device=dev)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = t.item()
-    value = world * B * args.steps / (total_ms * 1e-3)
-
-    # ---- e2e: host buffers in, predictions + loss out, through the public forward(batch) API ----
-    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
-    preds = torch.empty(B * L, dtype=torch.int64, device=dev)
-    preds_host = torch.empty(B * L, dtype=torch.int64).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in pinned.values() if torch.is_tensor(v)) + 4 * len(host["pho_lens"])
-    d2h = preds_host.numel() * 8 + 4
-
-    def e2e_step():
-        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in pinned.items()}
-        loss, logits = model(b)                       # pho_lens stays a Python list, like src/run.py:189
-        ops.argmax_rows(logits.view(B * L, -1), preds)
-        preds_host.copy_(preds, non_blocking=True)
-        return loss.item()                            # D2H + sync, like src/run.py:202
-
-    with torch.no_grad():
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / t.item()
-
-    train = None
-    if not args.no_train:
+    tr = measure_train(args, dev, rank, world, dist, peaks)
+    fwd = None
+    if not args.no_forward:
         try:
-            del model
-            torch.cuda.empty_cache()
-            train = measure_train(dev, rank, world, dist, steps=max(3, min(args.steps, 10)))
-        except Exception as e:  # noqa: BLE001 — the secondary line must never take the headline down
-            train = {"error": repr(e)[:300]}
+            fwd = measure_forward(args, dev, rank, world, dist, peaks)
+        except Exception as e:  # noqa: BLE001 — the secondary object must never take the headline down
+            fwd = {"error": repr(e)[:300]}
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, reps, _, _ = cpu_oracle_rate(8, L, budget_s=15.0)
-        cpu = {"value": rate, "unit": "sentences/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{reps} x eval forward of 8 sentences x {L} tokens (oracle/realise_oracle.py, fp32, all host threads)"}
+        rate, reps, threads, sample, _ = cpu_train_rate(budget_s=20.0, max_steps=20, warmup=1)
+        cpu = {"value": rate, "unit": "sentences/s", "cores": threads, "kind": "port", "sample": sample}
     line = {
-        "metric": METRIC, "value": value, "unit": "sentences/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": tr["value"], "unit": "sentences/s", "n_gpus": world, "steps": args.steps,
+        "warmup": tr["warmup"], "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: forward-only, batch 64/GPU x seq_len 128, 3 encoders + gate + "
-                               "3-layer output block + 21128-way classifier; random-init full-size weights",
-                   "global_batch": world * B, "seq_len": L, "parallelism": f"dp{world} (batch-sharded, no collective in forward)",
-                   "l2": "256 MB buffer written between timed steps (L2 flush)", "cuda_graph": True},
-        "model_tflops": value * FLOP_PER_SENTENCE_FWD / 1e12,
-        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tf / peaks["tf_sustained"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 GEMM launches of one
-                     # transformer layer in profiles/r01_ncu_full_summary.json (ncu --set full, round 1)
-                     "traffic": 40.2e6,
-                     "kernel": "gemm_bf16_kernel (tcgen05 GEMM + implicit-GEMM conv), executed 2*M*N*K over CUDA-event time, "
-                               f"{gemm_n // 3} launches/step", "peak_source": peaks["source"] + " bf16 sustained"},
-        "roofline_detail": {
-            "attention_tensor": None if not att else {"achieved_tflops": att[0] / att[1] / 1e12,
-                                                      "frac_of_peak": att[0] / att[1] / 1e12 / peaks["tf_sustained"]},
-            "glyph_conv_hbm": None if not stem else {"kernel": "glyph_block1_kernel (gather + res_block1 fused)",
-                                                     "achieved_gbs": stem[0] / stem[1] / 1e9,
-                                                     "frac_of_peak": stem[0] / stem[1] / 1e9 / peaks["hbm_gbs"]},
-            "per_kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in detail.items()},
-        },
-        "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "train_step": train,
-        "gpu_launches": (launches_per_step) * args.steps,
-        "clocks": clk,
+        "config": tr["config"], "model_tflops_per_gpu": tr["model_tflops"],
+        "roofline": tr["roofline"], "roofline_detail": tr["roofline_detail"],
+        "cpu_baseline": cpu, "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"], "clocks": tr["clocks"],
+        "final_loss": tr["final_loss"], "peak_mem_gb": tr["peak_mem_gb"], "forward_only": fwd,
     }
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
 
 
 def main():
@@ -407,7 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--no-forward", action="store_true", help="skip the secondary forward-only (configs[1]) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
