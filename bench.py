@@ -165,7 +165,7 @@ class CpuTrainStep:
             torch._foreach_addcdiv_(ps, ms, den, value=-step)
             for p in ps:
                 p.grad = None
-        return float(loss)
+        return float(loss.detach())
 
 
 def cpu_train_rate(budget_s, max_steps, sample_b=4, warmup=1):
