@@ -252,24 +252,42 @@ def measure_train(args, dev, rank, world, dist, peaks):
     db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
     db["pho_lens"] = torch.tensor(host["pho_lens"], dtype=torch.int32, device=dev)
 
-    def step(b=db):
+    def eager_step(b=db):
         loss = model(b)[0]
         loss.backward()
         opt.step()
         return loss
 
+    # the repo's public training-step API: fwd + bwd + (all-reduce) + clip + AdamW as one CUDA-graph replay
+    from realise_b200.graphed import GraphedTrainStep
+    gstep = GraphedTrainStep(model, opt)
+    graphed = not args.eager
+
+    def step(b=db):
+        return gstep(b) if graphed else eager_step(b)
+
     W = max(args.warmup, 3)
-    for _ in range(W):
-        step()
+    eager_step()
     torch.cuda.synchronize()
     # ---- launches per step + per-kernel roofline pass (CUDA events around every C-ABI call, eager) ----
     n0 = ops.LAUNCHES
-    step()
-    launches_per_step = ops.LAUNCHES - n0
+    eager_step()
+    launches_per_step = ops.LAUNCHES - n0 + 2          # + the two optimizer kernels (sum of squares, clip+AdamW)
     ops._prof = []
-    step()
+    eager_step()
     torch.cuda.synchronize()
     prof, ops._prof = ops._prof, None
+    try:
+        for _ in range(W):
+            step()                                         # first call of the shape is eager, the second captures
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001 — capture unsupported in this environment: time the eager loop instead
+        sys.stderr.write(f"bench: CUDA-graph capture of the train step failed ({e!r}); falling back to the eager loop\n")
+        graphed = False
+        torch.cuda.synchronize()
+        for _ in range(W):
+            step()
+        torch.cuda.synchronize()
     agg = _agg(prof)
     gw = agg.get("gemm", [0, 0, 0])[0] + agg.get("conv_gemm", [0, 0, 0])[0]
     gt = agg.get("gemm", [0, 1e-9, 0])[1] + agg.get("conv_gemm", [0, 0, 0])[1]
@@ -350,7 +368,7 @@ def measure_train(args, dev, rank, world, dist, peaks):
                    "trainable_params": n_params,
                    "l2": f"no explicit flush: a step streams {peak_mem:.1f} GB of activations/gradients/optimizer state "
                          "(>> 126 MB L2) between any two uses of the same data",
-                   "cuda_graph": False},
+                   "cuda_graph": graphed},
         "final_loss": final_loss, "peak_mem_gb": peak_mem,
     }
     del model, opt
@@ -463,6 +481,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager Python loop instead of the CUDA-graph step")
     ap.add_argument("--no-forward", action="store_true", help="skip the secondary forward-only (configs[1]) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

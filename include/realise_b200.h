@@ -255,6 +255,14 @@ RL_API int rl_bn_apply(const void* x1, const float* scale1, const float* shift1,
 RL_API int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const void* x,
                      int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
                      int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream);
+/* Two BatchNorms that fed the same ReLU (out = relu(bn2(c2) + bn_s(cs)), src/char_cnn.py:31-32) differentiated in one
+ * reduce + one apply pass: dy / act_out are read once for both branches.  x2 == NULL: single branch (== rl_bn_bwd with
+ * f32 x).  C must be 8*2^k (< 256) or a multiple of 256; all pointers 16-byte aligned. */
+RL_API int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const float* x1,
+                      const float* mean1, const float* rstd1, const float* gamma1, float* dbeta1, float* dgamma1, void* dx1,
+                      int64_t ldx1, const float* x2, const float* mean2, const float* rstd2, const float* gamma2,
+                      float* dbeta2, float* dgamma2, void* dx2, int64_t ldx2, int64_t M, int64_t C, int32_t remap,
+                      int32_t map_h, int32_t map_w, void* stream);
 RL_API int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C, int32_t W, int32_t H, int32_t P,
                           int32_t ntaps, const int8_t* tap_dw, const int8_t* tap_dh, const int8_t* tap_plane,
                           void* stream);
@@ -271,5 +279,21 @@ RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks
 RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                        float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
                        float grad_div, void* stream);
+/* GELU (erf form, transformers/modeling_bert.py:125-131) as element-wise passes next to the K = 768 GEMMs of
+ * BertIntermediate: h = u * Phi(u) over n bf16 elements; and its backward fused with the bias gradient:
+ * t[r, c] <- t[r, c] * gelu'(u[r, c]) in place (t = dy2 W2), dbias[c] += sum_r of the stored (bf16) result. */
+RL_API int rl_gelu_fwd(const void* u, void* h, int64_t n, void* stream);
+RL_API int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld, void* stream);
+
+/* Same update with the step's schedule read from device memory: hyper = {lr, 1 - beta1^t, 1 - beta2^t}.  Lets a
+ * CUDA graph that contains the optimizer be replayed while LambdaLR (src/run.py:153-160) and the bias corrections move. */
+RL_API int rl_mt_adamw_dev(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
+                           const float* hyper, float beta1, float beta2, float eps, float grad_div, void* stream);
+
+/* Dropout masks are pure functions of (seed, site, element).  With a non-NULL device counter registered here (process-
+ * wide), every dropout-bearing kernel launched afterwards uses seed + *dev_counter, read at run time: a captured CUDA
+ * graph of the whole train step draws fresh masks per replay by bumping the counter on the stream.  NULL switches back
+ * to the plain scalar seed (the mode the parity tests use with rl_dropout_mask). */
+RL_API int rl_set_dropout_seed_ptr(const uint64_t* dev_counter);
 
 #endif /* REALISE_B200_H */

@@ -2,12 +2,20 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<const unsigned long long*> g_seed_ptr{nullptr};  // process-wide: autograd runs backward on another thread
+}
+
+const unsigned long long* rl_dropout_seed_ptr() { return g_seed_ptr.load(std::memory_order_relaxed); }
+extern "C" int rl_set_dropout_seed_ptr(const uint64_t* dev_counter) {
+  g_seed_ptr.store(reinterpret_cast<const unsigned long long*>(dev_counter), std::memory_order_relaxed);
+  return 0;
 }
 
 void rl_set_error(const char* fmt, ...) {

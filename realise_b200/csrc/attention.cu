@@ -155,8 +155,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < 32; j += 4) sum += (e[j] + e[j + 1]) + (e[j + 2] + e[j + 3]);
     if (p.drop.thresh) {  // the row sum stays that of the undropped probabilities (softmax, then dropout)
       const unsigned long long e0 = (((unsigned long long)b * p.heads + head) * L + (q0 + r)) * L + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) e[j] = rl::drop_apply(p.drop, e0 + j, e[j]);
+      rl::DropSpec dsp = p.drop;
+      rl::drop_resolve(dsp);
+      rl::drop_apply32(dsp, e0, e);
     }
     // columns c*32 .. c*32+31 of P -> chunk tile (c/2), 16-byte pieces (c&1)*4 .. +3, swizzled by row
     uint8_t* tile = sP + (c >> 1) * Q_BYTES + (r >> 3) * 1024 + (r & 7) * 128;

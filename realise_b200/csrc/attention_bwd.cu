@@ -137,12 +137,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   }
   const float inv = r < L ? 1.0f / sum : 0.0f;  // query rows beyond the sentence contribute nothing to dK / dV
+  rl::DropSpec dsp = p.drop;
+  rl::drop_resolve(dsp);
   for (int c = 0; c < nchunk; ++c) {
     uint32_t v[32], w[32];
     rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
     rl::tmem_ld_32x32(t_row + COL_DP + c * 32, w);
     rl::tmem_ld_wait();
     float pr[32], ds[32];
+    unsigned int keep_bits = 0xFFFFFFFFu;
+    if (dsp.thresh) keep_bits = rl::drop_bits32(dsp, (((unsigned long long)b * p.heads + head) * L + r) * L + c * 32);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int col = c * 32 + j;
@@ -150,8 +154,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       pr[j] = rl::ex2(sc - mx) * inv;
       float dp = __uint_as_float(w[j]);  // gradient wrt the (dropped-out) probabilities
       if (p.drop.thresh) {
-        const unsigned long long e = (((unsigned long long)b * p.heads + head) * L + r) * L + col;
-        const bool keep = rl::drop_keep(p.drop.seed, p.drop.site, e, p.drop.thresh);
+        const bool keep = (keep_bits >> j) & 1u;
         dp = keep ? dp * p.drop.scale : 0.f;
         ds[j] = col < L ? pr[j] * (dp - delta) : 0.f;
         pr[j] = keep ? pr[j] * p.drop.scale : 0.f;  // the tile used for dV = P_drop^T dO

@@ -14,41 +14,51 @@ constexpr int MAX_V4 = 8;
 // (operand of the following weight/data-gradient GEMMs), and the column sums dgamma += sum dy*xhat,
 // dbeta += sum dy, dxsum += sum dx (bias gradient of the linear layer that produced x / type-embedding grad).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LNB_ROWS = 32;  // rows per CTA (8 warps x 4 rows)
-
-__global__ void __launch_bounds__(256)
+// Persistent layout: 3 CTAs per SM, each CTA owns a contiguous slab of rows (warp w takes rows w, w+8, ... of the
+// slab).  The three column partials (dgamma, dbeta, dxsum) of a warp live in that warp's PRIVATE shared-memory slice
+// ([3][NV][32 lanes] float4 = 9 KB at H = 768: plain LDS.128 / FADD / STS.128, no atomics — shared-memory float
+// atomics are CAS loops), which keeps the kernel at ~80 registers so that 24 warps per SM hide the HBM latency of
+// the row loads.  At the end the 8 slices are summed and flushed with one global atomic per column per CTA.
+template <int NV>
+__global__ void __launch_bounds__(256, 3)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ add_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int H,
-              float eps, rl::DropSpec drop_in, rl::DropSpec drop_out) {
-  extern __shared__ float s_part[];  // [8 warps][3][H]: per-warp column partials, no atomics
+              float eps, rl::DropSpec drop_in, rl::DropSpec drop_out, int rows_per_cta) {
+  extern __shared__ float4 s_acc4[];   // [8 warps][3][NV][32]
+  rl::drop_resolve(drop_in);
+  rl::drop_resolve(drop_out);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nv = H / 128;
-  float4 pg[MAX_V4], pb[MAX_V4], px[MAX_V4];
+  const int nv = NV < MAX_V4 ? NV : H / 128;
+  float4* mine = s_acc4 + (size_t)warp * 3 * NV * 32 + lane;
 #pragma unroll
-  for (int i = 0; i < MAX_V4; ++i) pg[i] = pb[i] = px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long row_begin = (long long)blockIdx.x * LNB_ROWS;
-  for (int rr = warp; rr < LNB_ROWS; rr += 8) {
+  for (int i = 0; i < 3 * NV; ++i) mine[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool want_g = dgamma != nullptr, want_b = dbeta != nullptr, want_x = dxsum != nullptr;
+  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+  for (int rr = warp; rr < rows_per_cta; rr += 8) {
     const long long row = row_begin + rr;
     if (row >= rows) break;
-    float4 xv[MAX_V4], gv[MAX_V4];
+    float4 xv[NV], gv[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i)
+    for (int i = 0; i < NV; ++i)
       if (i < nv) {
         xv[i] = reinterpret_cast<const float4*>(x + row * H)[i * 32 + lane];
         gv[i] = reinterpret_cast<const float4*>(dy + row * H)[i * 32 + lane];
+      }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i < nv) {
         if (drop_in.thresh) {  // the LN output went through dropout in the forward: dy_eff = dy * keep / (1-p)
           const long long e0 = row * H + (i * 32 + lane) * 4;
-          gv[i].x = rl::drop_apply(drop_in, e0, gv[i].x); gv[i].y = rl::drop_apply(drop_in, e0 + 1, gv[i].y);
-          gv[i].z = rl::drop_apply(drop_in, e0 + 2, gv[i].z); gv[i].w = rl::drop_apply(drop_in, e0 + 3, gv[i].w);
+          rl::drop_apply4(drop_in, e0, gv[i]);
         }
         s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
       }
     const float mean = rl::warp_sum(s) / (float)H;
     float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i)
+    for (int i = 0; i < NV; ++i)
       if (i < nv) {
         xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
         var += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
@@ -56,12 +66,21 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
     const float rstd = rsqrtf(rl::warp_sum(var) / (float)H + eps);
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i)
+    for (int i = 0; i < NV; ++i)
       if (i < nv) {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
         xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
-        pg[i].x += gv[i].x * xv[i].x; pg[i].y += gv[i].y * xv[i].y; pg[i].z += gv[i].z * xv[i].z; pg[i].w += gv[i].w * xv[i].w;
-        pb[i].x += gv[i].x; pb[i].y += gv[i].y; pb[i].z += gv[i].z; pb[i].w += gv[i].w;
+        if (want_g) {
+          float4 a = mine[i * 32];
+          a.x = fmaf(gv[i].x, xv[i].x, a.x); a.y = fmaf(gv[i].y, xv[i].y, a.y);
+          a.z = fmaf(gv[i].z, xv[i].z, a.z); a.w = fmaf(gv[i].w, xv[i].w, a.w);
+          mine[i * 32] = a;
+        }
+        if (want_b) {
+          float4 a = mine[(NV + i) * 32];
+          a.x += gv[i].x; a.y += gv[i].y; a.z += gv[i].z; a.w += gv[i].w;
+          mine[(NV + i) * 32] = a;
+        }
         gv[i].x *= gm.x; gv[i].y *= gm.y; gv[i].z *= gm.z; gv[i].w *= gm.w;  // g = dy * gamma
         m1 += gv[i].x + gv[i].y + gv[i].z + gv[i].w;
         m2 += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
@@ -69,7 +88,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
     m1 = rl::warp_sum(m1) / (float)H;
     m2 = rl::warp_sum(m2) / (float)H;
 #pragma unroll
-    for (int i = 0; i < MAX_V4; ++i)
+    for (int i = 0; i < NV; ++i)
       if (i < nv) {
         float4 d;
         d.x = rstd * (gv[i].x - m1 - xv[i].x * m2);
@@ -79,10 +98,13 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
         float4 dm = d;  // gradient of the producing linear layer's output: masked when that output was dropped out
         if (drop_out.thresh) {
           const long long e0 = row * H + (i * 32 + lane) * 4;
-          dm.x = rl::drop_apply(drop_out, e0, d.x); dm.y = rl::drop_apply(drop_out, e0 + 1, d.y);
-          dm.z = rl::drop_apply(drop_out, e0 + 2, d.z); dm.w = rl::drop_apply(drop_out, e0 + 3, d.w);
+          rl::drop_apply4(drop_out, e0, dm);
         }
-        px[i].x += dm.x; px[i].y += dm.y; px[i].z += dm.z; px[i].w += dm.w;
+        if (want_x) {
+          float4 a = mine[(2 * NV + i) * 32];
+          a.x += dm.x; a.y += dm.y; a.z += dm.z; a.w += dm.w;
+          mine[(2 * NV + i) * 32] = a;
+        }
         if (dx_bf16)
           reinterpret_cast<uint2*>(dx_bf16 + row * H)[i * 32 + lane] = make_uint2(rl::pack_bf16(dm.x, dm.y), rl::pack_bf16(dm.z, dm.w));
         if (add_in) {
@@ -92,29 +114,137 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
         if (dx) reinterpret_cast<float4*>(dx + row * H)[i * 32 + lane] = d;
       }
   }
-  // CTA-level reduction of the column partials (each warp owns a slice), then one global atomic per column
-  {
-    float* mine = s_part + (size_t)warp * 3 * H;
-#pragma unroll
-    for (int i = 0; i < MAX_V4; ++i)
-      if (i < nv) {
-        const int c = (i * 32 + lane) * 4;
-        *reinterpret_cast<float4*>(mine + c) = pg[i];
-        *reinterpret_cast<float4*>(mine + H + c) = pb[i];
-        *reinterpret_cast<float4*>(mine + 2 * H + c) = px[i];
-      }
-  }
   __syncthreads();
-  for (int c = threadIdx.x; c < 3 * H; c += blockDim.x) {
-    float t = 0.f;
+  // flush: float slot t of a slice = [which][i][lane][comp] -> column (i*32 + lane)*4 + comp
+  const float* s_f = reinterpret_cast<const float*>(s_acc4);
+  for (int t = threadIdx.x; t < 3 * NV * 128; t += 256) {
+    const int which = t / (NV * 128), u = t % (NV * 128);
+    if (u < H) {   // u == column
+      float tot = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_part[(size_t)w * 3 * H + c];
-    float* dst = c < H ? dgamma : (c < 2 * H ? dbeta : dxsum);
-    if (dst) atomicAdd(dst + (c % H), t);
+      for (int w = 0; w < 8; ++w) tot += s_f[w * 3 * NV * 128 + t];
+      float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+      if (dst) atomicAdd(dst + u, tot);
+    }
   }
 }
 
-// column sums of a bf16 [rows, cols] matrix (bias gradient): out[c] += sum_r x[r, c]
+// column sums of a bf16 [rows, cols] matrix (bias gradient): out[c] += sum_r x[r, c].
+// Vector path (cols, ld multiples of 8, 16-byte aligned base): a warp reads 512 contiguous bytes of one row (8 bf16
+// per lane), the 8 warps of the CTA take rows r, r+8, ... of the CTA's row slab, 4 rows in flight per warp.
+__global__ void __launch_bounds__(256)
+colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols, long long ld,
+                       int rows_per_cta) {
+  __shared__ float s[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols) {
+    const __nv_bfloat16* base = x + c0;
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(base + (r + 8 * u) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += rl::bf16_lo(v[u].x); acc[1] += rl::bf16_hi(v[u].x); acc[2] += rl::bf16_lo(v[u].y); acc[3] += rl::bf16_hi(v[u].y);
+        acc[4] += rl::bf16_lo(v[u].z); acc[5] += rl::bf16_hi(v[u].z); acc[6] += rl::bf16_lo(v[u].w); acc[7] += rl::bf16_hi(v[u].w);
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + r * ld);
+      acc[0] += rl::bf16_lo(v.x); acc[1] += rl::bf16_hi(v.x); acc[2] += rl::bf16_lo(v.y); acc[3] += rl::bf16_hi(v.y);
+      acc[4] += rl::bf16_lo(v.z); acc[5] += rl::bf16_hi(v.z); acc[6] += rl::bf16_lo(v.w); acc[7] += rl::bf16_hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GELU as stand-alone passes.  Inside a GEMM epilogue the erf polynomial is issued by 8 warps per SM and costs more
+// than the K = 768 main loop it should hide behind; as an element-wise pass every warp of the SM shares it and the
+// kernel runs at HBM speed.  gelu_fwd: h = u * Phi(u) (transformers/modeling_bert.py:125-131).
+// gelu_bwd_colsum: du = t * gelu'(u) in place over t (t = dy2 W2), and dbias[c] += sum_r du[r, c] (the bias gradient
+// of BertIntermediate.dense) in the same pass — same row-slab layout as colsum_bf16_vec_kernel.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(u)[i];
+  float x[8] = {rl::bf16_lo(v.x), rl::bf16_hi(v.x), rl::bf16_lo(v.y), rl::bf16_hi(v.y),
+                rl::bf16_lo(v.z), rl::bf16_hi(v.z), rl::bf16_lo(v.w), rl::bf16_hi(v.w)};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = rl::gelu_erf(x[j]);
+  reinterpret_cast<uint4*>(h)[i] =
+      make_uint4(rl::pack_bf16(x[0], x[1]), rl::pack_bf16(x[2], x[3]), rl::pack_bf16(x[4], x[5]), rl::pack_bf16(x[6], x[7]));
+}
+
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ u, float* __restrict__ dbias,
+                       long long rows, int cols, long long ld, int rows_per_cta) {
+  __shared__ float s[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols) {
+    for (long long r = r0 + warp; r < r1; r += 16) {
+      const bool two = r + 8 < r1;
+      const uint4 ta = *reinterpret_cast<const uint4*>(t + r * ld + c0);
+      const uint4 ua = *reinterpret_cast<const uint4*>(u + r * ld + c0);
+      uint4 tb = make_uint4(0, 0, 0, 0), ub = tb;
+      if (two) {
+        tb = *reinterpret_cast<const uint4*>(t + (r + 8) * ld + c0);
+        ub = *reinterpret_cast<const uint4*>(u + (r + 8) * ld + c0);
+      }
+      const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+      const uint32_t uw[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+      uint32_t ow[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        // the products are rounded to bf16 first: the column sum must be that of the stored du (what dW1 sees)
+        const uint32_t pk = rl::pack_bf16(rl::bf16_lo(tw[k]) * rl::gelu_grad(rl::bf16_lo(uw[k])),
+                                          rl::bf16_hi(tw[k]) * rl::gelu_grad(rl::bf16_hi(uw[k])));
+        ow[k] = pk;
+        acc[(k & 3) * 2] += rl::bf16_lo(pk);
+        acc[(k & 3) * 2 + 1] += rl::bf16_hi(pk);
+      }
+      *reinterpret_cast<uint4*>(t + r * ld + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      if (two) *reinterpret_cast<uint4*>(t + (r + 8) * ld + c0) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols && dbias) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s[w][threadIdx.x];
+    atomicAdd(dbias + c, tot);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols, long long ld) {
   // block = 32 columns x 8 row-groups; grid = (cols/32 rounded up, row chunks)
@@ -153,9 +283,23 @@ ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
   const float lse = row_lse[row];
   const int t = (int)tgt[row];
   const float* x = logits + row * ld;
-  for (int j = threadIdx.x; j < (int)ldd; j += blockDim.x) {
+  int j0 = 0;
+  if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {   // 8 logits -> one 16-byte bf16 store
+    const int V8 = V >> 3;
+    for (int g = threadIdx.x; g < V8; g += blockDim.x) {
+      const float4 a = reinterpret_cast<const float4*>(x)[2 * g], b = reinterpret_cast<const float4*>(x)[2 * g + 1];
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = coef * __expf(v[k] - lse);
+      if ((t >> 3) == g) v[t & 7] -= coef;
+      *reinterpret_cast<uint4*>(d + 8 * g) =
+          make_uint4(rl::pack_bf16(v[0], v[1]), rl::pack_bf16(v[2], v[3]), rl::pack_bf16(v[4], v[5]), rl::pack_bf16(v[6], v[7]));
+    }
+    j0 = V8 * 8;
+  }
+  for (int j = j0 + threadIdx.x; j < (int)ldd; j += blockDim.x) {
     float v = 0.f;
-    if (j < V) v = coef * (expf(x[j] - lse) - (j == t ? 1.0f : 0.0f));
+    if (j < V) v = coef * (__expf(x[j] - lse) - (j == t ? 1.0f : 0.0f));
     d[j] = __float2bfloat16(v);
   }
 }
@@ -352,7 +496,13 @@ mt_sumsq_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ ch
 
 __global__ void __launch_bounds__(256)
 mt_adamw_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ chunks, const float* __restrict__ sumsq,
-                float max_norm, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_div) {
+                float max_norm, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_div,
+                const float* __restrict__ hyper) {
+  if (hyper) {  // device-resident schedule (CUDA-graph replay): {lr, 1 - beta1^t, 1 - beta2^t}
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2 = hyper[2];
+  }
   const int2 ck = chunks[blockIdx.x];
   const TensorEntry e = tab[ck.x];
   const long long base = (long long)ck.y * OPT_CHUNK;
@@ -392,23 +542,71 @@ extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* ga
   RL_REQUIRE(dy && x && gamma && (dx || dx_bf16), RL_EINVAL, "rl_layernorm_bwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_bwd: bad H");
   if (rows <= 0) return 0;
+  // 8 rows per CTA at least (one per warp); at most 3 CTAs per SM
+  const long long max_ctas = 3LL * rl_num_sms();
+  long long ctas = (rows + 7) / 8;
+  if (ctas > max_ctas) ctas = max_ctas;
+  const int rows_per_cta = (int)((rows + ctas - 1) / ctas);
+  ctas = (rows + rows_per_cta - 1) / rows_per_cta;
+  const rl::DropSpec din = rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in);
+  const rl::DropSpec dout = rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * (int)sizeof(float));
+    cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 6 * 512);
+    cudaFuncSetAttribute(ln_bwd_kernel<MAX_V4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * MAX_V4 * 512);
     configured = true;
   }
-  ln_bwd_kernel<<<(unsigned)((rows + LNB_ROWS - 1) / LNB_ROWS), 256, 8 * 3 * H * sizeof(float), (cudaStream_t)stream>>>(
-      dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps,
-      rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in), rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out));
+  if (H == 768)
+    ln_bwd_kernel<6><<<(unsigned)ctas, 256, 8 * 3 * 6 * 512, (cudaStream_t)stream>>>(
+        dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps, din, dout, rows_per_cta);
+  else
+    ln_bwd_kernel<MAX_V4><<<(unsigned)ctas, 256, 8 * 3 * MAX_V4 * 512, (cudaStream_t)stream>>>(
+        dy, x, gamma, add_in, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, dxsum, rows, (int)H, eps, din, dout, rows_per_cta);
   return rl_check_launch("rl_layernorm_bwd");
 }
 
 extern "C" int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream) {
   RL_REQUIRE(x && out && cols > 0 && ld >= cols, RL_EINVAL, "rl_colsum_bf16: bad arguments");
   if (rows <= 0) return 0;
+  if (cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+    const long long col_blocks = (cols + 255) / 256;
+    long long row_chunks = (8LL * rl_num_sms() + col_blocks - 1) / col_blocks;   // ~8 CTAs per SM in total
+    if (row_chunks > (rows + 63) / 64) row_chunks = (rows + 63) / 64;
+    if (row_chunks < 1) row_chunks = 1;
+    const int rows_per_cta = (int)((rows + row_chunks - 1) / row_chunks);
+    row_chunks = (rows + rows_per_cta - 1) / rows_per_cta;
+    dim3 grid((unsigned)col_blocks, (unsigned)row_chunks);
+    colsum_bf16_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, (int)cols, ld, rows_per_cta);
+    return rl_check_launch("rl_colsum_bf16");
+  }
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 1023) / 1024));
   colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, (int)cols, ld);
   return rl_check_launch("rl_colsum_bf16");
+}
+
+extern "C" int rl_gelu_fwd(const void* u, void* h, int64_t n, void* stream) {
+  RL_REQUIRE(u && h && n >= 0 && n % 8 == 0 && (((uintptr_t)u | (uintptr_t)h) & 15) == 0, RL_EALIGN,
+             "rl_gelu_fwd: n must be a multiple of 8 and the pointers 16-byte aligned");
+  if (n == 0) return 0;
+  const long long n8 = n / 8;
+  gelu_fwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)u, (__nv_bfloat16*)h, n8);
+  return rl_check_launch("rl_gelu_fwd");
+}
+
+extern "C" int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld, void* stream) {
+  RL_REQUIRE(t && u && cols > 0 && ld >= cols && cols % 8 == 0 && ld % 8 == 0 && (((uintptr_t)t | (uintptr_t)u) & 15) == 0,
+             RL_EALIGN, "rl_gelu_bwd_colsum: cols / ld must be multiples of 8 and the pointers 16-byte aligned");
+  if (rows <= 0) return 0;
+  const long long col_blocks = (cols + 255) / 256;
+  long long row_chunks = (8LL * rl_num_sms() + col_blocks - 1) / col_blocks;
+  if (row_chunks > (rows + 63) / 64) row_chunks = (rows + 63) / 64;
+  if (row_chunks < 1) row_chunks = 1;
+  const int rows_per_cta = (int)((rows + row_chunks - 1) / row_chunks);
+  row_chunks = (rows + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid((unsigned)col_blocks, (unsigned)row_chunks);
+  gelu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)t, (const __nv_bfloat16*)u, dbias, rows, (int)cols,
+                                                                ld, rows_per_cta);
+  return rl_check_launch("rl_gelu_bwd_colsum");
 }
 
 extern "C" int rl_masked_ce_bwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, const float* row_lse,
@@ -472,6 +670,15 @@ extern "C" int rl_mt_adamw(const void* table, const void* chunks, int64_t num_ch
   if (num_chunks <= 0) return 0;
   mt_adamw_kernel<<<(unsigned)num_chunks, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, sumsq,
                                                                         max_norm, lr, beta1, beta2, eps, bias_corr1,
-                                                                        bias_corr2, grad_div);
+                                                                        bias_corr2, grad_div, nullptr);
   return rl_check_launch("rl_mt_adamw");
+}
+
+extern "C" int rl_mt_adamw_dev(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
+                               const float* hyper, float beta1, float beta2, float eps, float grad_div, void* stream) {
+  RL_REQUIRE(table && chunks && sumsq && hyper, RL_EINVAL, "rl_mt_adamw_dev: null pointer");
+  if (num_chunks <= 0) return 0;
+  mt_adamw_kernel<<<(unsigned)num_chunks, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, sumsq,
+                                                                        max_norm, 0.f, beta1, beta2, eps, 1.f, 1.f, grad_div, hyper);
+  return rl_check_launch("rl_mt_adamw_dev");
 }

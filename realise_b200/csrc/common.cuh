@@ -14,6 +14,7 @@
 void rl_set_error(const char* fmt, ...);
 int rl_check_launch(const char* what);  // returns 0 or positive cudaError_t
 int rl_num_sms();
+const unsigned long long* rl_dropout_seed_ptr();   // process-wide, set by rl_set_dropout_seed_ptr (NULL = off)
 
 #define RL_REQUIRE(cond, code, ...)    \
   do {                                 \
@@ -242,18 +243,25 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 // Counter-based dropout mask: keep(seed, site, idx) is a pure function, so the backward kernels regenerate
-// exactly the mask the forward used.  splitmix64 finalizer over (seed, site, element index); an element is
-// dropped when the low 32 bits fall below thresh = p * 2^32.
-__host__ __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned int site, unsigned long long idx,
-                                                   unsigned int thresh) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)site + 1ull) + idx * 0xD1342543DE82EF95ull;
+// exactly the mask the forward used.  One splitmix64 finalizer over (seed, site, idx / 4) yields four 16-bit
+// lanes, one per element of an aligned group of 4; an element is dropped when its lane falls below
+// thresh = round(p * 2^16) (p = 0.1 -> 0.100006).  Kernels that walk aligned groups hash once per 4 elements.
+__host__ __device__ __forceinline__ unsigned long long drop_hash4(unsigned long long seed, unsigned int site,
+                                                                  unsigned long long idx4) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)site + 1ull) + idx4 * 0xD1342543DE82EF95ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (unsigned int)z >= thresh;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned int site, unsigned long long idx,
+                                                   unsigned int thresh) {
+  const unsigned long long h = drop_hash4(seed, site, idx >> 2);
+  return ((unsigned int)(h >> ((unsigned int)(idx & 3ull) * 16u)) & 0xFFFFu) >= thresh;
 }
 struct DropSpec {   // passed by value to kernels; thresh == 0 means "no dropout"
   unsigned long long seed;
+  const unsigned long long* seed_ptr;   // optional device-resident step counter added to `seed` at run time, so that a
+                                        // captured CUDA graph draws fresh masks on every replay (rl_set_dropout_seed_ptr)
   unsigned int site;
   unsigned int thresh;
   float scale;      // 1 / (1 - p)
@@ -261,15 +269,95 @@ struct DropSpec {   // passed by value to kernels; thresh == 0 means "no dropout
 __host__ __device__ __forceinline__ DropSpec make_drop(float p, unsigned long long seed, unsigned int site) {
   DropSpec d;
   d.seed = seed;
+#ifndef __CUDA_ARCH__
+  d.seed_ptr = rl_dropout_seed_ptr();
+#else
+  d.seed_ptr = nullptr;
+#endif
   d.site = site;
-  d.thresh = p > 0.f ? (unsigned int)(p * 4294967296.0) : 0u;
+  d.thresh = p > 0.f ? (unsigned int)(p * 65536.0 + 0.5) : 0u;
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   return d;
+}
+// Effective seed of a launch: kernels call this ONCE (per thread) and keep the result in `seed`.
+__device__ __forceinline__ void drop_resolve(DropSpec& d) {
+  if (d.thresh != 0u && d.seed_ptr != nullptr) d.seed += __ldg(d.seed_ptr);
+  d.seed_ptr = nullptr;
 }
 __device__ __forceinline__ float drop_apply(const DropSpec& d, unsigned long long idx, float x) {
   if (d.thresh == 0u) return x;
   return drop_keep(d.seed, d.site, idx, d.thresh) ? x * d.scale : 0.0f;
 }
+
+// 4 consecutive elements starting at e0 (e0 % 4 == 0): one hash
+__device__ __forceinline__ void drop_apply4(const DropSpec& d, unsigned long long e0, float4& v) {
+  if (d.thresh == 0u) return;
+  const unsigned long long h = drop_hash4(d.seed, d.site, e0 >> 2);
+  const unsigned int lo = (unsigned int)h, hi = (unsigned int)(h >> 32);
+  v.x = (lo & 0xFFFFu) >= d.thresh ? v.x * d.scale : 0.f;
+  v.y = (lo >> 16) >= d.thresh ? v.y * d.scale : 0.f;
+  v.z = (hi & 0xFFFFu) >= d.thresh ? v.z * d.scale : 0.f;
+  v.w = (hi >> 16) >= d.thresh ? v.w * d.scale : 0.f;
+}
+// 32 consecutive elements starting at e0: 8 hashes when e0 % 4 == 0, per-element otherwise
+__device__ __forceinline__ void drop_apply32(const DropSpec& d, unsigned long long e0, float (&x)[32]) {
+  if (d.thresh == 0u) return;
+  if ((e0 & 3ull) == 0ull) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const unsigned long long h = drop_hash4(d.seed, d.site, (e0 >> 2) + g);
+      const unsigned int lo = (unsigned int)h, hi = (unsigned int)(h >> 32);
+      x[4 * g] = (lo & 0xFFFFu) >= d.thresh ? x[4 * g] * d.scale : 0.f;
+      x[4 * g + 1] = (lo >> 16) >= d.thresh ? x[4 * g + 1] * d.scale : 0.f;
+      x[4 * g + 2] = (hi & 0xFFFFu) >= d.thresh ? x[4 * g + 2] * d.scale : 0.f;
+      x[4 * g + 3] = (hi >> 16) >= d.thresh ? x[4 * g + 3] * d.scale : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = drop_keep(d.seed, d.site, e0 + j, d.thresh) ? x[j] * d.scale : 0.f;
+  }
+}
+// keep bits (bit j = element e0 + j kept) of 32 consecutive elements
+__device__ __forceinline__ unsigned int drop_bits32(const DropSpec& d, unsigned long long e0) {
+  unsigned int bits = 0u;
+  if ((e0 & 3ull) == 0ull) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const unsigned long long h = drop_hash4(d.seed, d.site, (e0 >> 2) + g);
+      const unsigned int lo = (unsigned int)h, hi = (unsigned int)(h >> 32);
+      bits |= ((lo & 0xFFFFu) >= d.thresh ? 1u : 0u) << (4 * g);
+      bits |= ((lo >> 16) >= d.thresh ? 1u : 0u) << (4 * g + 1);
+      bits |= ((hi & 0xFFFFu) >= d.thresh ? 1u : 0u) << (4 * g + 2);
+      bits |= ((hi >> 16) >= d.thresh ? 1u : 0u) << (4 * g + 3);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bits |= (drop_keep(d.seed, d.site, e0 + j, d.thresh) ? 1u : 0u) << j;
+  }
+  return bits;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result)
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float y = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + fast_erf(u * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  return fmaf(u, pdf, cdf);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -43,25 +43,8 @@ struct KParams {
   int dbg;        // tuning experiments only: 1 = no epilogue work, 2 = no TMA loads, 4 = no MMA
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result)
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float y = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(y, x);
-}
-
-// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
-__device__ __forceinline__ float gelu_grad(float u) {
-  const float cdf = 0.5f * (1.0f + fast_erf(u * 0.70710678118654752440f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
-  return fmaf(u, pdf, cdf);
-}
+using rl::fast_erf;
+using rl::gelu_grad;
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == RL_ACT_GELU) return x * 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f));
@@ -186,8 +169,9 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         }
         if (p.drop.thresh) {
           const unsigned long long e0 = (unsigned long long)row * p.N + nb;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = rl::drop_apply(p.drop, e0 + j, x[j]);
+          rl::DropSpec dsp = p.drop;
+          rl::drop_resolve(dsp);
+          rl::drop_apply32(dsp, e0, x);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] += xr[j];

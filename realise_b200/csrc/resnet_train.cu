@@ -192,6 +192,249 @@ bn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32, const void* __restr
       make_uint4(rl::pack_bf16(o[0], o[1]), rl::pack_bf16(o[2], o[3]), rl::pack_bf16(o[4], o[5]), rl::pack_bf16(o[6], o[7]));
 }
 
+
+// ---- vectorised variants (C % 8 == 0, dense rows): 8 channels per lane, a warp spans min(C, 256) channels --------
+// lanes_per_row = min(32, C/8) (a power of two); a warp covers 32/lanes_per_row consecutive rows per iteration and the
+// CTA's 8 warps stride through the CTA's row slab.  Column partials stay in registers for the whole slab; one smem
+// reduction over the 8 warps and one atomic per (lane-column) at the end.
+__device__ __forceinline__ void load8(const void* p, int is_f32, long long i, float (&v)[8]) { load_raw8(p, is_f32, i, v); }
+
+__global__ void __launch_bounds__(256)
+bn_stats_vec_kernel(const float* __restrict__ x, float* __restrict__ sums, long long M, int C, int lpr_shift, int rows_per_cta) {
+  __shared__ float s1[8][256], s2[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
+  const int col = blockIdx.x * 256 + (lane & (lpr - 1)) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  const int step = 8 * rpw;
+  long long r = r0 + warp * rpw + (lane >> lpr_shift);
+  for (; r + step < r1; r += 2 * step) {
+    float v[8], w[8];
+    load_raw8(x, 1, r * C + col, v);
+    load_raw8(x, 1, (r + step) * C + col, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] += v[j] + w[j];
+      b[j] = fmaf(v[j], v[j], fmaf(w[j], w[j], b[j]));
+    }
+  }
+  for (; r < r1; r += step) {
+    float v[8];
+    load_raw8(x, 1, r * C + col, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] += v[j];
+      b[j] = fmaf(v[j], v[j], b[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[warp][lane * 8 + j] = a[j];
+    s2[warp][lane * 8 + j] = b[j];
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    t1 += s1[w][t];
+    t2 += s2[w][t];
+  }
+  const int c = blockIdx.x * 256 + ((t >> 3) & (lpr - 1)) * 8 + (t & 7);
+  atomicAdd(sums + c, t1);
+  atomicAdd(sums + C + c, t2);
+}
+
+struct BnBranch {          // one BatchNorm whose output fed the (shared) ReLU
+  const float* x;          // raw conv output [M, C] f32, plain rows
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  float* dbeta;
+  float* dgamma;
+  __nv_bfloat16* dx;       // [M, ldx] bf16, plain rows
+  long long ldx;
+};
+
+// reduce: dbeta = sum g, dgamma = rstd * (sum g*x - mean * sum g) — mean/rstd are applied once at the end, so the loop
+// carries only 8 * (1 + NB) accumulators (4 CTAs per SM); two row groups in flight per warp.
+template <int NB>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
+                         BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
+  __shared__ float sm[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
+  const int col = blockIdx.x * 256 + (lane & (lpr - 1)) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float sg[8], sx[NB][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sg[j] = 0.f;
+    sx[0][j] = 0.f;
+    if (NB == 2) sx[NB - 1][j] = 0.f;
+  }
+  const int step = 8 * rpw;
+  long long r = r0 + warp * rpw + (lane >> lpr_shift);
+  for (; r + step < r1; r += 2 * step) {
+    const long long ra = r, rb = r + step;
+    const long long da = remap ? split_row(ra, hw_shift, w_shift) : ra, db = remap ? split_row(rb, hw_shift, w_shift) : rb;
+    float ga[8], gb[8], xa[8], xb[8];
+    load8(dy, dy_f32, da * C + col, ga);
+    load8(dy, dy_f32, db * C + col, gb);
+    if (act_out) {
+      float aa[8], ab[8];
+      load8(act_out, act_f32, da * C + col, aa);
+      load8(act_out, act_f32, db * C + col, ab);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ga[j] = aa[j] > 0.f ? ga[j] : 0.f;
+        gb[j] = ab[j] > 0.f ? gb[j] : 0.f;
+      }
+    }
+    load_raw8(b0.x, 1, ra * C + col, xa);
+    load_raw8(b0.x, 1, rb * C + col, xb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sg[j] += ga[j] + gb[j];
+      sx[0][j] = fmaf(ga[j], xa[j], fmaf(gb[j], xb[j], sx[0][j]));
+    }
+    if (NB == 2) {
+      load_raw8(b1.x, 1, ra * C + col, xa);
+      load_raw8(b1.x, 1, rb * C + col, xb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sx[NB - 1][j] = fmaf(ga[j], xa[j], fmaf(gb[j], xb[j], sx[NB - 1][j]));
+    }
+  }
+  for (; r < r1; r += step) {
+    const long long dr = remap ? split_row(r, hw_shift, w_shift) : r;
+    float g[8], xv[8];
+    load8(dy, dy_f32, dr * C + col, g);
+    if (act_out) {
+      float a[8];
+      load8(act_out, act_f32, dr * C + col, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+    }
+    load_raw8(b0.x, 1, r * C + col, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sg[j] += g[j];
+      sx[0][j] = fmaf(g[j], xv[j], sx[0][j]);
+    }
+    if (NB == 2) {
+      load_raw8(b1.x, 1, r * C + col, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sx[NB - 1][j] = fmaf(g[j], xv[j], sx[NB - 1][j]);
+    }
+  }
+  const int t = threadIdx.x;
+  const int c = blockIdx.x * 256 + ((t >> 3) & (lpr - 1)) * 8 + (t & 7);
+  float tot_g = 0.f;
+#pragma unroll
+  for (int q = 0; q < 1 + NB; ++q) {
+    if (q) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[warp][lane * 8 + j] = q == 0 ? sg[j] : sx[q - 1][j];
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sm[w][t];
+    if (q == 0) {
+      tot_g = tot;
+      atomicAdd(b0.dbeta + c, tot);
+      if (NB == 2) atomicAdd(b1.dbeta + c, tot);
+    } else {
+      const BnBranch& b = q == 1 ? b0 : b1;
+      atomicAdd(b.dgamma + c, b.rstd[c] * (tot - b.mean[c] * tot_g));
+    }
+  }
+}
+
+// apply: dx = A*g + B*x + D per channel with A = gamma*rstd, B = -gamma*rstd^2*dgamma/M,
+// D = gamma*rstd*(mean*rstd*dgamma/M - dbeta/M): the per-channel coefficients are derived once per thread (it owns 8
+// channels and walks the rows of its slab), so the row loop is 4 vector loads, 2 vector stores and 6 FMAs per channel.
+template <int NB>
+__global__ void __launch_bounds__(256, NB == 2 ? 3 : 4)
+bn_bwd_apply_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
+                        BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
+  const int col = blockIdx.x * 256 + (lane & (lpr - 1)) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  const float invM = 1.0f / (float)M;
+  float A[NB][8], Bc[NB][8], D[NB][8];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const BnBranch& b = q == 0 ? b0 : b1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float rs = b.rstd[col + j], mu = b.mean[col + j], gm = b.gamma[col + j];
+      const float dg = b.dgamma[col + j] * invM, db = b.dbeta[col + j] * invM;
+      A[q][j] = gm * rs;
+      Bc[q][j] = -gm * rs * rs * dg;
+      D[q][j] = gm * rs * (mu * rs * dg - db);
+    }
+  }
+  const int step = 8 * rpw;
+  for (long long r = r0 + warp * rpw + (lane >> lpr_shift); r < r1; r += step) {
+    const long long dr = remap ? split_row(r, hw_shift, w_shift) : r;
+    float g[8], xv[NB][8];
+    load8(dy, dy_f32, dr * C + col, g);
+    load_raw8(b0.x, 1, r * C + col, xv[0]);
+    if (NB == 2) load_raw8(b1.x, 1, r * C + col, xv[NB - 1]);
+    if (act_out) {
+      float a[8];
+      load8(act_out, act_f32, dr * C + col, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const BnBranch& b = q == 0 ? b0 : b1;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[q][j], g[j], fmaf(Bc[q][j], xv[q][j], D[q][j]));
+      *reinterpret_cast<uint4*>(b.dx + r * b.ldx + col) =
+          make_uint4(rl::pack_bf16(o[0], o[1]), rl::pack_bf16(o[2], o[3]), rl::pack_bf16(o[4], o[5]), rl::pack_bf16(o[6], o[7]));
+    }
+  }
+}
+
+// vector-path geometry for a [M, C] matrix: lanes per row (log2) or -1 when C does not fit the scheme
+int vec_lpr_shift(long long C) {
+  if (C % 8) return -1;
+  if (C >= 256) return (C % 256 == 0) ? 5 : -1;
+  const int l = (int)(C / 8);
+  if (l & (l - 1)) return -1;
+  int s = 0;
+  while ((1 << s) < l) ++s;
+  return s;
+}
+
+void vec_grid(long long M, long long C, int lpr_shift, dim3* grid, int* rows_per_cta) {
+  const long long col_blocks = (C + 255) / 256;
+  const int rows_per_iter = 8 * (32 >> lpr_shift);
+  long long chunks = (6LL * rl_num_sms() + col_blocks - 1) / col_blocks;
+  const long long max_chunks = (M + 4 * rows_per_iter - 1) / (4 * rows_per_iter);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  long long rpc = (M + chunks - 1) / chunks;
+  rpc = (rpc + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
+  chunks = (M + rpc - 1) / rpc;
+  *rows_per_cta = (int)rpc;
+  *grid = dim3((unsigned)col_blocks, (unsigned)chunks);
+}
+
 // ---- im2col for weight gradients: col[m, t*C + ci] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] (0 outside) ------
 // so that dW[co, t, ci] = sum_m dY[m, co] * col[m, t*C + ci] is one plain (split-K) GEMM; the small result is
 // permuted to the reference's [co, ci, kh, kw] layout afterwards.
@@ -269,6 +512,14 @@ int ilog2x(int v) {
 
 extern "C" int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t M, int64_t C, int64_t ld, void* stream) {
   RL_REQUIRE(x && sums && M > 0 && C > 0 && ld >= C, RL_EINVAL, "rl_bn_stats: bad arguments");
+  const int ls = vec_lpr_shift(C);
+  if (x_dtype == RL_DT_F32 && ld == C && ls >= 0 && ((uintptr_t)x & 15) == 0) {
+    dim3 vg;
+    int rpc;
+    vec_grid(M, C, ls, &vg, &rpc);
+    bn_stats_vec_kernel<<<vg, 256, 0, (cudaStream_t)stream>>>((const float*)x, sums, M, (int)C, ls, rpc);
+    return rl_check_launch("rl_bn_stats");
+  }
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
   bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == RL_DT_F32, sums, M, (int)C, ld);
   return rl_check_launch("rl_bn_stats");
@@ -303,6 +554,46 @@ extern "C" int rl_bn_apply(const void* x1, const float* scale1, const float* shi
   return rl_check_launch("rl_bn_apply");
 }
 
+extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const float* x1,
+                          const float* mean1, const float* rstd1, const float* gamma1, float* dbeta1, float* dgamma1, void* dx1,
+                          int64_t ldx1, const float* x2, const float* mean2, const float* rstd2, const float* gamma2,
+                          float* dbeta2, float* dgamma2, void* dx2, int64_t ldx2, int64_t M, int64_t C, int32_t remap,
+                          int32_t map_h, int32_t map_w, void* stream) {
+  RL_REQUIRE(dy && x1 && mean1 && rstd1 && gamma1 && dbeta1 && dgamma1 && dx1 && M > 0 && C > 0 && ldx1 >= C && ldx1 % 8 == 0,
+             RL_EINVAL, "rl_bn_bwd2: bad arguments");
+  RL_REQUIRE(!x2 || (mean2 && rstd2 && gamma2 && dbeta2 && dgamma2 && dx2 && ldx2 >= C && ldx2 % 8 == 0), RL_EINVAL,
+             "rl_bn_bwd2: incomplete second branch");
+  const int ls = vec_lpr_shift(C);
+  RL_REQUIRE(ls >= 0, RL_EINVAL, "rl_bn_bwd2: C must be 8*2^k (< 256) or a multiple of 256");
+  RL_REQUIRE((((uintptr_t)dy | (uintptr_t)x1 | (uintptr_t)dx1 | (uintptr_t)x2 | (uintptr_t)dx2 | (uintptr_t)act_out) & 15) == 0,
+             RL_EALIGN, "rl_bn_bwd2: pointers must be 16-byte aligned");
+  int hs = 0, ws = 0;
+  if (remap) {
+    hs = ilog2x(map_h);
+    ws = ilog2x(map_w);
+    RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_bwd2: parity split needs a power-of-two map >= 2x2");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  BnBranch b0{x1, mean1, rstd1, gamma1, dbeta1, dgamma1, (__nv_bfloat16*)dx1, ldx1};
+  BnBranch b1{x2, mean2, rstd2, gamma2, dbeta2, dgamma2, (__nv_bfloat16*)dx2, ldx2};
+  dim3 vg;
+  int rpc;
+  vec_grid(M, C, ls, &vg, &rpc);
+  const int df = dy_dtype == RL_DT_F32, af = act_dtype == RL_DT_F32;
+  if (x2) {
+    bn_bwd_reduce_vec_kernel<2><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
+    int rc = rl_check_launch("rl_bn_bwd2(reduce)");
+    if (rc) return rc;
+    bn_bwd_apply_vec_kernel<2><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
+  } else {
+    bn_bwd_reduce_vec_kernel<1><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
+    int rc = rl_check_launch("rl_bn_bwd2(reduce)");
+    if (rc) return rc;
+    bn_bwd_apply_vec_kernel<1><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
+  }
+  return rl_check_launch("rl_bn_bwd2");
+}
+
 extern "C" int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const void* x,
                          int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
                          int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream) {
@@ -315,6 +606,10 @@ extern "C" int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, 
     RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_bwd: parity split needs a power-of-two map >= 2x2");
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == RL_DT_F32 && vec_lpr_shift(C) >= 0 && ldx % 8 == 0 && (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0 &&
+      (!act_out || ((uintptr_t)act_out & 15) == 0))
+    return rl_bn_bwd2(dy, dy_dtype, act_out, act_dtype, (const float*)x, mean, rstd, gamma, dbeta, dgamma, dx, ldx, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, remap, map_h, map_w, stream);
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, dy_dtype == RL_DT_F32, act_out, act_dtype == RL_DT_F32, x, x_dtype == RL_DT_F32,
                                              mean, rstd, dbeta, dgamma, M, (int)C, remap, hs + ws, ws);

@@ -23,8 +23,8 @@ __device__ __forceinline__ void ln_row_store(const float4* x, int nv, float mean
       y.w = (x[i].w - mean) * rstd * g.w + b.w;
       float4 yd = y;
       if (drop.thresh) {  // dropout after the LayerNorm (BertEmbeddings.forward :192, src/models.py:858)
-        yd.x = rl::drop_apply(drop, elem0 + col, y.x); yd.y = rl::drop_apply(drop, elem0 + col + 1, y.y);
-        yd.z = rl::drop_apply(drop, elem0 + col + 2, y.z); yd.w = rl::drop_apply(drop, elem0 + col + 3, y.w);
+        yd = y;
+        rl::drop_apply4(drop, elem0 + col, yd);
       }
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = drop_f32 ? yd : y;
       if (out_bf16)
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float* out_f32,
                                                         __nv_bfloat16* out_bf16, long long rows, int H, float eps,
                                                         rl::DropSpec drop, int drop_f32) {
+  rl::drop_resolve(drop);
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -78,6 +79,7 @@ embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ wor
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* out_f32, __nv_bfloat16* out_bf16, float* pre_out, long long rows,
                 int L, int H, int pos_mode, float eps, rl::DropSpec drop) {
+  rl::drop_resolve(drop);
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -202,30 +204,50 @@ ce_row_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
     return;
   }
   const float* x = logits + row * ld;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
-  mx = rl::warp_max(mx);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  // one pass, online softmax: running (max, sum of exp) per thread, float4 loads when the row is 16-byte aligned
+  float mx = -INFINITY, s = 0.f;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int V4 = vec ? (V >> 2) : 0;
+  for (int i = threadIdx.x; i < V4; i += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (m4 > mx) {
+      s *= __expf(mx - m4);
+      mx = m4;
+    }
+    s += (__expf(v.x - mx) + __expf(v.y - mx)) + (__expf(v.z - mx) + __expf(v.w - mx));
+  }
+  for (int i = V4 * 4 + threadIdx.x; i < V; i += blockDim.x) {
+    const float v = x[i];
+    if (v > mx) {
+      s *= __expf(mx - v);
+      mx = v;
+    }
+    s += __expf(v - mx);
+  }
+  // combine (max, sum) pairs: warp shuffle, then the 8 warp results
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, mx, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float m = fmaxf(mx, m2);
+    s = (mx == -INFINITY ? 0.f : s * __expf(mx - m)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - m));
+    mx = m;
+  }
+  __shared__ float s_sum[8];
+  if ((threadIdx.x & 31) == 0) {
+    s_red[threadIdx.x >> 5] = mx;
+    s_sum[threadIdx.x >> 5] = s;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = s_red[0];
     for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
-    s_bc = m;
-  }
-  __syncthreads();
-  mx = s_bc;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - mx);
-  s = rl::warp_sum(s);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += s_red[w];
-    const float lse = logf(t) + mx;
+    for (int w = 0; w < 8; ++w) t += s_red[w] == -INFINITY ? 0.f : s_sum[w] * __expf(s_red[w] - m);
+    const float lse = logf(t) + m;
     if (row_lse) row_lse[row] = lse;
     row_loss[row] = lse - x[tgt[row]];
+    s_bc = lse;
   }
 }
 
@@ -298,6 +320,7 @@ argmax_rows_kernel(const float* __restrict__ logits, long long* __restrict__ out
 }
 
 __global__ void __launch_bounds__(256) dropout_mask_kernel(unsigned char* out, long long n, rl::DropSpec d) {
+  rl::drop_resolve(d);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (d.thresh == 0u || rl::drop_keep(d.seed, d.site, (unsigned long long)i, d.thresh)) ? 1 : 0;
 }

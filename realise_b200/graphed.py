@@ -1,0 +1,108 @@
+"""One optimizer step as ONE CUDA-graph replay.
+
+The reference's loop body (src/run.py:186-212) is
+
+    loss = model(batch)[0]; loss.backward(); clip_grad_norm_(...); optimizer.step(); scheduler.step(); model.zero_grad()
+
+i.e. ~700 kernel launches per step on this implementation; issued one by one from Python they cost about as much
+host time as the GPU needs to run them.  `GraphedTrainStep` captures forward + backward + (data-parallel gradient
+all-reduce) + clip + AdamW of one batch shape once and replays it:
+
+    step = GraphedTrainStep(model, optimizer)          # optimizer = realise_b200.optim.FusedAdamW(model=model)
+    for batch in loader:
+        loss = step(batch)                             # device scalar (static buffer); .item() when needed
+        scheduler.step()                               # LambdaLR keeps working: lr is re-read before every replay
+
+What makes the capture replayable:
+  * dropout masks are counter based; the kernels add a device-resident step counter to their seed
+    (rl_set_dropout_seed_ptr), and the graph itself increments that counter, so every replay draws fresh masks;
+  * lr and the Adam bias corrections are read from a 3-float device buffer written before each replay
+    (rl_mt_adamw_dev);
+  * the batch is copied into static input buffers; shapes (B, L, T) key the graph cache, the first step of a new
+    shape runs eagerly (it is a real training step) and doubles as the warm-up the capture needs.
+"""
+import ctypes
+
+import torch
+
+from ._lib import check, lib
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, max_graphs=4):
+        if not hasattr(optimizer, "hyper_values"):
+            raise TypeError("GraphedTrainStep needs realise_b200.optim.FusedAdamW (the update must be capturable)")
+        self.model, self.opt = model, optimizer
+        self.max_graphs = max_graphs
+        self._graphs = {}
+        self._seen = set()
+        dev = next(model.parameters()).device
+        self._hyper = torch.zeros(3, device=dev, dtype=torch.float32)
+        self._counter = torch.zeros(1, device=dev, dtype=torch.int64)   # dropout step counter (read as uint64)
+        self._ones = torch.ones(1, device=dev, dtype=torch.float32)
+        self.replays = 0
+
+    # ---- batch plumbing --------------------------------------------------------------------------------------
+    def _inputs(self, batch):
+        dev = self._hyper.device
+        c = self.model.config
+        out = {}
+        for k in ("src_idx", "masks", "tgt_idx", "loss_masks"):
+            out[k] = batch[k]
+        if c.with_pho == "yes":
+            lens = batch["pho_lens"]
+            if not torch.is_tensor(lens):
+                lens = torch.tensor(lens, dtype=torch.int32)
+            out["pho_lens"] = lens
+            out["pho_idx"] = batch["pho_idx"]
+        return {k: v.to(device=dev, dtype=(torch.int32 if k == "pho_lens" else v.dtype), non_blocking=True).contiguous()
+                for k, v in out.items()}
+
+    def _eager(self, inputs):
+        loss = self.model(inputs)[0]
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def _capture(self, inputs):
+        m, opt = self.model, self.opt
+        eng = m._engine
+        static = {k: v.clone() for k, v in inputs.items()}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()          # the eager step's activations go back to the driver; the graph gets its own pool
+        graph = torch.cuda.CUDAGraph()
+        opt.device_hyper = self._hyper
+        check(lib().rl_set_dropout_seed_ptr(ctypes.c_void_p(self._counter.data_ptr())), "rl_set_dropout_seed_ptr")
+        seed0, step0 = eng.seed, opt._step
+        try:
+            with torch.cuda.graph(graph):
+                self._counter.add_(1)
+                loss, _ = eng.forward(static)
+                eng.backward_and_sync(self._ones)
+                opt.step()
+        finally:
+            check(lib().rl_set_dropout_seed_ptr(None), "rl_set_dropout_seed_ptr")
+            opt.device_hyper = None
+            eng.seed, opt._step = seed0, step0     # recording a graph is not a training step
+        return graph, static, loss
+
+    def __call__(self, batch):
+        m = self.model
+        if not m.training:
+            raise RuntimeError("GraphedTrainStep: model.train() first")
+        inputs = self._inputs(batch)
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if key not in self._seen or len(self._graphs) >= self.max_graphs:
+                self._seen.add(key)
+                return self._eager(inputs)             # first step of a shape: eager (real step + warm-up)
+            entry = self._graphs[key] = self._capture(inputs)
+        graph, static, loss = entry
+        for k, v in inputs.items():
+            static[k].copy_(v, non_blocking=True)
+        self.opt._step += 1
+        self._hyper.copy_(torch.tensor(self.opt.hyper_values(self.opt._step), dtype=torch.float32), non_blocking=True)
+        graph.replay()
+        self.replays += 1
+        return loss

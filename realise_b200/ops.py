@@ -294,6 +294,28 @@ def colsum_bf16(x, out):
     _count()
 
 
+def gelu(u, h):
+    """h = gelu_erf(u), bf16 -> bf16 (may be in place)."""
+    _req(u, torch.bfloat16, "u")
+    _req(h, torch.bfloat16, "h")
+    assert u.is_contiguous() and h.is_contiguous() and u.numel() == h.numel()
+    with _Timed("gelu", u.numel() * 4):
+        check(lib().rl_gelu_fwd(_ptr(u), _ptr(h), _c(u.numel()), _stream()), "rl_gelu_fwd")
+    _count()
+
+
+def gelu_bwd_colsum(t, u, dbias):
+    """t <- t * gelu'(u) in place ([rows, cols] bf16); dbias[cols] += column sums of the result."""
+    _req(t, torch.bfloat16, "t")
+    _req(u, torch.bfloat16, "u")
+    rows, cols = t.shape
+    assert t.stride(1) == 1 and u.stride() == t.stride()
+    with _Timed("gelu_bwd_colsum", t.numel() * 6):
+        check(lib().rl_gelu_bwd_colsum(_ptr(t), _ptr(u), _ptr(dbias), _c(rows), _c(cols), _c(t.stride(0)), _stream()),
+              "rl_gelu_bwd_colsum")
+    _count()
+
+
 def masked_ce_bwd(logits, tgt, loss_mask, row_lse, count, gscale, dlogits):
     rows, V = logits.shape
     _req(dlogits, torch.bfloat16, "dlogits")
@@ -377,6 +399,22 @@ def bn_bwd(dy, act_out, x, mean, rstd, gamma, dbeta, dgamma, dx, remap=False, ma
     _count(2)
 
 
+def bn_bwd2(dy, act_out, br1, br2, M, C, remap=False, map_hw=(1, 1)):
+    """Backward of out = relu(bn_a(x_a) + bn_b(x_b)) for both branches in one reduce + one apply pass.
+    br = (x f32 [M,C], mean, rstd, gamma, dbeta, dgamma, dx bf16 view with row stride)."""
+    args = []
+    for br in (br1, br2):
+        x, mean, rstd, gamma, dbeta, dgamma, dx = br
+        _req(x, torch.float32, "x")
+        _req(dx, torch.bfloat16, "dx")
+        args += [_ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dbeta), _ptr(dgamma), _ptr(dx), _c(dx.stride(0))]
+    with _Timed("bn_bwd", 0):
+        check(lib().rl_bn_bwd2(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out), ctypes.c_int32(_DT[act_out.dtype]),
+                               *args, _c(M), _c(C), ctypes.c_int32(int(remap)), ctypes.c_int32(map_hw[0]),
+                               ctypes.c_int32(map_hw[1]), _stream()), "rl_bn_bwd2")
+    _count(2)
+
+
 def im2col(x, col, nimg, C, W, H, P, taps):
     n = len(taps)
     arr = ctypes.c_int8 * n
@@ -390,3 +428,24 @@ def glyph_im2col(glyphs, ids, col1, colsc, n_img, C):
     check(lib().rl_glyph_im2col(_ptr(glyphs), _ptr(ids), _ptr(col1), _ptr(colsc), _c(n_img), ctypes.c_int32(C), _stream()),
           "rl_glyph_im2col")
     _count()
+
+
+def _wrap_untimed():
+    """Give every wrapper without its own _Timed bracket one (work = 0), so a profiling pass sees the whole step."""
+    import functools
+
+    def make(fn, name):
+        @functools.wraps(fn)
+        def inner(*a, **k):
+            if _prof is None:
+                return fn(*a, **k)
+            with _Timed(name, 0):
+                return fn(*a, **k)
+        return inner
+
+    for name in ("colsum_bf16", "masked_ce_bwd", "embed_bwd", "gate_fuse_bwd", "gru_step_bwd", "gru_table_bwd",
+                 "gru_input_table", "bn_stats", "bn_finalize", "bn_apply", "bn_bwd", "im2col", "glyph_im2col"):
+        globals()[name] = make(globals()[name], name)
+
+
+_wrap_untimed()

@@ -32,6 +32,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step = 0
         self._sig = None
         self._sumsq = None
+        self.device_hyper = None          # f32[3] device tensor {lr, 1-b1^t, 1-b2^t}: set by GraphedTrainStep so that a
+                                          # captured step() reads its schedule from memory instead of kernel arguments
 
     def _build(self):
         entries, sig = [], []
@@ -84,8 +86,21 @@ class FusedAdamW(torch.optim.Optimizer):
         ss = ctypes.c_void_p(self._sumsq.data_ptr())
         f = ctypes.c_float
         check(lib().rl_mt_sumsq(tab, ck, ctypes.c_int64(self._nchunks), ss, st), "rl_mt_sumsq")
+        if self.device_hyper is not None:
+            check(lib().rl_mt_adamw_dev(tab, ck, ctypes.c_int64(self._nchunks), ss, f(self.max_grad_norm or 0.0),
+                                        ctypes.c_void_p(self.device_hyper.data_ptr()), f(b1), f(b2), f(g0["eps"]),
+                                        f(grad_div), st), "rl_mt_adamw_dev")
+            return
         check(lib().rl_mt_adamw(tab, ck, ctypes.c_int64(self._nchunks), ss, f(self.max_grad_norm or 0.0), f(g0["lr"]),
                                 f(b1), f(b2), f(g0["eps"]), f(bc1), f(bc2), f(grad_div), st), "rl_mt_adamw")
+
+    def hyper_values(self, step):
+        """{lr, 1 - beta1^t, 1 - beta2^t} of optimizer step `step` (1-based) for the device-resident schedule."""
+        g0 = self.param_groups[0]
+        b1, b2 = g0["betas"]
+        if not self.correct_bias:
+            return [float(g0["lr"]), 1.0, 1.0]
+        return [float(g0["lr"]), 1.0 - b1 ** step, 1.0 - b2 ** step]
 
     def grad_norm(self):
         """Global L2 norm of the last step's gradients (device scalar -> host)."""

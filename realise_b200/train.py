@@ -30,15 +30,7 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _glogits):
         eng = ctx.engine
-        eng.backward(gloss)
-        hook = getattr(eng.m, "_post_backward", None)   # realise_b200.ddp.DataParallel: one all-reduce of eng.flat
-        if hook is not None:
-            hook(eng)
-        # gradients live in persistent buffers (stable pointers for the fused optimizer); they are attached to the
-        # parameters directly instead of being handed to autograd, which would copy or alias them
-        for p, g in zip(eng.params, eng.grads):
-            if g is not None:
-                p.grad = g
+        eng.backward_and_sync(gloss)
         return (None, None) + (None,) * len(eng.params)
 
 
@@ -50,6 +42,7 @@ class TrainEngine:
             raise NotImplementedError("glyph kernels are built for 1 or 3 fonts")
         self.saved = None
         self.debug = None             # tests set a dict to receive intermediate gradients
+        self._tap_idx = {}
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
         # trainable parameters in a fixed order
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -111,6 +104,19 @@ class TrainEngine:
     def run(self, inputs):
         return _StepFn.apply(self, inputs, *self.params)
 
+    def backward_and_sync(self, gloss):
+        """Backward of the saved forward, the data-parallel gradient exchange, and .grad attachment.  Called by
+        autograd (loss.backward()) or directly by realise_b200.graphed.GraphedTrainStep."""
+        self.backward(gloss)
+        hook = getattr(self.m, "_post_backward", None)   # realise_b200.ddp.DataParallel: one all-reduce of self.flat
+        if hook is not None:
+            hook(self)
+        # gradients live in persistent buffers (stable pointers for the fused optimizer); they are attached to the
+        # parameters directly instead of being handed to autograd, which would copy or alias them
+        for p, g in zip(self.params, self.grads):
+            if g is not None:
+                p.grad = g
+
     def set_seed(self, seed):
         self.seed = int(seed)
 
@@ -168,7 +174,8 @@ class TrainEngine:
             x1, s["x1b"] = self._new((N, H), F32), self._new((N, H), BF16)
             ops.layernorm(s["y1"], lw["ln1_w"], lw["ln1_b"], x1, s["x1b"], c.layer_norm_eps)
             s["u"], s["h"] = self._new((N, I), BF16), self._new((N, I), BF16)
-            ops.gemm(s["x1b"], lw["w_1"], s["h"], bias=lw["b_1"], act=ops.ACT_GELU_SAVE, out2=s["u"])
+            ops.gemm(s["x1b"], lw["w_1"], s["u"], bias=lw["b_1"])
+            ops.gelu(s["u"], s["h"])       # stand-alone pass: cheaper than erf in the epilogue of a K = 768 GEMM
             s["y2"] = self._new((N, H), F32)
             ops.gemm(s["h"], lw["w_2"], s["y2"], bias=lw["b_2"], res=x1, drop=self.hdrop(self.site(name, li, 3)))
             x, xb = self._new((N, H), F32), self._new((N, H), BF16)
@@ -319,7 +326,10 @@ class TrainEngine:
         if T == 9:
             gw.copy_(tmp.view(cout, 9, cin).permute(0, 2, 1))
         else:
-            idx = torch.tensor([kh * 3 + kw for (_, _, _, kh, kw) in taps], device=tmp.device)
+            key = tuple(kh * 3 + kw for (_, _, _, kh, kw) in taps)
+            idx = self._tap_idx.get(key)
+            if idx is None:   # built once: a host->device copy here would synchronise every step (and break graph capture)
+                idx = self._tap_idx[key] = torch.tensor(key, device=tmp.device)
             gw[:, :, idx] = tmp.view(cout, T, cin).permute(0, 2, 1)
 
     def _resnet_bwd(self, sv, dout, N):
@@ -337,10 +347,10 @@ class TrainEngine:
             dcat = self._new((M, 2 * cout), BF16)
             dc2 = self._new((M, cout), BF16)
             # out = relu(bn2(c2) + bns(cs))
-            ops.bn_bwd(dout, s["out"], s["c2"], s["bn2"][2], s["bn2"][3], e["bn2"].weight.detach(), g(e["bn2"].bias),
-                       g(e["bn2"].weight), dc2, remap=remap, map_hw=(S, S))
-            ops.bn_bwd(dout, s["out"], s["cs"], s["bns"][2], s["bns"][3], e["bns"].weight.detach(), g(e["bns"].bias),
-                       g(e["bns"].weight), dcat[:, cout:], remap=remap, map_hw=(S, S))
+            ops.bn_bwd2(dout, s["out"],
+                        (s["c2"], s["bn2"][2], s["bn2"][3], e["bn2"].weight.detach(), g(e["bn2"].bias), g(e["bn2"].weight), dc2),
+                        (s["cs"], s["bns"][2], s["bns"][3], e["bns"].weight.detach(), g(e["bns"].bias), g(e["bns"].weight),
+                         dcat[:, cout:]), M, cout, remap=remap, map_hw=(S, S))
             # conv2 weight gradient (reference layout [cout, cin, kh, kw]) and data gradient
             T2 = len(e["taps2"])
             if T2 == 9:
@@ -500,8 +510,8 @@ class TrainEngine:
                               site_out=self.site(name, li, 3) if hp > 0 else 0)
             ops.gemm(dy2b, s["h"], self._grad(out.dense.weight), a_t=True, b_t=True, split_k=-1)              # dW2 = dy2^T h
             du = self._new((N, I), BF16)
-            ops.gemm(dy2b, lw["w_2"], du, b_t=True, res=s["u"], act=ops.ACT_GELU_GRAD)              # du = (dy2 W2) gelu'(u)
-            ops.colsum_bf16(du, self._grad(lyr.intermediate.dense.bias, True))
+            ops.gemm(dy2b, lw["w_2"], du, b_t=True)
+            ops.gelu_bwd_colsum(du, s["u"], self._grad(lyr.intermediate.dense.bias, True))          # du = (dy2 W2) gelu'(u), db1
             ops.gemm(du, s["x1b"], self._grad(lyr.intermediate.dense.weight), a_t=True, b_t=True, split_k=-1)  # dW1 = du^T x1
             dx1 = self._new((N, H), F32)
             ops.gemm(du, lw["w_1"], dx1, b_t=True, res=dy2)                                         # dx1 = du W1 + dy2

@@ -296,3 +296,141 @@ def test_flat_gradient_buffer_layout():
     assert sorted(no_grad) == sorted(["bert.pooler.dense.weight", "bert.pooler.dense.bias",
                                       "output_block.pooler.dense.weight", "output_block.pooler.dense.bias",
                                       "output_block.embeddings.word_embeddings.weight"])
+
+
+def test_colsum_and_bn_kernels_match_torch():
+    """Vectorised bias-gradient column sums, BN batch statistics and the fused two-branch BN backward vs torch."""
+    from realise_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for rows, cols in [(1000, 768), (4096, 2304), (333, 21128), (77, 40)]:
+        x = torch.randn(rows, cols, device="cuda", generator=g).bfloat16()
+        out = torch.zeros(cols, device="cuda")
+        ops.colsum_bf16(x, out)
+        ref = x.float().sum(0)
+        assert (out - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+    for M, C, S in [(2 * 256, 64, 16), (3 * 64, 128, 8), (5 * 16, 256, 4), (7 * 4, 512, 2), (9, 768, 1)]:
+        x1 = torch.randn(M, C, device="cuda", generator=g) * 2 + 0.5
+        x2 = torch.randn(M, C, device="cuda", generator=g)
+        sums = torch.zeros(2 * C, device="cuda")
+        ops.bn_stats(x1, sums)
+        assert torch.allclose(sums[:C], x1.sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(sums[C:], (x1 * x1).sum(0), rtol=1e-4, atol=1e-2)
+        # out = relu(bn(x1) + bn(x2)) with gamma/beta; dy arrives parity-split when S >= 2 (layout of the next block's input)
+        gam = [torch.rand(C, device="cuda", generator=g) + 0.5 for _ in range(2)]
+        bet = [torch.randn(C, device="cuda", generator=g) * 0.1 for _ in range(2)]
+        xs = [x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)]
+        gl = [t.clone().requires_grad_(True) for t in gam]
+        bl = [t.clone().requires_grad_(True) for t in bet]
+        stats = []
+        y = 0
+        for x, ga, be in zip(xs, gl, bl):
+            mu, var = x.mean(0), x.var(0, unbiased=False)
+            rstd = (var + 1e-5).rsqrt()
+            stats.append((mu.detach(), rstd.detach()))
+            y = y + (x - mu) * rstd * ga + be
+        out = torch.relu(y)
+        dy = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+        out.backward(dy.float())
+        remap = S >= 2
+        if remap:
+            n = M // (S * S)
+            perm = out.detach().view(n, S // 2, 2, S // 2, 2, C).permute(0, 2, 4, 1, 3, 5).reshape(M, C)
+            dperm = dy.view(n, S // 2, 2, S // 2, 2, C).permute(0, 2, 4, 1, 3, 5).reshape(M, C).contiguous()
+        else:
+            perm, dperm = out.detach(), dy
+        act = perm.bfloat16().contiguous()
+        dcat = torch.zeros(M, 2 * C, device="cuda", dtype=torch.bfloat16)
+        dx1 = torch.zeros(M, C, device="cuda", dtype=torch.bfloat16)
+        db = [torch.zeros(C, device="cuda") for _ in range(2)]
+        dg = [torch.zeros(C, device="cuda") for _ in range(2)]
+        ops.bn_bwd2(dperm, act, (x1, stats[0][0], stats[0][1], gam[0], db[0], dg[0], dx1),
+                    (x2, stats[1][0], stats[1][1], gam[1], db[1], dg[1], dcat[:, C:]), M, C, remap=remap, map_hw=(S, S))
+        for i in range(2):
+            assert torch.allclose(db[i], bl[i].grad, rtol=2e-3, atol=2e-2), (M, C, i)
+            assert torch.allclose(dg[i], gl[i].grad, rtol=2e-3, atol=2e-2), (M, C, i)
+        for got, ref in ((dx1, xs[0].grad), (dcat[:, C:], xs[1].grad)):
+            rel = (got.float() - ref).norm().item() / ref.norm().item()
+            assert rel <= 1e-2, (M, C, rel)
+
+
+def test_dropout_seed_pointer_offsets_the_seed():
+    """rl_set_dropout_seed_ptr: kernels use seed + *counter, read at run time (what makes graph replays draw new masks)."""
+    import ctypes
+    from realise_b200 import ops
+    from realise_b200._lib import lib
+    ctr = torch.tensor([5], device="cuda", dtype=torch.int64)
+    base = ops.dropout_mask(1 << 16, 0.1, 1000, 77)
+    plus5 = ops.dropout_mask(1 << 16, 0.1, 1005, 77)
+    lib().rl_set_dropout_seed_ptr(ctypes.c_void_p(ctr.data_ptr()))
+    try:
+        via_ptr = ops.dropout_mask(1 << 16, 0.1, 1000, 77)
+    finally:
+        lib().rl_set_dropout_seed_ptr(None)
+    again = ops.dropout_mask(1 << 16, 0.1, 1000, 77)
+    assert torch.equal(via_ptr, plus5) and torch.equal(again, base) and not torch.equal(base, plus5)
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """GraphedTrainStep (fwd + bwd + clip + AdamW as one CUDA-graph replay) follows the eager loop: same losses and
+    parameters after 4 steps with dropout off (split-K atomics reorder fp32 sums -> small tolerance); with dropout on,
+    replays draw different masks."""
+    from realise_b200.graphed import GraphedTrainStep
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    from realise_b200.optim import FusedAdamW
+    cfg = ArchConfig(num_hidden_layers=1, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd = cached_state_dict(cfg, 13)
+    batches = [synth_batch(2, 16, seed=20 + i, ragged=False) for i in range(4)]
+    T = max(b["pho_idx"].shape[1] for b in batches)
+    for b in batches:   # one (B, L, T) shape so that the graph is reused
+        pad = torch.zeros(b["pho_idx"].shape[0], T, dtype=torch.int64)
+        pad[:, :b["pho_idx"].shape[1]] = b["pho_idx"]
+        b["pho_idx"] = pad
+    results = []
+    for graphed in (False, True):
+        model = SpellBertPho2ResArch3Abla(cfg)
+        model.tie_cls_weight()
+        model.load_state_dict(sd, strict=True)
+        model.train().cuda()
+        opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, max_grad_norm=1.0, model=model)
+        step = GraphedTrainStep(model, opt)
+        losses = []
+        for i, b in enumerate(batches):
+            for gr in opt.param_groups:
+                gr["lr"] = 1e-3 * (1 + i)                     # a moving schedule must reach the captured update
+            if graphed:
+                losses.append(step(b).item())
+            else:
+                db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+                loss = model(db)[0]
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        if graphed:
+            assert step.replays == 3                           # first step of the shape is eager, the rest replay
+        results.append((losses, {n: p.detach().clone() for n, p in model.named_parameters()}))
+    (l0, p0), (l1, p1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
+    # Adam's first steps are sign-like (|update| ~ lr whatever |g|): an element whose tiny gradient flips sign under the
+    # split-K atomics' reordering moves the other way, so parameters are compared through the size of their UPDATE
+    init = {n: v.cuda() for n, v in sd.items()}
+    moved = 0
+    for n in p0:
+        if n == "classifier.weight":
+            continue
+        upd = (p0[n] - init[n]).norm().item()
+        if upd == 0.0:
+            assert torch.equal(p0[n], p1[n]), n
+            continue
+        moved += 1
+        assert (p0[n] - p1[n]).norm().item() <= 0.5 * upd, (n, (p0[n] - p1[n]).norm().item(), upd)
+    assert moved >= 100
+    # dropout on: two replays on the same batch and (nearly) the same weights see different masks
+    cfg2 = ArchConfig(num_hidden_layers=1, with_pho="no", with_res="no")
+    model = SpellBertPho2ResArch3Abla(cfg2)
+    model.tie_cls_weight()
+    model.train().cuda()
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=0.0, max_grad_norm=1.0, model=model)
+    step = GraphedTrainStep(model, opt)
+    ls = [step(batches[0]).item() for _ in range(4)]
+    assert step.replays == 3 and len({round(x, 6) for x in ls[1:]}) == 3, ls

@@ -1,0 +1,56 @@
+"""Launch each kernel of interest ONCE between cudaProfilerStart/Stop at the train-bench shapes
+(for `ncu --profile-from-start off --set full`)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from realise_b200 import ops  # noqa: E402
+
+dev = "cuda"
+N, H, I = 16384, 768, 3072
+B, L, heads = 128, 128, 12
+
+
+def f32(*s):
+    return torch.randn(*s, device=dev)
+
+
+def bf(*s):
+    return torch.randn(*s, device=dev).bfloat16()
+
+
+dy, x, g = f32(N, H), f32(N, H), f32(H)
+dx, dxb = f32(N, H), bf(N, H)
+z3 = [torch.zeros(H, device=dev) for _ in range(3)]
+M, C, S = N * 256, 64, 16
+x1, x2 = f32(M, C), f32(M, C)
+sc = torch.ones(C, device=dev)
+dyb, act = bf(M, C), bf(M, C)
+d1, dcat = bf(M, C), bf(M, 2 * C)
+z = [torch.zeros(C, device=dev) for _ in range(4)]
+qkv, ctx, dctx, dqkv = bf(N, 3 * H), bf(N, H), bf(N, H), bf(N, 3 * H)
+mask = torch.ones(B, L, dtype=torch.int64, device=dev)
+xb, w_o, w_1, w_2 = bf(N, H), bf(H, H), bf(I, H), bf(H, I)
+b1, bI = f32(H), f32(I)
+res, y32, h, u, dy2 = f32(N, H), f32(N, H), bf(N, I), bf(N, I), bf(N, H)
+
+
+def run():
+    ops.layernorm_bwd(dy, x, g, None, dx, dxb, z3[0], z3[1], z3[2], 1e-12, drop_p=0.1, drop_seed=1, site_out=1013)
+    ops.bn_bwd2(dyb, act, (x1, sc, sc, sc, z[0], z[1], d1), (x2, sc, sc, sc, z[2], z[3], dcat[:, C:]), M, C, remap=True, map_hw=(S, S))
+    ops.attention(qkv, mask, ctx, B, L, heads, drop=(0.1, 1, 1011))
+    ops.attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=(0.1, 1, 1011))
+    ops.gemm(xb, w_o, y32, bias=b1, res=res, drop=(0.1, 1, 1012))
+    ops.gemm(xb, w_1, h, bias=bI, act=ops.ACT_GELU_SAVE, out2=u)
+    ops.gemm(dy2, w_2, h, b_t=True, res=u, act=ops.ACT_GELU_GRAD)
+    ops.gemm(dy2, ctx, y32[:H], a_t=True, b_t=True, split_k=-1)
+
+
+run()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+run()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("done")
