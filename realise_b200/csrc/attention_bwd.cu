@@ -27,15 +27,18 @@ struct AttBwdParams {
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                      const __grid_constant__ CUtensorMap tmDO, const AttBwdParams p) {
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u);
+  // Two CTAs per SM: 256 TMEM columns and 7 x 16 KB of shared memory each.  S / dP (phase 1) are dead once every
+  // thread has turned them into the bf16 P / dS tiles, so the phase-2 accumulators dV / dK / dQ reuse their columns;
+  // V is dead once dP = dO V^T has completed (bar_s), so kv-tile 0 of P overwrites it.
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 0, COL_DK = 64, COL_DQ = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((rl::smem_u32(smem) & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles need 1 KB alignment (no slack is budgeted)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + T16K;
   uint8_t* sV = sK + T16K;
   uint8_t* sDO = sV + T16K;
-  uint8_t* sP = sDO + T16K;        // two [128 q x 64 kv] tiles
-  uint8_t* sDS = sP + 2 * T16K;    // two tiles
+  uint8_t* sP1 = sDO + T16K;       // P, kv tile 1 ([128 q x 64 kv]); kv tile 0 aliases sV
+  uint8_t* sDS = sP1 + T16K;       // dS, two tiles
   float* s_mask = reinterpret_cast<float*>(sDS + 2 * T16K);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 128);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
@@ -57,14 +60,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     rl::mbar_init(bar_o, 1);
     rl::fence_barrier_init();
   }
-  if (warp == 0) rl::tmem_alloc(tmem_ptr, 512);
+  if (warp == 0) rl::tmem_alloc(tmem_ptr, 256);
   for (int j = tid; j < 128; j += ATT_THREADS) {
     float m = -INFINITY;
     if (j < L) m = (1.0f - (float)p.mask[(long long)b * L + j]) * -10000.0f * 1.4426950408889634f;
     s_mask[j] = m;
   }
   // zero the P / dS tiles once: chunk tiles or rows that are never written must not feed NaNs into the MMAs
-  for (int i = tid; i < 4 * T16K / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 3 * T16K / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP1)[i] = make_uint4(0, 0, 0, 0);
   rl::fence_proxy_async();
   rl::tc_fence_before();
   __syncthreads();
@@ -162,7 +165,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ds[j] = col < L ? pr[j] * (dp - delta) : 0.f;
       }
     }
-    uint8_t* tp = sP + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* tp = ((c >> 1) ? sP1 : sV) + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* td = sDS + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -175,19 +178,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      rl::pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), rl::pack_bf16(ds[8 * g + 6], ds[8 * g + 7]));
     }
   }
+  if (nchunk < 2) {  // kv columns 32..63 of P tile 0 still hold V: clear them (their dV rows are never stored, but
+                     // stale bit patterns must not reach the tensor core as NaNs)
+    uint8_t* tp = sV + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(tp + (((4 + g) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+  }
   rl::fence_proxy_async();
   rl::tc_fence_before();
   __syncthreads();
 
   if (tid == 0) {
     rl::tc_fence_after();
-    const uint32_t pa = rl::smem_u32(sP), dsa = rl::smem_u32(sDS), qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK),
+    const uint32_t pa = rl::smem_u32(sV), dsa = rl::smem_u32(sDS), qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK),
                    da = rl::smem_u32(sDO);
     // dV[kv, d] = sum_q P[q, kv] dO[q, d] : A = P^T (MN-major: kv contiguous, 64-kv blocks one tile apart), B = dO^T
     const uint32_t idesc_t = rl::make_idesc_bf16(128, HEAD_DIM, 1, 1);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      rl::tc_mma_f16(tmem_base + COL_DV, rl::make_smem_desc_sw128(pa + k * 2048, T16K, 1024),
+      rl::tc_mma_f16(tmem_base + COL_DV, rl::make_smem_desc_sw128(pa + k * 2048, 2 * T16K, 1024),  // P tiles: sV, sP1
                      rl::make_smem_desc_sw128(da + k * 2048, 1024, 1024), idesc_t, k != 0);
     // dK[kv, d] = sum_q dS[q, kv] Q[q, d]
 #pragma unroll
@@ -232,11 +241,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   if (warp == 0) {
     rl::tc_fence_after();
-    rl::tmem_dealloc(tmem_base, 512);
+    rl::tmem_dealloc(tmem_base, 256);
   }
 }
 
-constexpr int ATT_BWD_SMEM = 8 * T16K + 128 * 4 + 3 * 8 + 16 + 1024;
+constexpr int ATT_BWD_SMEM = 7 * T16K + 128 * 4 + 3 * 8 + 16;   // 115,240 B: two CTAs per SM
 
 }  // namespace
 

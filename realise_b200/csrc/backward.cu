@@ -416,13 +416,14 @@ gate_bwd_mean_kernel(float* __restrict__ dm0, const float* __restrict__ dmean, c
 __global__ void __launch_bounds__(256)
 gate_bwd_weight_kernel(const float* __restrict__ dz, const float* __restrict__ src, const float* __restrict__ mean_src,
                        float* __restrict__ dgate_w, long long rows, int L, int H, int G, int j) {
-  // grid: (H/32, row chunks of 2048); block: 32 columns x 8 row lanes
+  // grid: (H/32, row chunks of 512); block: 32 columns x 8 row lanes
   __shared__ float s[3][8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
-  const long long r0 = (long long)blockIdx.y * 2048;
+  const long long r0 = (long long)blockIdx.y * 512;
   float acc[3] = {0.f, 0.f, 0.f};
-  for (long long r = r0 + ry; r < r0 + 2048 && r < rows; r += 8) {
+#pragma unroll 4
+  for (long long r = r0 + ry; r < r0 + 512 && r < rows; r += 8) {
     const float v = mean_src ? mean_src[(r / L) * H + col] : src[r * H + col];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -649,7 +650,7 @@ extern "C" int rl_gate_fuse_bwd(const float* dhid, const float* m0, const float*
   gate_bwd_mean_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(dm0, dmean, (const long long*)mask, rows, (int)L, (int)H);
   masked_mean_kernel<<<(unsigned)B, 256, 0, st>>>(m0, (const long long*)mask, mean, (int)L, (int)H);
   const float* srcs[3] = {m0, m1, m2};
-  dim3 grid((unsigned)(H / 32), (unsigned)((rows + 2047) / 2048));
+  dim3 grid((unsigned)(H / 32), (unsigned)((rows + 511) / 512));
   for (int j = 0; j <= num_modal; ++j)
     gate_bwd_weight_kernel<<<grid, 256, 0, st>>>(dz, j < num_modal ? srcs[j] : nullptr, j < num_modal ? nullptr : mean, dgate_w,
                                                 rows, (int)L, (int)H, num_modal, j);

@@ -274,13 +274,21 @@ gru_table_bwd_w_kernel(const float* __restrict__ dT, const float* __restrict__ e
     dw_ih[(long long)j * H + c] += acc;
   }
 }
+// demb[v, c] += sum_j dT[v, j] W_ih[j, c]: one CTA per (symbol v, 128-row slab of W_ih), partial sums by atomics
+// (V = 33 symbols alone would leave most SMs idle)
 __global__ void __launch_bounds__(256)
 gru_table_bwd_e_kernel(const float* __restrict__ dT, const float* __restrict__ w_ih, float* __restrict__ demb, int V, int H) {
   const int v = blockIdx.x;
+  const int j0 = blockIdx.y * 128;
+  const int j1 = min(j0 + 128, 3 * H);
+  __shared__ float s_d[128];
+  if (threadIdx.x < 128) s_d[threadIdx.x] = j0 + threadIdx.x < j1 ? dT[(long long)v * 3 * H + j0 + threadIdx.x] : 0.f;
+  __syncthreads();
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float acc = 0.f;
-    for (int j = 0; j < 3 * H; ++j) acc += dT[(long long)v * 3 * H + j] * __ldg(w_ih + (long long)j * H + c);
-    demb[(long long)v * H + c] += acc;
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) acc = fmaf(s_d[j - j0], __ldg(w_ih + (long long)j * H + c), acc);
+    atomicAdd(demb + (long long)v * H + c, acc);
   }
 }
 
@@ -304,7 +312,7 @@ extern "C" int rl_gru_table_bwd(const float* dtable, const float* emb, const flo
   RL_REQUIRE(dtable && emb && w_ih && dw_ih && db_ih && demb && V > 0 && V <= 64, RL_EINVAL, "rl_gru_table_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   gru_table_bwd_w_kernel<<<(unsigned)(3 * H), 256, 0, st>>>(dtable, emb, dw_ih, db_ih, (int)V, (int)H);
-  gru_table_bwd_e_kernel<<<(unsigned)V, 256, 0, st>>>(dtable, w_ih, demb, (int)V, (int)H);
+  gru_table_bwd_e_kernel<<<dim3((unsigned)V, (unsigned)((3 * H + 127) / 128)), 256, 0, st>>>(dtable, w_ih, demb, (int)V, (int)H);
   return rl_check_launch("rl_gru_table_bwd");
 }
 
