@@ -37,6 +37,15 @@ FLOP_PER_SENTENCE_FWD = 59.39e9      # SURVEY.md §8(d), nominal, L=128
 FLOP_PER_SENTENCE_TRAIN = 178.2e9    # 3 x forward
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -45,6 +54,15 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "r01_train_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["gemm_dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -206,7 +224,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -214,7 +232,7 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------------
 def _agg(prof):
     agg = {}
-    for kind, work, e0, e1 in prof:
+    for kind, work, e0, e1, *_ in prof:
         a = agg.setdefault(kind, [0.0, 0.0, 0])
         a[0] += work
         a[1] += e0.elapsed_time(e1) * 1e-3
@@ -346,9 +364,9 @@ def measure_train(args, dev, rank, world, dist, peaks):
         "model_tflops": value * FLOP_PER_SENTENCE_TRAIN / 1e12 / world,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tf / peaks["tf_sustained"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch: mean over the 4 forward GEMM launches of
-                     # one transformer layer (B=64) in profiles/r01_ncu_full_summary.json (ncu --set full, round 1)
-                     "traffic": 40.2e6,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, from the committed ncu pass over one
+                     # train step (profiles/r01_train_traffic.json); null when that file is absent
+                     "traffic": load_traffic(),
                      "kernel": "gemm_bf16_kernel / gemm2_bf16_kernel (tcgen05 GEMM, implicit-GEMM conv, split-K wgrad): "
                                f"executed 2*M*N*K over CUDA-event time of its {gn} launches in one train step",
                      "peak_source": peaks["source"] + " bf16 sustained"},
@@ -471,10 +489,16 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu, "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"], "clocks": tr["clocks"],
         "final_loss": tr["final_loss"], "peak_mem_gb": tr["peak_mem_gb"], "forward_only": fwd,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # the contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner, warnings) is
+    # sent to stderr instead; the line itself goes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -89,6 +89,11 @@ typedef struct rl_gemm_desc {
   uint64_t drop_seed;  /* by the backward kernels.  drop_p = 0 disables it. */
   int32_t b_major;   /* 0: B stored [N, K].  1: B stored [K, N] with row stride ldb, e.g. B = W^T for a data
                         gradient straight from W [out, in], or B = X^T for a weight gradient */
+  int32_t b_mode;    /* 0: B is a 2-D matrix.  1 (needs b_major = 1, a_mode = 0): B is the im2col matrix of the conv
+                        activation `b` ([NIMG, P, H, W, C], geometry / taps in the conv_* fields), never materialised:
+                        B[k = output pixel (img, oh, ow), n = tap * Cuse + c] = x[img, plane_t, oh+dh_t, ow+dw_t, c],
+                        one 5-D TMA box per (64 pixels, 64 channels), zero outside the map.  With A = dY^T (a_major 1)
+                        and split_k this is a conv weight gradient dW[co, tap, ci] in ONE GEMM (K = NIMG*H*W). */
 } rl_gemm_desc;
 
 RL_API int rl_gemm_bf16(const rl_gemm_desc* d, void* stream);

@@ -30,6 +30,7 @@ class GemmDesc(ctypes.Structure):
         ("a_major", ctypes.c_int32),
         ("drop_p", ctypes.c_float), ("drop_site", ctypes.c_uint32), ("drop_seed", ctypes.c_uint64),
         ("b_major", ctypes.c_int32),
+        ("b_mode", ctypes.c_int32),
     ]
 
 

@@ -39,6 +39,10 @@ struct KParams {
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
   rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
+  int b_mode;     // 1: B tiles are gathered from a conv activation (implicit im2col, weight gradients)
+  int ks_major;   // tile order: split index outermost, so that the N tiles sharing a K range run side by side (L2 reuse)
+  int nimg;       // conv: number of images (an image index >= nimg makes a TMA box read zeros)
+  int ntaps;
   int a_mn, b_mn; // operand stored MN-major: A as [K, M] (M contiguous), B as [K, N] (N contiguous)
   int dbg;        // tuning experiments only: 1 = no epilogue work, 2 = no TMA loads, 4 = no MMA
 };
@@ -332,7 +336,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mn = tile / p.k_splits, ks = tile - mn * p.k_splits;
+        const int tiles_mn = p.tiles_m * p.tiles_n;
+        const int mn = p.ks_major ? tile % tiles_mn : tile / p.k_splits;
+        const int ks = p.ks_major ? tile / tiles_mn : tile - mn * p.k_splits;
         const int m_blk = mn / p.tiles_n;
         const int n_blk = mn - m_blk * p.tiles_n;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -360,7 +366,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             rl::tma_load_5d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], cb * BK,
                             (int)p.tap_dw[t], h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
           }
-          if (p.b_mn) {
+          if (p.b_mode == 1) {
+            // implicit im2col: k-block = 64 consecutive output pixels, each 64-wide N block = 64 channels of one tap
+            const int pix0 = kb * BK;
+            const int imgk = pix0 >> p.hw_shift;
+            const int hk = (pix0 & ((1 << p.hw_shift) - 1)) >> p.w_shift;
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b) {
+              const int nb = (n0 >> 6) + b;
+              const int t = nb / p.cin_blocks;
+              const int cb = nb - t * p.cin_blocks;
+              if (t < p.ntaps)
+                rl::tma_load_5d(smem_b + stage * B_BYTES + b * 8192, &tmB, &full_bar[stage], cb * 64, (int)p.tap_dw[t],
+                                hk + (int)p.tap_dh[t], (int)p.tap_plane[t], imgk);
+              else  // N tail of the last tile: a box beyond the last image reads zeros (and still counts its bytes)
+                rl::tma_load_5d(smem_b + stage * B_BYTES + b * 8192, &tmB, &full_bar[stage], 0, 0, 0, 0, p.nimg);
+            }
+          } else if (p.b_mn) {
 #pragma unroll
             for (int b = 0; b < BN / 64; ++b)
               rl::tma_load_2d(smem_b + stage * B_BYTES + b * 8192, &tmB, &full_bar[stage], n0 + b * 64, kb * BK);
@@ -390,7 +412,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ks = tile % p.k_splits;
+        const int ks = p.ks_major ? tile / (p.tiles_m * p.tiles_n) : tile % p.k_splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         rl::tc_fence_after();
@@ -434,7 +456,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mn = tile / p.k_splits;
+      const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
       const int m_blk = mn / p.tiles_n;
       const int n_blk = mn - m_blk * p.tiles_n;
       const int row0 = m_blk * BM + q * 32;
@@ -599,7 +621,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int mn = tile / p.k_splits, ks = tile - mn * p.k_splits;
+        const int tiles_mn = p.tiles_m * p.tiles_n;
+        const int mn = p.ks_major ? tile % tiles_mn : tile / p.k_splits;
+        const int ks = p.ks_major ? tile / tiles_mn : tile - mn * p.k_splits;
         const int m_blk = mn / p.tiles_n;
         const int n_blk = mn - m_blk * p.tiles_n;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -627,7 +651,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma2_load_5d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], cb * BK, (int)p.tap_dw[t],
                          h0 + (int)p.tap_dh[t], (int)p.tap_plane[t], img0);
           }
-          if (p.b_mn) {
+          if (p.b_mode == 1) {
+            // implicit im2col (see gemm_bf16_kernel): this CTA gathers its half of the pair's N tile
+            const int pix0 = kb * BK;
+            const int imgk = pix0 >> p.hw_shift;
+            const int hk = (pix0 & ((1 << p.hw_shift) - 1)) >> p.w_shift;
+#pragma unroll
+            for (int b = 0; b < BN / 128; ++b) {
+              const int nb = (n0 >> 6) + b;
+              const int t = nb / p.cin_blocks;
+              const int cb = nb - t * p.cin_blocks;
+              if (t < p.ntaps)
+                tma2_load_5d(smem_b + stage * BH_BYTES + b * 8192, &tmB, &full_bar[stage], cb * 64, (int)p.tap_dw[t],
+                             hk + (int)p.tap_dh[t], (int)p.tap_plane[t], imgk);
+              else
+                tma2_load_5d(smem_b + stage * BH_BYTES + b * 8192, &tmB, &full_bar[stage], 0, 0, 0, 0, p.nimg);
+            }
+          } else if (p.b_mn) {
 #pragma unroll
             for (int b = 0; b < BN / 128; ++b)
               tma2_load_2d(smem_b + stage * BH_BYTES + b * 8192, &tmB, &full_bar[stage], n0 + b * 64, kb * BK);
@@ -655,7 +695,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int ks = tile % p.k_splits;
+        const int ks = p.ks_major ? tile / (p.tiles_m * p.tiles_n) : tile % p.k_splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         rl::tc_fence_after();
@@ -694,7 +734,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int mn = tile / p.k_splits;
+      const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
       const int m_blk = mn / p.tiles_n;
       const int n_blk = mn - m_blk * p.tiles_n;
       const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
@@ -800,6 +840,12 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.b_mn = d->b_major;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.a_mode = d->a_mode;
+  p.b_mode = d->b_mode;
+  p.ks_major = 0;
+  p.nimg = d->conv_NIMG;
+  p.ntaps = d->ntaps;
+  RL_REQUIRE(d->b_mode == 0 || (d->b_mode == 1 && d->b_major == 1 && d->a_mode == 0), RL_EINVAL,
+             "rl_gemm_bf16: b_mode 1 (implicit im2col B) needs b_major = 1 and a_mode = 0");
   p.out = d->out;
   p.ldo = d->ldo;
   p.out_f32 = d->out_dtype == RL_DT_F32;
@@ -849,6 +895,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
       bn = 64;
       pair = 0;
     }
+    if (d->b_mode == 1 && bn == 256 && p.N % 256 != 0 && p.N % 128 == 0) bn = 128;   // no padded N tile of gathers
     if (g_force_bn == 64) {
       bn = 64;
       pair = 0;
@@ -864,13 +911,37 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     RL_REQUIRE(d->out_dtype == RL_DT_F32 && !d->res && !d->bias && !d->scale && d->act == RL_ACT_NONE && !d->out2 &&
                    d->out_remap == 0 && d->drop_p == 0.f,
                RL_EINVAL, "rl_gemm_bf16: split_k needs a plain f32 accumulate-into output (no epilogue operands)");
-    const long long ctas = (long long)p.tiles_m * p.tiles_n * (pair ? 2 : 1);
-    int want = d->split_k > 0 ? d->split_k : (int)((2LL * rl_num_sms() + ctas - 1) / ctas);
+    // Work items = output tiles x splits, executed in waves over the SMs (CTA pairs in pair mode).  Pick the split
+    // count that minimises waves x (k-blocks per split + the tile's fixed cost: pipeline fill and the atomic
+    // epilogue, ~10 k-blocks' worth), e.g. 27 tiles on 74 pairs: 8 splits (3 full waves of 32 k-blocks) beat 6
+    // (3 ragged waves of 43).
+    const long long tiles = (long long)p.tiles_m * p.tiles_n;
+    const long long units = pair ? rl_num_sms() / 2 : rl_num_sms();
     int maxs = p.num_kb / 8;
+    if (maxs < 1) maxs = 1;
+    int want = 1;
+    if (d->split_k > 0) {
+      want = d->split_k;
+    } else {
+      double best_cost = 1e30;
+      for (int sp = 1; sp <= maxs && sp <= 512; ++sp) {
+        const long long per = (p.num_kb + sp - 1) / sp;
+        const long long real = (p.num_kb + per - 1) / per;          // splits that actually exist
+        const long long waves = (tiles * real + units - 1) / units;
+        const double cost = (double)waves * ((double)per + 10.0);
+        if (cost < best_cost - 1e-9) {
+          best_cost = cost;
+          want = sp;
+        }
+      }
+    }
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     p.kb_per_split = (p.num_kb + want - 1) / want;
     p.k_splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    // split index outermost: the output tiles of one K range run side by side and share its operand panels in L2
+    // (tile-major order makes every output tile re-read its full A / B panels from HBM)
+    if (p.k_splits > 1) p.ks_major = 1;
   }
 
   CUtensorMap tmA, tmB;
@@ -932,7 +1003,40 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   if (d->out_remap == 2)
     RL_REQUIRE(d->a_mode == 1 && d->remap_plane >= 0 && d->remap_plane < 4, RL_EINVAL,
                "rl_gemm_bf16: out_remap=2 needs conv geometry and a plane in 0..3");
-  if (d->b_major == 1) {
+  if (d->b_mode == 1) {
+    const int C = d->conv_C, W = d->conv_W, H = d->conv_H, P = d->conv_P, NI = d->conv_NIMG;
+    const int Cuse = d->conv_Cuse > 0 ? d->conv_Cuse : C;
+    RL_REQUIRE(C > 0 && C % 8 == 0 && Cuse % 64 == 0 && Cuse <= C, RL_EINVAL,
+               "rl_gemm_bf16(im2col B): C=%d / used channels %d (must be a multiple of 64)", C, Cuse);
+    RL_REQUIRE(d->ntaps >= 1 && d->ntaps <= 12, RL_EINVAL, "rl_gemm_bf16(im2col B): ntaps=%d", d->ntaps);
+    RL_REQUIRE(d->N == (int64_t)d->ntaps * Cuse, RL_EINVAL, "rl_gemm_bf16(im2col B): N != ntaps*C");
+    const int ws = ilog2_exact(W), hs = ilog2_exact(H);
+    RL_REQUIRE(ws >= 0 && hs >= 0 && W <= 64 && W * H <= 256, RL_EINVAL,
+               "rl_gemm_bf16(im2col B): map %dx%d must be power-of-two with <= 256 pixels", W, H);
+    RL_REQUIRE(d->K == (int64_t)NI * W * H, RL_EINVAL, "rl_gemm_bf16(im2col B): K != NIMG*H*W");
+    RL_REQUIRE(P == 1 || P == 4, RL_EINVAL, "rl_gemm_bf16(im2col B): P must be 1 or 4");
+    p.hw_shift = ws + hs;
+    p.w_shift = ws;
+    p.cin_blocks = Cuse / 64;
+    p.ks_major = 1;
+    for (int t = 0; t < d->ntaps; ++t) {
+      p.tap_dw[t] = d->tap_dw[t];
+      p.tap_dh[t] = d->tap_dh[t];
+      p.tap_plane[t] = d->tap_plane[t];
+      RL_REQUIRE(d->tap_plane[t] >= 0 && d->tap_plane[t] < P, RL_EINVAL, "rl_gemm_bf16(im2col B): tap plane");
+    }
+    const int hw = W * H;
+    uint32_t box[5];
+    box[0] = 64;
+    box[1] = (uint32_t)W;
+    box[2] = (uint32_t)(hw >= BK ? BK / W : H);
+    box[3] = 1;
+    box[4] = (uint32_t)(hw >= BK ? 1 : BK / hw);
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)P, (uint64_t)NI};
+    uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)C * W * 2, (uint64_t)C * W * H * 2, (uint64_t)C * W * H * P * 2};
+    rc = rl_make_tmap_bf16(&tmB, d->b, 5, dims, strides, box);
+    if (rc) return rc;
+  } else if (d->b_major == 1) {
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->K};  // stored [K, N], N contiguous
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
     uint32_t box[2] = {64, BK};

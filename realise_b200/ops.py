@@ -23,8 +23,8 @@ def _count(n=1):
 class _Timed:
     """CUDA-event bracket around one C-ABI call on the current stream (only when profiling)."""
 
-    def __init__(self, kind, work):
-        self.kind, self.work = kind, work
+    def __init__(self, kind, work, detail=None):
+        self.kind, self.work, self.detail = kind, work, detail
 
     def __enter__(self):
         if _prof is not None:
@@ -35,7 +35,7 @@ class _Timed:
     def __exit__(self, *exc):
         if _prof is not None:
             self.e1.record()
-            _prof.append((self.kind, self.work, self.e0, self.e1))
+            _prof.append((self.kind, self.work, self.e0, self.e1, self.detail))
         return False
 _DT = {torch.bfloat16: 0, torch.float32: 1}
 
@@ -76,7 +76,8 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
     d.split_k = split_k
     d.a_mode = 0
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
-    with _Timed("gemm", 2.0 * M * N * K):
+    with _Timed("gemm", 2.0 * M * N * K, (M, N, K, int(a_t), int(b_t), split_k, act, str(out.dtype)[6:], res is not None,
+                                          drop is not None)):
         check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16")
     _count()
     return out
@@ -106,8 +107,37 @@ def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res
     for i, (dw, dh, pl) in enumerate(taps):
         d.tap_dw[i], d.tap_dh[i], d.tap_plane[i] = dw, dh, pl
     _fill_epilogue(d, out, scale, bias, res, act, None, out_remap)
-    with _Timed("conv_gemm", 2.0 * M * N * K):
+    with _Timed("conv_gemm", 2.0 * M * N * K, (M, N, K, "conv", len(taps), out_remap, act, str(out.dtype)[6:], res is not None, False)):
         check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16(conv)")
+    _count()
+    return out
+
+
+def conv_wgrad(dy, x, out, *, nimg, H, W, planes, taps, split_k=-1):
+    """Conv weight gradient without an im2col matrix: out[co, t*C + ci] += sum over output pixels m = (img, oh, ow) of
+    dy[m, co] * x[img, plane_t, oh+dh_t, ow+dw_t, ci].  dy: bf16 [nimg*H*W, Cout]; x: bf16 activation
+    [nimg, planes, H, W, C] (C % 64 == 0); out: f32 [Cout, ntaps*C], accumulated into (split-K atomics)."""
+    _req(dy, torch.bfloat16, "dy")
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.float32, "out")
+    assert x.is_contiguous() and dy.stride(1) == 1 and out.stride(1) == 1
+    C = x.shape[-1]
+    Kpix, M = dy.shape
+    N = len(taps) * C
+    assert Kpix == nimg * H * W and x.numel() == nimg * planes * H * W * C and tuple(out.shape) == (M, N)
+    d = GemmDesc()
+    d.a, d.b = dy.data_ptr(), x.data_ptr()
+    d.M, d.N, d.K = M, N, Kpix
+    d.lda, d.ldb = dy.stride(0), C
+    d.a_major, d.b_major, d.b_mode, d.a_mode = 1, 1, 1, 0
+    d.conv_C, d.conv_W, d.conv_H, d.conv_P, d.conv_NIMG = C, W, H, planes, nimg
+    d.ntaps = len(taps)
+    for i, (dw, dh, pl) in enumerate(taps):
+        d.tap_dw[i], d.tap_dh[i], d.tap_plane[i] = dw, dh, pl
+    d.split_k = split_k
+    _fill_epilogue(d, out, None, None, None, ACT_NONE, None, 0)
+    with _Timed("gemm", 2.0 * M * N * Kpix, (M, N, Kpix, "wgrad", len(taps), split_k, 0, "float32", False, False)):
+        check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16(conv wgrad)")
     _count()
     return out
 

@@ -317,11 +317,16 @@ class TrainEngine:
         sv["res"] = blocks
         return x   # f32 [N, 768]
 
-    def _conv_wgrad(self, dy, col, weight, taps, cout, cin):
-        """dW[co, t, ci] = dy^T col (split-K GEMM, tap-major) -> the parameter's [co, ci, kh, kw] gradient view."""
+    def _conv_wgrad(self, dy, col, weight, taps, cout, cin, conv=None):
+        """dW[co, t, ci] = dy^T col (split-K GEMM, tap-major) -> the parameter's [co, ci, kh, kw] gradient view.
+        conv = (x, nimg, S, planes): the im2col matrix is implicit (gathered by TMA inside the GEMM), col is None."""
         T = len(taps)
         tmp = self._new((cout, T * cin), F32, zero=True)
-        ops.gemm(dy, col, tmp, a_t=True, b_t=True, split_k=-1)
+        if conv is not None:
+            x, nimg, S, planes = conv
+            ops.conv_wgrad(dy, x, tmp, nimg=nimg, H=S, W=S, planes=planes, taps=[t[:3] for t in taps])
+        else:
+            ops.gemm(dy, col, tmp, a_t=True, b_t=True, split_k=-1)
         gw = self._grad(weight).view(cout, cin, 9)
         if T == 9:
             gw.copy_(tmp.view(cout, 9, cin).permute(0, 2, 1))
@@ -354,9 +359,7 @@ class TrainEngine:
             # conv2 weight gradient (reference layout [cout, cin, kh, kw]) and data gradient
             T2 = len(e["taps2"])
             if T2 == 9:
-                col = self._new((M, cout * 9), BF16)
-                ops.im2col(s["a1"], col, N, cout, S, S, 1, [t[:3] for t in e["taps2"]])
-                self._conv_wgrad(dc2, col, e["conv2"].weight, e["taps2"], cout, cout)
+                self._conv_wgrad(dc2, None, e["conv2"].weight, e["taps2"], cout, cout, conv=(s["a1"], N, S, 1))
                 da1 = self._new((M, cout), BF16)
                 ops.conv_gemm(dc2.view(N, 1, S, S, cout), e["w2t"], da1, nimg=N, H=S, W=S, planes=1, taps=e["taps2t"])
             else:  # 1x1 map: only the centre tap touched data
@@ -378,12 +381,16 @@ class TrainEngine:
                 return
             x_in = s["x_in"]
             t1 = e["taps1"]
-            col = self._new((M, cin * len(t1)), BF16)
-            ops.im2col(x_in, col, N, cin, S, S, 4, [t[:3] for t in t1])
-            self._conv_wgrad(dc1, col, e["conv1"].weight, t1, cout, cin)
-            colsc = self._new((M, cin), BF16)
-            ops.im2col(x_in, colsc, N, cin, S, S, 4, [(0, 0, 0)])
-            ops.gemm(dcs, colsc, gws.view(cout, cin), a_t=True, b_t=True, split_k=-1)
+            if S >= 2:   # parity-split block input gathered inside the GEMM (implicit im2col)
+                self._conv_wgrad(dc1, None, e["conv1"].weight, t1, cout, cin, conv=(x_in, N, S, 4))
+                ops.conv_wgrad(dcs, x_in, gws.view(cout, cin), nimg=N, H=S, W=S, planes=4, taps=[(0, 0, 0)])
+            else:        # 1x1 map: the 4 parity planes of the input are 4 column blocks of one row
+                col = self._new((M, cin * len(t1)), BF16)
+                ops.im2col(x_in, col, N, cin, S, S, 4, [t[:3] for t in t1])
+                self._conv_wgrad(dc1, col, e["conv1"].weight, t1, cout, cin)
+                colsc = self._new((M, cin), BF16)
+                ops.im2col(x_in, colsc, N, cin, S, S, 4, [(0, 0, 0)])
+                ops.gemm(dcs, colsc, gws.view(cout, cin), a_t=True, b_t=True, split_k=-1)
             # data gradient wrt the block input (parity-split rows = the previous block's output layout)
             dx = self._new((N * 4 * S * S, cin), BF16)
             if S == 1:
