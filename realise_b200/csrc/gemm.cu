@@ -224,10 +224,16 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         rl::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(tmC_ptr)),
-                       "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
-                       : "memory");
+          if (p.atomic_out)  // split-K: the tile is ADDED to the (zero-initialised) f32 output by the TMA unit itself
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(tmC_ptr)),
+                         "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(tmC_ptr)),
+                         "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
+                         : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       } else if (p.atomic_out) {
@@ -1052,7 +1058,8 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   // output path: TMA store for plain row-major outputs with 16-byte aligned rows
   const int oelt = p.out_f32 ? 4 : 2;
   const bool aligned16 = ((uintptr_t)d->out & 15) == 0 && (d->ldo * oelt) % 16 == 0;
-  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16 && !p.atomic_out) ? 1 : 0;  // else direct stores
+  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16) ? 1 : 0;  // else direct stores / scalar atomics
+  // (split-K with a TMA-able output: the per-chunk store becomes a cp.reduce.async.bulk .add — no per-element atomics)
   p.vec_store = (aligned16 && (d->out2 == nullptr || (((uintptr_t)d->out2 & 15) == 0 && d->ldo2 % 8 == 0))) ? 1 : 0;
   if (d->res) {
     const int relt = p.res_f32 ? 4 : 2;
