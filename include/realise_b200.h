@@ -197,6 +197,14 @@ RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const vo
 RL_API int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
                             int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed,
                             uint32_t drop_site, void* stream);
+/* Same pair with the log2-domain logsumexp of every query row ([B, heads, L] f32) written by the forward and read by
+ * the backward, which then recomputes P = exp2(s - lse) in one pass over S instead of three. */
+RL_API int rl_attention_fwd_lse(const void* qkv, const int64_t* mask, void* ctx, float* row_lse, int64_t B, int64_t L,
+                                int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                                void* stream);
+RL_API int rl_attention_bwd_lse(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
+                                const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p,
+                                uint64_t drop_seed, uint32_t drop_site, void* stream);
 
 /* ---- LayerNorm backward: x = LN input (f32), dy = grad of the LN output; dx (+= add_in) in f32 and/or bf16;
  * dgamma/dbeta/dxsum (column sums of dy*xhat, dy, dx) are ACCUMULATED into (caller zeroes them per step). */
@@ -249,7 +257,8 @@ RL_API int rl_gru_table_bwd(const float* dtable, const float* emb, const float* 
  *   followed (act_out > 0); dbeta/dgamma accumulated, dx written as bf16 with row stride ldx.
  * rl_im2col_bf16: col[m, t*C + ci] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] so that a conv weight gradient
  *   dW[co, t, ci] is ONE split-K rl_gemm_bf16 (A = dY MN-major, B = col MN-major).
- * rl_glyph_im2col: the same for res_block1 straight from the glyph table: col1 [n*256, 32] (27 used), colsc [n*256, 8]. */
+ * rl_glyph_im2col: the same for res_block1 straight from the glyph table: col1 [n*256, 32] (27 used), colsc [n*256, 8]
+ *   (optional, may be NULL: the shortcut's pixel is the centre tap of col1). */
 RL_API int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t M, int64_t C, int64_t ld, void* stream);
 RL_API int rl_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* mean_out,
@@ -286,7 +295,7 @@ RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks
                        float grad_div, void* stream);
 /* GELU (erf form, transformers/modeling_bert.py:125-131) as element-wise passes next to the K = 768 GEMMs of
  * BertIntermediate: h = u * Phi(u) over n bf16 elements; and its backward fused with the bias gradient:
- * t[r, c] <- t[r, c] * gelu'(u[r, c]) in place (t = dy2 W2), dbias[c] += sum_r of the stored (bf16) result. */
+ * t[r, c] <- t[r, c] * gelu'(u[r, c]) in place (t = dy2 W2), dbias[c] += sum_r of the fp32 products. */
 RL_API int rl_gelu_fwd(const void* u, void* h, int64_t n, void* stream);
 RL_API int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld, void* stream);
 

@@ -18,6 +18,7 @@ struct AttParams {
   float scale_log2;       // (1/sqrt(d)) * log2(e)
   int heads;
   rl::DropSpec drop;      // dropout on the attention probabilities (modeling_bert.py:250)
+  float* lse;             // optional [B, heads, L]: log2-domain logsumexp of every query row (saved for the backward)
 };
 
 template <int LKV_MAX>
@@ -194,6 +195,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   {
     const float inv = 1.0f / sum;
     const int q = q0 + r;
+    if (p.lse && q < L) p.lse[((long long)b * p.heads + head) * L + q] = mx + log2f(sum);
     __nv_bfloat16* dst = p.ctx + (long long)(row0 + q) * p.H + head * HEAD_DIM;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -246,6 +248,12 @@ int launch_att(const CUtensorMap& tq, const CUtensorMap& tkv, const AttParams& p
 extern "C" int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, int64_t B, int64_t L,
                                 int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
                                 void* stream) {
+  return rl_attention_fwd_lse(qkv, mask, ctx, nullptr, B, L, heads, head_dim, drop_p, drop_seed, drop_site, stream);
+}
+
+extern "C" int rl_attention_fwd_lse(const void* qkv, const int64_t* mask, void* ctx, float* row_lse, int64_t B, int64_t L,
+                                    int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                                    void* stream) {
   RL_REQUIRE(qkv && mask && ctx, RL_EINVAL, "rl_attention_fwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_fwd: head_dim must be 64, got %lld", (long long)head_dim);
   RL_REQUIRE(B > 0 && heads > 0 && L > 0, RL_EINVAL, "rl_attention_fwd: empty problem");
@@ -271,6 +279,7 @@ extern "C" int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx,
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.heads = (int)heads;
   p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
+  p.lse = row_lse;
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)heads, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (lkv16 <= 128) return launch_att<128>(tq, tkv, p, grid, st);

@@ -22,6 +22,7 @@ struct AttBwdParams {
   float scale_log2;
   int heads;
   rl::DropSpec drop;
+  const float* lse;           // optional [B, heads, L] log2-domain logsumexp saved by the forward: skips two passes over S
 };
 
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -116,30 +117,37 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   const int nchunk = (lkv16 + 31) / 32;
   float mx = -INFINITY;
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t v[32];
-    rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
-    rl::tmem_ld_wait();
+  float inv = 0.f;
+  if (p.lse) {
+    // P = exp2(s - lse) directly; rows beyond the sentence get lse = +inf -> P = 0 (nothing for dK / dV)
+    mx = r < L ? p.lse[((long long)b * p.heads + head) * L + r] : INFINITY;
+    inv = 1.0f;
+  } else {
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t v[32];
+      rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
+      rl::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
-      mx = fmaxf(mx, sc);
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+        mx = fmaxf(mx, sc);
+      }
     }
-  }
-  float sum = 0.f;
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t v[32];
-    rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
-    rl::tmem_ld_wait();
+    float sum = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t v[32];
+      rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
+      rl::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
-      sum += rl::ex2(sc - mx);
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        const float sc = col < L ? fmaf(__uint_as_float(v[j]), p.scale_log2, s_mask[col]) : -INFINITY;
+        sum += rl::ex2(sc - mx);
+      }
     }
+    inv = r < L ? 1.0f / sum : 0.0f;  // query rows beyond the sentence contribute nothing to dK / dV
   }
-  const float inv = r < L ? 1.0f / sum : 0.0f;  // query rows beyond the sentence contribute nothing to dK / dV
   rl::DropSpec dsp = p.drop;
   rl::drop_resolve(dsp);
   for (int c = 0; c < nchunk; ++c) {
@@ -252,6 +260,12 @@ constexpr int ATT_BWD_SMEM = 7 * T16K + 128 * 4 + 3 * 8 + 16;   // 115,240 B: tw
 extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
                                 int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed,
                                 uint32_t drop_site, void* stream) {
+  return rl_attention_bwd_lse(qkv, mask, ctx, dctx, dqkv, nullptr, B, L, heads, head_dim, drop_p, drop_seed, drop_site, stream);
+}
+
+extern "C" int rl_attention_bwd_lse(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
+                                    const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p,
+                                    uint64_t drop_seed, uint32_t drop_site, void* stream) {
   RL_REQUIRE(qkv && mask && ctx && dctx && dqkv, RL_EINVAL, "rl_attention_bwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_bwd: head_dim must be 64");
   RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 128, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..128", (long long)L);
@@ -290,6 +304,7 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.heads = (int)heads;
   p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
+  p.lse = row_lse;
   attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, p);
   return rl_check_launch("rl_attention_bwd");
 }

@@ -222,12 +222,11 @@ gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ t, const __nv_bfloat16* __res
       uint32_t ow[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        // the products are rounded to bf16 first: the column sum must be that of the stored du (what dW1 sees)
-        const uint32_t pk = rl::pack_bf16(rl::bf16_lo(tw[k]) * rl::gelu_grad(rl::bf16_lo(uw[k])),
-                                          rl::bf16_hi(tw[k]) * rl::gelu_grad(rl::bf16_hi(uw[k])));
-        ow[k] = pk;
-        acc[(k & 3) * 2] += rl::bf16_lo(pk);
-        acc[(k & 3) * 2 + 1] += rl::bf16_hi(pk);
+        const float lo = rl::bf16_lo(tw[k]) * rl::gelu_grad(rl::bf16_lo(uw[k]));
+        const float hi = rl::bf16_hi(tw[k]) * rl::gelu_grad(rl::bf16_hi(uw[k]));
+        ow[k] = rl::pack_bf16(lo, hi);
+        acc[(k & 3) * 2] += lo;       // bias gradient from the unrounded products (fp32, like the reference's autograd)
+        acc[(k & 3) * 2 + 1] += hi;
       }
       *reinterpret_cast<uint4*>(t + r * ld + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       if (two) *reinterpret_cast<uint4*>(t + (r + 8) * ld + c0) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
@@ -471,17 +470,31 @@ struct TensorEntry {   // mirrored by realise_b200/optim.py (ctypes) — keep in
 };
 constexpr int OPT_CHUNK = 4096;
 
+// grid-stride over the 4096-element chunks: ~8 CTAs per SM, ONE atomic per CTA (one atomic per chunk is 50 k atomics
+// on a single address, which serialise in L2 and cost more than reading the 816 MB of gradients)
 __global__ void __launch_bounds__(256)
-mt_sumsq_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ chunks, float* __restrict__ out) {
-  const int2 ck = chunks[blockIdx.x];
-  const TensorEntry e = tab[ck.x];
-  const long long base = (long long)ck.y * OPT_CHUNK;
+mt_sumsq_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ chunks, float* __restrict__ out,
+                long long num_chunks) {
   float s = 0.f;
-  for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
-    const long long idx = base + i;
-    if (idx < e.n) {
-      const float g = e.g[idx];
-      s += g * g;
+  for (long long c = blockIdx.x; c < num_chunks; c += gridDim.x) {
+    const int2 ck = chunks[c];
+    const TensorEntry e = tab[ck.x];
+    const long long base = (long long)ck.y * OPT_CHUNK;
+    if (base + OPT_CHUNK <= e.n && ((reinterpret_cast<uintptr_t>(e.g) & 15) == 0)) {
+      const float4* g4 = reinterpret_cast<const float4*>(e.g + base);
+#pragma unroll
+      for (int i = 0; i < OPT_CHUNK / 4 / 256; ++i) {
+        const float4 g = g4[i * 256 + threadIdx.x];
+        s += (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
+        const long long idx = base + i;
+        if (idx < e.n) {
+          const float g = e.g[idx];
+          s += g * g;
+        }
+      }
     }
   }
   s = rl::warp_sum(s);
@@ -660,7 +673,9 @@ extern "C" int rl_gate_fuse_bwd(const float* dhid, const float* m0, const float*
 extern "C" int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, void* stream) {
   RL_REQUIRE(table && chunks && out, RL_EINVAL, "rl_mt_sumsq: null pointer");
   if (num_chunks <= 0) return 0;
-  mt_sumsq_kernel<<<(unsigned)num_chunks, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, out);
+  long long grid = 8LL * rl_num_sms();
+  if (grid > num_chunks) grid = num_chunks;
+  mt_sumsq_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, out, num_chunks);
   return rl_check_launch("rl_mt_sumsq");
 }
 

@@ -350,11 +350,19 @@ __device__ __forceinline__ float fast_erf(float x) {
   return copysignf(y, x);
 }
 
-// d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x).  erf(u/sqrt2) and phi(u) share one exponential: exp(-(u/sqrt2)^2) = exp(-u^2/2).
 __device__ __forceinline__ float gelu_grad(float u) {
-  const float cdf = 0.5f * (1.0f + fast_erf(u * 0.70710678118654752440f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
-  return fmaf(u, pdf, cdf);
+  const float x = u * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float erfv = copysignf(1.0f - poly * t * e, x);
+  return fmaf(u, 0.3989422804014327f * e, fmaf(0.5f, erfv, 0.5f));
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f)); }

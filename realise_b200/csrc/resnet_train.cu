@@ -495,11 +495,13 @@ glyph_im2col_kernel(const float* __restrict__ glyphs, const long long* __restric
   for (int g = 0; g < 4; ++g)
     d1[g] = make_uint4(rl::pack_bf16(a[8 * g], a[8 * g + 1]), rl::pack_bf16(a[8 * g + 2], a[8 * g + 3]),
                        rl::pack_bf16(a[8 * g + 4], a[8 * g + 5]), rl::pack_bf16(a[8 * g + 6], a[8 * g + 7]));
-  float s[8];
+  if (colsc) {
+    float s[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s[k] = k < C ? s_img[k * 1024 + (2 * oh) * 32 + 2 * ow] : 0.f;
-  *reinterpret_cast<uint4*>(colsc + (img * 256 + tid) * 8) =
-      make_uint4(rl::pack_bf16(s[0], s[1]), rl::pack_bf16(s[2], s[3]), rl::pack_bf16(s[4], s[5]), rl::pack_bf16(s[6], s[7]));
+    for (int k = 0; k < 8; ++k) s[k] = k < C ? s_img[k * 1024 + (2 * oh) * 32 + 2 * ow] : 0.f;
+    *reinterpret_cast<uint4*>(colsc + (img * 256 + tid) * 8) =
+        make_uint4(rl::pack_bf16(s[0], s[1]), rl::pack_bf16(s[2], s[3]), rl::pack_bf16(s[4], s[5]), rl::pack_bf16(s[6], s[7]));
+  }
 }
 
 int ilog2x(int v) {
@@ -646,7 +648,7 @@ extern "C" int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C
 
 extern "C" int rl_glyph_im2col(const float* glyphs, const int64_t* ids, void* col1, void* colsc, int64_t n_img, int32_t C,
                                void* stream) {
-  RL_REQUIRE(glyphs && ids && col1 && colsc && (C == 1 || C == 3), RL_EINVAL, "rl_glyph_im2col: bad arguments");
+  RL_REQUIRE(glyphs && ids && col1 && (C == 1 || C == 3), RL_EINVAL, "rl_glyph_im2col: bad arguments");  // colsc optional
   if (n_img <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 3)

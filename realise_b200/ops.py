@@ -175,15 +175,16 @@ def _drop(drop):
     return ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_uint32(site)
 
 
-def attention(qkv, mask, ctx, B, L, heads, drop=None):
-    """ctx = softmax(QK^T/8 + (1-mask)*-1e4) V per head; qkv bf16 [B*L, 3*heads*64], mask int64 [B, L]."""
+def attention(qkv, mask, ctx, B, L, heads, drop=None, lse=None):
+    """ctx = softmax(QK^T/8 + (1-mask)*-1e4) V per head; qkv bf16 [B*L, 3*heads*64], mask int64 [B, L].
+    lse (optional f32 [B*heads*L]) receives the log2-domain logsumexp of every query row for the backward."""
     _req(qkv, torch.bfloat16, "qkv")
     _req(ctx, torch.bfloat16, "ctx")
     _req(mask, torch.int64, "mask")
     assert qkv.is_contiguous() and ctx.is_contiguous() and mask.is_contiguous()
     with _Timed("attention", 4.0 * B * heads * L * L * 64):
-        check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _c(B), _c(L), _c(heads), _c(64), *_drop(drop),
-                                     _stream()), "rl_attention_fwd")
+        check(lib().rl_attention_fwd_lse(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), _c(B), _c(L), _c(heads), _c(64),
+                                         *_drop(drop), _stream()), "rl_attention_fwd")
     _count()
     return ctx
 
@@ -292,12 +293,12 @@ def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
 # ---------------------------------------------------------------------------------------------------------
 # training path
 # ---------------------------------------------------------------------------------------------------------
-def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None):
+def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None, lse=None):
     for t, n in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, n)
     with _Timed("attention_bwd", 14.0 * B * heads * L * L * 64):
-        check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _c(B), _c(L), _c(heads),
-                                     _c(64), *_drop(drop), _stream()), "rl_attention_bwd")
+        check(lib().rl_attention_bwd_lse(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _ptr(lse), _c(B), _c(L),
+                                         _c(heads), _c(64), *_drop(drop), _stream()), "rl_attention_bwd")
     _count()
 
 

@@ -168,7 +168,9 @@ class TrainEngine:
             s["qkv"] = self._new((N, 3 * H), BF16)
             ops.gemm(xb, lw["w_qkv"], s["qkv"], bias=lw["b_qkv"])
             s["ctx"] = self._new((N, H), BF16)
-            ops.attention(s["qkv"], mask, s["ctx"], B, L, c.num_attention_heads, drop=self.adrop(self.site(name, li, 1)))
+            s["lse"] = self._new((B * c.num_attention_heads * L,), F32)
+            ops.attention(s["qkv"], mask, s["ctx"], B, L, c.num_attention_heads, drop=self.adrop(self.site(name, li, 1)),
+                          lse=s["lse"])
             s["y1"] = self._new((N, H), F32)
             ops.gemm(s["ctx"], lw["w_o"], s["y1"], bias=lw["b_o"], res=x, drop=self.hdrop(self.site(name, li, 2)))
             x1, s["x1b"] = self._new((N, H), F32), self._new((N, H), BF16)
@@ -228,8 +230,10 @@ class TrainEngine:
             if b == 1:
                 w1g = torch.zeros(cout, 32, device=w1.device)
                 w1g[:, :9 * cin] = w1.reshape(cout, 9 * cin)
-                wsg = torch.zeros(cout, 8, device=w1.device)
-                wsg[:, :cin] = wsc
+                # the 1x1 stride-2 shortcut samples the centre tap of conv1's patch: same im2col matrix, weights on
+                # columns c*9 + 4 only (a K = 8 operand would make TMA fetch 16-byte rows)
+                wsg = torch.zeros(cout, 32, device=w1.device)
+                wsg[:, 4:9 * cin:9] = wsc
                 e["w1g"], e["wscg"] = w1g.bfloat16().contiguous(), wsg.bfloat16().contiguous()
             else:
                 t1 = self._s2_taps(S)
@@ -285,10 +289,10 @@ class TrainEngine:
             s = {"e": e, "x_in": x}
             c1, cs = self._new((M, cout), F32), self._new((M, cout), F32)   # raw conv outputs stay f32 (batch stats)
             if bi == 0:
-                s["col1"], s["colsc"] = self._new((M, 32), BF16), self._new((M, 8), BF16)
-                ops.glyph_im2col(glyphs, ids_flat, s["col1"], s["colsc"], N, c.num_fonts)
+                s["col1"] = self._new((M, 32), BF16)
+                ops.glyph_im2col(glyphs, ids_flat, s["col1"], None, N, c.num_fonts)
                 ops.gemm(s["col1"], e["w1g"], c1)
-                ops.gemm(s["colsc"], e["wscg"], cs)
+                ops.gemm(s["col1"], e["wscg"], cs)
             elif S == 1:
                 xin = x.view(N, 4 * cin)
                 ops.gemm(xin, e["w1f"], c1)
@@ -372,12 +376,11 @@ class TrainEngine:
             dc1, dcs = dcat[:, :cout], dcat[:, cout:]
             gw1, gws = g(e["conv1"].weight), g(e["convs"].weight)
             if bi == 0:
-                tmp = self._new((cout, 32), F32, zero=True)
-                ops.gemm(dc1, s["col1"], tmp, a_t=True, b_t=True, split_k=-1)
-                gw1.view(cout, 9 * cin).copy_(tmp[:, :9 * cin])
-                tmp2 = self._new((cout, 8), F32, zero=True)
-                ops.gemm(dcs, s["colsc"], tmp2, a_t=True, b_t=True, split_k=-1)
-                gws.view(cout, cin).copy_(tmp2[:, :cin])
+                # [dc1 | dcs]^T col1 in ONE split-K GEMM (a full 128-row tile): rows 0..63 = dW1, rows 64..127 = dWsc
+                tmp = self._new((2 * cout, 32), F32, zero=True)
+                ops.gemm(dcat, s["col1"], tmp, a_t=True, b_t=True, split_k=-1)
+                gw1.view(cout, 9 * cin).copy_(tmp[:cout, :9 * cin])
+                gws.view(cout, cin).copy_(tmp[cout:, 4:9 * cin:9])
                 return
             x_in = s["x_in"]
             t1 = e["taps1"]
@@ -532,7 +535,7 @@ class TrainEngine:
             ops.gemm(dy1b, lw["w_o"], dctx, b_t=True)
             dqkv = self._new((N, 3 * H), BF16)
             ops.attention_bwd(s["qkv"], mask, s["ctx"], dctx, dqkv, B, L, c.num_attention_heads,
-                              drop=self.adrop(self.site(name, li, 1)))
+                              drop=self.adrop(self.site(name, li, 1)), lse=s["lse"])
             dw, db = self._qkv_grads(att, H)
             ops.colsum_bf16(dqkv, db)
             ops.gemm(dqkv, s["xb"], dw, a_t=True, b_t=True, split_k=-1)                                         # dWqkv = dqkv^T x
