@@ -293,6 +293,11 @@ RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks
 RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                        float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
                        float grad_div, void* stream);
+/* Split-precision operand for the tied classifier (src/models.py:859): out[r] = [hi | lo | hi] with hi = bf16(x[r]),
+ * lo = bf16(x[r] - hi), width 3*cols.  Against B = [W_hi | W_hi | W_lo] one rl_gemm_bf16 with K = 3*cols computes
+ * x W^T with ~16-bit mantissa operands: the 21128-way logits no longer carry the bf16 rounding of seq and E. */
+RL_API int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, void* stream);
+
 /* GELU (erf form, transformers/modeling_bert.py:125-131) as element-wise passes next to the K = 768 GEMMs of
  * BertIntermediate: h = u * Phi(u) over n bf16 elements; and its backward fused with the bias gradient:
  * t[r, c] <- t[r, c] * gelu'(u[r, c]) in place (t = dy2 W2), dbias[c] += sum_r of the fp32 products. */
@@ -303,6 +308,13 @@ RL_API int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows
  * CUDA graph that contains the optimizer be replayed while LambdaLR (src/run.py:153-160) and the bias corrections move. */
 RL_API int rl_mt_adamw_dev(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                            const float* hyper, float beta1, float beta2, float eps, float grad_div, void* stream);
+
+/* 16-bit operand format, process-wide: 0 (default) = bf16, 1 = IEEE fp16.  While 1, every kernel launched through this
+ * library reads its 16-bit GEMM / attention operands and residuals, and writes its 16-bit outputs, as fp16 (tcgen05
+ * kind::f16 takes either at the same rate).  The inference path uses fp16 for the transformer stacks, the GRU and the
+ * classifier (three more mantissa bits: max |logit error| vs the fp32 reference drops below the 1e-2 the reference's
+ * bf16 tolerance allows); training keeps bf16 (gradient range).  Callers pass tensors of the matching dtype. */
+RL_API int rl_set_half_format(int f16);
 
 /* Dropout masks are pure functions of (seed, site, element).  With a non-NULL device counter registered here (process-
  * wide), every dropout-bearing kernel launched afterwards uses seed + *dev_counter, read at run time: a captured CUDA

@@ -12,6 +12,15 @@ thread_local char g_err[512] = "";
 std::atomic<const unsigned long long*> g_seed_ptr{nullptr};  // process-wide: autograd runs backward on another thread
 }
 
+namespace {
+std::atomic<int> g_half_f16{0};
+}
+int rl_half_is_f16() { return g_half_f16.load(std::memory_order_relaxed); }
+extern "C" int rl_set_half_format(int f16) {
+  g_half_f16.store(f16 ? 1 : 0, std::memory_order_relaxed);
+  return 0;
+}
+
 const unsigned long long* rl_dropout_seed_ptr() { return g_seed_ptr.load(std::memory_order_relaxed); }
 extern "C" int rl_set_dropout_seed_ptr(const uint64_t* dev_counter) {
   g_seed_ptr.store(reinterpret_cast<const unsigned long long*>(dev_counter), std::memory_order_relaxed);

@@ -18,6 +18,7 @@ struct AttParams {
   float scale_log2;       // (1/sqrt(d)) * log2(e)
   int heads;
   rl::DropSpec drop;      // dropout on the attention probabilities (modeling_bert.py:250)
+  int f16;                // Q/K/V, P and ctx are fp16 instead of bf16 (rl_set_half_format)
   float* lse;             // optional [B, heads, L]: log2-domain logsumexp of every query row (saved for the backward)
 };
 
@@ -88,7 +89,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // S = Q K^T : M=128, N=lkv16, K=64
     rl::mbar_wait(bar_qk, 0);
     rl::tc_fence_after();
-    const uint32_t idesc_s = rl::make_idesc_bf16(128, lkv16);
+    const uint32_t idesc_s = rl::make_idesc_bf16(128, lkv16, 0, 0, p.f16);
     const uint32_t qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK);
 #pragma unroll
     for (int k = 0; k < HEAD_DIM / 16; ++k) {
@@ -166,8 +167,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int g = 0; g < 4; ++g) {
       const int piece = ((c & 1) * 4 + g) ^ (r & 7);
       *reinterpret_cast<uint4*>(tile + piece * 16) =
-          make_uint4(rl::pack_bf16(e[8 * g], e[8 * g + 1]), rl::pack_bf16(e[8 * g + 2], e[8 * g + 3]),
-                     rl::pack_bf16(e[8 * g + 4], e[8 * g + 5]), rl::pack_bf16(e[8 * g + 6], e[8 * g + 7]));
+          make_uint4(rl::pack_h(e[8 * g], e[8 * g + 1], p.f16), rl::pack_h(e[8 * g + 2], e[8 * g + 3], p.f16),
+                     rl::pack_h(e[8 * g + 4], e[8 * g + 5], p.f16), rl::pack_h(e[8 * g + 6], e[8 * g + 7], p.f16));
     }
   }
   rl::fence_proxy_async();
@@ -179,7 +180,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     rl::tc_fence_after();
     rl::mbar_wait(bar_v, 0);
     rl::tc_fence_after();
-    const uint32_t idesc_o = rl::make_idesc_bf16(128, HEAD_DIM, 0, 1);
+    const uint32_t idesc_o = rl::make_idesc_bf16(128, HEAD_DIM, 0, 1, p.f16);
     const uint32_t pa = rl::smem_u32(sP), va = rl::smem_u32(sV);
     const int nk = lkv16 / 16;
     for (int k = 0; k < nk; ++k) {
@@ -206,10 +207,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint4* o = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          o[g] = make_uint4(rl::pack_bf16(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv),
-                            rl::pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv),
-                            rl::pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv),
-                            rl::pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv));
+          o[g] = make_uint4(rl::pack_h(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv, p.f16),
+                            rl::pack_h(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv, p.f16),
+                            rl::pack_h(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv, p.f16),
+                            rl::pack_h(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv, p.f16));
       }
     }
   }
@@ -280,6 +281,7 @@ extern "C" int rl_attention_fwd_lse(const void* qkv, const int64_t* mask, void* 
   p.heads = (int)heads;
   p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
   p.lse = row_lse;
+  p.f16 = rl_half_is_f16();
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)heads, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (lkv16 <= 128) return launch_att<128>(tq, tkv, p, grid, st);

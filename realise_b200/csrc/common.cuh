@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,6 +15,7 @@
 void rl_set_error(const char* fmt, ...);
 int rl_check_launch(const char* what);  // returns 0 or positive cudaError_t
 int rl_num_sms();
+int rl_half_is_f16();   // process-wide 16-bit operand format set by rl_set_half_format (0 = bf16, 1 = fp16)
 const unsigned long long* rl_dropout_seed_ptr();   // process-wide, set by rl_set_dropout_seed_ptr (NULL = off)
 
 #define RL_REQUIRE(cond, code, ...)    \
@@ -169,10 +171,10 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
 
 // instruction descriptor: bf16 x bf16 -> f32, M x N tile, majors: 0 = K-major, 1 = MN-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0,
-                                                       int b_mn_major = 0) {
+                                                       int b_mn_major = 0, int f16 = 0) {
   return (1u << 4)                        // c_format = F32
-         | (1u << 7)                      // a_format = BF16
-         | (1u << 10)                     // b_format = BF16
+         | ((f16 ? 0u : 1u) << 7)         // a_format: 0 = F16, 1 = BF16
+         | ((f16 ? 0u : 1u) << 10)        // b_format
          | ((uint32_t)a_mn_major << 15)   // a_major
          | ((uint32_t)b_mn_major << 16)   // b_major
          | ((uint32_t)(N >> 3) << 17)     // n_dim
@@ -234,6 +236,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// 16-bit operand format of a launch: bf16 (default, training) or IEEE fp16 (rl_set_half_format(1): inference — three more
+// mantissa bits for the same tensor-core rate; activations of this model stay far inside the fp16 range)
+__device__ __forceinline__ uint32_t pack_h(float a, float b, int f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(a, b);
+}
+__device__ __forceinline__ float half_lo(uint32_t v, int f16) {
+  return f16 ? __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))) : bf16_lo(v);
+}
+__device__ __forceinline__ float half_hi(uint32_t v, int f16) {
+  return f16 ? __half2float(__ushort_as_half((unsigned short)(v >> 16))) : bf16_hi(v);
+}
 
 // 2^x, one MUFU op (ex2.approx: <= 2 ulp; -inf -> 0)
 __device__ __forceinline__ float ex2(float x) {

@@ -39,6 +39,7 @@ struct KParams {
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
   rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
+  int f16;        // 16-bit operands / outputs / residuals are IEEE fp16 instead of bf16 (rl_set_half_format)
   int b_mode;     // 1: B tiles are gathered from a conv activation (implicit im2col, weight gradients)
   int ks_major;   // tile order: split index outermost, so that the N tiles sharing a K range run side by side (L2 reuse)
   int nimg;       // conv: number of images (an image index >= nimg makes a TMA box read zeros)
@@ -93,10 +94,10 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 t = r[j];
-          x[8 * j] = rl::bf16_lo(t.x); x[8 * j + 1] = rl::bf16_hi(t.x);
-          x[8 * j + 2] = rl::bf16_lo(t.y); x[8 * j + 3] = rl::bf16_hi(t.y);
-          x[8 * j + 4] = rl::bf16_lo(t.z); x[8 * j + 5] = rl::bf16_hi(t.z);
-          x[8 * j + 6] = rl::bf16_lo(t.w); x[8 * j + 7] = rl::bf16_hi(t.w);
+          x[8 * j] = rl::half_lo(t.x, p.f16); x[8 * j + 1] = rl::half_hi(t.x, p.f16);
+          x[8 * j + 2] = rl::half_lo(t.y, p.f16); x[8 * j + 3] = rl::half_hi(t.y, p.f16);
+          x[8 * j + 4] = rl::half_lo(t.z, p.f16); x[8 * j + 5] = rl::half_hi(t.z, p.f16);
+          x[8 * j + 6] = rl::half_lo(t.w, p.f16); x[8 * j + 7] = rl::half_hi(t.w, p.f16);
         }
       }
     } else {
@@ -105,7 +106,7 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
         x[j] = 0.f;
         if (nb + j < p.N)
           x[j] = p.res_f32 ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + nb + j]
-                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.res)[(long long)row * p.ldr + nb + j]);
+                           : rl::half_lo((uint32_t)reinterpret_cast<const unsigned short*>(p.res)[(long long)row * p.ldr + nb + j], p.f16);
       }
     }
   } else {
@@ -186,12 +187,12 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
           uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                              rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.f16),
+                              rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.f16));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
+            if (nb + j < p.N) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.f16) & 0xFFFFu);
         }
       }
       if (p.act == RL_ACT_GELU || p.act == RL_ACT_GELU_SAVE) {
@@ -218,8 +219,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(rl::pack_bf16(x[8 * g], x[8 * g + 1]), rl::pack_bf16(x[8 * g + 2], x[8 * g + 3]),
-                           rl::pack_bf16(x[8 * g + 4], x[8 * g + 5]), rl::pack_bf16(x[8 * g + 6], x[8 * g + 7]));
+                make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], p.f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], p.f16),
+                           rl::pack_h(x[8 * g + 4], x[8 * g + 5], p.f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], p.f16));
         }
         rl::fence_proxy_async();
         __syncwarp();
@@ -260,15 +261,15 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
             uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.f16),
+                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.f16));
           }
           if (p.out2 && p.act != RL_ACT_GELU_SAVE) {
             uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(rl::pack_bf16(x[8 * j], x[8 * j + 1]), rl::pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                rl::pack_bf16(x[8 * j + 4], x[8 * j + 5]), rl::pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.f16),
+                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.f16));
           }
         } else {
 #pragma unroll
@@ -277,8 +278,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
               if (p.out_f32)
                 reinterpret_cast<float*>(p.out)[orow * p.ldo + nb + j] = x[j];
               else
-                reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + nb + j] = __float2bfloat16(x[j]);
-              if (p.out2 && p.act != RL_ACT_GELU_SAVE) p.out2[orow * p.ldo2 + nb + j] = __float2bfloat16(x[j]);
+                reinterpret_cast<unsigned short*>(p.out)[orow * p.ldo + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.f16) & 0xFFFFu);
+              if (p.out2 && p.act != RL_ACT_GELU_SAVE) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.f16) & 0xFFFFu);
             }
           }
         }
@@ -407,7 +408,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       // ===================== MMA issuer =====================
       // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
-      const uint32_t idesc = rl::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      const uint32_t idesc = rl::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn, p.f16);
       const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
       // K-major: 128-byte rows, 8-row atoms 1024 B apart, a k-step of 16 is +32 B.  MN-major: 64-wide MN blocks
       // 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), a k-step of 16 rows is +2048 B.
@@ -692,7 +693,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (leader) {
       // ===================== MMA issuer (leader CTA only) =====================
       // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
-      const uint32_t idesc = rl::make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn);
+      const uint32_t idesc = rl::make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn, p.f16);
       const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
       const uint32_t a_lbo = p.a_mn ? 8192 : 16, b_lbo = p.b_mn ? 8192 : 16;
       const uint32_t a_kstep = p.a_mn ? 128 : 2, b_kstep = p.b_mn ? 128 : 2;  // in 16-byte units
@@ -846,6 +847,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.b_mn = d->b_major;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.a_mode = d->a_mode;
+  p.f16 = rl_half_is_f16();
   p.b_mode = d->b_mode;
   p.ks_major = 0;
   p.nimg = d->conv_NIMG;

@@ -29,7 +29,7 @@ gru_table_kernel(const float* __restrict__ emb, const float* __restrict__ w_ih, 
 __global__ void __launch_bounds__(256)
 gru_step_kernel(const float* __restrict__ gh, const float* __restrict__ b_hh, const float* __restrict__ table,
                 const long long* __restrict__ pho_idx, const int* __restrict__ lens, const float* __restrict__ h_prev,
-                float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_out_bf16, long long rows, int H, int T, int t) {
+                float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_out_bf16, long long rows, int H, int T, int t, int f16) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -43,7 +43,7 @@ gru_step_kernel(const float* __restrict__ gh, const float* __restrict__ b_hh, co
       const float4 h = h_prev ? reinterpret_cast<const float4*>(h_prev + row * H)[i * 32 + lane]
                               : make_float4(0.f, 0.f, 0.f, 0.f);
       ho[i * 32 + lane] = h;
-      hb[i * 32 + lane] = make_uint2(rl::pack_bf16(h.x, h.y), rl::pack_bf16(h.z, h.w));
+      hb[i * 32 + lane] = make_uint2(rl::pack_h(h.x, h.y, f16), rl::pack_h(h.z, h.w, f16));
     }
     return;
   }
@@ -77,7 +77,7 @@ gru_step_kernel(const float* __restrict__ gh, const float* __restrict__ b_hh, co
     RL_GRU_ELT(x) RL_GRU_ELT(y) RL_GRU_ELT(z) RL_GRU_ELT(w)
 #undef RL_GRU_ELT
     ho[i * 32 + lane] = o;
-    hb[i * 32 + lane] = make_uint2(rl::pack_bf16(o.x, o.y), rl::pack_bf16(o.z, o.w));
+    hb[i * 32 + lane] = make_uint2(rl::pack_h(o.x, o.y, f16), rl::pack_h(o.z, o.w, f16));
   }
 }
 
@@ -340,7 +340,7 @@ extern "C" int rl_gru_step_fwd(const float* gh, const float* b_hh, const float* 
   const int wpb = 8;
   gru_step_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       gh, b_hh, table, (const long long*)pho_idx, lens, h_prev, h_out, (__nv_bfloat16*)h_out_bf16, rows, (int)H, (int)T,
-      (int)t);
+      (int)t, rl_half_is_f16());
   return rl_check_launch("rl_gru_step_fwd");
 }
 

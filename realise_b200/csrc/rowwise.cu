@@ -9,7 +9,7 @@ constexpr int MAX_V4 = 8;  // per-lane float4 count: H <= 1024
 __device__ __forceinline__ void ln_row_store(const float4* x, int nv, float mean, float rstd,
                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                              float* out_f32, __nv_bfloat16* out_bf16, int lane,
-                                             const rl::DropSpec& drop, bool drop_f32, long long elem0) {
+                                             const rl::DropSpec& drop, bool drop_f32, long long elem0, int f16 = 0) {
 #pragma unroll
   for (int i = 0; i < MAX_V4; ++i) {
     if (i < nv) {
@@ -28,7 +28,7 @@ __device__ __forceinline__ void ln_row_store(const float4* x, int nv, float mean
       }
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = drop_f32 ? yd : y;
       if (out_bf16)
-        *reinterpret_cast<uint2*>(out_bf16 + col) = make_uint2(rl::pack_bf16(yd.x, yd.y), rl::pack_bf16(yd.z, yd.w));
+        *reinterpret_cast<uint2*>(out_bf16 + col) = make_uint2(rl::pack_h(yd.x, yd.y, f16), rl::pack_h(yd.z, yd.w, f16));
     }
   }
 }
@@ -55,7 +55,7 @@ __device__ __forceinline__ void ln_stats(const float4* x, int nv, int H, float e
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* out_f32,
                                                         __nv_bfloat16* out_bf16, long long rows, int H, float eps,
-                                                        rl::DropSpec drop, int drop_f32) {
+                                                        rl::DropSpec drop, int drop_f32, int f16) {
   rl::drop_resolve(drop);
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float mean, rstd;
   ln_stats(v, nv, H, eps, mean, rstd);
   ln_row_store(v, nv, mean, rstd, gamma, beta, out_f32 ? out_f32 + row * H : nullptr,
-               out_bf16 ? out_bf16 + row * H : nullptr, lane, drop, drop_f32 != 0, row * H);
+               out_bf16 ? out_bf16 + row * H : nullptr, lane, drop, drop_f32 != 0, row * H, f16);
 }
 
 // BertEmbeddings.forward: LN(word[ids] (or inputs_embeds) + pos[position] + type[0])
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ inputs_embeds,
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* out_f32, __nv_bfloat16* out_bf16, float* pre_out, long long rows,
-                int L, int H, int pos_mode, float eps, rl::DropSpec drop) {
+                int L, int H, int pos_mode, float eps, rl::DropSpec drop, int f16) {
   rl::drop_resolve(drop);
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -100,7 +100,7 @@ embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ wor
   float mean, rstd;
   ln_stats(v, nv, H, eps, mean, rstd);
   ln_row_store(v, nv, mean, rstd, gamma, beta, out_f32 ? out_f32 + row * H : nullptr,
-               out_bf16 ? out_bf16 + row * H : nullptr, lane, drop, true, row * H);
+               out_bf16 ? out_bf16 + row * H : nullptr, lane, drop, true, row * H, f16);
 }
 
 // ---- gated fusion (src/models.py:840-850) ----
@@ -338,7 +338,7 @@ extern "C" int rl_layernorm_fwd(const float* x, const float* gamma, const float*
   const int wpb = 8;
   layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows, (int)H, eps, rl::make_drop(drop_p, drop_seed, drop_site),
-      drop_f32);
+      drop_f32, rl_half_is_f16());
   return rl_check_launch("rl_layernorm_fwd");
 }
 
@@ -353,7 +353,7 @@ extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const floa
   const int wpb = 8;
   embed_ln_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       (const long long*)ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, pre_ln_out,
-      rows, (int)L, (int)H, pos_mode, eps, rl::make_drop(drop_p, drop_seed, drop_site));
+      rows, (int)L, (int)H, pos_mode, eps, rl::make_drop(drop_p, drop_seed, drop_site), rl_half_is_f16());
   return rl_check_launch("rl_embed_ln_fwd");
 }
 
@@ -393,6 +393,34 @@ extern "C" int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const i
   if (rc) return rc;
   ce_reduce_kernel<<<1, 1024, 0, st>>>(row_loss_ws, (const long long*)loss_mask, loss, count_out, rows);
   return rl_check_launch("rl_masked_ce_fwd");
+}
+
+// x (f32) -> [hi | lo | hi] bf16 rows of width 3*cols: hi = bf16(x), lo = bf16(x - hi).  With B = [W_hi | W_hi | W_lo]
+// one K = 3*cols GEMM evaluates x W^T with 16-bit mantissa operands (hi*hi + lo*hi + hi*lo) on the bf16 tensor path.
+__global__ void __launch_bounds__(256)
+split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int cols, int f16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over rows * cols/4
+  const int c4 = cols >> 2;
+  if (i >= rows * c4) return;
+  const long long r = i / c4;
+  const int c = (int)(i - r * c4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * cols + c);
+  const uint32_t h0 = rl::pack_h(v.x, v.y, f16), h1 = rl::pack_h(v.z, v.w, f16);
+  const uint32_t l0 = rl::pack_h(v.x - rl::half_lo(h0, f16), v.y - rl::half_hi(h0, f16), f16);
+  const uint32_t l1 = rl::pack_h(v.z - rl::half_lo(h1, f16), v.w - rl::half_hi(h1, f16), f16);
+  __nv_bfloat16* o = out + r * 3 * cols + c;
+  *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(o + cols) = make_uint2(l0, l1);
+  *reinterpret_cast<uint2*>(o + 2 * cols) = make_uint2(h0, h1);
+}
+
+extern "C" int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, void* stream) {
+  RL_REQUIRE(x && out && cols > 0 && cols % 4 == 0 && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 7) == 0), RL_EALIGN,
+             "rl_split3_bf16: cols must be a multiple of 4 and the pointers aligned");
+  if (rows <= 0) return 0;
+  const long long n = rows * (cols / 4);
+  split3_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, rows, (int)cols, rl_half_is_f16());
+  return rl_check_launch("rl_split3_bf16");
 }
 
 extern "C" int rl_argmax_rows(const float* logits, int64_t* out, int64_t rows, int64_t V, int64_t ld, void* stream) {

@@ -37,7 +37,17 @@ class _Timed:
             self.e1.record()
             _prof.append((self.kind, self.work, self.e0, self.e1, self.detail))
         return False
-_DT = {torch.bfloat16: 0, torch.float32: 1}
+_DT = {torch.bfloat16: 0, torch.float16: 0, torch.float32: 1}   # 16-bit outputs: the format follows set_half_format
+_HALF_F16 = False
+
+
+def set_half_format(f16):
+    """16-bit operand format of every following launch: bf16 (False, default) or IEEE fp16 (True, inference)."""
+    global _HALF_F16
+    f16 = bool(f16)
+    if f16 != _HALF_F16:
+        check(lib().rl_set_half_format(ctypes.c_int(int(f16))), "rl_set_half_format")
+        _HALF_F16 = f16
 
 
 def _stream():
@@ -51,6 +61,8 @@ def _ptr(t):
 def _req(t, dtype, name):
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (realise_b200 has no CPU path)")
+    if dtype is torch.bfloat16 and _HALF_F16:
+        dtype = torch.float16
     if t.dtype != dtype:
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 
@@ -322,6 +334,16 @@ def colsum_bf16(x, out):
     _req(out, torch.float32, "out")
     rows, cols = x.shape
     check(lib().rl_colsum_bf16(_ptr(x), _ptr(out), _c(rows), _c(cols), _c(x.stride(0)), _stream()), "rl_colsum_bf16")
+    _count()
+
+
+def split3_bf16(x, out):
+    """out[r] = [bf16(x) | bf16(x - bf16(x)) | bf16(x)] (split-precision classifier operand)."""
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    rows, cols = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and tuple(out.shape) == (rows, 3 * cols)
+    check(lib().rl_split3_bf16(_ptr(x), _ptr(out), _c(rows), _c(cols), _stream()), "rl_split3_bf16")
     _count()
 
 

@@ -464,6 +464,7 @@ class TrainEngine:
         N, H, V = B * L, c.hidden_size, c.vocab_size
         if L > 128:
             raise NotImplementedError("attention backward kernel supports seq_len <= 128")
+        ops.set_half_format(False)   # training computes with bf16 operands
         self.step_seed = self.seed
         self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         sv = {"B": B, "L": L, "mask": mask, "inp": inp, "seed": self.step_seed}

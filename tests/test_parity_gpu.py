@@ -14,7 +14,8 @@ from realise_b200.synth import ArchConfig, synth_batch
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 1.5e-2     # bf16 operands / fp32 accumulate, 19 transformer layers + 15 convs deep
+LOGIT_TOL = 1.0e-2     # north_star's 16-bit tolerance; inference runs fp16 operands / fp32 accumulate (measured 5.2e-3 on
+                       # the full 19-layer model; with bf16 operands the max over ~10^7 logits sits at 1.2-1.4e-2)
 HIDDEN_TOL = 3e-2      # post-LayerNorm hidden states (|x| up to ~6)
 
 
