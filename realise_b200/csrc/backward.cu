@@ -20,7 +20,7 @@ constexpr int MAX_V4 = 8;
 // atomics are CAS loops), which keeps the kernel at ~80 registers so that 24 warps per SM hide the HBM latency of
 // the row loads.  At the end the 8 slices are summed and flushed with one global atomic per column per CTA.
 template <int NV>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ add_in, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int H,
@@ -556,8 +556,8 @@ extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* ga
   RL_REQUIRE(dy && x && gamma && (dx || dx_bf16), RL_EINVAL, "rl_layernorm_bwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_bwd: bad H");
   if (rows <= 0) return 0;
-  // 8 rows per CTA at least (one per warp); at most 3 CTAs per SM
-  const long long max_ctas = 3LL * rl_num_sms();
+  // 8 rows per CTA at least (one per warp); at most 2 CTAs per SM (128 registers: no spills)
+  const long long max_ctas = 2LL * rl_num_sms();
   long long ctas = (rows + 7) / 8;
   if (ctas > max_ctas) ctas = max_ctas;
   const int rows_per_cta = (int)((rows + ctas - 1) / ctas);

@@ -264,7 +264,7 @@ struct BnBranch {          // one BatchNorm whose output fed the (shared) ReLU
 // reduce: dbeta = sum g, dgamma = rstd * (sum g*x - mean * sum g) — mean/rstd are applied once at the end, so the loop
 // carries only 8 * (1 + NB) accumulators (4 CTAs per SM); two row groups in flight per warp.
 template <int NB>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, NB == 2 ? 3 : 4)
 bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
                          BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
   __shared__ float sm[8][256];
@@ -362,7 +362,7 @@ bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __
 // D = gamma*rstd*(mean*rstd*dgamma/M - dbeta/M): the per-channel coefficients are derived once per thread (it owns 8
 // channels and walks the rows of its slab), so the row loop is 4 vector loads, 2 vector stores and 6 FMAs per channel.
 template <int NB>
-__global__ void __launch_bounds__(256, NB == 2 ? 3 : 4)
+__global__ void __launch_bounds__(256, NB == 2 ? 2 : 4)
 bn_bwd_apply_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
                         BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
