@@ -52,3 +52,42 @@ def test_gemm_desc_layout_matches_header():
             m = re.search(r"(\w+)\s*(\[\d+\])?\s*$", part.strip())
             names.append(m.group(1))
     assert names == [f[0] for f in _lib.GemmDesc._fields_]
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Implicit-im2col GEMM operand, format / seed switches and the fused passes reject bad arguments on the host."""
+    from realise_b200 import _lib
+    lib = _lib.lib()
+    d = _lib.GemmDesc()
+    d.a, d.b, d.out = 16, 16, 16           # non-null, never dereferenced: validation fails first
+    d.M, d.N, d.K = 64, 576, 1 << 20
+    d.lda, d.ldb, d.ldo = 64, 64, 576
+    d.b_mode, d.b_major, d.a_major = 1, 0, 1
+    assert lib.rl_gemm_bf16(ctypes.byref(d), None) < 0
+    assert b"b_mode" in lib.rl_last_error()
+    assert lib.rl_set_half_format(1) == 0 and lib.rl_set_half_format(0) == 0
+    assert lib.rl_set_dropout_seed_ptr(None) == 0
+    assert lib.rl_gelu_fwd(None, None, ctypes.c_int64(8), None) < 0
+    assert lib.rl_gelu_bwd_colsum(None, None, None, ctypes.c_int64(8), ctypes.c_int64(8), ctypes.c_int64(8), None) < 0
+    assert lib.rl_split3_bf16(None, None, ctypes.c_int64(1), ctypes.c_int64(8), None) < 0
+    assert lib.rl_mt_adamw_dev(None, None, ctypes.c_int64(1), None, ctypes.c_float(1.0), None, ctypes.c_float(0.9),
+                               ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_float(1.0), None) < 0
+
+
+def test_graphed_step_and_schedule_helpers_on_cpu():
+    """Host logic of the CUDA-graph step that needs no GPU: optimizer type check, device-schedule values."""
+    import math
+
+    import pytest
+    import torch
+
+    from realise_b200.graphed import GraphedTrainStep
+    from realise_b200.optim import FusedAdamW
+    lin = torch.nn.Linear(4, 4)
+    with pytest.raises(TypeError):
+        GraphedTrainStep(lin, torch.optim.SGD(lin.parameters(), lr=0.1))
+    opt = FusedAdamW(lin.parameters(), lr=5e-5, betas=(0.9, 0.999))
+    lr, bc1, bc2 = opt.hyper_values(3)
+    assert lr == 5e-5 and math.isclose(bc1, 1 - 0.9 ** 3) and math.isclose(bc2, 1 - 0.999 ** 3)
+    opt.param_groups[0]["lr"] = 1e-5          # LambdaLR writes the group's lr: the next replay must read it
+    assert opt.hyper_values(4)[0] == 1e-5
