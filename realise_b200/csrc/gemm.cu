@@ -891,7 +891,10 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
         const long long waves = (tm * tn + sms - 1) / sms;
         const double bytes = A_BYTES + (mode ? cand / 2 : cand) * BK * 2.0;
         const double per_kb = bytes / 42.6 > 2.0 * cand ? bytes / 42.6 : 2.0 * cand;
-        const double cost = waves * (per_kb * p.num_kb + 1500.0);  // + per-tile epilogue / pipeline bubble
+        double cost = waves * (per_kb * p.num_kb + 1500.0);  // + per-tile epilogue / pipeline bubble
+        // split-K fills the machine whatever the tile count (the split chooser below sizes the waves): what matters
+        // is the total operand traffic, tiles x bytes per k-block — the larger tile moves fewer bytes per FLOP
+        if (d->split_k != 0) cost = (double)(tm * tn) * per_kb;
         if (cost < best) {
           best = cost;
           bn = cand;
