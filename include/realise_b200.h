@@ -293,6 +293,10 @@ RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks
 RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                        float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
                        float grad_div, void* stream);
+/* out[r, :] = table[ids[r], :] for f32 rows of H (inference glyph cache: in eval mode CharResNet + its LayerNorm input
+ * is a pure function of the token id, so a [vocab, 768] table replaces the CNN; src/models.py:829-838). */
+RL_API int rl_gather_rows_f32(const float* table, const int64_t* ids, float* out, int64_t rows, int64_t H, void* stream);
+
 /* Split-precision operand for the tied classifier (src/models.py:859): out[r] = [hi | lo | hi] with hi = bf16(x[r]),
  * lo = bf16(x[r] - hi), width 3*cols.  Against B = [W_hi | W_hi | W_lo] one rl_gemm_bf16 with K = 3*cols computes
  * x W^T with ~16-bit mantissa operands: the 21128-way logits no longer carry the bf16 rounding of seq and E. */

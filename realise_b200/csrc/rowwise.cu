@@ -414,6 +414,27 @@ split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
   *reinterpret_cast<uint2*>(o + 2 * cols) = make_uint2(h0, h1);
 }
 
+// out[r] = table[ids[r]] (f32 rows of H): the inference-time glyph cache lookup (CharResNet in eval mode is a pure
+// function of the token id, src/models.py:829-838)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ ids, float* __restrict__ out, long long rows,
+                   int H) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(table + ids[row] * (long long)H);
+  float4* dst = reinterpret_cast<float4*>(out + row * H);
+  for (int i = lane; i < H / 4; i += 32) dst[i] = __ldg(src + i);
+}
+
+extern "C" int rl_gather_rows_f32(const float* table, const int64_t* ids, float* out, int64_t rows, int64_t H, void* stream) {
+  RL_REQUIRE(table && ids && out && H > 0 && H % 4 == 0 && ((((uintptr_t)table | (uintptr_t)out) & 15) == 0), RL_EALIGN,
+             "rl_gather_rows_f32: H must be a multiple of 4 and the pointers 16-byte aligned");
+  if (rows <= 0) return 0;
+  gather_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(table, (const long long*)ids, out, rows, (int)H);
+  return rl_check_launch("rl_gather_rows_f32");
+}
+
 extern "C" int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, void* stream) {
   RL_REQUIRE(x && out && cols > 0 && cols % 4 == 0 && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 7) == 0), RL_EALIGN,
              "rl_split3_bf16: cols must be a multiple of 4 and the pointers aligned");

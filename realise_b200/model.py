@@ -172,6 +172,8 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         self.use_cuda_graph = True
         self.precise_classifier = False  # eval logits through the split-precision classifier (see prepare()): measured
                                          # to cut the logit error rms by only 15 % (the error is upstream), so off
+        self.glyph_cache = False         # inference: replace the glyph CNN by a [vocab, 768] lookup built once (bit-identical;
+                                         # off by default so that benchmarks time the CNN itself)
         self.eval_fp16 = True            # inference: fp16 (not bf16) operands for the transformer stacks, GRU and classifier
         self._engine = None       # realise_b200.train.TrainEngine, built on the first train-mode forward
         self.fuse_block1 = True   # eval: glyph gather + whole res_block1 in one tcgen05 kernel
@@ -475,6 +477,23 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         self._keep("res_block1_split", x)
         return self._resnet_tail(P, x, N)
 
+    def _glyph_cache_table(self, P):
+        """[vocab, 768] f32: CharResNet output of every vocabulary glyph, computed once per operand cache (eval mode:
+        BatchNorm uses running statistics, so the CNN output depends on the token id only — SURVEY.md §8f).  Each row
+        is produced by the same kernels, per image, as the uncached path: the lookup is bit-identical to it."""
+        if "glyph_cache" not in P:
+            V, H = self.config.vocab_size, self.config.hidden_size
+            table = torch.empty(V, H, device=P["res"]["glyphs"].device, dtype=torch.float32)
+            ws, self._ws = self._ws, {}            # private workspace for the chunked build
+            try:
+                for i in range(0, V, 4096):
+                    ids = torch.arange(i, min(i + 4096, V), device=table.device, dtype=torch.int64)
+                    table[i:i + ids.numel()].copy_(self._resnet(P, ids, ids.numel()))
+            finally:
+                self._ws = ws
+            P["glyph_cache"] = table
+        return P["glyph_cache"]
+
     def _resnet_tail(self, P, x, N):
         """res_block2..5 as implicit GEMMs over the parity-split block-1 output."""
         R = P["res"]
@@ -587,7 +606,11 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             mods.append(pho_h)
         if c.with_res == "yes":
             ops.set_half_format(False)     # the glyph CNN keeps bf16 operands (its fused block-1 kernel is bf16-only)
-            res_raw = self._resnet(P, ids_flat, N)
+            if self.glyph_cache and self.collect is None:
+                res_raw = self._buf("res.cached", (N, H), f32)
+                ops.gather_rows(self._glyph_cache_table(P), ids_flat, res_raw)
+            else:
+                res_raw = self._resnet(P, ids_flat, N)
             ops.set_half_format(f16)
             res_h = self._buf("res.h", (N, H), f32)
             ops.layernorm(res_raw, P["res_ln_w"], P["res_ln_b"], res_h, None, c.layer_norm_eps)

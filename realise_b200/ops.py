@@ -337,6 +337,17 @@ def colsum_bf16(x, out):
     _count()
 
 
+def gather_rows(table, ids, out):
+    """out[r] = table[ids[r]] for f32 rows (glyph cache lookup)."""
+    _req(table, torch.float32, "table")
+    _req(ids, torch.int64, "ids")
+    _req(out, torch.float32, "out")
+    rows, H = out.shape
+    assert table.is_contiguous() and out.is_contiguous() and ids.numel() == rows and table.shape[1] == H
+    check(lib().rl_gather_rows_f32(_ptr(table), _ptr(ids), _ptr(out), _c(rows), _c(H), _stream()), "rl_gather_rows_f32")
+    _count()
+
+
 def split3_bf16(x, out):
     """out[r] = [bf16(x) | bf16(x - bf16(x)) | bf16(x)] (split-precision classifier operand)."""
     _req(x, torch.float32, "x")

@@ -141,3 +141,46 @@ def test_error_paths():
         ops.gemm(a, b, out)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.gemm(a.cpu(), b, out)
+
+
+def test_glyph_cache_and_device_batch_builder_are_exact():
+    """§8f rows: (1) the [vocab, 768] glyph cache replaces the CNN in inference bit for bit; (2) a batch whose pinyin
+    comes from the device-side table lookup (fixed T = 7) gives the same logits as the host-built batch."""
+    from realise_b200.batch import MAX_PHO_LEN, PinyinTable
+    cfg = ArchConfig(num_hidden_layers=2)
+    model = build(cfg, 21)
+    host = synth_batch(3, 24, seed=31)
+    batch = to_dev(host)
+    model.use_cuda_graph = False
+    with torch.no_grad():
+        ref = model(batch)[1].clone()
+        model.glyph_cache = True
+        cached = model(batch)[1].clone()
+        model.glyph_cache = False
+    assert torch.equal(ref, cached)
+    # device batch builder: a table that maps every token id to the pinyin the synthetic batch gave it
+    V = cfg.vocab_size
+    table = torch.zeros(V, MAX_PHO_LEN, dtype=torch.int64)
+    lens = torch.ones(V, dtype=torch.int32)
+    table[:, 0] = 32                                            # 'U' for tokens that do not occur
+    flat = host["src_idx"].flatten()
+    T = host["pho_idx"].shape[1]
+    first = {}
+    for i, tok in enumerate(flat.tolist()):
+        first.setdefault(tok, i)
+    keep = torch.tensor([first[t] == i for i, t in enumerate(flat.tolist())])
+    # a repeated token keeps the pinyin of its first occurrence in BOTH batches, as a function of the id must
+    for i in torch.nonzero(keep).flatten().tolist():
+        tok = int(flat[i])
+        table[tok] = 0
+        table[tok, :T] = host["pho_idx"][i]
+        lens[tok] = host["pho_lens"][i]
+    tab = PinyinTable(table, lens).to("cuda")
+    b2 = {k: v for k, v in batch.items() if k not in ("pho_idx", "pho_lens")}
+    tab.build_batch(b2)
+    b1 = dict(batch)
+    b1["pho_idx"], b1["pho_lens"] = tab.table.cpu()[flat][:, :T].cuda(), [int(x) for x in tab.lens.cpu()[flat]]
+    with torch.no_grad():
+        l1 = model(b1)[1].clone()
+        l2 = model(b2)[1].clone()
+    assert b2["pho_idx"].shape[1] == MAX_PHO_LEN and torch.equal(l1, l2)
