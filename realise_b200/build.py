@@ -63,13 +63,25 @@ def build(verbose=False, force=False):
     return LIB
 
 
+def _stale():
+    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
+
+
 def ensure_built():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime():
+    if _stale():
         if subprocess.call(["which", os.environ.get("NVCC", "nvcc")], stdout=subprocess.DEVNULL) != 0:
             if os.path.exists(LIB):
                 return LIB  # GPU box without a fresher build: use what travelled
             raise RuntimeError("librealise_b200.so is missing and nvcc is not available")
-        build()
+        # one process builds, the others (torchrun ranks importing at the same moment) wait for it
+        import fcntl
+        with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if _stale():
+                    build()
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
