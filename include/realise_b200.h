@@ -270,11 +270,11 @@ RL_API int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int3
                      int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
                      int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream);
 /* Two BatchNorms that fed the same ReLU (out = relu(bn2(c2) + bn_s(cs)), src/char_cnn.py:31-32) differentiated in one
- * reduce + one apply pass: dy / act_out are read once for both branches.  x2 == NULL: single branch (== rl_bn_bwd with
- * f32 x).  C must be 8*2^k (< 256) or a multiple of 256; all pointers 16-byte aligned. */
-RL_API int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const float* x1,
+ * reduce + one apply pass: dy / act_out are read once for both branches.  x2 == NULL: single branch (== rl_bn_bwd).
+ * x1 / x2 are f32 or bf16 (x_dtype; res_block1-2 keep their raw conv outputs in bf16 to halve the BatchNorm traffic).  C must be 8*2^k (< 256) or a multiple of 256; all pointers 16-byte aligned. */
+RL_API int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, int32_t x_dtype, const void* x1,
                       const float* mean1, const float* rstd1, const float* gamma1, float* dbeta1, float* dgamma1, void* dx1,
-                      int64_t ldx1, const float* x2, const float* mean2, const float* rstd2, const float* gamma2,
+                      int64_t ldx1, const void* x2, const float* mean2, const float* rstd2, const float* gamma2,
                       float* dbeta2, float* dgamma2, void* dx2, int64_t ldx2, int64_t M, int64_t C, int32_t remap,
                       int32_t map_h, int32_t map_w, void* stream);
 RL_API int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C, int32_t W, int32_t H, int32_t P,

@@ -200,7 +200,8 @@ bn_bwd_apply_kernel(const void* __restrict__ dy, int dy_f32, const void* __restr
 __device__ __forceinline__ void load8(const void* p, int is_f32, long long i, float (&v)[8]) { load_raw8(p, is_f32, i, v); }
 
 __global__ void __launch_bounds__(256)
-bn_stats_vec_kernel(const float* __restrict__ x, float* __restrict__ sums, long long M, int C, int lpr_shift, int rows_per_cta) {
+bn_stats_vec_kernel(const void* __restrict__ x, int x_f32, float* __restrict__ sums, long long M, int C, int lpr_shift,
+                    int rows_per_cta) {
   __shared__ float s1[8][256], s2[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
@@ -213,19 +214,21 @@ bn_stats_vec_kernel(const float* __restrict__ x, float* __restrict__ sums, long 
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
   const int step = 8 * rpw;
   long long r = r0 + warp * rpw + (lane >> lpr_shift);
-  for (; r + step < r1; r += 2 * step) {
-    float v[8], w[8];
-    load_raw8(x, 1, r * C + col, v);
-    load_raw8(x, 1, (r + step) * C + col, w);
+  for (; r + 3 * step < r1; r += 4 * step) {   // four row groups in flight (64 B per lane even with bf16 rows)
+    float v[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[j] += v[j] + w[j];
-      b[j] = fmaf(v[j], v[j], fmaf(w[j], w[j], b[j]));
-    }
+    for (int u = 0; u < 4; ++u) load_raw8(x, x_f32, (r + u * step) * C + col, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] += v[u][j];
+        b[j] = fmaf(v[u][j], v[u][j], b[j]);
+      }
   }
   for (; r < r1; r += step) {
     float v[8];
-    load_raw8(x, 1, r * C + col, v);
+    load_raw8(x, x_f32, r * C + col, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       a[j] += v[j];
@@ -251,7 +254,8 @@ bn_stats_vec_kernel(const float* __restrict__ x, float* __restrict__ sums, long 
 }
 
 struct BnBranch {          // one BatchNorm whose output fed the (shared) ReLU
-  const float* x;          // raw conv output [M, C] f32, plain rows
+  const void* x;           // raw conv output [M, C], plain rows; f32, or bf16 when x_f32 == 0
+  int x_f32;
   const float* mean;
   const float* rstd;
   const float* gamma;
@@ -264,7 +268,7 @@ struct BnBranch {          // one BatchNorm whose output fed the (shared) ReLU
 // reduce: dbeta = sum g, dgamma = rstd * (sum g*x - mean * sum g) — mean/rstd are applied once at the end, so the loop
 // carries only 8 * (1 + NB) accumulators (4 CTAs per SM); two row groups in flight per warp.
 template <int NB>
-__global__ void __launch_bounds__(256, NB == 2 ? 3 : 4)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
                          BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
   __shared__ float sm[8][256];
@@ -283,34 +287,40 @@ bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __
   }
   const int step = 8 * rpw;
   long long r = r0 + warp * rpw + (lane >> lpr_shift);
-  for (; r + step < r1; r += 2 * step) {
-    const long long ra = r, rb = r + step;
-    const long long da = remap ? split_row(ra, hw_shift, w_shift) : ra, db = remap ? split_row(rb, hw_shift, w_shift) : rb;
-    float ga[8], gb[8], xa[8], xb[8];
-    load8(dy, dy_f32, da * C + col, ga);
-    load8(dy, dy_f32, db * C + col, gb);
-    if (act_out) {
-      float aa[8], ab[8];
-      load8(act_out, act_f32, da * C + col, aa);
-      load8(act_out, act_f32, db * C + col, ab);
+  constexpr int U = 4;   // row groups in flight per warp (bf16 rows are only 16 B per lane and tensor)
+  for (; r + (U - 1) * step < r1; r += U * step) {
+    float g[U][8], xv[U][8];
+    long long dr[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ga[j] = aa[j] > 0.f ? ga[j] : 0.f;
-        gb[j] = ab[j] > 0.f ? gb[j] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u * step;
+      dr[u] = remap ? split_row(rr, hw_shift, w_shift) : rr;
+      load8(dy, dy_f32, dr[u] * C + col, g[u]);
+      load_raw8(b0.x, b0.x_f32, rr * C + col, xv[u]);
+    }
+    if (act_out) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float a[8];
+        load8(act_out, act_f32, dr[u] * C + col, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[u][j] = a[j] > 0.f ? g[u][j] : 0.f;
       }
     }
-    load_raw8(b0.x, 1, ra * C + col, xa);
-    load_raw8(b0.x, 1, rb * C + col, xb);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sg[j] += ga[j] + gb[j];
-      sx[0][j] = fmaf(ga[j], xa[j], fmaf(gb[j], xb[j], sx[0][j]));
-    }
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sg[j] += g[u][j];
+        sx[0][j] = fmaf(g[u][j], xv[u][j], sx[0][j]);
+      }
     if (NB == 2) {
-      load_raw8(b1.x, 1, ra * C + col, xa);
-      load_raw8(b1.x, 1, rb * C + col, xb);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sx[NB - 1][j] = fmaf(ga[j], xa[j], fmaf(gb[j], xb[j], sx[NB - 1][j]));
+      for (int u = 0; u < U; ++u) load_raw8(b1.x, b1.x_f32, (r + u * step) * C + col, xv[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sx[NB - 1][j] = fmaf(g[u][j], xv[u][j], sx[NB - 1][j]);
     }
   }
   for (; r < r1; r += step) {
@@ -323,14 +333,14 @@ bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
     }
-    load_raw8(b0.x, 1, r * C + col, xv);
+    load_raw8(b0.x, b0.x_f32, r * C + col, xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sg[j] += g[j];
       sx[0][j] = fmaf(g[j], xv[j], sx[0][j]);
     }
     if (NB == 2) {
-      load_raw8(b1.x, 1, r * C + col, xv);
+      load_raw8(b1.x, b1.x_f32, r * C + col, xv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) sx[NB - 1][j] = fmaf(g[j], xv[j], sx[NB - 1][j]);
     }
@@ -359,53 +369,86 @@ bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __
 }
 
 // apply: dx = A*g + B*x + D per channel with A = gamma*rstd, B = -gamma*rstd^2*dgamma/M,
-// D = gamma*rstd*(mean*rstd*dgamma/M - dbeta/M): the per-channel coefficients are derived once per thread (it owns 8
-// channels and walks the rows of its slab), so the row loop is 4 vector loads, 2 vector stores and 6 FMAs per channel.
+// D = gamma*rstd*(mean*rstd*dgamma/M - dbeta/M).  The CTA derives the coefficients of its 256-column block once into
+// shared memory (so they cost no registers) and every thread walks the rows of the slab two row groups at a time: with
+// bf16 raw conv outputs a single group is only 64 bytes in flight per lane, too little to cover the HBM latency.
 template <int NB>
-__global__ void __launch_bounds__(256, NB == 2 ? 2 : 4)
+__global__ void __launch_bounds__(256, NB == 2 ? 2 : 3)
 bn_bwd_apply_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
                         BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
+  __shared__ __align__(16) float s_coef[NB][3][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
-  const int col = blockIdx.x * 256 + (lane & (lpr - 1)) * 8;
+  {
+    const int ct = blockIdx.x * 256 + threadIdx.x;
+    const float invM = 1.0f / (float)M;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const BnBranch& b = q == 0 ? b0 : b1;
+      float A = 0.f, Bc = 0.f, D = 0.f;
+      if (ct < C) {
+        const float rs = b.rstd[ct], mu = b.mean[ct], gm = b.gamma[ct];
+        const float dg = b.dgamma[ct] * invM, db = b.dbeta[ct] * invM;
+        A = gm * rs;
+        Bc = -gm * rs * rs * dg;
+        D = gm * rs * (mu * rs * dg - db);
+      }
+      s_coef[q][0][threadIdx.x] = A;
+      s_coef[q][1][threadIdx.x] = Bc;
+      s_coef[q][2][threadIdx.x] = D;
+    }
+  }
+  __syncthreads();
+  const int lc = (lane & (lpr - 1)) * 8;   // column inside the CTA's 256-column block
+  const int col = blockIdx.x * 256 + lc;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > M) r1 = M;
-  const float invM = 1.0f / (float)M;
-  float A[NB][8], Bc[NB][8], D[NB][8];
-#pragma unroll
-  for (int q = 0; q < NB; ++q) {
-    const BnBranch& b = q == 0 ? b0 : b1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float rs = b.rstd[col + j], mu = b.mean[col + j], gm = b.gamma[col + j];
-      const float dg = b.dgamma[col + j] * invM, db = b.dbeta[col + j] * invM;
-      A[q][j] = gm * rs;
-      Bc[q][j] = -gm * rs * rs * dg;
-      D[q][j] = gm * rs * (mu * rs * dg - db);
-    }
-  }
   const int step = 8 * rpw;
-  for (long long r = r0 + warp * rpw + (lane >> lpr_shift); r < r1; r += step) {
-    const long long dr = remap ? split_row(r, hw_shift, w_shift) : r;
-    float g[8], xv[NB][8];
-    load8(dy, dy_f32, dr * C + col, g);
-    load_raw8(b0.x, 1, r * C + col, xv[0]);
-    if (NB == 2) load_raw8(b1.x, 1, r * C + col, xv[NB - 1]);
+  for (long long r = r0 + warp * rpw + (lane >> lpr_shift); r < r1; r += 2 * step) {
+    const long long rb = r + step;
+    const bool two = rb < r1;
+    const long long da = remap ? split_row(r, hw_shift, w_shift) : r;
+    const long long db = two ? (remap ? split_row(rb, hw_shift, w_shift) : rb) : da;
+    const long long xb_row = two ? rb : r;
+    float g[2][8], xv[2][NB][8];
+    load8(dy, dy_f32, da * C + col, g[0]);
+    load8(dy, dy_f32, db * C + col, g[1]);
+    load_raw8(b0.x, b0.x_f32, r * C + col, xv[0][0]);
+    load_raw8(b0.x, b0.x_f32, xb_row * C + col, xv[1][0]);
+    if (NB == 2) {
+      load_raw8(b1.x, b1.x_f32, r * C + col, xv[0][NB - 1]);
+      load_raw8(b1.x, b1.x_f32, xb_row * C + col, xv[1][NB - 1]);
+    }
     if (act_out) {
-      float a[8];
-      load8(act_out, act_f32, dr * C + col, a);
+      float a0[8], a1[8];
+      load8(act_out, act_f32, da * C + col, a0);
+      load8(act_out, act_f32, db * C + col, a1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        g[0][j] = a0[j] > 0.f ? g[0][j] : 0.f;
+        g[1][j] = a1[j] > 0.f ? g[1][j] : 0.f;
+      }
     }
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
       const BnBranch& b = q == 0 ? b0 : b1;
-      float o[8];
+      float A[8], Bc[8], D[8];
+      *reinterpret_cast<float4*>(A) = *reinterpret_cast<const float4*>(&s_coef[q][0][lc]);
+      *reinterpret_cast<float4*>(A + 4) = *reinterpret_cast<const float4*>(&s_coef[q][0][lc + 4]);
+      *reinterpret_cast<float4*>(Bc) = *reinterpret_cast<const float4*>(&s_coef[q][1][lc]);
+      *reinterpret_cast<float4*>(Bc + 4) = *reinterpret_cast<const float4*>(&s_coef[q][1][lc + 4]);
+      *reinterpret_cast<float4*>(D) = *reinterpret_cast<const float4*>(&s_coef[q][2][lc]);
+      *reinterpret_cast<float4*>(D + 4) = *reinterpret_cast<const float4*>(&s_coef[q][2][lc + 4]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[q][j], g[j], fmaf(Bc[q][j], xv[q][j], D[q][j]));
-      *reinterpret_cast<uint4*>(b.dx + r * b.ldx + col) =
-          make_uint4(rl::pack_bf16(o[0], o[1]), rl::pack_bf16(o[2], o[3]), rl::pack_bf16(o[4], o[5]), rl::pack_bf16(o[6], o[7]));
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[h][j], fmaf(Bc[j], xv[h][q][j], D[j]));
+        *reinterpret_cast<uint4*>(b.dx + (h ? rb : r) * b.ldx + col) =
+            make_uint4(rl::pack_bf16(o[0], o[1]), rl::pack_bf16(o[2], o[3]), rl::pack_bf16(o[4], o[5]), rl::pack_bf16(o[6], o[7]));
+      }
     }
   }
 }
@@ -433,6 +476,85 @@ void vec_grid(long long M, long long C, int lpr_shift, dim3* grid, int* rows_per
   chunks = (M + rpc - 1) / rpc;
   *rows_per_cta = (int)rpc;
   *grid = dim3((unsigned)col_blocks, (unsigned)chunks);
+}
+
+// forward apply, vector path: out = [relu](x1*sc1 + sh1 [+ x2*sc2 + sh2]); the CTA's 256-column scale/shift block sits in
+// shared memory, every thread owns 8 channels and walks the rows of its slab two row groups at a time
+template <int NX>
+__global__ void __launch_bounds__(256, NX == 2 ? 3 : 4)
+bn_apply_vec_kernel(const void* __restrict__ x1, const float* __restrict__ sc1, const float* __restrict__ sh1,
+                    const void* __restrict__ x2, const float* __restrict__ sc2, const float* __restrict__ sh2, int x_f32,
+                    void* __restrict__ out, int out_f32, int relu, long long M, int C, int lpr_shift, int rows_per_cta, int remap,
+                    int hw_shift, int w_shift) {
+  __shared__ __align__(16) float s_c[NX][2][256];
+  {
+    const int ct = blockIdx.x * 256 + threadIdx.x;
+    s_c[0][0][threadIdx.x] = ct < C ? sc1[ct] : 0.f;
+    s_c[0][1][threadIdx.x] = ct < C ? sh1[ct] : 0.f;
+    if (NX == 2) {
+      s_c[NX - 1][0][threadIdx.x] = ct < C ? sc2[ct] : 0.f;
+      s_c[NX - 1][1][threadIdx.x] = ct < C ? sh2[ct] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
+  const int lc = (lane & (lpr - 1)) * 8;
+  const int col = blockIdx.x * 256 + lc;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  const int step = 8 * rpw;
+  for (long long r = r0 + warp * rpw + (lane >> lpr_shift); r < r1; r += 2 * step) {
+    const long long rb = r + step;
+    const bool two = rb < r1;
+    const long long rb_ld = two ? rb : r;
+    float v[2][8], w[2][8];
+    load_raw8(x1, x_f32, r * C + col, v[0]);
+    load_raw8(x1, x_f32, rb_ld * C + col, v[1]);
+    if (NX == 2) {
+      load_raw8(x2, x_f32, r * C + col, w[0]);
+      load_raw8(x2, x_f32, rb_ld * C + col, w[1]);
+    }
+    float a[8], b[8];
+    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&s_c[0][0][lc]);
+    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&s_c[0][0][lc + 4]);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&s_c[0][1][lc]);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&s_c[0][1][lc + 4]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[h][j] = fmaf(v[h][j], a[j], b[j]);
+    if (NX == 2) {
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&s_c[NX - 1][0][lc]);
+      *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&s_c[NX - 1][0][lc + 4]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&s_c[NX - 1][1][lc]);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&s_c[NX - 1][1][lc + 4]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[h][j] += fmaf(w[h][j], a[j], b[j]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[h][j] = fmaxf(v[h][j], 0.f);
+      }
+      const long long row = h ? rb : r;
+      const long long orow = remap ? split_row(row, hw_shift, w_shift) : row;
+      if (out_f32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow * C + col);
+        o[0] = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
+        o[1] = make_float4(v[h][4], v[h][5], v[h][6], v[h][7]);
+      } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * C + col) =
+            make_uint4(rl::pack_bf16(v[h][0], v[h][1]), rl::pack_bf16(v[h][2], v[h][3]), rl::pack_bf16(v[h][4], v[h][5]),
+                       rl::pack_bf16(v[h][6], v[h][7]));
+      }
+    }
+  }
 }
 
 // ---- im2col for weight gradients: col[m, t*C + ci] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] (0 outside) ------
@@ -515,11 +637,11 @@ int ilog2x(int v) {
 extern "C" int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t M, int64_t C, int64_t ld, void* stream) {
   RL_REQUIRE(x && sums && M > 0 && C > 0 && ld >= C, RL_EINVAL, "rl_bn_stats: bad arguments");
   const int ls = vec_lpr_shift(C);
-  if (x_dtype == RL_DT_F32 && ld == C && ls >= 0 && ((uintptr_t)x & 15) == 0) {
+  if (ld == C && ls >= 0 && ((uintptr_t)x & 15) == 0) {
     dim3 vg;
     int rpc;
     vec_grid(M, C, ls, &vg, &rpc);
-    bn_stats_vec_kernel<<<vg, 256, 0, (cudaStream_t)stream>>>((const float*)x, sums, M, (int)C, ls, rpc);
+    bn_stats_vec_kernel<<<vg, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == RL_DT_F32, sums, M, (int)C, ls, rpc);
     return rl_check_launch("rl_bn_stats");
   }
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
@@ -549,6 +671,20 @@ extern "C" int rl_bn_apply(const void* x1, const float* scale1, const float* shi
     ws = ilog2x(map_w);
     RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_apply: parity split needs a power-of-two map >= 2x2");
   }
+  const int ls = vec_lpr_shift(C);
+  if (ls >= 0 && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) & 15) == 0) {
+    dim3 vg;
+    int rpc;
+    vec_grid(M, C, ls, &vg, &rpc);
+    if (x2)
+      bn_apply_vec_kernel<2><<<vg, 256, 0, (cudaStream_t)stream>>>(x1, scale1, shift1, x2, scale2, shift2, x_dtype == RL_DT_F32, out,
+                                                                  out_dtype == RL_DT_F32, relu, M, (int)C, ls, rpc, remap, hs + ws, ws);
+    else
+      bn_apply_vec_kernel<1><<<vg, 256, 0, (cudaStream_t)stream>>>(x1, scale1, shift1, nullptr, nullptr, nullptr, x_dtype == RL_DT_F32,
+                                                                  out, out_dtype == RL_DT_F32, relu, M, (int)C, ls, rpc, remap,
+                                                                  hs + ws, ws);
+    return rl_check_launch("rl_bn_apply");
+  }
   const long long n = M * (C / 8);
   bn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       x1, scale1, shift1, x2, scale2, shift2, x_dtype == RL_DT_F32, out, out_dtype == RL_DT_F32, relu, M, (int)C, remap, hs + ws,
@@ -556,9 +692,9 @@ extern "C" int rl_bn_apply(const void* x1, const float* scale1, const float* shi
   return rl_check_launch("rl_bn_apply");
 }
 
-extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const float* x1,
+extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, int32_t x_dtype, const void* x1,
                           const float* mean1, const float* rstd1, const float* gamma1, float* dbeta1, float* dgamma1, void* dx1,
-                          int64_t ldx1, const float* x2, const float* mean2, const float* rstd2, const float* gamma2,
+                          int64_t ldx1, const void* x2, const float* mean2, const float* rstd2, const float* gamma2,
                           float* dbeta2, float* dgamma2, void* dx2, int64_t ldx2, int64_t M, int64_t C, int32_t remap,
                           int32_t map_h, int32_t map_w, void* stream) {
   RL_REQUIRE(dy && x1 && mean1 && rstd1 && gamma1 && dbeta1 && dgamma1 && dx1 && M > 0 && C > 0 && ldx1 >= C && ldx1 % 8 == 0,
@@ -576,8 +712,9 @@ extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out,
     RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_bwd2: parity split needs a power-of-two map >= 2x2");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  BnBranch b0{x1, mean1, rstd1, gamma1, dbeta1, dgamma1, (__nv_bfloat16*)dx1, ldx1};
-  BnBranch b1{x2, mean2, rstd2, gamma2, dbeta2, dgamma2, (__nv_bfloat16*)dx2, ldx2};
+  const int xf = x_dtype == RL_DT_F32;
+  BnBranch b0{x1, xf, mean1, rstd1, gamma1, dbeta1, dgamma1, (__nv_bfloat16*)dx1, ldx1};
+  BnBranch b1{x2, xf, mean2, rstd2, gamma2, dbeta2, dgamma2, (__nv_bfloat16*)dx2, ldx2};
   dim3 vg;
   int rpc;
   vec_grid(M, C, ls, &vg, &rpc);
@@ -608,9 +745,9 @@ extern "C" int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, 
     RL_REQUIRE(hs >= 1 && ws >= 1, RL_EINVAL, "rl_bn_bwd: parity split needs a power-of-two map >= 2x2");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == RL_DT_F32 && vec_lpr_shift(C) >= 0 && ldx % 8 == 0 && (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0 &&
+  if (vec_lpr_shift(C) >= 0 && ldx % 8 == 0 && (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0 &&
       (!act_out || ((uintptr_t)act_out & 15) == 0))
-    return rl_bn_bwd2(dy, dy_dtype, act_out, act_dtype, (const float*)x, mean, rstd, gamma, dbeta, dgamma, dx, ldx, nullptr, nullptr,
+    return rl_bn_bwd2(dy, dy_dtype, act_out, act_dtype, x_dtype, x, mean, rstd, gamma, dbeta, dgamma, dx, ldx, nullptr, nullptr,
                       nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, remap, map_h, map_w, stream);
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, dy_dtype == RL_DT_F32, act_out, act_dtype == RL_DT_F32, x, x_dtype == RL_DT_F32,

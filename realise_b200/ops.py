@@ -465,17 +465,17 @@ def bn_bwd(dy, act_out, x, mean, rstd, gamma, dbeta, dgamma, dx, remap=False, ma
 
 def bn_bwd2(dy, act_out, br1, br2, M, C, remap=False, map_hw=(1, 1)):
     """Backward of out = relu(bn_a(x_a) + bn_b(x_b)) for both branches in one reduce + one apply pass.
-    br = (x f32 [M,C], mean, rstd, gamma, dbeta, dgamma, dx bf16 view with row stride)."""
+    br = (x f32 or bf16 [M,C], mean, rstd, gamma, dbeta, dgamma, dx bf16 view with row stride)."""
     args = []
     for br in (br1, br2):
         x, mean, rstd, gamma, dbeta, dgamma, dx = br
-        _req(x, torch.float32, "x")
+        assert x.is_cuda and x.dtype == br1[0].dtype and x.dtype in _DT
         _req(dx, torch.bfloat16, "dx")
         args += [_ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dbeta), _ptr(dgamma), _ptr(dx), _c(dx.stride(0))]
     with _Timed("bn_bwd", 0):
         check(lib().rl_bn_bwd2(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out), ctypes.c_int32(_DT[act_out.dtype]),
-                               *args, _c(M), _c(C), ctypes.c_int32(int(remap)), ctypes.c_int32(map_hw[0]),
-                               ctypes.c_int32(map_hw[1]), _stream()), "rl_bn_bwd2")
+                               ctypes.c_int32(_DT[br1[0].dtype]), *args, _c(M), _c(C), ctypes.c_int32(int(remap)),
+                               ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), _stream()), "rl_bn_bwd2")
     _count(2)
 
 

@@ -43,6 +43,7 @@ class TrainEngine:
         self.saved = None
         self.debug = None             # tests set a dict to receive intermediate gradients
         self._tap_idx = {}
+        self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
         # trainable parameters in a fixed order
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -287,7 +288,11 @@ class TrainEngine:
             S, cin, cout = e["S"], e["cin"], e["cout"]
             M = N * S * S
             s = {"e": e, "x_in": x}
-            c1, cs = self._new((M, cout), F32), self._new((M, cout), F32)   # raw conv outputs stay f32 (batch stats)
+            # raw (pre-BatchNorm) conv outputs: f32, except in res_block1-2 (16x16 / 8x8 maps: 97 % of the BatchNorm
+            # bytes), where bf16 halves every BN pass; their statistics average >= 10^4 pixels per channel and the
+            # normalised activation is rounded to bf16 right afterwards anyway
+            raw_dt = BF16 if (self.raw_bf16 and S >= 8) else F32
+            c1, cs = self._new((M, cout), raw_dt), self._new((M, cout), raw_dt)
             if bi == 0:
                 s["col1"] = self._new((M, 32), BF16)
                 ops.glyph_im2col(glyphs, ids_flat, s["col1"], None, N, c.num_fonts)
@@ -304,7 +309,7 @@ class TrainEngine:
             s["bn1"] = self._bn_train(c1, e["bn1"], M)
             a1 = self._new((M, cout), BF16)
             ops.bn_apply(c1, s["bn1"][0], s["bn1"][1], None, None, None, a1, relu=True)
-            c2 = self._new((M, cout), F32)
+            c2 = self._new((M, cout), raw_dt)
             if S == 1:
                 ops.gemm(a1, e["w2f"], c2)
             else:

@@ -308,17 +308,19 @@ def test_colsum_and_bn_kernels_match_torch():
         ops.colsum_bf16(x, out)
         ref = x.float().sum(0)
         assert (out - ref).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
-    for M, C, S in [(2 * 256, 64, 16), (3 * 64, 128, 8), (5 * 16, 256, 4), (7 * 4, 512, 2), (9, 768, 1)]:
-        x1 = torch.randn(M, C, device="cuda", generator=g) * 2 + 0.5
-        x2 = torch.randn(M, C, device="cuda", generator=g)
+    for M, C, S, xdt in [(2 * 256, 64, 16, torch.float32), (3 * 64, 128, 8, torch.float32), (5 * 16, 256, 4, torch.float32),
+                         (7 * 4, 512, 2, torch.float32), (9, 768, 1, torch.float32), (2 * 256, 64, 16, torch.bfloat16),
+                         (3 * 64, 128, 8, torch.bfloat16)]:   # res_block1-2 keep raw conv outputs in bf16
+        x1 = (torch.randn(M, C, device="cuda", generator=g) * 2 + 0.5).to(xdt)
+        x2 = torch.randn(M, C, device="cuda", generator=g).to(xdt)
         sums = torch.zeros(2 * C, device="cuda")
         ops.bn_stats(x1, sums)
-        assert torch.allclose(sums[:C], x1.sum(0), rtol=1e-4, atol=1e-2)
-        assert torch.allclose(sums[C:], (x1 * x1).sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(sums[:C], x1.float().sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(sums[C:], (x1.float() * x1.float()).sum(0), rtol=1e-4, atol=1e-2)
         # out = relu(bn(x1) + bn(x2)) with gamma/beta; dy arrives parity-split when S >= 2 (layout of the next block's input)
         gam = [torch.rand(C, device="cuda", generator=g) + 0.5 for _ in range(2)]
         bet = [torch.randn(C, device="cuda", generator=g) * 0.1 for _ in range(2)]
-        xs = [x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)]
+        xs = [x1.float().clone().requires_grad_(True), x2.float().clone().requires_grad_(True)]
         gl = [t.clone().requires_grad_(True) for t in gam]
         bl = [t.clone().requires_grad_(True) for t in bet]
         stats = []

@@ -78,7 +78,16 @@ for M, C, S in ((N * 256, 64, 16), (N * 64, 128, 8), (N * 16, 256, 4)):
                                map_hw=(S, S)), nbytes=M * C * (2 * (2 + 2 + 8) + 4))
     timeit(f"bn_bwd (1 branch) M={M} C={C}", lambda: ops.bn_bwd(dyb, act, x1, sc, sc, sc, z[0], z[1], dcat[:, :C]),
            nbytes=M * C * (2 * (2 + 2 + 4) + 2))
-    del x1, x2, o, dyb, act, d1, dcat
+    x1h, x2h = x1.bfloat16(), x2.bfloat16()
+    timeit(f"bn_stats bf16-x M={M} C={C}", lambda: ops.bn_stats(x1h, sums), nbytes=M * C * 2)
+    timeit(f"bn_apply 2-in remap bf16-x M={M} C={C}", lambda: ops.bn_apply(x1h, sc, sc, x2h, sc, sc, o, relu=True, remap=True, map_hw=(S, S)),
+           nbytes=M * C * 6)
+    timeit(f"bn_bwd2 (2 branches) bf16-x M={M} C={C}",
+           lambda: ops.bn_bwd2(dyb, act, (x1h, sc, sc, sc, z[0], z[1], d1), (x2h, sc, sc, sc, z[2], z[3], dcat[:, C:]), M, C, remap=True,
+                               map_hw=(S, S)), nbytes=M * C * (2 * (2 + 2 + 4) + 4))
+    timeit(f"bn_bwd (1 branch) bf16-x M={M} C={C}", lambda: ops.bn_bwd(dyb, act, x1h, sc, sc, sc, z[0], z[1], dcat[:, :C]),
+           nbytes=M * C * (2 * (2 + 2 + 2) + 2))
+    del x1, x2, o, dyb, act, d1, dcat, x1h, x2h
 torch.cuda.empty_cache()
 
 # ---- attention ----
