@@ -231,7 +231,7 @@ constexpr int att_smem_bytes() {
 template <int LKV_MAX>
 int launch_att(const CUtensorMap& tq, const CUtensorMap& tkv, const AttParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = att_smem_bytes<LKV_MAX>();
-  static bool configured = false;
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<LKV_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {

@@ -284,7 +284,7 @@ extern "C" int rl_attention_bwd_lse(const void* qkv, const int64_t* mask, const 
   uint64_t strideso[1] = {(uint64_t)H * 2};
   rc = rl_make_tmap_bf16(&tdo, dctx, 2, dimso, strideso, boxq);
   if (rc) return rc;
-  static bool configured = false;
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
     if (e != cudaSuccess) {

@@ -564,7 +564,7 @@ extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* ga
   ctas = (rows + rows_per_cta - 1) / rows_per_cta;
   const rl::DropSpec din = rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in);
   const rl::DropSpec dout = rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out);
-  static bool configured = false;
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 6 * 512);
     cudaFuncSetAttribute(ln_bwd_kernel<MAX_V4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * MAX_V4 * 512);

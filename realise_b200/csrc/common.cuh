@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -500,7 +500,7 @@ template <int BN, int STAGES>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
                 cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
-  static bool configured = false;  // benign race: attribute set is idempotent
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -778,7 +778,7 @@ template <int BN, int STAGES>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
                  cudaStream_t st) {
   constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
-  static bool configured = false;
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {

@@ -263,7 +263,7 @@ constexpr int b1_smem_bytes() {
 template <int C>
 int launch_b1(const CUtensorMap& t1, const CUtensorMap& tsc, const CUtensorMap& t2, const B1Params& p, cudaStream_t st) {
   constexpr int smem = b1_smem_bytes<C>();
-  static bool configured = false;
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(glyph_block1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
