@@ -26,10 +26,11 @@ import ctypes
 import torch
 
 from ._lib import check, lib
+from .batch import MAX_PHO_LEN
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, max_graphs=4):
+    def __init__(self, model, optimizer, max_graphs=2):
         if not hasattr(optimizer, "hyper_values"):
             raise TypeError("GraphedTrainStep needs realise_b200.optim.FusedAdamW (the update must be capturable)")
         self.model, self.opt = model, optimizer
@@ -40,6 +41,7 @@ class GraphedTrainStep:
         self._hyper = torch.zeros(3, device=dev, dtype=torch.float32)
         self._counter = torch.zeros(1, device=dev, dtype=torch.int64)   # dropout step counter (read as uint64)
         self._ones = torch.ones(1, device=dev, dtype=torch.float32)
+        self._pool = None                 # graphs of different shapes replay one at a time: they share one memory pool
         self.replays = 0
 
     # ---- batch plumbing --------------------------------------------------------------------------------------
@@ -54,7 +56,10 @@ class GraphedTrainStep:
             if not torch.is_tensor(lens):
                 lens = torch.tensor(lens, dtype=torch.int32)
             out["pho_lens"] = lens
-            out["pho_idx"] = batch["pho_idx"]
+            pho = batch["pho_idx"]
+            if pho.shape[1] < MAX_PHO_LEN:    # pad_sequence pads to the batch maximum (src/utils.py:92-96): fix T = 7 so that
+                pho = torch.nn.functional.pad(pho, (0, MAX_PHO_LEN - pho.shape[1]))   # every batch replays the same graph
+            out["pho_idx"] = pho
         return {k: v.to(device=dev, dtype=(torch.int32 if k == "pho_lens" else v.dtype), non_blocking=True).contiguous()
                 for k, v in out.items()}
 
@@ -71,11 +76,13 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         torch.cuda.empty_cache()          # the eager step's activations go back to the driver; the graph gets its own pool
         graph = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
         opt.device_hyper = self._hyper
         check(lib().rl_set_dropout_seed_ptr(ctypes.c_void_p(self._counter.data_ptr())), "rl_set_dropout_seed_ptr")
         seed0, step0 = eng.seed, opt._step
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, pool=self._pool):
                 self._counter.add_(1)
                 loss, _ = eng.forward(static)
                 eng.backward_and_sync(self._ones)
