@@ -187,12 +187,14 @@ gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const uint4 v = reinterpret_cast<const uint4*>(u)[i];
-  float x[8] = {rl::bf16_lo(v.x), rl::bf16_hi(v.x), rl::bf16_lo(v.y), rl::bf16_hi(v.y),
-                rl::bf16_lo(v.z), rl::bf16_hi(v.z), rl::bf16_lo(v.w), rl::bf16_hi(v.w)};
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = rl::gelu_erf(x[j]);
-  reinterpret_cast<uint4*>(h)[i] =
-      make_uint4(rl::pack_bf16(x[0], x[1]), rl::pack_bf16(x[2], x[3]), rl::pack_bf16(x[4], x[5]), rl::pack_bf16(x[6], x[7]));
+  for (int j = 0; j < 4; ++j) {
+    const rl::f2 r = rl::gelu_erf2(rl::f2{rl::bf16_lo(w[j]), rl::bf16_hi(w[j])});
+    o[j] = rl::pack_bf16(r.x, r.y);
+  }
+  reinterpret_cast<uint4*>(h)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -222,11 +224,11 @@ gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ t, const __nv_bfloat16* __res
       uint32_t ow[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float lo = rl::bf16_lo(tw[k]) * rl::gelu_grad(rl::bf16_lo(uw[k]));
-        const float hi = rl::bf16_hi(tw[k]) * rl::gelu_grad(rl::bf16_hi(uw[k]));
-        ow[k] = rl::pack_bf16(lo, hi);
-        acc[(k & 3) * 2] += lo;       // bias gradient from the unrounded products (fp32, like the reference's autograd)
-        acc[(k & 3) * 2 + 1] += hi;
+        const rl::f2 d = rl::mul2(rl::f2{rl::bf16_lo(tw[k]), rl::bf16_hi(tw[k])},
+                                  rl::gelu_grad2(rl::f2{rl::bf16_lo(uw[k]), rl::bf16_hi(uw[k])}));
+        ow[k] = rl::pack_bf16(d.x, d.y);
+        acc[(k & 3) * 2] += d.x;      // bias gradient from the unrounded products (fp32, like the reference's autograd)
+        acc[(k & 3) * 2 + 1] += d.y;
       }
       *reinterpret_cast<uint4*>(t + r * ld + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       if (two) *reinterpret_cast<uint4*>(t + (r + 8) * ld + c0) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
