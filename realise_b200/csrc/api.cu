@@ -56,6 +56,27 @@ int rl_num_sms() {
   return sms;
 }
 
+int rl_ctas_per_sm(const void* func, int threads, int dyn_smem) {
+  static std::mutex mu;
+  static const void* keys[64];
+  static int vals[64];
+  static int n = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n; ++i)
+    if (keys[i] == func) return vals[i];
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, (size_t)dyn_smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 2;
+  }
+  if (n < 64) {
+    keys[n] = func;
+    vals[n] = occ;
+    ++n;
+  }
+  return occ;
+}
+
 rl_tmap_encode_fn rl_get_tmap_encode() {
   static rl_tmap_encode_fn fn = nullptr;
   static std::once_flag once;

@@ -586,7 +586,8 @@ extern "C" int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t c
   if (rows <= 0) return 0;
   if (cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
     const long long col_blocks = (cols + 255) / 256;
-    long long row_chunks = (8LL * rl_num_sms() + col_blocks - 1) / col_blocks;   // ~8 CTAs per SM in total
+    const long long wave = (long long)rl_ctas_per_sm((const void*)colsum_bf16_vec_kernel, 256, 0) * rl_num_sms();
+    long long row_chunks = wave / col_blocks;   // one full wave of resident CTAs, never a partial second one
     if (row_chunks > (rows + 63) / 64) row_chunks = (rows + 63) / 64;
     if (row_chunks < 1) row_chunks = 1;
     const int rows_per_cta = (int)((rows + row_chunks - 1) / row_chunks);
@@ -614,7 +615,8 @@ extern "C" int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t 
              RL_EALIGN, "rl_gelu_bwd_colsum: cols / ld must be multiples of 8 and the pointers 16-byte aligned");
   if (rows <= 0) return 0;
   const long long col_blocks = (cols + 255) / 256;
-  long long row_chunks = (8LL * rl_num_sms() + col_blocks - 1) / col_blocks;
+  const long long wave = (long long)rl_ctas_per_sm((const void*)gelu_bwd_colsum_kernel, 256, 0) * rl_num_sms();
+  long long row_chunks = wave / col_blocks;   // one full wave of resident CTAs, never a partial second one
   if (row_chunks > (rows + 63) / 64) row_chunks = (rows + 63) / 64;
   if (row_chunks < 1) row_chunks = 1;
   const int rows_per_cta = (int)((rows + row_chunks - 1) / row_chunks);

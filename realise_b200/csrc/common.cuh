@@ -16,7 +16,10 @@
 void rl_set_error(const char* fmt, ...);
 int rl_check_launch(const char* what);  // returns 0 or positive cudaError_t
 int rl_num_sms();
-int rl_half_is_f16();   // process-wide 16-bit operand format set by rl_set_half_format (0 = bf16, 1 = fp16)
+int rl_half_is_f16();
+// resident CTAs per SM of a kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor, cached per function; 2 when the query
+// fails, e.g. without a device).  Slab kernels size their grid to ONE full wave: a few CTAs beyond it cost a whole extra pass.
+int rl_ctas_per_sm(const void* func, int threads, int dyn_smem);   // process-wide 16-bit operand format set by rl_set_half_format (0 = bf16, 1 = fp16)
 const unsigned long long* rl_dropout_seed_ptr();   // process-wide, set by rl_set_dropout_seed_ptr (NULL = off)
 
 #define RL_REQUIRE(cond, code, ...)    \

@@ -464,10 +464,11 @@ int vec_lpr_shift(long long C) {
   return s;
 }
 
-void vec_grid(long long M, long long C, int lpr_shift, dim3* grid, int* rows_per_cta) {
+void vec_grid(long long M, long long C, int lpr_shift, dim3* grid, int* rows_per_cta, const void* func) {
   const long long col_blocks = (C + 255) / 256;
   const int rows_per_iter = 8 * (32 >> lpr_shift);
-  long long chunks = (6LL * rl_num_sms() + col_blocks - 1) / col_blocks;
+  // one full wave of resident CTAs (occupancy x SMs): a handful of CTAs beyond it would cost a whole extra pass
+  long long chunks = (long long)rl_ctas_per_sm(func, 256, 0) * rl_num_sms() / col_blocks;
   const long long max_chunks = (M + 4 * rows_per_iter - 1) / (4 * rows_per_iter);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -640,7 +641,7 @@ extern "C" int rl_bn_stats(const void* x, int32_t x_dtype, float* sums, int64_t 
   if (ld == C && ls >= 0 && ((uintptr_t)x & 15) == 0) {
     dim3 vg;
     int rpc;
-    vec_grid(M, C, ls, &vg, &rpc);
+    vec_grid(M, C, ls, &vg, &rpc, (const void*)bn_stats_vec_kernel);
     bn_stats_vec_kernel<<<vg, 256, 0, (cudaStream_t)stream>>>(x, x_dtype == RL_DT_F32, sums, M, (int)C, ls, rpc);
     return rl_check_launch("rl_bn_stats");
   }
@@ -675,7 +676,7 @@ extern "C" int rl_bn_apply(const void* x1, const float* scale1, const float* shi
   if (ls >= 0 && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) & 15) == 0) {
     dim3 vg;
     int rpc;
-    vec_grid(M, C, ls, &vg, &rpc);
+    vec_grid(M, C, ls, &vg, &rpc, x2 ? (const void*)bn_apply_vec_kernel<2> : (const void*)bn_apply_vec_kernel<1>);
     if (x2)
       bn_apply_vec_kernel<2><<<vg, 256, 0, (cudaStream_t)stream>>>(x1, scale1, shift1, x2, scale2, shift2, x_dtype == RL_DT_F32, out,
                                                                   out_dtype == RL_DT_F32, relu, M, (int)C, ls, rpc, remap, hs + ws, ws);
@@ -715,20 +716,21 @@ extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out,
   const int xf = x_dtype == RL_DT_F32;
   BnBranch b0{x1, xf, mean1, rstd1, gamma1, dbeta1, dgamma1, (__nv_bfloat16*)dx1, ldx1};
   BnBranch b1{x2, xf, mean2, rstd2, gamma2, dbeta2, dgamma2, (__nv_bfloat16*)dx2, ldx2};
-  dim3 vg;
-  int rpc;
-  vec_grid(M, C, ls, &vg, &rpc);
+  dim3 vg, va;
+  int rpc, rpa;
+  vec_grid(M, C, ls, &vg, &rpc, x2 ? (const void*)bn_bwd_reduce_vec_kernel<2> : (const void*)bn_bwd_reduce_vec_kernel<1>);
+  vec_grid(M, C, ls, &va, &rpa, x2 ? (const void*)bn_bwd_apply_vec_kernel<2> : (const void*)bn_bwd_apply_vec_kernel<1>);
   const int df = dy_dtype == RL_DT_F32, af = act_dtype == RL_DT_F32;
   if (x2) {
     bn_bwd_reduce_vec_kernel<2><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
     int rc = rl_check_launch("rl_bn_bwd2(reduce)");
     if (rc) return rc;
-    bn_bwd_apply_vec_kernel<2><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
+    bn_bwd_apply_vec_kernel<2><<<va, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpa, remap, hs + ws, ws);
   } else {
     bn_bwd_reduce_vec_kernel<1><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
     int rc = rl_check_launch("rl_bn_bwd2(reduce)");
     if (rc) return rc;
-    bn_bwd_apply_vec_kernel<1><<<vg, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpc, remap, hs + ws, ws);
+    bn_bwd_apply_vec_kernel<1><<<va, 256, 0, st>>>(dy, df, act_out, af, b0, b1, M, (int)C, ls, rpa, remap, hs + ws, ws);
   }
   return rl_check_launch("rl_bn_bwd2");
 }
