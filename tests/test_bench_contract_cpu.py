@@ -1,0 +1,24 @@
+"""CPU: the reference arm of bench.py (the oracle's train step on the host cores) prints ONE JSON line on stdout with
+the keys the driver reads; bench.py's module-level constants name the BASELINE metric."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def test_reference_arm_prints_one_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS="8")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "sentences/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert "fwd+bwd" in d["metric"] and d["config"]["seq_len"] == 128 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "train step" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
