@@ -56,3 +56,36 @@ def test_synth_batch_shape_contract():
     special = (b["src_idx"].view(-1) == 0) | (b["src_idx"].view(-1) == 101) | (b["src_idx"].view(-1) == 102)
     assert (lens[special] == 1).all() and (b["pho_idx"][special, 0] == 32).all()
     assert ((b["pho_idx"] != 0).sum(1) == lens).all()
+
+
+def test_flat_gradient_layout_on_cpu():
+    """TrainEngine's flat gradient buffer (host logic, no kernels): every trainable parameter that the reference gives
+    a gradient owns a 256-byte-aligned, non-overlapping slice; a layer's q/k/v weights (biases) are adjacent so the
+    fused [3H, H] weight gradient is one view; poolers and unused word embeddings own none (grad stays None)."""
+    from realise_b200.train import TrainEngine
+    m = SpellBertPho2ResArch3Abla(ArchConfig(num_hidden_layers=1))
+    m.tie_cls_weight()
+    eng = TrainEngine(m)
+    base = eng.flat.data_ptr()
+    spans = []
+    for p, g in zip(eng.params, eng.grads):
+        if g is None:
+            continue
+        assert g.shape == p.shape and g.dtype == torch.float32
+        off = g.data_ptr() - base
+        assert 0 <= off and off + g.numel() * 4 <= eng.flat.numel() * 4
+        spans.append((off, off + g.numel() * 4))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))              # disjoint
+    names = {id(p): n for n, p in m.named_parameters()}
+    no_grad = sorted(names[id(p)] for p, g in zip(eng.params, eng.grads) if g is None)
+    assert no_grad == sorted(["bert.pooler.dense.weight", "bert.pooler.dense.bias", "pho_model.pooler.dense.weight",
+                              "pho_model.pooler.dense.bias", "pho_model.embeddings.word_embeddings.weight",
+                              "output_block.pooler.dense.weight", "output_block.pooler.dense.bias",
+                              "output_block.embeddings.word_embeddings.weight"])
+    att = m.bert.encoder.layer[0].attention
+    w, b = eng._qkv_grads(att, 768)
+    assert w.shape == (2304, 768) and w.data_ptr() == eng._grad(att.self.query.weight).data_ptr()
+    assert eng._grad(att.self.key.weight).data_ptr() == w.data_ptr() + 768 * 768 * 4
+    assert eng._grad(att.self.value.bias).data_ptr() == b.data_ptr() + 2 * 768 * 4
+    assert (w.data_ptr() - base) % 256 == 0 and (b.data_ptr() - base) % 256 == 0
