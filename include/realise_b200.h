@@ -12,6 +12,18 @@
  *   - return 0 on success, negative RL_E* for host-side argument errors, positive = cudaError_t;
  *     rl_last_error() returns a thread-local message for the last non-zero return;
  *   - bf16 = __nv_bfloat16 storage, f32 = float.  "K-major" = row-major with K contiguous.
+ *   - the library holds NO mutable process-wide state: the 16-bit storage format of a tensor (bf16 or IEEE fp16) and
+ *     the optional device-resident dropout step counter are per-call arguments (`*_dtype`, `drop_counter`); the only
+ *     statics are one-time cudaFuncSetAttribute flags, cached occupancy queries and the thread-local error string.
+ *
+ * 16-bit formats: every "bf16" tensor below may instead be IEEE fp16 when the call says so (RL_DT_F16).  tcgen05
+ * kind::f16 multiplies bf16 and fp16 operands at the same rate and takes the format PER OPERAND, so the training path
+ * keeps forward tensors (weights, activations) in fp16 — three more mantissa bits: logits land within the reference's
+ * 1e-2 tolerance — and gradients in bf16 (range), mixing both inside one MMA (dW = dY^T X, dX = dY W).
+ *
+ * Dropout: masks are pure functions of (seed, site, element).  With a non-NULL `drop_counter` (device pointer) the
+ * kernel uses seed + *drop_counter, read at run time: a captured CUDA graph of the whole train step draws fresh masks
+ * per replay by bumping the counter on the stream.
  */
 #ifndef REALISE_B200_H
 #define REALISE_B200_H
@@ -48,7 +60,7 @@ enum {
   RL_ACT_GELU_GRAD = 4, /* out = (acc*scale+bias) * gelu'(res): data gradient through GELU, res = saved pre-activation */
   RL_ACT_GELU_SAVE = 5  /* out = gelu(pre), out2 = pre (bf16): training forward keeps the pre-activation */
 };
-enum { RL_DT_BF16 = 0, RL_DT_F32 = 1 };
+enum { RL_DT_BF16 = 0, RL_DT_F32 = 1, RL_DT_F16 = 2 };
 
 typedef struct rl_gemm_desc {
   const void* a; /* bf16.  a_mode 0: [M, K] row-major, row stride lda (elements).
@@ -89,6 +101,12 @@ typedef struct rl_gemm_desc {
   uint64_t drop_seed;  /* by the backward kernels.  drop_p = 0 disables it. */
   int32_t b_major;   /* 0: B stored [N, K].  1: B stored [K, N] with row stride ldb, e.g. B = W^T for a data
                         gradient straight from W [out, in], or B = X^T for a weight gradient */
+  int32_t a_dtype, b_dtype; /* RL_DT_BF16 or RL_DT_F16, independently (out_dtype / res_dtype take RL_DT_F16 too; out2
+                               shares out's 16-bit format) */
+  const uint64_t* drop_counter; /* optional device step counter added to drop_seed at run time (NULL = plain seed) */
+  int32_t tune_tile_n;  /* 0: the cost model picks the N tile.  64 / 128 / 256: force it (tuning and tests; results do
+                           not depend on it) */
+  int32_t tune_no_pair; /* 1: never use the CTA-pair (cta_group::2) kernel */
   int32_t b_mode;    /* 0: B is a 2-D matrix.  1 (needs b_major = 1, a_mode = 0): B is the im2col matrix of the conv
                         activation `b` ([NIMG, P, H, W, C], geometry / taps in the conv_* fields), never materialised:
                         B[k = output pixel (img, oh, ow), n = tap * Cuse + c] = x[img, plane_t, oh+dh_t, ow+dw_t, c],
@@ -97,29 +115,26 @@ typedef struct rl_gemm_desc {
 } rl_gemm_desc;
 
 RL_API int rl_gemm_bf16(const rl_gemm_desc* d, void* stream);
-/* tuning/debug: force the GEMM N tile (128 or 256; 0 = heuristic). */
-RL_API int rl_gemm_set_tile_n(int bn);
-/* tuning/debug: 0 disables the CTA-pair (cta_group::2) kernel, 1 (default) lets the cost model pick it. */
-RL_API int rl_gemm_set_pair_mode(int on);
-/* tuning experiments only (results become meaningless): bit0 skip epilogue, bit1 skip TMA loads, bit2 skip MMAs. */
-RL_API int rl_gemm_set_debug_mode(int flags);
-
 /* ---- fused attention core -------------------------------------------------------------------
  * ctx[b*L+q, h*64:(h+1)*64] = softmax(Q K^T / 8 + (1 - mask[b,:]) * -10000) V  per head.
  * qkv: bf16 [B*L, 3*heads*64] = [Q | K | V] as written by the fused QKV projection GEMM;
  * mask: int64 [B, L] (batch['masks']); ctx: bf16 [B*L, heads*64].  L <= 256, head_dim == 64.
  * Replaces BertSelfAttention.forward score/softmax/context path (modeling_bert.py:234-260) and the
  * extended-mask construction of BertModel.forward (:687, :696-697).  Dropout is identity (eval). */
-RL_API int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, int64_t B, int64_t L,
-                            int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
-                            void* stream);
+RL_API int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx,
+                            float* row_lse /* optional [B, heads, L] f32: log2-domain logsumexp of every query row, saved
+                                              for rl_attention_bwd */,
+                            int64_t B, int64_t L, int64_t heads, int64_t head_dim,
+                            int32_t act_dtype /* format of qkv / ctx: RL_DT_BF16 or RL_DT_F16 */, float drop_p,
+                            uint64_t drop_seed, uint32_t drop_site, const uint64_t* drop_counter, void* stream);
 
 /* ---- LayerNorm (biased variance, eps inside sqrt) over rows of f32 [rows, H] ------------------
  * Replaces BertLayerNorm in BertSelfOutput/BertOutput (modeling_bert.py:276, :342) and
  * resnet_layernorm (src/models.py:838).  Writes f32 and/or bf16 (either may be NULL). */
 RL_API int rl_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32,
                             void* out_bf16, int64_t rows, int64_t H, float eps, float drop_p, uint64_t drop_seed,
-                            uint32_t drop_site, int32_t drop_f32 /* mask the f32 output too */, void* stream);
+                            uint32_t drop_site, const uint64_t* drop_counter, int32_t drop_f32 /* mask the f32 output too */,
+                            int32_t out16_dtype /* format of out_bf16: RL_DT_BF16 or RL_DT_F16 */, void* stream);
 
 /* ---- BertEmbeddings.forward (modeling_bert.py:169-193) ---------------------------------------
  * out = LN(src + pos[position] + type[0]); src = word[ids[row]] when inputs_embeds is NULL else
@@ -129,7 +144,8 @@ RL_API int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* i
                            const float* pos, const float* type0, const float* gamma, const float* beta,
                            float* out_f32, void* out_bf16, float* pre_ln_out /* optional: the summed embedding */,
                            int64_t rows, int64_t L, int64_t H, int32_t pos_mode, float eps, float drop_p,
-                           uint64_t drop_seed, uint32_t drop_site, void* stream);
+                           uint64_t drop_seed, uint32_t drop_site, const uint64_t* drop_counter, int32_t out16_dtype,
+                           void* stream);
 
 /* ---- gated fusion (src/models.py:840-850; src/models_abla.py:243-279) -------------------------
  * m0 = bert_hiddens, m1/m2 = the other present modalities in the reference's concat order, all
@@ -164,7 +180,7 @@ RL_API int rl_gru_input_table(const float* emb, const float* w_ih, const float* 
 RL_API int rl_gru_step_fwd(const float* gh, const float* b_hh, const float* table,
                            const int64_t* pho_idx, const int32_t* lens, const float* h_prev,
                            float* h_out, void* h_out_bf16, int64_t rows, int64_t H, int64_t T,
-                           int64_t t, void* stream);
+                           int64_t t, int32_t out16_dtype, void* stream);
 
 /* ---- glyph stem (src/models.py:829-834 gather; src/char_cnn.py:15-29 for res_block1) ----------
  * For every token: image = glyphs[ids[i]] (f32 [C,32,32]);  y1 = relu(bn1(conv3x3 s2 p1)),
@@ -191,30 +207,27 @@ RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const vo
 
 /* ======================= training path (src/run.py:191-212) =========================================== */
 
-/* ---- attention backward (seq_len <= 128): dqkv = [dQ | dK | dV] from dctx, recomputing the probabilities ----
- * Differentiates BertSelfAttention.forward (modeling_bert.py:234-260) with dropout = identity.
- * ctx is the forward output (needed for delta = rowsum(dO o O)). */
+/* ---- attention backward: dqkv = [dQ | dK | dV] (bf16) from dctx (bf16), recomputing the probabilities ----
+ * Differentiates BertSelfAttention.forward (modeling_bert.py:234-260) including its dropout on the probabilities.
+ * qkv / ctx are the forward tensors (act_dtype: bf16 or fp16; ctx is needed for delta = rowsum(dO o O)); row_lse
+ * (optional) is the logsumexp saved by rl_attention_fwd: P = exp2(s - lse) is then recomputed in one pass over S.
+ * seq_len <= 256. */
 RL_API int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                            int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed,
-                            uint32_t drop_site, void* stream);
-/* Same pair with the log2-domain logsumexp of every query row ([B, heads, L] f32) written by the forward and read by
- * the backward, which then recomputes P = exp2(s - lse) in one pass over S instead of three. */
-RL_API int rl_attention_fwd_lse(const void* qkv, const int64_t* mask, void* ctx, float* row_lse, int64_t B, int64_t L,
-                                int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
-                                void* stream);
-RL_API int rl_attention_bwd_lse(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                                const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p,
-                                uint64_t drop_seed, uint32_t drop_site, void* stream);
+                            const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t act_dtype,
+                            float drop_p, uint64_t drop_seed, uint32_t drop_site, const uint64_t* drop_counter,
+                            void* stream);
 
 /* ---- LayerNorm backward: x = LN input (f32), dy = grad of the LN output; dx (+= add_in) in f32 and/or bf16;
  * dgamma/dbeta/dxsum (column sums of dy*xhat, dy, dx) are ACCUMULATED into (caller zeroes them per step). */
 RL_API int rl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* add_in, float* dx,
                             void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int64_t H,
                             float eps, float drop_p, uint64_t drop_seed, uint32_t site_in /* 0 = none: dy is masked */,
-                            uint32_t site_out /* 0 = none: dx_bf16 and dxsum are masked */, void* stream);
+                            uint32_t site_out /* 0 = none: dx_bf16 and dxsum are masked */, const uint64_t* drop_counter,
+                            void* stream);
 
 /* ---- keep mask of a dropout site as bytes (tests feed the kernel's masks to the CPU oracle) ---- */
-RL_API int rl_dropout_mask(uint8_t* out, int64_t n, float drop_p, uint64_t drop_seed, uint32_t drop_site, void* stream);
+RL_API int rl_dropout_mask(uint8_t* out, int64_t n, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                           const uint64_t* drop_counter, void* stream);
 
 /* ---- out[c] += sum_r x[r, c] for a bf16 matrix (bias gradients of nn.Linear) ---- */
 RL_API int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld, void* stream);
@@ -285,7 +298,7 @@ RL_API int rl_glyph_im2col(const float* glyphs, const int64_t* ids, void* col1, 
 
 /* ---- multi-tensor grad-norm and fused clip + AdamW (src/run.py:207 clip_grad_norm_,
  * transformers/optimization.py:113-169).  table: device array of {float* p; const float* g; float* m;
- * float* v; bf16* shadow; float* shadow32; int64 n; float wd; int pad}; chunks: device array of int2 {tensor, chunk} covering
+ * float* v; bf16* shadow; float* shadow32; int64 n; float wd; int shadow_f16 (the shadow is fp16, not bf16)}; chunks: device array of int2 {tensor, chunk} covering
  * every 4096-element block.  rl_mt_sumsq accumulates sum(g^2) into out (caller zeroes it);
  * rl_mt_adamw applies g *= min(1, max_norm / (sqrt(sumsq)/grad_div + 1e-6)) / grad_div, then the AdamW update
  * with bias corrections bias_corr1 = 1-beta1^t, bias_corr2 = 1-beta2^t, and refreshes the bf16 shadow copy. */
@@ -300,30 +313,22 @@ RL_API int rl_gather_rows_f32(const float* table, const int64_t* ids, float* out
 /* Split-precision operand for the tied classifier (src/models.py:859): out[r] = [hi | lo | hi] with hi = bf16(x[r]),
  * lo = bf16(x[r] - hi), width 3*cols.  Against B = [W_hi | W_hi | W_lo] one rl_gemm_bf16 with K = 3*cols computes
  * x W^T with ~16-bit mantissa operands: the 21128-way logits no longer carry the bf16 rounding of seq and E. */
-RL_API int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, void* stream);
+RL_API int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, int32_t out_dtype, void* stream);
 
 /* GELU (erf form, transformers/modeling_bert.py:125-131) as element-wise passes next to the K = 768 GEMMs of
  * BertIntermediate: h = u * Phi(u) over n bf16 elements; and its backward fused with the bias gradient:
  * t[r, c] <- t[r, c] * gelu'(u[r, c]) in place (t = dy2 W2), dbias[c] += sum_r of the fp32 products. */
-RL_API int rl_gelu_fwd(const void* u, void* h, int64_t n, void* stream);
-RL_API int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld, void* stream);
+RL_API int rl_gelu_fwd(const void* u, void* h, int64_t n, int32_t dtype /* of u and h */, void* stream);
+RL_API int rl_gelu_bwd_colsum(void* t /* bf16 gradient */, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld,
+                              int32_t u_dtype, void* stream);
 
 /* Same update with the step's schedule read from device memory: hyper = {lr, 1 - beta1^t, 1 - beta2^t}.  Lets a
  * CUDA graph that contains the optimizer be replayed while LambdaLR (src/run.py:153-160) and the bias corrections move. */
 RL_API int rl_mt_adamw_dev(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                            const float* hyper, float beta1, float beta2, float eps, float grad_div, void* stream);
 
-/* 16-bit operand format, process-wide: 0 (default) = bf16, 1 = IEEE fp16.  While 1, every kernel launched through this
- * library reads its 16-bit GEMM / attention operands and residuals, and writes its 16-bit outputs, as fp16 (tcgen05
- * kind::f16 takes either at the same rate).  The inference path uses fp16 for the transformer stacks, the GRU and the
- * classifier (three more mantissa bits: max |logit error| vs the fp32 reference drops below the 1e-2 the reference's
- * bf16 tolerance allows); training keeps bf16 (gradient range).  Callers pass tensors of the matching dtype. */
-RL_API int rl_set_half_format(int f16);
-
-/* Dropout masks are pure functions of (seed, site, element).  With a non-NULL device counter registered here (process-
- * wide), every dropout-bearing kernel launched afterwards uses seed + *dev_counter, read at run time: a captured CUDA
- * graph of the whole train step draws fresh masks per replay by bumping the counter on the stream.  NULL switches back
- * to the plain scalar seed (the mode the parity tests use with rl_dropout_mask). */
-RL_API int rl_set_dropout_seed_ptr(const uint64_t* dev_counter);
+/* Scratch sizes (bytes) of the entry points that take a caller-owned workspace: op is one of "gate_fuse_fwd"
+ * (mean_dot_ws), "gate_fuse_bwd" (ws), "masked_ce_fwd" (row_loss_ws).  Returns -1 for an unknown op. */
+RL_API int64_t rl_workspace_bytes(const char* op, int64_t B, int64_t L, int64_t H);
 
 #endif /* REALISE_B200_H */

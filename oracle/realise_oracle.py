@@ -71,7 +71,7 @@ def dropout(x, p, train, site=None, gen=None):
     if MASK_FN is not None and site is not None:
         keep = MASK_FN(site, tuple(x.shape)).to(x.dtype)
     else:
-        keep = (torch.rand(x.shape, generator=gen) >= p).to(x.dtype)
+        keep = (torch.rand(x.shape, generator=gen, device=x.device) >= p).to(x.dtype)
     return x * keep / (1.0 - p)
 
 
@@ -81,7 +81,7 @@ def embeddings(sd, prefix, cfg, input_ids=None, inputs_embeds=None, position_ids
         inputs_embeds = sd[f"{prefix}.embeddings.word_embeddings.weight"][input_ids]
     B, L = inputs_embeds.shape[:2]
     if position_ids is None:
-        position_ids = torch.arange(L).unsqueeze(0).expand(B, L)
+        position_ids = torch.arange(L, device=inputs_embeds.device).unsqueeze(0).expand(B, L)
     pos = sd[f"{prefix}.embeddings.position_embeddings.weight"][position_ids]
     typ = sd[f"{prefix}.embeddings.token_type_embeddings.weight"][torch.zeros_like(position_ids)]
     x = inputs_embeds + pos + typ
@@ -138,12 +138,12 @@ def gru_final(sd, pho_idx, pho_lens):
     N, T, H = emb.shape
     if FAST:
         packed = torch.nn.utils.rnn.pack_padded_sequence(emb, pho_lens, batch_first=True, enforce_sorted=False)
-        gru = torch.nn.GRU(H, H, num_layers=1, batch_first=True)
+        gru = torch.nn.GRU(H, H, num_layers=1, batch_first=True, device=emb.device)
         gru.weight_ih_l0, gru.weight_hh_l0 = torch.nn.Parameter(w_ih), torch.nn.Parameter(w_hh)
         gru.bias_ih_l0, gru.bias_hh_l0 = torch.nn.Parameter(b_ih), torch.nn.Parameter(b_hh)
         return gru(packed)[1].squeeze(0)
-    lens = torch.as_tensor(pho_lens, dtype=torch.long)
-    h = torch.zeros(N, H)
+    lens = torch.as_tensor(pho_lens, dtype=torch.long, device=emb.device)
+    h = torch.zeros(N, H, device=emb.device, dtype=emb.dtype)
     for t in range(T):
         gi = emb[:, t] @ w_ih.t() + b_ih
         gh = h @ w_hh.t() + b_hh
@@ -249,7 +249,7 @@ def forward(sd, batch, cfg, train=False, collect=None, bn_stats=None):
         hid = sum(modal)
     c["fused"] = hid
     seq = bert_model(sd, "output_block", 3, cfg, attention_mask, inputs_embeds=hid,
-                     position_ids=torch.zeros(B, L, dtype=torch.long), train=train)
+                     position_ids=torch.zeros(B, L, dtype=torch.long, device=hid.device), train=train)
     c["sequence_output"] = seq
     seq = dropout(seq, cfg.hidden_dropout_prob, train, site=SITE_FINAL)
     logits = F.linear(seq, sd["classifier.weight"], sd["classifier.bias"])

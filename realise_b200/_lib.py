@@ -30,6 +30,9 @@ class GemmDesc(ctypes.Structure):
         ("a_major", ctypes.c_int32),
         ("drop_p", ctypes.c_float), ("drop_site", ctypes.c_uint32), ("drop_seed", ctypes.c_uint64),
         ("b_major", ctypes.c_int32),
+        ("a_dtype", ctypes.c_int32), ("b_dtype", ctypes.c_int32),
+        ("drop_counter", ctypes.c_void_p),
+        ("tune_tile_n", ctypes.c_int32), ("tune_no_pair", ctypes.c_int32),
         ("b_mode", ctypes.c_int32),
     ]
 
@@ -43,6 +46,7 @@ def lib():
         _LIB = ctypes.CDLL(path)
         _LIB.rl_last_error.restype = ctypes.c_char_p
         _LIB.rl_version.restype = ctypes.c_int
+        _LIB.rl_workspace_bytes.restype = ctypes.c_int64
     return _LIB
 
 

@@ -4,27 +4,12 @@
 
 #include <atomic>
 #include <mutex>
+#include <string>
 
 #include "common.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
-std::atomic<const unsigned long long*> g_seed_ptr{nullptr};  // process-wide: autograd runs backward on another thread
-}
-
-namespace {
-std::atomic<int> g_half_f16{0};
-}
-int rl_half_is_f16() { return g_half_f16.load(std::memory_order_relaxed); }
-extern "C" int rl_set_half_format(int f16) {
-  g_half_f16.store(f16 ? 1 : 0, std::memory_order_relaxed);
-  return 0;
-}
-
-const unsigned long long* rl_dropout_seed_ptr() { return g_seed_ptr.load(std::memory_order_relaxed); }
-extern "C" int rl_set_dropout_seed_ptr(const uint64_t* dev_counter) {
-  g_seed_ptr.store(reinterpret_cast<const unsigned long long*>(dev_counter), std::memory_order_relaxed);
-  return 0;
 }
 
 void rl_set_error(const char* fmt, ...) {
@@ -120,5 +105,14 @@ int rl_make_tmap(CUtensorMap* out, const void* base, int dtype, int swizzle_byte
   return 0;
 }
 
-extern "C" int rl_version(void) { return 100; }
+extern "C" int64_t rl_workspace_bytes(const char* op, int64_t B, int64_t L, int64_t H) {
+  if (!op) return -1;
+  const std::string s(op);
+  if (s == "gate_fuse_fwd") return B * 3 * (int64_t)sizeof(float);
+  if (s == "gate_fuse_bwd") return (B * L * 3 + 2 * B * H) * (int64_t)sizeof(float);
+  if (s == "masked_ce_fwd") return B * L * (int64_t)sizeof(float);
+  return -1;
+}
+
+extern "C" int rl_version(void) { return 200; }
 extern "C" const char* rl_last_error(void) { return g_err; }

@@ -18,7 +18,7 @@ struct AttParams {
   float scale_log2;       // (1/sqrt(d)) * log2(e)
   int heads;
   rl::DropSpec drop;      // dropout on the attention probabilities (modeling_bert.py:250)
-  int f16;                // Q/K/V, P and ctx are fp16 instead of bf16 (rl_set_half_format)
+  int f16;                // Q/K/V, P and ctx are fp16 instead of bf16 (act_dtype == RL_DT_F16)
   float* lse;             // optional [B, heads, L]: log2-domain logsumexp of every query row (saved for the backward)
 };
 
@@ -246,15 +246,9 @@ int launch_att(const CUtensorMap& tq, const CUtensorMap& tkv, const AttParams& p
 
 }  // namespace
 
-extern "C" int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, int64_t B, int64_t L,
-                                int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
-                                void* stream) {
-  return rl_attention_fwd_lse(qkv, mask, ctx, nullptr, B, L, heads, head_dim, drop_p, drop_seed, drop_site, stream);
-}
-
-extern "C" int rl_attention_fwd_lse(const void* qkv, const int64_t* mask, void* ctx, float* row_lse, int64_t B, int64_t L,
-                                    int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed, uint32_t drop_site,
-                                    void* stream) {
+extern "C" int rl_attention_fwd(const void* qkv, const int64_t* mask, void* ctx, float* row_lse, int64_t B, int64_t L,
+                                int64_t heads, int64_t head_dim, int32_t act_dtype, float drop_p, uint64_t drop_seed,
+                                uint32_t drop_site, const uint64_t* drop_counter, void* stream) {
   RL_REQUIRE(qkv && mask && ctx, RL_EINVAL, "rl_attention_fwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_fwd: head_dim must be 64, got %lld", (long long)head_dim);
   RL_REQUIRE(B > 0 && heads > 0 && L > 0, RL_EINVAL, "rl_attention_fwd: empty problem");
@@ -279,9 +273,9 @@ extern "C" int rl_attention_fwd_lse(const void* qkv, const int64_t* mask, void* 
   p.lkv16 = lkv16;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.heads = (int)heads;
-  p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
+  p.drop = rl::make_drop(drop_p, drop_seed, drop_site, drop_counter);
   p.lse = row_lse;
-  p.f16 = rl_half_is_f16();
+  p.f16 = act_dtype == RL_DT_F16;
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)heads, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (lkv16 <= 128) return launch_att<128>(tq, tkv, p, grid, st);

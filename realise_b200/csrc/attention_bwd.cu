@@ -23,6 +23,8 @@ struct AttBwdParams {
   int heads;
   rl::DropSpec drop;
   const float* lse;           // optional [B, heads, L] log2-domain logsumexp saved by the forward: skips two passes over S
+  int f16;                    // forward tensors (Q/K/V, ctx, the recomputed P) are fp16; gradients (dO, dS, dqkv) stay bf16 —
+                              // tcgen05 kind::f16 takes the format per operand
 };
 
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -83,7 +85,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     rl::tma_load_2d(sDO, &tmDO, bar_ld, head * HEAD_DIM, row0);
     rl::mbar_wait(bar_ld, 0);
     rl::tc_fence_after();
-    const uint32_t idesc = rl::make_idesc_bf16(128, lkv16);
+    const uint32_t idesc = rl::make_idesc_h(128, lkv16, 0, 0, p.f16, p.f16);      // S = Q K^T
+    const uint32_t idesc_dp = rl::make_idesc_h(128, lkv16, 0, 0, 0, p.f16);       // dP = dO (bf16) V^T
     const uint32_t qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK), va = rl::smem_u32(sV), da = rl::smem_u32(sDO);
 #pragma unroll
     for (int k = 0; k < 4; ++k)  // S = Q K^T
@@ -92,7 +95,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
     for (int k = 0; k < 4; ++k)  // dP = dO V^T
       rl::tc_mma_f16(tmem_base + COL_DP, rl::make_smem_desc_sw128(da + k * 32, 16, 1024),
-                     rl::make_smem_desc_sw128(va + k * 32, 16, 1024), idesc, k != 0);
+                     rl::make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_dp, k != 0);
     rl::tc_commit(bar_s);
   }
 
@@ -105,10 +108,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 a = o[i], c = g[i];
-      delta += rl::bf16_lo(a.x) * rl::bf16_lo(c.x) + rl::bf16_hi(a.x) * rl::bf16_hi(c.x) +
-               rl::bf16_lo(a.y) * rl::bf16_lo(c.y) + rl::bf16_hi(a.y) * rl::bf16_hi(c.y) +
-               rl::bf16_lo(a.z) * rl::bf16_lo(c.z) + rl::bf16_hi(a.z) * rl::bf16_hi(c.z) +
-               rl::bf16_lo(a.w) * rl::bf16_lo(c.w) + rl::bf16_hi(a.w) * rl::bf16_hi(c.w);
+      delta += rl::half_lo(a.x, p.f16) * rl::bf16_lo(c.x) + rl::half_hi(a.x, p.f16) * rl::bf16_hi(c.x) +
+               rl::half_lo(a.y, p.f16) * rl::bf16_lo(c.y) + rl::half_hi(a.y, p.f16) * rl::bf16_hi(c.y) +
+               rl::half_lo(a.z, p.f16) * rl::bf16_lo(c.z) + rl::half_hi(a.z, p.f16) * rl::bf16_hi(c.z) +
+               rl::half_lo(a.w, p.f16) * rl::bf16_lo(c.w) + rl::half_hi(a.w, p.f16) * rl::bf16_hi(c.w);
     }
   }
 
@@ -179,8 +182,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int g = 0; g < 4; ++g) {
       const int piece = (((c & 1) * 4 + g) ^ (r & 7)) << 4;
       *reinterpret_cast<uint4*>(tp + piece) =
-          make_uint4(rl::pack_bf16(pr[8 * g], pr[8 * g + 1]), rl::pack_bf16(pr[8 * g + 2], pr[8 * g + 3]),
-                     rl::pack_bf16(pr[8 * g + 4], pr[8 * g + 5]), rl::pack_bf16(pr[8 * g + 6], pr[8 * g + 7]));
+          make_uint4(rl::pack_h(pr[8 * g], pr[8 * g + 1], p.f16), rl::pack_h(pr[8 * g + 2], pr[8 * g + 3], p.f16),
+                     rl::pack_h(pr[8 * g + 4], pr[8 * g + 5], p.f16), rl::pack_h(pr[8 * g + 6], pr[8 * g + 7], p.f16));
       *reinterpret_cast<uint4*>(td + piece) =
           make_uint4(rl::pack_bf16(ds[8 * g], ds[8 * g + 1]), rl::pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
                      rl::pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), rl::pack_bf16(ds[8 * g + 6], ds[8 * g + 7]));
@@ -201,7 +204,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t pa = rl::smem_u32(sV), dsa = rl::smem_u32(sDS), qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK),
                    da = rl::smem_u32(sDO);
     // dV[kv, d] = sum_q P[q, kv] dO[q, d] : A = P^T (MN-major: kv contiguous, 64-kv blocks one tile apart), B = dO^T
-    const uint32_t idesc_t = rl::make_idesc_bf16(128, HEAD_DIM, 1, 1);
+    const uint32_t idesc_t = rl::make_idesc_h(128, HEAD_DIM, 1, 1, p.f16, 0);     // P (forward format) x dO (bf16)
+    const uint32_t idesc_k = rl::make_idesc_h(128, HEAD_DIM, 1, 1, 0, p.f16);     // dS (bf16) x Q
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       rl::tc_mma_f16(tmem_base + COL_DV, rl::make_smem_desc_sw128(pa + k * 2048, 2 * T16K, 1024),  // P tiles: sV, sP1
@@ -210,9 +214,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       rl::tc_mma_f16(tmem_base + COL_DK, rl::make_smem_desc_sw128(dsa + k * 2048, T16K, 1024),
-                     rl::make_smem_desc_sw128(qa + k * 2048, 1024, 1024), idesc_t, k != 0);
+                     rl::make_smem_desc_sw128(qa + k * 2048, 1024, 1024), idesc_k, k != 0);
     // dQ[q, d] = sum_kv dS[q, kv] K[kv, d] : A = dS K-major over kv, B = K^T (MN-major)
-    const uint32_t idesc_q = rl::make_idesc_bf16(128, HEAD_DIM, 0, 1);
+    const uint32_t idesc_q = rl::make_idesc_h(128, HEAD_DIM, 0, 1, 0, p.f16);     // dS (bf16) x K
     const int nk = lkv16 / 16;
     for (int k = 0; k < nk; ++k)
       rl::tc_mma_f16(tmem_base + COL_DQ, rl::make_smem_desc_sw128(dsa + (k >> 2) * T16K + (k & 3) * 32, 16, 1024),
@@ -258,14 +262,9 @@ constexpr int ATT_BWD_SMEM = 7 * T16K + 128 * 4 + 3 * 8 + 16;   // 115,240 B: tw
 }  // namespace
 
 extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                                int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p, uint64_t drop_seed,
-                                uint32_t drop_site, void* stream) {
-  return rl_attention_bwd_lse(qkv, mask, ctx, dctx, dqkv, nullptr, B, L, heads, head_dim, drop_p, drop_seed, drop_site, stream);
-}
-
-extern "C" int rl_attention_bwd_lse(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                                    const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, float drop_p,
-                                    uint64_t drop_seed, uint32_t drop_site, void* stream) {
+                                const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t act_dtype,
+                                float drop_p, uint64_t drop_seed, uint32_t drop_site, const uint64_t* drop_counter,
+                                void* stream) {
   RL_REQUIRE(qkv && mask && ctx && dctx && dqkv, RL_EINVAL, "rl_attention_bwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_bwd: head_dim must be 64");
   RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 128, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..128", (long long)L);
@@ -303,7 +302,8 @@ extern "C" int rl_attention_bwd_lse(const void* qkv, const int64_t* mask, const 
   p.lkv16 = lkv16;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.heads = (int)heads;
-  p.drop = rl::make_drop(drop_p, drop_seed, drop_site);
+  p.drop = rl::make_drop(drop_p, drop_seed, drop_site, drop_counter);
+  p.f16 = act_dtype == RL_DT_F16;
   p.lse = row_lse;
   attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, p);
   return rl_check_launch("rl_attention_bwd");

@@ -183,7 +183,7 @@ colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ 
 // of BertIntermediate.dense) in the same pass — same row-slab layout as colsum_bf16_vec_kernel.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, long long n8) {
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, long long n8, int f16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const uint4 v = reinterpret_cast<const uint4*>(u)[i];
@@ -191,15 +191,15 @@ gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__
   uint32_t o[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const rl::f2 r = rl::gelu_erf2(rl::f2{rl::bf16_lo(w[j]), rl::bf16_hi(w[j])});
-    o[j] = rl::pack_bf16(r.x, r.y);
+    const rl::f2 r = rl::gelu_erf2(rl::f2{rl::half_lo(w[j], f16), rl::half_hi(w[j], f16)});
+    o[j] = rl::pack_h(r.x, r.y, f16);
   }
   reinterpret_cast<uint4*>(h)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(256)
 gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ u, float* __restrict__ dbias,
-                       long long rows, int cols, long long ld, int rows_per_cta) {
+                       long long rows, int cols, long long ld, int rows_per_cta, int u_f16) {
   __shared__ float s[8][256 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -225,7 +225,7 @@ gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ t, const __nv_bfloat16* __res
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const rl::f2 d = rl::mul2(rl::f2{rl::bf16_lo(tw[k]), rl::bf16_hi(tw[k])},
-                                  rl::gelu_grad2(rl::f2{rl::bf16_lo(uw[k]), rl::bf16_hi(uw[k])}));
+                                  rl::gelu_grad2(rl::f2{rl::half_lo(uw[k], u_f16), rl::half_hi(uw[k], u_f16)}));
         ow[k] = rl::pack_bf16(d.x, d.y);
         acc[(k & 3) * 2] += d.x;      // bias gradient from the unrounded products (fp32, like the reference's autograd)
         acc[(k & 3) * 2 + 1] += d.y;
@@ -464,11 +464,11 @@ struct TensorEntry {   // mirrored by realise_b200/optim.py (ctypes) — keep in
   const float* g;
   float* m;
   float* v;
-  __nv_bfloat16* shadow;  // optional bf16 operand copy refreshed in the same pass
+  __nv_bfloat16* shadow;  // optional 16-bit operand copy refreshed in the same pass (bf16, or fp16 when shadow_f16)
   float* shadow32;        // optional f32 copy (e.g. the slice of a fused QKV bias vector)
   long long n;
   float wd;
-  int pad;
+  int shadow_f16;
 };
 constexpr int OPT_CHUNK = 4096;
 
@@ -541,7 +541,10 @@ mt_adamw_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ ch
       e.m[idx] = m;
       e.v[idx] = v;
       e.p[idx] = pv;
-      if (e.shadow) e.shadow[idx] = __float2bfloat16(pv);
+      if (e.shadow) {
+        if (e.shadow_f16) reinterpret_cast<__half*>(e.shadow)[idx] = __float2half_rn(pv);
+        else e.shadow[idx] = __float2bfloat16(pv);
+      }
       if (e.shadow32) e.shadow32[idx] = pv;
     }
   }
@@ -554,7 +557,7 @@ bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
 extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* add_in, float* dx,
                                 void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int64_t H,
                                 float eps, float drop_p, uint64_t drop_seed, uint32_t site_in, uint32_t site_out,
-                                void* stream) {
+                                const uint64_t* drop_counter, void* stream) {
   RL_REQUIRE(dy && x && gamma && (dx || dx_bf16), RL_EINVAL, "rl_layernorm_bwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_bwd: bad H");
   if (rows <= 0) return 0;
@@ -564,8 +567,8 @@ extern "C" int rl_layernorm_bwd(const float* dy, const float* x, const float* ga
   if (ctas > max_ctas) ctas = max_ctas;
   const int rows_per_cta = (int)((rows + ctas - 1) / ctas);
   ctas = (rows + rows_per_cta - 1) / rows_per_cta;
-  const rl::DropSpec din = rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in);
-  const rl::DropSpec dout = rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out);
+  const rl::DropSpec din = rl::make_drop(site_in ? drop_p : 0.f, drop_seed, site_in, drop_counter);
+  const rl::DropSpec dout = rl::make_drop(site_out ? drop_p : 0.f, drop_seed, site_out, drop_counter);
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 6 * 512);
@@ -601,16 +604,18 @@ extern "C" int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t c
   return rl_check_launch("rl_colsum_bf16");
 }
 
-extern "C" int rl_gelu_fwd(const void* u, void* h, int64_t n, void* stream) {
+extern "C" int rl_gelu_fwd(const void* u, void* h, int64_t n, int32_t dtype, void* stream) {
   RL_REQUIRE(u && h && n >= 0 && n % 8 == 0 && (((uintptr_t)u | (uintptr_t)h) & 15) == 0, RL_EALIGN,
              "rl_gelu_fwd: n must be a multiple of 8 and the pointers 16-byte aligned");
   if (n == 0) return 0;
   const long long n8 = n / 8;
-  gelu_fwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)u, (__nv_bfloat16*)h, n8);
+  gelu_fwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)u, (__nv_bfloat16*)h, n8,
+                                                                                dtype == RL_DT_F16);
   return rl_check_launch("rl_gelu_fwd");
 }
 
-extern "C" int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld, void* stream) {
+extern "C" int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t rows, int64_t cols, int64_t ld,
+                                  int32_t u_dtype, void* stream) {
   RL_REQUIRE(t && u && cols > 0 && ld >= cols && cols % 8 == 0 && ld % 8 == 0 && (((uintptr_t)t | (uintptr_t)u) & 15) == 0,
              RL_EALIGN, "rl_gelu_bwd_colsum: cols / ld must be multiples of 8 and the pointers 16-byte aligned");
   if (rows <= 0) return 0;
@@ -623,7 +628,7 @@ extern "C" int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t 
   row_chunks = (rows + rows_per_cta - 1) / rows_per_cta;
   dim3 grid((unsigned)col_blocks, (unsigned)row_chunks);
   gelu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)t, (const __nv_bfloat16*)u, dbias, rows, (int)cols,
-                                                                ld, rows_per_cta);
+                                                                ld, rows_per_cta, u_dtype == RL_DT_F16);
   return rl_check_launch("rl_gelu_bwd_colsum");
 }
 

@@ -16,11 +16,9 @@
 void rl_set_error(const char* fmt, ...);
 int rl_check_launch(const char* what);  // returns 0 or positive cudaError_t
 int rl_num_sms();
-int rl_half_is_f16();
 // resident CTAs per SM of a kernel (cudaOccupancyMaxActiveBlocksPerMultiprocessor, cached per function; 2 when the query
 // fails, e.g. without a device).  Slab kernels size their grid to ONE full wave: a few CTAs beyond it cost a whole extra pass.
-int rl_ctas_per_sm(const void* func, int threads, int dyn_smem);   // process-wide 16-bit operand format set by rl_set_half_format (0 = bf16, 1 = fp16)
-const unsigned long long* rl_dropout_seed_ptr();   // process-wide, set by rl_set_dropout_seed_ptr (NULL = off)
+int rl_ctas_per_sm(const void* func, int threads, int dyn_smem);
 
 #define RL_REQUIRE(cond, code, ...)    \
   do {                                 \
@@ -185,6 +183,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | ((uint32_t)(M >> 4) << 24);    // m_dim
 }
 
+// the same with the 16-bit format chosen per operand (tcgen05 kind::f16 multiplies bf16 by fp16 operands as they are:
+// training keeps forward tensors in fp16 and gradients in bf16)
+__host__ __device__ constexpr uint32_t make_idesc_h(int M, int N, int a_mn_major, int b_mn_major, int a_f16, int b_f16) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // shared-memory matrix descriptor, SWIZZLE_128B.  K-major: rows of 128 B (64 bf16), 8-row atoms,
 // SBO = byte stride between consecutive 8-row groups.  MN-major: 128-B rows along MN, 8 k-rows per
 // atom; LBO = byte stride between 64-element MN blocks, SBO = byte stride between 8-k groups.
@@ -240,8 +245,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
-// 16-bit operand format of a launch: bf16 (default, training) or IEEE fp16 (rl_set_half_format(1): inference — three more
-// mantissa bits for the same tensor-core rate; activations of this model stay far inside the fp16 range)
+// 16-bit storage format of a tensor: bf16 or IEEE fp16 (RL_DT_F16: three more mantissa bits for the same tensor-core
+// rate; forward activations / weights of this model stay far inside the fp16 range, gradients stay bf16)
 __device__ __forceinline__ uint32_t pack_h(float a, float b, int f16) {
   if (f16) {
     __half2 h = __floats2half2_rn(a, b);
@@ -282,19 +287,16 @@ __host__ __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsi
 struct DropSpec {   // passed by value to kernels; thresh == 0 means "no dropout"
   unsigned long long seed;
   const unsigned long long* seed_ptr;   // optional device-resident step counter added to `seed` at run time, so that a
-                                        // captured CUDA graph draws fresh masks on every replay (rl_set_dropout_seed_ptr)
+                                        // captured CUDA graph draws fresh masks on every replay (the drop_counter argument)
   unsigned int site;
   unsigned int thresh;
   float scale;      // 1 / (1 - p)
 };
-__host__ __device__ __forceinline__ DropSpec make_drop(float p, unsigned long long seed, unsigned int site) {
+__host__ __device__ __forceinline__ DropSpec make_drop(float p, unsigned long long seed, unsigned int site,
+                                                       const uint64_t* counter = nullptr) {
   DropSpec d;
   d.seed = seed;
-#ifndef __CUDA_ARCH__
-  d.seed_ptr = rl_dropout_seed_ptr();
-#else
-  d.seed_ptr = nullptr;
-#endif
+  d.seed_ptr = reinterpret_cast<const unsigned long long*>(counter);
   d.site = site;
   d.thresh = p > 0.f ? (unsigned int)(p * 65536.0 + 0.5) : 0u;
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;

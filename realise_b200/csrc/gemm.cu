@@ -39,13 +39,13 @@ struct KParams {
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int vec_store;  // direct path may use 16-byte stores
   rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
-  int f16;        // 16-bit operands / outputs / residuals are IEEE fp16 instead of bf16 (rl_set_half_format)
+  int a_f16, b_f16;   // operand formats of the MMA: IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either, per operand)
+  int o_f16, r_f16;   // 16-bit outputs (out, out2) / 16-bit residual stored as fp16 instead of bf16
   int b_mode;     // 1: B tiles are gathered from a conv activation (implicit im2col, weight gradients)
   int ks_major;   // tile order: split index outermost, so that the N tiles sharing a K range run side by side (L2 reuse)
   int nimg;       // conv: number of images (an image index >= nimg makes a TMA box read zeros)
   int ntaps;
   int a_mn, b_mn; // operand stored MN-major: A as [K, M] (M contiguous), B as [K, N] (N contiguous)
-  int dbg;        // tuning experiments only: 1 = no epilogue work, 2 = no TMA loads, 4 = no MMA
 };
 
 using rl::fast_erf;
@@ -94,10 +94,10 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 t = r[j];
-          x[8 * j] = rl::half_lo(t.x, p.f16); x[8 * j + 1] = rl::half_hi(t.x, p.f16);
-          x[8 * j + 2] = rl::half_lo(t.y, p.f16); x[8 * j + 3] = rl::half_hi(t.y, p.f16);
-          x[8 * j + 4] = rl::half_lo(t.z, p.f16); x[8 * j + 5] = rl::half_hi(t.z, p.f16);
-          x[8 * j + 6] = rl::half_lo(t.w, p.f16); x[8 * j + 7] = rl::half_hi(t.w, p.f16);
+          x[8 * j] = rl::half_lo(t.x, p.r_f16); x[8 * j + 1] = rl::half_hi(t.x, p.r_f16);
+          x[8 * j + 2] = rl::half_lo(t.y, p.r_f16); x[8 * j + 3] = rl::half_hi(t.y, p.r_f16);
+          x[8 * j + 4] = rl::half_lo(t.z, p.r_f16); x[8 * j + 5] = rl::half_hi(t.z, p.r_f16);
+          x[8 * j + 6] = rl::half_lo(t.w, p.r_f16); x[8 * j + 7] = rl::half_hi(t.w, p.r_f16);
         }
       }
     } else {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
         x[j] = 0.f;
         if (nb + j < p.N)
           x[j] = p.res_f32 ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + nb + j]
-                           : rl::half_lo((uint32_t)reinterpret_cast<const unsigned short*>(p.res)[(long long)row * p.ldr + nb + j], p.f16);
+                           : rl::half_lo((uint32_t)reinterpret_cast<const unsigned short*>(p.res)[(long long)row * p.ldr + nb + j], p.r_f16);
       }
     }
   } else {
@@ -187,12 +187,12 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
           uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.f16),
-                              rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.f16));
+            o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.o_f16),
+                              rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.o_f16));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.f16) & 0xFFFFu);
+            if (nb + j < p.N) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.o_f16) & 0xFFFFu);
         }
       }
       if (p.act == RL_ACT_GELU || p.act == RL_ACT_GELU_SAVE) {
@@ -219,8 +219,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], p.f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], p.f16),
-                           rl::pack_h(x[8 * g + 4], x[8 * g + 5], p.f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], p.f16));
+                make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], p.o_f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], p.o_f16),
+                           rl::pack_h(x[8 * g + 4], x[8 * g + 5], p.o_f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], p.o_f16));
         }
         rl::fence_proxy_async();
         __syncwarp();
@@ -261,15 +261,15 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
             uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.f16),
-                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.f16));
+              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.o_f16),
+                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.o_f16));
           }
           if (p.out2 && p.act != RL_ACT_GELU_SAVE) {
             uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.f16),
-                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.f16));
+              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.o_f16),
+                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.o_f16));
           }
         } else {
 #pragma unroll
@@ -278,8 +278,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
               if (p.out_f32)
                 reinterpret_cast<float*>(p.out)[orow * p.ldo + nb + j] = x[j];
               else
-                reinterpret_cast<unsigned short*>(p.out)[orow * p.ldo + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.f16) & 0xFFFFu);
-              if (p.out2 && p.act != RL_ACT_GELU_SAVE) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.f16) & 0xFFFFu);
+                reinterpret_cast<unsigned short*>(p.out)[orow * p.ldo + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.o_f16) & 0xFFFFu);
+              if (p.out2 && p.act != RL_ACT_GELU_SAVE) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.o_f16) & 0xFFFFu);
             }
           }
         }
@@ -358,9 +358,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           rl::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p.dbg & 2) {
-            rl::mbar_arrive(&full_bar[stage]);
-          } else {
+          {
           rl::mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           if (p.a_mn) {
             rl::tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], m0, kb * BK);
@@ -408,7 +406,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     {
       // ===================== MMA issuer =====================
       // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
-      const uint32_t idesc = rl::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn, p.f16);
+      const uint32_t idesc = rl::make_idesc_h(BM, BN, p.a_mn, p.b_mn, p.a_f16, p.b_f16);
       const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
       // K-major: 128-byte rows, 8-row atoms 1024 B apart, a k-step of 16 is +32 B.  MN-major: 64-wide MN blocks
       // 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), a k-step of 16 rows is +2048 B.
@@ -432,8 +430,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * B_BYTES, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              if (!(p.dbg & 4))
-                rl::tc_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              rl::tc_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             rl::tc_commit(&empty_bar[stage]);
           }
           __syncwarp();
@@ -473,7 +470,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (!(p.dbg & 1)) epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
+      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) rl::mbar_arrive(&tmem_empty[acc]);
@@ -643,9 +640,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           rl::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (p.dbg & 2) {
-            if (leader) rl::mbar_arrive(&full_bar[stage]);
-          } else {
+          {
           if (leader) rl::mbar_expect_tx(&full_bar[stage], 2 * (A_BYTES + BH_BYTES));
           if (p.a_mn) {
             tma2_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], m0, kb * BK);
@@ -693,7 +688,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (leader) {
       // ===================== MMA issuer (leader CTA only) =====================
       // The whole warp runs the loop converged (addresses stay in uniform registers); one elected lane issues.
-      const uint32_t idesc = rl::make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn, p.f16);
+      const uint32_t idesc = rl::make_idesc_h(2 * BM, BN, p.a_mn, p.b_mn, p.a_f16, p.b_f16);
       const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
       const uint32_t a_lbo = p.a_mn ? 8192 : 16, b_lbo = p.b_mn ? 8192 : 16;
       const uint32_t a_kstep = p.a_mn ? 128 : 2, b_kstep = p.b_mn ? 128 : 2;  // in 16-byte units
@@ -715,8 +710,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + stage * BH_BYTES, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              if (!(p.dbg & 4))
-                tc2_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              tc2_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             tc2_commit_mc(&empty_bar[stage]);
           }
           __syncwarp();
@@ -751,7 +745,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (!(p.dbg & 1)) epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
+      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -800,26 +794,7 @@ int ilog2_exact(int v) {
   return ((1 << s) == v) ? s : -1;
 }
 
-int g_force_bn = 0;
-int g_pair_mode = 1;
-int g_dbg = 0;  // 1: use the cta_group::2 kernel when the problem is large enough
-
 }  // namespace
-
-extern "C" int rl_gemm_set_tile_n(int bn) {
-  g_force_bn = bn;
-  return 0;
-}
-
-extern "C" int rl_gemm_set_debug_mode(int flags) {
-  g_dbg = flags;
-  return 0;
-}
-
-extern "C" int rl_gemm_set_pair_mode(int on) {
-  g_pair_mode = on;
-  return 0;
-}
 
 extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   RL_REQUIRE(d != nullptr, RL_EINVAL, "rl_gemm_bf16: null descriptor");
@@ -847,7 +822,12 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.b_mn = d->b_major;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.a_mode = d->a_mode;
-  p.f16 = rl_half_is_f16();
+  RL_REQUIRE((d->a_dtype == RL_DT_BF16 || d->a_dtype == RL_DT_F16) && (d->b_dtype == RL_DT_BF16 || d->b_dtype == RL_DT_F16),
+             RL_EINVAL, "rl_gemm_bf16: a_dtype / b_dtype must be RL_DT_BF16 or RL_DT_F16");
+  p.a_f16 = d->a_dtype == RL_DT_F16;
+  p.b_f16 = d->b_dtype == RL_DT_F16;
+  p.o_f16 = d->out_dtype == RL_DT_F16;
+  p.r_f16 = d->res_dtype == RL_DT_F16;
   p.b_mode = d->b_mode;
   p.ks_major = 0;
   p.nimg = d->conv_NIMG;
@@ -867,14 +847,15 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.act = d->act;
   p.out_remap = d->out_remap;
   p.remap_plane = d->remap_plane;
-  p.dbg = g_dbg;
-  p.drop = rl::make_drop(d->drop_p, d->drop_seed, d->drop_site);
+  p.drop = rl::make_drop(d->drop_p, d->drop_seed, d->drop_site, d->drop_counter);
 
   // Tile / kernel selection.  Cost model per 64-deep k-block of one CTA tile (cycles): the tensor pipe needs
   // 2*bn, the operand bytes need bytes / 42.6 (measured L2->SM ingress per SM, ~6.3 KB/clk chip-wide);
   // a CTA pair (cta_group::2) stages only half of B per CTA.  Total = waves * max(mma, load).
   int bn = 256;
   int pair = 0;
+  const int g_force_bn = d->tune_tile_n;          // 0 = cost model; 64 / 128 / 256 force the N tile (tuning, tests)
+  const int g_pair_mode = d->tune_no_pair ? 0 : 1;  // tune_no_pair: never use the cta_group::2 kernel
   {
     const int sms = rl_num_sms();
     double best = 1e30;

@@ -332,7 +332,7 @@ extern "C" int rl_gru_input_table(const float* emb, const float* w_ih, const flo
 
 extern "C" int rl_gru_step_fwd(const float* gh, const float* b_hh, const float* table, const int64_t* pho_idx,
                                const int32_t* lens, const float* h_prev, float* h_out, void* h_out_bf16, int64_t rows,
-                               int64_t H, int64_t T, int64_t t, void* stream) {
+                               int64_t H, int64_t T, int64_t t, int32_t out16_dtype, void* stream) {
   RL_REQUIRE(table && pho_idx && lens && h_out && h_out_bf16 && b_hh, RL_EINVAL, "rl_gru_step_fwd: null pointer");
   RL_REQUIRE((gh == nullptr) == (h_prev == nullptr), RL_EINVAL, "rl_gru_step_fwd: gh and h_prev go together");
   RL_REQUIRE(H % 128 == 0 && t >= 0 && t < T, RL_EINVAL, "rl_gru_step_fwd: bad shape");
@@ -340,7 +340,7 @@ extern "C" int rl_gru_step_fwd(const float* gh, const float* b_hh, const float* 
   const int wpb = 8;
   gru_step_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       gh, b_hh, table, (const long long*)pho_idx, lens, h_prev, h_out, (__nv_bfloat16*)h_out_bf16, rows, (int)H, (int)T,
-      (int)t, rl_half_is_f16());
+      (int)t, out16_dtype == RL_DT_F16);
   return rl_check_launch("rl_gru_step_fwd");
 }
 

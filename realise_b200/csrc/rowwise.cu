@@ -331,21 +331,23 @@ bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
 
 extern "C" int rl_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32,
                                 void* out_bf16, int64_t rows, int64_t H, float eps, float drop_p, uint64_t drop_seed,
-                                uint32_t drop_site, int32_t drop_f32, void* stream) {
+                                uint32_t drop_site, const uint64_t* drop_counter, int32_t drop_f32, int32_t out16_dtype,
+                                void* stream) {
   RL_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), RL_EINVAL, "rl_layernorm_fwd: null pointer");
   RL_REQUIRE(h_ok(H), RL_EINVAL, "rl_layernorm_fwd: H=%lld must be a multiple of 128, <= 1024", (long long)H);
   if (rows <= 0) return 0;
   const int wpb = 8;
   layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows, (int)H, eps, rl::make_drop(drop_p, drop_seed, drop_site),
-      drop_f32, rl_half_is_f16());
+      x, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, rows, (int)H, eps, rl::make_drop(drop_p, drop_seed, drop_site, drop_counter),
+      drop_f32, out16_dtype == RL_DT_F16);
   return rl_check_launch("rl_layernorm_fwd");
 }
 
 extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const float* inputs_embeds, const float* pos,
                                const float* type0, const float* gamma, const float* beta, float* out_f32,
                                void* out_bf16, float* pre_ln_out, int64_t rows, int64_t L, int64_t H, int32_t pos_mode,
-                               float eps, float drop_p, uint64_t drop_seed, uint32_t drop_site, void* stream) {
+                               float eps, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                               const uint64_t* drop_counter, int32_t out16_dtype, void* stream) {
   RL_REQUIRE((inputs_embeds || (ids && word)) && pos && type0 && gamma && beta && (out_f32 || out_bf16), RL_EINVAL,
              "rl_embed_ln_fwd: null pointer");
   RL_REQUIRE(h_ok(H) && L > 0, RL_EINVAL, "rl_embed_ln_fwd: bad H/L");
@@ -353,7 +355,8 @@ extern "C" int rl_embed_ln_fwd(const int64_t* ids, const float* word, const floa
   const int wpb = 8;
   embed_ln_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       (const long long*)ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, (__nv_bfloat16*)out_bf16, pre_ln_out,
-      rows, (int)L, (int)H, pos_mode, eps, rl::make_drop(drop_p, drop_seed, drop_site), rl_half_is_f16());
+      rows, (int)L, (int)H, pos_mode, eps, rl::make_drop(drop_p, drop_seed, drop_site, drop_counter),
+      out16_dtype == RL_DT_F16);
   return rl_check_launch("rl_embed_ln_fwd");
 }
 
@@ -435,12 +438,12 @@ extern "C" int rl_gather_rows_f32(const float* table, const int64_t* ids, float*
   return rl_check_launch("rl_gather_rows_f32");
 }
 
-extern "C" int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, void* stream) {
+extern "C" int rl_split3_bf16(const float* x, void* out, int64_t rows, int64_t cols, int32_t out_dtype, void* stream) {
   RL_REQUIRE(x && out && cols > 0 && cols % 4 == 0 && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 7) == 0), RL_EALIGN,
              "rl_split3_bf16: cols must be a multiple of 4 and the pointers aligned");
   if (rows <= 0) return 0;
   const long long n = rows * (cols / 4);
-  split3_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, rows, (int)cols, rl_half_is_f16());
+  split3_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, rows, (int)cols, out_dtype == RL_DT_F16);
   return rl_check_launch("rl_split3_bf16");
 }
 
@@ -451,9 +454,10 @@ extern "C" int rl_argmax_rows(const float* logits, int64_t* out, int64_t rows, i
   return rl_check_launch("rl_argmax_rows");
 }
 
-extern "C" int rl_dropout_mask(uint8_t* out, int64_t n, float drop_p, uint64_t drop_seed, uint32_t drop_site, void* stream) {
+extern "C" int rl_dropout_mask(uint8_t* out, int64_t n, float drop_p, uint64_t drop_seed, uint32_t drop_site,
+                               const uint64_t* drop_counter, void* stream) {
   RL_REQUIRE(out && n >= 0, RL_EINVAL, "rl_dropout_mask: bad arguments");
   if (n == 0) return 0;
-  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, rl::make_drop(drop_p, drop_seed, drop_site));
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, rl::make_drop(drop_p, drop_seed, drop_site, drop_counter));
   return rl_check_launch("rl_dropout_mask");
 }

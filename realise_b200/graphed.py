@@ -15,17 +15,15 @@ all-reduce) + clip + AdamW of one batch shape once and replays it:
 
 What makes the capture replayable:
   * dropout masks are counter based; the kernels add a device-resident step counter to their seed
-    (rl_set_dropout_seed_ptr), and the graph itself increments that counter, so every replay draws fresh masks;
+    (the kernels' drop_counter argument), and the graph itself increments that counter, so every replay draws fresh masks;
   * lr and the Adam bias corrections are read from a 3-float device buffer written before each replay
     (rl_mt_adamw_dev);
   * the batch is copied into static input buffers; shapes (B, L, T) key the graph cache, the first step of a new
     shape runs eagerly (it is a real training step) and doubles as the warm-up the capture needs.
 """
-import ctypes
-
 import torch
 
-from ._lib import check, lib
+from . import ops
 from .batch import MAX_PHO_LEN
 
 
@@ -79,16 +77,14 @@ class GraphedTrainStep:
         if self._pool is None:
             self._pool = torch.cuda.graph_pool_handle()
         opt.device_hyper = self._hyper
-        check(lib().rl_set_dropout_seed_ptr(ctypes.c_void_p(self._counter.data_ptr())), "rl_set_dropout_seed_ptr")
         seed0, step0 = eng.seed, opt._step
         try:
-            with torch.cuda.graph(graph, pool=self._pool):
+            with ops.dropout_counter(self._counter), torch.cuda.graph(graph, pool=self._pool):
                 self._counter.add_(1)
                 loss, _ = eng.forward(static)
                 eng.backward_and_sync(self._ones)
                 opt.step()
         finally:
-            check(lib().rl_set_dropout_seed_ptr(None), "rl_set_dropout_seed_ptr")
             opt.device_hyper = None
             eng.seed, opt._step = seed0, step0     # recording a graph is not a training step
         return graph, static, loss

@@ -37,17 +37,41 @@ class _Timed:
             self.e1.record()
             _prof.append((self.kind, self.work, self.e0, self.e1, self.detail))
         return False
-_DT = {torch.bfloat16: 0, torch.float16: 0, torch.float32: 1}   # 16-bit outputs: the format follows set_half_format
-_HALF_F16 = False
+_DT = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}   # RL_DT_*: the tensor's dtype IS the per-call format argument
+_H16 = (torch.bfloat16, torch.float16)
+
+# tuning knobs of the GEMM (per call through the descriptor; the library keeps no global switches)
+TUNE_TILE_N = 0
+TUNE_NO_PAIR = 0
+
+# Device-resident dropout step counter (int64 tensor of one element) handed to every dropout-bearing kernel while set:
+# the kernels then use seed + *counter, read at run time (realise_b200.graphed bumps it inside the captured graph).
+_COUNTER = None
 
 
-def set_half_format(f16):
-    """16-bit operand format of every following launch: bf16 (False, default) or IEEE fp16 (True, inference)."""
-    global _HALF_F16
-    f16 = bool(f16)
-    if f16 != _HALF_F16:
-        check(lib().rl_set_half_format(ctypes.c_int(int(f16))), "rl_set_half_format")
-        _HALF_F16 = f16
+class dropout_counter:
+    """with ops.dropout_counter(t): ... — every launch inside passes t as its drop_counter argument."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __enter__(self):
+        global _COUNTER
+        self.prev, _COUNTER = _COUNTER, self.t
+        return self
+
+    def __exit__(self, *exc):
+        global _COUNTER
+        _COUNTER = self.prev
+        return False
+
+
+def _ctr():
+    return ctypes.c_void_p(_COUNTER.data_ptr()) if _COUNTER is not None else None
+
+
+def _dt(t):
+    return ctypes.c_int32(_DT[t.dtype])
 
 
 def _stream():
@@ -61,8 +85,8 @@ def _ptr(t):
 def _req(t, dtype, name):
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (realise_b200 has no CPU path)")
-    if dtype is torch.bfloat16 and _HALF_F16:
-        dtype = torch.float16
+    if dtype is torch.bfloat16 and t.dtype is torch.float16:
+        return            # any "bf16" tensor may be IEEE fp16: the call passes its format along
     if t.dtype != dtype:
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 
@@ -83,8 +107,10 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldb = a.stride(0), b.stride(0)
     d.a_major, d.b_major = int(a_t), int(b_t)
+    d.a_dtype, d.b_dtype = _DT[a.dtype], _DT[b.dtype]
     if drop:
         d.drop_p, d.drop_seed, d.drop_site = drop
+        d.drop_counter = _COUNTER.data_ptr() if _COUNTER is not None else None
     d.split_k = split_k
     d.a_mode = 0
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
@@ -112,6 +138,7 @@ def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldb = C, w.stride(0)
     d.a_mode = 1
+    d.a_dtype, d.b_dtype = _DT[x.dtype], _DT[w.dtype]
     d.conv_C, d.conv_W, d.conv_H, d.conv_P, d.conv_NIMG = C, W, H, planes, nimg
     d.ntaps = len(taps)
     d.conv_Cuse = c_use
@@ -142,6 +169,7 @@ def conv_wgrad(dy, x, out, *, nimg, H, W, planes, taps, split_k=-1):
     d.M, d.N, d.K = M, N, Kpix
     d.lda, d.ldb = dy.stride(0), C
     d.a_major, d.b_major, d.b_mode, d.a_mode = 1, 1, 1, 0
+    d.a_dtype, d.b_dtype = _DT[dy.dtype], _DT[x.dtype]
     d.conv_C, d.conv_W, d.conv_H, d.conv_P, d.conv_NIMG = C, W, H, planes, nimg
     d.ntaps = len(taps)
     for i, (dw, dh, pl) in enumerate(taps):
@@ -158,8 +186,10 @@ def _fill_epilogue(d, out, scale, bias, res, act, out2, out_remap):
     if not out.is_cuda or out.dtype not in _DT:
         raise RuntimeError("out must be a CUDA bf16/f32 tensor")
     d.out, d.ldo, d.out_dtype = out.data_ptr(), out.stride(0), _DT[out.dtype]
+    d.tune_tile_n, d.tune_no_pair = TUNE_TILE_N, TUNE_NO_PAIR
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")
+        assert out2.dtype == out.dtype, "out2 shares out's 16-bit format"
         d.out2, d.ldo2 = out2.data_ptr(), out2.stride(0)
     if scale is not None:
         _req(scale, torch.float32, "scale")
@@ -195,8 +225,9 @@ def attention(qkv, mask, ctx, B, L, heads, drop=None, lse=None):
     _req(mask, torch.int64, "mask")
     assert qkv.is_contiguous() and ctx.is_contiguous() and mask.is_contiguous()
     with _Timed("attention", 4.0 * B * heads * L * L * 64):
-        check(lib().rl_attention_fwd_lse(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), _c(B), _c(L), _c(heads), _c(64),
-                                         *_drop(drop), _stream()), "rl_attention_fwd")
+        assert ctx.dtype == qkv.dtype
+        check(lib().rl_attention_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), _c(B), _c(L), _c(heads), _c(64), _dt(qkv),
+                                     *_drop(drop), _ctr(), _stream()), "rl_attention_fwd")
     _count()
     return ctx
 
@@ -207,7 +238,8 @@ def layernorm(x, gamma, beta, out_f32, out_bf16, eps, drop=None, drop_f32=False)
     nbytes = rows * H * (4 + (4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))
     with _Timed("layernorm", nbytes):
         check(lib().rl_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _c(rows), _c(H),
-                                     ctypes.c_float(eps), *_drop(drop), ctypes.c_int32(int(drop_f32)), _stream()),
+                                     ctypes.c_float(eps), *_drop(drop), _ctr(), ctypes.c_int32(int(drop_f32)),
+                                     _dt(out_bf16) if out_bf16 is not None else ctypes.c_int32(0), _stream()),
               "rl_layernorm_fwd")
     _count()
 
@@ -219,7 +251,8 @@ def embed_ln(ids, word, inputs_embeds, pos, type0, gamma, beta, out_f32, out_bf1
     with _Timed("embed_ln", rows * H * 10):
         check(lib().rl_embed_ln_fwd(_ptr(ids), _ptr(word), _ptr(inputs_embeds), _ptr(pos), _ptr(type0), _ptr(gamma),
                                     _ptr(beta), _ptr(out_f32), _ptr(out_bf16), _ptr(pre_out), _c(rows), _c(L), _c(H),
-                                    ctypes.c_int32(pos_mode), ctypes.c_float(eps), *_drop(drop), _stream()),
+                                    ctypes.c_int32(pos_mode), ctypes.c_float(eps), *_drop(drop), _ctr(),
+                                    _dt(out_bf16) if out_bf16 is not None else ctypes.c_int32(0), _stream()),
               "rl_embed_ln_fwd")
     _count()
 
@@ -261,7 +294,7 @@ def gru_step(gh, b_hh, table, pho_idx, lens, h_prev, h_out, h_out_bf16, t):
     H = h_out.shape[1]
     with _Timed("gru_step", rows * H * (12 + 6 + 4 + 6)):
         check(lib().rl_gru_step_fwd(_ptr(gh), _ptr(b_hh), _ptr(table), _ptr(pho_idx), _ptr(lens), _ptr(h_prev),
-                                    _ptr(h_out), _ptr(h_out_bf16), _c(rows), _c(H), _c(T), _c(t), _stream()),
+                                    _ptr(h_out), _ptr(h_out_bf16), _c(rows), _c(H), _c(T), _c(t), _dt(h_out_bf16), _stream()),
               "rl_gru_step_fwd")
     _count()
 
@@ -308,9 +341,10 @@ def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
 def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None, lse=None):
     for t, n in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, n)
+    assert ctx.dtype == qkv.dtype and dctx.dtype is torch.bfloat16 and dqkv.dtype is torch.bfloat16   # gradients stay bf16
     with _Timed("attention_bwd", 14.0 * B * heads * L * L * 64):
-        check(lib().rl_attention_bwd_lse(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _ptr(lse), _c(B), _c(L),
-                                         _c(heads), _c(64), *_drop(drop), _stream()), "rl_attention_bwd")
+        check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _ptr(lse), _c(B), _c(L),
+                                     _c(heads), _c(64), _dt(qkv), *_drop(drop), _ctr(), _stream()), "rl_attention_bwd")
     _count()
 
 
@@ -325,7 +359,7 @@ def layernorm_bwd(dy, x, gamma, add_in, dx, dx_bf16, dgamma, dbeta, dxsum, eps, 
         check(lib().rl_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(add_in), _ptr(dx), _ptr(dx_bf16), _ptr(dgamma),
                                      _ptr(dbeta), _ptr(dxsum), _c(rows), _c(H), ctypes.c_float(eps), ctypes.c_float(drop_p),
                                      ctypes.c_uint64(drop_seed), ctypes.c_uint32(site_in), ctypes.c_uint32(site_out),
-                                     _stream()), "rl_layernorm_bwd")
+                                     _ctr(), _stream()), "rl_layernorm_bwd")
     _count()
 
 
@@ -354,7 +388,7 @@ def split3_bf16(x, out):
     _req(out, torch.bfloat16, "out")
     rows, cols = x.shape
     assert x.is_contiguous() and out.is_contiguous() and tuple(out.shape) == (rows, 3 * cols)
-    check(lib().rl_split3_bf16(_ptr(x), _ptr(out), _c(rows), _c(cols), _stream()), "rl_split3_bf16")
+    check(lib().rl_split3_bf16(_ptr(x), _ptr(out), _c(rows), _c(cols), _dt(out), _stream()), "rl_split3_bf16")
     _count()
 
 
@@ -362,9 +396,9 @@ def gelu(u, h):
     """h = gelu_erf(u), bf16 -> bf16 (may be in place)."""
     _req(u, torch.bfloat16, "u")
     _req(h, torch.bfloat16, "h")
-    assert u.is_contiguous() and h.is_contiguous() and u.numel() == h.numel()
+    assert u.is_contiguous() and h.is_contiguous() and u.numel() == h.numel() and u.dtype == h.dtype
     with _Timed("gelu", u.numel() * 4):
-        check(lib().rl_gelu_fwd(_ptr(u), _ptr(h), _c(u.numel()), _stream()), "rl_gelu_fwd")
+        check(lib().rl_gelu_fwd(_ptr(u), _ptr(h), _c(u.numel()), _dt(u), _stream()), "rl_gelu_fwd")
     _count()
 
 
@@ -373,9 +407,9 @@ def gelu_bwd_colsum(t, u, dbias):
     _req(t, torch.bfloat16, "t")
     _req(u, torch.bfloat16, "u")
     rows, cols = t.shape
-    assert t.stride(1) == 1 and u.stride() == t.stride()
+    assert t.stride(1) == 1 and u.stride() == t.stride() and t.dtype is torch.bfloat16
     with _Timed("gelu_bwd_colsum", t.numel() * 6):
-        check(lib().rl_gelu_bwd_colsum(_ptr(t), _ptr(u), _ptr(dbias), _c(rows), _c(cols), _c(t.stride(0)), _stream()),
+        check(lib().rl_gelu_bwd_colsum(_ptr(t), _ptr(u), _ptr(dbias), _c(rows), _c(cols), _c(t.stride(0)), _dt(u), _stream()),
               "rl_gelu_bwd_colsum")
     _count()
 
@@ -407,7 +441,7 @@ def gate_fuse_bwd(dhid, mods, mask, gates, gate_w, dmods, dgate_w, dgate_b, ws, 
 def dropout_mask(n, p, seed, site, device="cuda"):
     """uint8 keep mask of a dropout site (what the kernels compute on the fly) — for tests."""
     out = torch.empty(n, dtype=torch.uint8, device=device)
-    check(lib().rl_dropout_mask(_ptr(out), _c(n), ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_uint32(site),
+    check(lib().rl_dropout_mask(_ptr(out), _c(n), ctypes.c_float(p), ctypes.c_uint64(seed), ctypes.c_uint32(site), _ctr(),
                                 _stream()), "rl_dropout_mask")
     return out
 

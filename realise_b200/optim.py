@@ -15,7 +15,7 @@ from ._lib import check, lib
 class _Entry(ctypes.Structure):
     _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("shadow", ctypes.c_void_p), ("shadow32", ctypes.c_void_p), ("n", ctypes.c_int64), ("wd", ctypes.c_float),
-                ("pad", ctypes.c_int32)]
+                ("shadow_f16", ctypes.c_int32)]
 
 
 CHUNK = 4096
@@ -54,7 +54,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 sh, s32 = sh16.get(id(p)), sh32.get(id(p))
                 entries.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                 sh.data_ptr() if sh is not None else 0, s32.data_ptr() if s32 is not None else 0,
-                                p.numel(), float(group["weight_decay"]), gi))
+                                p.numel(), float(group["weight_decay"]), int(sh is not None and sh.dtype is torch.float16)))
                 sig.append((p.data_ptr(), p.grad.data_ptr(), entries[-1][4], entries[-1][5]))
         if sig == self._sig:
             return
@@ -62,8 +62,8 @@ class FusedAdamW(torch.optim.Optimizer):
         dev = self.param_groups[0]["params"][0].device
         arr = (_Entry * len(entries))()
         chunks = []
-        for i, (pp, g, m, v, sh, s32, n, wd, gi) in enumerate(entries):
-            arr[i] = _Entry(pp, g, m, v, sh or None, s32 or None, n, wd, 0)
+        for i, (pp, g, m, v, sh, s32, n, wd, f16) in enumerate(entries):
+            arr[i] = _Entry(pp, g, m, v, sh or None, s32 or None, n, wd, f16)
             chunks += [(i, c) for c in range((n + CHUNK - 1) // CHUNK)]
         self._table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self._chunks = torch.tensor(chunks, dtype=torch.int32).to(dev).contiguous()

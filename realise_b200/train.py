@@ -159,29 +159,30 @@ class TrainEngine:
         N, H, I = B * L, c.hidden_size, c.intermediate_size
         sv = {"layers": [], "ids": ids, "pos_mode": pos_mode, "mod": mod, "P": P, "from_embeds": inputs_embeds is not None,
               "name": name, "last_drop": last_drop}
-        x, xb = self._new((N, H), F32), self._new((N, H), BF16)
+        A16 = self.act16
+        x, xb = self._new((N, H), F32), self._new((N, H), A16)
         sv["e_pre"] = self._new((N, H), F32)
         ops.embed_ln(ids, P["word"], inputs_embeds, P["pos"], P["type0"], P["ln_w"], P["ln_b"], x, xb, N, L, H, pos_mode,
                      c.layer_norm_eps, pre_out=sv["e_pre"], drop=self.hdrop(self.site(name, 0, 9)))
         nl = len(P["layers"])
         for li, lw in enumerate(P["layers"]):
             s = {"xb": xb}
-            s["qkv"] = self._new((N, 3 * H), BF16)
+            s["qkv"] = self._new((N, 3 * H), A16)
             ops.gemm(xb, lw["w_qkv"], s["qkv"], bias=lw["b_qkv"])
-            s["ctx"] = self._new((N, H), BF16)
+            s["ctx"] = self._new((N, H), A16)
             s["lse"] = self._new((B * c.num_attention_heads * L,), F32)
             ops.attention(s["qkv"], mask, s["ctx"], B, L, c.num_attention_heads, drop=self.adrop(self.site(name, li, 1)),
                           lse=s["lse"])
             s["y1"] = self._new((N, H), F32)
             ops.gemm(s["ctx"], lw["w_o"], s["y1"], bias=lw["b_o"], res=x, drop=self.hdrop(self.site(name, li, 2)))
-            x1, s["x1b"] = self._new((N, H), F32), self._new((N, H), BF16)
+            x1, s["x1b"] = self._new((N, H), F32), self._new((N, H), A16)
             ops.layernorm(s["y1"], lw["ln1_w"], lw["ln1_b"], x1, s["x1b"], c.layer_norm_eps)
-            s["u"], s["h"] = self._new((N, I), BF16), self._new((N, I), BF16)
+            s["u"], s["h"] = self._new((N, I), A16), self._new((N, I), A16)
             ops.gemm(s["x1b"], lw["w_1"], s["u"], bias=lw["b_1"])
             ops.gelu(s["u"], s["h"])       # stand-alone pass: cheaper than erf in the epilogue of a K = 768 GEMM
             s["y2"] = self._new((N, H), F32)
             ops.gemm(s["h"], lw["w_2"], s["y2"], bias=lw["b_2"], res=x1, drop=self.hdrop(self.site(name, li, 3)))
-            x, xb = self._new((N, H), F32), self._new((N, H), BF16)
+            x, xb = self._new((N, H), F32), self._new((N, H), A16)
             # the classifier consumes dropout(sequence_output) (src/models.py:858): only the bf16 operand copy of
             # the last LayerNorm of output_block is masked
             fin = self.hdrop(self.SITE_FINAL) if (last_drop and li == nl - 1) else None
@@ -421,14 +422,14 @@ class TrainEngine:
         ops.gru_input_table(m.pho_embeddings.weight.detach(), m.pho_gru.weight_ih_l0.detach(), m.pho_gru.bias_ih_l0.detach(),
                             G["table"])
         hs, hbs, ghs = [], [], [None]
-        h, hb = self._new((N, H), F32), self._new((N, H), BF16)
+        h, hb = self._new((N, H), F32), self._new((N, H), self.act16)
         ops.gru_step(None, G["b_hh"], G["table"], pho_idx, lens_dev, None, h, hb, 0)
         hs.append(h)
         hbs.append(hb)
         for t in range(1, T):
             gh = self._new((N, 3 * H), F32)
             ops.gemm(hbs[-1], G["w_hh"], gh, bias=G["b_hh"])
-            h, hb = self._new((N, H), F32), self._new((N, H), BF16)
+            h, hb = self._new((N, H), F32), self._new((N, H), self.act16)
             ops.gru_step(gh, G["b_hh"], G["table"], pho_idx, lens_dev, hs[-1], h, hb, t)
             hs.append(h)
             hbs.append(hb)
@@ -469,7 +470,7 @@ class TrainEngine:
         N, H, V = B * L, c.hidden_size, c.vocab_size
         if L > 128:
             raise NotImplementedError("attention backward kernel supports seq_len <= 128")
-        ops.set_half_format(False)   # training computes with bf16 operands
+        self.act16 = P["half"]       # forward tensors: fp16 (default) or bf16; gradients are always bf16
         self.step_seed = self.seed
         self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         sv = {"B": B, "L": L, "mask": mask, "inp": inp, "seed": self.step_seed}

@@ -1,0 +1,157 @@
+"""Worker of tests/test_ddp_gpu.py — one process per rank (torchrun).  Checks the data-parallel training path on
+hardware against the reference's DDP semantics (src/run.py:165-167, :200):
+
+  1. the buffer every rank holds after the exchange is exactly the SUM of the per-rank gradient buffers (the optimizer
+     divides by W: mean of per-rank gradients, as DistributedDataParallel does);
+  2. parameters are bit-identical across ranks after 3 eager steps and after 4 more CUDA-graph steps (the all-reduce
+     captured inside the graph);
+  3. W ranks x (global batch / W) gives the W=1 gradient of the global batch (model without BatchNorm: statistics are
+     per-rank in the reference, so the glyph branch legitimately differs).
+
+Backend: nccl when every rank has its own GPU, else gloo over ONE shared GPU (the driver's single-GPU test box) — the
+code under test (realise_b200.ddp + the in-graph all-reduce) is the same.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from realise_b200.ddp import DataParallel, shard_examples  # noqa: E402
+from realise_b200.graphed import GraphedTrainStep  # noqa: E402
+from realise_b200.model import SpellBertPho2ResArch3Abla  # noqa: E402
+from realise_b200.optim import FusedAdamW  # noqa: E402
+from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict  # noqa: E402
+
+
+def rows(batch, idx, L):
+    """Sentences `idx` of a synthetic batch (pho_idx / pho_lens are per token)."""
+    B = batch["src_idx"].shape[0]
+    out = {k: batch[k][idx] for k in ("src_idx", "masks", "loss_masks", "tgt_idx")}
+    T = batch["pho_idx"].shape[1]
+    out["pho_idx"] = batch["pho_idx"].view(B, L, T)[idx].reshape(-1, T)
+    out["pho_lens"] = torch.tensor(batch["pho_lens"]).view(B, L)[idx].reshape(-1).tolist()
+    return out
+
+
+def to_dev(b, dev):
+    return {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+
+def make(cfg, sd, dev):
+    m = SpellBertPho2ResArch3Abla(cfg)
+    m.tie_cls_weight()
+    m.load_state_dict(sd, strict=True)
+    return m.train().to(dev)
+
+
+def gather(vec, world):
+    """all_gather of a device vector (through host memory under gloo, which only moves CUDA tensors for
+    broadcast / all_reduce)."""
+    src = vec if dist.get_backend() == "nccl" else vec.cpu()
+    got = [torch.empty_like(src) for _ in range(world)]
+    dist.all_gather(got, src)
+    return [g.to(vec.device) for g in got]
+
+
+def all_equal_across_ranks(vec, world):
+    got = gather(vec, world)
+    return all(torch.equal(got[0], g) for g in got[1:])
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    own_gpu = torch.cuda.device_count() >= world
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) if own_gpu else 0)
+    torch.cuda.set_device(dev)
+    if own_gpu:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
+    res = {"backend": dist.get_backend(), "world": world}
+    L, per = 32, 2
+    # ---- (1) + (2): the full model (dropout 0.1, batch-stat BN) ------------------------------------------------
+    cfg = ArchConfig(num_hidden_layers=1)
+    sd = synth_state_dict(cfg, seed=rank)                    # ranks start from DIFFERENT weights: the broadcast must fix it
+    model = make(cfg, sd, dev)
+    dp = DataParallel(model)
+    dp.broadcast_parameters()
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, max_grad_norm=1.0, model=model)
+    seen = {}
+    inner = model._post_backward
+
+    def spy(engine):
+        seen["pre"] = engine.flat.clone()
+        inner(engine)
+        seen["post"] = engine.flat.clone()
+
+    model._post_backward = spy
+    for step in range(3):
+        g = synth_batch(per * world, L, seed=100 + step, ragged=False)
+        local = rows(g, torch.tensor(shard_examples(list(range(per * world)), rank, world)), L)
+        loss = model(to_dev(local, dev))[0]
+        loss.backward()
+        if step == 0:
+            pres = gather(seen["pre"], world)
+            total = pres[0].clone()
+            for p in pres[1:]:
+                total += p
+            diff = float((seen["post"] - total).abs().max())
+            scale = float(total.abs().max())
+            res["sum_exact"] = bool(torch.equal(seen["post"], total))
+            res["sum_max_diff_rel"] = diff / max(scale, 1e-30)
+            res["ranks_differ_before_sync"] = not torch.equal(pres[0], pres[-1])
+        opt.step()
+    model._post_backward = inner
+    flat_params = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
+    res["params_identical_after_3_eager_steps"] = all_equal_across_ranks(flat_params, world)
+    if own_gpu:       # the all-reduce inside a captured graph needs NCCL (gloo synchronises with the host)
+        gstep = GraphedTrainStep(model, opt)
+        for step in range(5):                                     # first call eager, second captures, then replays
+            g = synth_batch(per * world, L, seed=200 + step, ragged=False)
+            gstep(rows(g, torch.tensor(shard_examples(list(range(per * world)), rank, world)), L))
+        torch.cuda.synchronize()
+        res["graph_replays"] = gstep.replays
+        flat_params = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
+        res["params_identical_after_graph_steps"] = all_equal_across_ranks(flat_params, world)
+        del gstep
+    else:
+        res["graph_replays"], res["params_identical_after_graph_steps"] = None, None
+    del model, opt, dp
+    # ---- (3): W ranks x B/W  ==  1 rank x B  (no BatchNorm in the model, dropout off) ---------------------------
+    cfg2 = ArchConfig(num_hidden_layers=1, with_res="no", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd2 = synth_state_dict(cfg2, seed=7)
+    g = synth_batch(per * world, L, seed=300, ragged=False)
+    m_dp = make(cfg2, sd2, dev)
+    DataParallel(m_dp)
+    local = rows(g, torch.tensor(shard_examples(list(range(per * world)), rank, world)), L)
+    m_dp(to_dev(local, dev))[0].backward()
+    m_one = make(cfg2, sd2, dev)
+    m_one(to_dev(g, dev))[0].backward()
+    worst = 0.0
+    gmax = max(float(p.grad.abs().max()) for p in m_one.parameters() if p.grad is not None)
+    for (n, a), (_, b) in zip(m_dp.named_parameters(), m_one.named_parameters()):
+        if a.grad is None or float(b.grad.norm()) < 1e-6 * gmax:
+            continue
+        worst = max(worst, float((a.grad / world - b.grad).norm() / b.grad.norm()))
+    res["w_ranks_vs_one_rank_worst_rel_l2"] = worst
+    ok = (res["sum_max_diff_rel"] <= (0.0 if world == 2 else 1e-6) and res["ranks_differ_before_sync"]
+          and res["params_identical_after_3_eager_steps"] and worst <= 2e-2
+          and (not own_gpu or (res["params_identical_after_graph_steps"] and res["graph_replays"] >= 3)))
+    res["ok"] = bool(ok)
+    oks = [None] * world
+    dist.all_gather_object(oks, res["ok"])
+    if rank == 0:
+        res["ok"] = all(oks)
+        print("DP_RESULT " + json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if all(oks) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,8 +33,22 @@ def test_argument_errors_are_reported_without_a_gpu():
     rc = lib.rl_gemm_bf16(ctypes.byref(d), None)
     assert rc < 0
     assert b"rl_gemm_bf16" in lib.rl_last_error()
-    assert lib.rl_attention_fwd(None, None, None, 1, 1, 1, 64, None) < 0
-    assert lib.rl_layernorm_fwd(None, None, None, None, None, 1, 768, ctypes.c_float(1e-12), None) < 0
+    i64, i32, f32, u64, u32 = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32
+    assert lib.rl_attention_fwd(None, None, None, None, i64(1), i64(1), i64(1), i64(64), i32(0), f32(0), u64(0), u32(0), None,
+                                None) < 0
+    assert lib.rl_attention_bwd(None, None, None, None, None, None, i64(1), i64(1), i64(1), i64(64), i32(2), f32(0), u64(0),
+                                u32(0), None, None) < 0
+    assert lib.rl_layernorm_fwd(None, None, None, None, None, i64(1), i64(768), f32(1e-12), f32(0), u64(0), u32(0), None, i32(0),
+                                i32(0), None) < 0
+
+
+def test_no_process_wide_switches_in_the_abi():
+    """re-entrant, no mutable global state — formats, the dropout counter and tuning knobs are per call."""
+    syms = declared_symbols()
+    assert not [s for s in syms if s.startswith("rl_set_") or "_set_" in s], syms
+    src = "".join(open(os.path.join(ROOT, "realise_b200", "csrc", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "realise_b200", "csrc")))
+    assert "rl_set_half_format" not in src and "rl_set_dropout_seed_ptr" not in src and "set_debug_mode" not in src
 
 
 def test_gemm_desc_layout_matches_header():
@@ -65,11 +79,15 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     d.b_mode, d.b_major, d.a_major = 1, 0, 1
     assert lib.rl_gemm_bf16(ctypes.byref(d), None) < 0
     assert b"b_mode" in lib.rl_last_error()
-    assert lib.rl_set_half_format(1) == 0 and lib.rl_set_half_format(0) == 0
-    assert lib.rl_set_dropout_seed_ptr(None) == 0
-    assert lib.rl_gelu_fwd(None, None, ctypes.c_int64(8), None) < 0
-    assert lib.rl_gelu_bwd_colsum(None, None, None, ctypes.c_int64(8), ctypes.c_int64(8), ctypes.c_int64(8), None) < 0
-    assert lib.rl_split3_bf16(None, None, ctypes.c_int64(1), ctypes.c_int64(8), None) < 0
+    d.b_mode, d.b_major, d.a_major, d.a_dtype = 0, 0, 0, 1        # f32 is not an MMA operand format
+    assert lib.rl_gemm_bf16(ctypes.byref(d), None) < 0
+    assert b"a_dtype" in lib.rl_last_error()
+    assert lib.rl_gelu_fwd(None, None, ctypes.c_int64(8), ctypes.c_int32(0), None) < 0
+    assert lib.rl_gelu_bwd_colsum(None, None, None, ctypes.c_int64(8), ctypes.c_int64(8), ctypes.c_int64(8), ctypes.c_int32(0),
+                                  None) < 0
+    assert lib.rl_split3_bf16(None, None, ctypes.c_int64(1), ctypes.c_int64(8), ctypes.c_int32(0), None) < 0
+    assert lib.rl_workspace_bytes(b"gate_fuse_bwd", ctypes.c_int64(2), ctypes.c_int64(16), ctypes.c_int64(768)) == (2 * 16 * 3 + 2 * 2 * 768) * 4
+    assert lib.rl_workspace_bytes(b"nope", ctypes.c_int64(1), ctypes.c_int64(1), ctypes.c_int64(1)) == -1
     assert lib.rl_mt_adamw_dev(None, None, ctypes.c_int64(1), None, ctypes.c_float(1.0), None, ctypes.c_float(0.9),
                                ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_float(1.0), None) < 0
 

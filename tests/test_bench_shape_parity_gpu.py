@@ -1,0 +1,296 @@
+"""GPU parity AT THE SHAPES bench.py MEASURES (BASELINE.json configs[1] and configs[2]) — full 12+4+3-layer model.
+
+  (a) eval  B=64  x L=128, ragged lengths           vs the CPU oracle            (configs[1]: "logits vs reference within tol")
+  (b) train B=16  x L=128, dropout 0.1 (exported masks), UNSHARED ReLU gates     vs the CPU oracle's autograd
+  (c) train B=128 x L=128, same protocol             vs the oracle run in fp32 on the GPU (torch eager, TF32 off),
+      which is pinned to the CPU oracle at a small shape inside the same test (SURVEY.md §8c sanctions the cross-check)
+  (d) the CUDA train path vs the reference's own train-mode golden (tests/golden/arch3_train_B2_L16.npz)
+  (e) fusion='sum' training (src/models_abla.py:279)
+
+These are the code paths the benchmark runs and the toy-shape tests never reach: multi-wave persistent GEMM
+scheduling, wave-aware split-K with TMA reduce-add, 256-wide pair tiles, implicit-im2col weight gradients over 4.2 M
+pixels, one-wave slab grids.  Tolerances: north_star's 1e-2 on logits; relative L2 <= 2e-2 per gradient tensor outside
+the glyph CNN.  Inside the CNN a 16-bit forward flips the ReLU gate of pre-activations that sit within its rounding
+error of zero, and every flipped gate moves a whole gradient element: the UNSHARED error is therefore reported next to
+the same error of an independent 16-bit implementation (the oracle under torch.autocast) and bounded by it.
+
+Every measured number is also written to gpurun_out/parity_report.json (copied to profiles/ by the builder).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, cached_state_dict, load_golden
+from realise_b200.synth import ArchConfig, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1.0e-2
+GRAD_TOL = 2.0e-2          # relative L2 per tensor, everything outside the glyph CNN
+CNN_GRAD_TOL = 5.0e-2      # glyph CNN tensors at the benchmark's BatchNorm batch (16 384 images), unshared gates
+
+
+def report(section, payload):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, "parity_report.json")
+    try:
+        with open(p) as f:
+            rep = json.load(f)
+    except (OSError, ValueError):
+        rep = {}
+    rep[section] = payload
+    with open(p, "w") as f:
+        json.dump(rep, f, indent=1, sort_keys=True)
+
+
+def to_dev(batch):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def build_model(cfg, seed, train):
+    from realise_b200.model import SpellBertPho2ResArch3Abla
+    m = SpellBertPho2ResArch3Abla(cfg)
+    m.tie_cls_weight()
+    m.load_state_dict(cached_state_dict(cfg, seed), strict=True)
+    return (m.train() if train else m.eval()).cuda()
+
+
+def oracle_leaves(sd, device="cpu"):
+    rsd = {k: v.clone().to(device) for k, v in sd.items()}
+    rsd["classifier.weight"] = rsd["bert.embeddings.word_embeddings.weight"]
+    leaves = {}
+    for k, v in rsd.items():
+        if v.dtype.is_floating_point and "running" not in k and not k.startswith("char_images") and k != "classifier.weight":
+            v.requires_grad_(True)
+            leaves[k] = v
+    return rsd, leaves
+
+
+def argmax_stats(logits, rlogits, tol):
+    n = rlogits.shape[0] * rlogits.shape[1]
+    a, r = logits.reshape(n, -1), rlogits.reshape(n, -1)
+    top2 = r.topk(2, -1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * tol
+    agree = a.argmax(-1) == r.argmax(-1)
+    return float(agree.float().mean()), bool(agree[safe].all()), float(safe.float().mean())
+
+
+def grad_errors(model, leaves):
+    """name -> relative L2 error of the CUDA path's gradient against the oracle's (analytically-zero ones skipped)."""
+    gmax = max(float(v.grad.abs().max()) for v in leaves.values() if v.grad is not None)
+    out = {}
+    for name, p in model.named_parameters():
+        if name == "classifier.weight" or name.startswith("char_images"):
+            continue
+        rg = leaves[name].grad
+        if p.grad is None:
+            assert rg is None or float(rg.abs().max()) == 0.0, name
+            continue
+        rg = rg.to(p.grad.device)
+        if float(rg.norm()) < 1e-6 * gmax:
+            assert float(p.grad.abs().max()) <= 1e-4 * gmax, name
+            continue
+        out[name] = float((p.grad.float() - rg).norm() / rg.norm())
+    return out
+
+
+def summarize(errs):
+    cnn = {k: v for k, v in errs.items() if k.startswith("resnet.")}
+    rest = {k: v for k, v in errs.items() if not k.startswith("resnet.")}
+    s = {"n_tensors": len(errs), "rest_max": max(rest.values()), "rest_median": float(np.median(list(rest.values()))),
+         "rest_worst": max(rest, key=rest.get)}
+    if cnn:
+        s.update({"cnn_max": max(cnn.values()), "cnn_median": float(np.median(list(cnn.values()))),
+                  "cnn_worst": max(cnn, key=cnn.get),
+                  "cnn_conv_max": max(v for k, v in cnn.items() if k.endswith(("0.weight", "3.weight")) and "shortcut.1" not in k)})
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_eval_B64_L128_full_model_matches_cpu_oracle():
+    """BASELINE configs[1]: batch 64 x seq_len 128, all three encoders + fusion, logits vs the reference within tol."""
+    from oracle import realise_oracle as O
+    cfg = ArchConfig()
+    sd = cached_state_dict(cfg, 0)
+    model = build_model(cfg, 0, train=False)
+    batch = synth_batch(64, 128, seed=2024, ragged=True)
+    O.FAST = True
+    try:
+        with torch.no_grad():
+            rloss, rlogits = O.forward(sd, batch, cfg)
+    finally:
+        O.FAST = False
+    with torch.no_grad():
+        loss, logits = model(to_dev(batch))
+    logits = logits.float().cpu()
+    err = float((logits - rlogits).abs().max())
+    rms = float((logits - rlogits).pow(2).mean().sqrt())
+    raw, safe_ok, safe_frac = argmax_stats(logits, rlogits, LOGIT_TOL)
+    report("eval_B64_L128", {"max_abs_logit_err": err, "rms_logit_err": rms, "loss": loss.item(), "ref_loss": rloss.item(),
+                             "argmax_agreement_raw": raw, "argmax_exact_where_margin_gt_2tol": safe_ok,
+                             "rows_with_margin_gt_2tol": safe_frac, "ref_logit_absmax": float(rlogits.abs().max())})
+    assert err <= LOGIT_TOL, err
+    assert safe_ok and raw >= 0.99, (raw, safe_ok)
+    assert abs(loss.item() - rloss.item()) <= 5e-3
+
+
+def _train_case(B, L, device, seed=4242, bseed=99, autocast_compare=False):
+    """One train-mode forward/backward of the full model on the CUDA path and on the oracle (same dropout masks, the
+    oracle's OWN ReLU gates).  Returns (stats dict, model, leaves)."""
+    from oracle import realise_oracle as O
+    from realise_b200 import ops
+    from realise_b200.train import TrainEngine
+    cfg = ArchConfig()
+    assert cfg.hidden_dropout_prob == 0.1 and cfg.attention_probs_dropout_prob == 0.1
+    sd = cached_state_dict(cfg, 0)
+    model = build_model(cfg, 0, train=True)
+    model._engine = TrainEngine(model)
+    model._engine.set_seed(seed)
+    batch = synth_batch(B, L, seed=bseed, ragged=True)
+    loss, logits = model(to_dev(batch))
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def mask_fn(site, shape):
+        n = int(np.prod(shape))
+        return ops.dropout_mask(n, 0.1, seed, site).to(device).reshape(shape).float()
+
+    obatch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    rsd, leaves = oracle_leaves(sd, device)
+    stats = {}
+    O.MASK_FN, O.FAST = mask_fn, True
+    try:
+        rloss, rlogits = O.forward(rsd, obatch, cfg, train=True, bn_stats=stats)
+        rloss.backward()
+        ac = None
+        if autocast_compare:
+            # an independent 16-bit implementation of the same step: how far does IT land from fp32?
+            rsd2, leaves2 = oracle_leaves(sd, device)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                l2, _ = O.forward(rsd2, obatch, cfg, train=True)
+            l2.backward()
+            ac = {}
+            for k, v in leaves.items():
+                if v.grad is not None and leaves2[k].grad is not None and float(v.grad.norm()) > 0:
+                    ac[k] = float((leaves2[k].grad.float() - v.grad).norm() / v.grad.norm())
+            del rsd2, leaves2, l2
+    finally:
+        O.MASK_FN, O.FAST = None, False
+    errs = grad_errors(model, leaves)
+    lg, rl = logits.float().to(device), rlogits.detach()
+    out = {"B": B, "L": L, "loss": loss.item(), "ref_loss": rloss.item(), "max_abs_logit_err": float((lg - rl).abs().max()),
+           "rms_logit_err": float((lg - rl).pow(2).mean().sqrt()), "grads": summarize(errs)}
+    raw, safe_ok, safe_frac = argmax_stats(lg, rl, LOGIT_TOL)
+    out.update({"argmax_agreement_raw": raw, "argmax_exact_where_margin_gt_2tol": safe_ok})
+    bn_err = 0.0
+    for b in range(1, 6):
+        for idx, mod in ((1, "residual_function"), (4, "residual_function"), (1, "shortcut")):
+            bn = getattr(getattr(model.resnet, f"res_block{b}"), mod)[idx]
+            key = f"resnet.res_block{b}.{mod}.{idx}"
+            bn_err = max(bn_err, float((bn.running_mean - stats[key + ".running_mean"].cuda()).abs().max()),
+                         float((bn.running_var - stats[key + ".running_var"].cuda()).abs().max()))
+            assert bn.num_batches_tracked.item() == 1
+    out["bn_running_stat_max_err"] = bn_err
+    if ac is not None:
+        cnn = [v for k, v in ac.items() if k.startswith("resnet.")]
+        rest = [v for k, v in ac.items() if not k.startswith("resnet.")]
+        out["autocast_bf16_oracle_vs_fp32"] = {"cnn_max": max(cnn), "cnn_median": float(np.median(cnn)), "rest_max": max(rest),
+                                               "rest_median": float(np.median(rest))}
+    return out, errs
+
+
+def test_train_step_B16_L128_full_model_matches_cpu_oracle():
+    out, errs = _train_case(16, 128, "cpu")
+    report("train_B16_L128_vs_cpu_oracle", out)
+    assert abs(out["loss"] - out["ref_loss"]) <= 1e-2
+    assert out["max_abs_logit_err"] <= LOGIT_TOL, out
+    assert out["grads"]["rest_max"] <= GRAD_TOL, out["grads"]
+    assert out["bn_running_stat_max_err"] <= 2e-3
+    assert out["grads"]["n_tensors"] >= 360
+
+
+def test_train_step_B128_L128_full_model_matches_gpu_fp32_oracle():
+    """BASELINE configs[2] — the shape of the headline number."""
+    from oracle import realise_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    # pin the GPU run of the oracle to its CPU run (which tests/test_oracle.py pins to the reference's goldens)
+    cfg1 = ArchConfig(num_hidden_layers=1, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd1 = cached_state_dict(cfg1, 3)
+    small = synth_batch(2, 16, seed=5)
+    pins = []
+    for dev in ("cpu", "cuda"):
+        rsd, leaves = oracle_leaves(sd1, dev)
+        l, lg = O.forward(rsd, {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in small.items()}, cfg1, train=True)
+        l.backward()
+        pins.append((l.item(), lg.detach().cpu(), {k: v.grad.cpu() for k, v in leaves.items() if v.grad is not None}))
+    assert abs(pins[0][0] - pins[1][0]) <= 1e-5 and float((pins[0][1] - pins[1][1]).abs().max()) <= 1e-4
+    for k, g in pins[0][2].items():
+        assert float((g - pins[1][2][k]).norm()) <= 1e-3 * float(g.norm()) + 1e-9, k
+    del pins
+    out, errs = _train_case(128, 128, "cuda", autocast_compare=True)
+    out["worst10"] = sorted(errs.items(), key=lambda kv: -kv[1])[:10]
+    report("train_B128_L128_vs_gpu_fp32_oracle", out)
+    assert abs(out["loss"] - out["ref_loss"]) <= 1e-2
+    assert out["max_abs_logit_err"] <= LOGIT_TOL, out
+    assert out["grads"]["rest_max"] <= GRAD_TOL, out["grads"]
+    ac = out["autocast_bf16_oracle_vs_fp32"]
+    # unshared ReLU gates: within the stated bound, or no worse than an independent 16-bit implementation of the step
+    assert out["grads"]["cnn_max"] <= max(CNN_GRAD_TOL, 1.25 * ac["cnn_max"]), (out["grads"], ac)
+    assert out["bn_running_stat_max_err"] <= 2e-3
+
+
+def test_cuda_train_path_matches_reference_train_golden():
+    """The reference's own train-mode run (dropout modules zeroed, batch-stat BN, B2 x L16, 12 layers): loss, per-tensor
+    gradient norms and BatchNorm running statistics.  32 glyph images per BN batch make this the noisiest case for the
+    CNN (unshared gates): its gradient NORMS are held to 10 %, everything else to 2 %."""
+    g, meta = load_golden("arch3_train_B2_L16.npz")
+    cfg = ArchConfig(**meta["cfg"])
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = 0.0     # make_golden.py sets every nn.Dropout.p = 0
+    model = build_model(cfg, meta["wseed"], train=True)
+    loss, logits = model(to_dev(synth_batch(meta["B"], meta["L"], seed=meta["bseed"])))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 5e-3
+    flat = logits.reshape(meta["B"] * meta["L"], -1).float().cpu()
+    assert np.abs(flat[torch.from_numpy(g["logits_rows"])].numpy() - g["logits_kept"]).max() <= LOGIT_TOL
+    names = [str(n) for n in g["grad_names"]]
+    got = dict(model.named_parameters())
+    worst = {"cnn": 0.0, "rest": 0.0}
+    gmax = g["grad_stats"][:, 0].max()
+    for n, st in zip(names, g["grad_stats"]):
+        if n == "classifier.weight" or st[0] < 1e-6 * gmax:
+            continue
+        assert got[n].grad is not None, n
+        rel = abs(float(got[n].grad.float().norm()) - st[0]) / st[0]
+        kind = "cnn" if n.startswith("resnet.") else "rest"
+        worst[kind] = max(worst[kind], rel)
+    report("train_golden_B2_L16", worst)
+    assert worst["rest"] <= 2e-2 and worst["cnn"] <= 1e-1, worst
+    bn = {n: b for n, b in model.named_buffers() if "running" in n}
+    for n, s in zip([str(x) for x in g["bn_names"]], g["bn_sums"]):
+        assert abs(float(bn[n].double().sum()) - s) <= 2e-3 * max(1.0, abs(s)), n
+
+
+def test_sum_fusion_training_matches_oracle_autograd():
+    """fusion='sum' (src/models_abla.py:279): plain add of the three modalities, no gate_net."""
+    from oracle import realise_oracle as O
+    cfg = ArchConfig(num_hidden_layers=1, fusion="sum", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd = cached_state_dict(cfg, 17)
+    model = build_model(cfg, 17, train=True)
+    batch = synth_batch(4, 32, seed=41)
+    loss, _ = model(to_dev(batch))
+    loss.backward()
+    rsd, leaves = oracle_leaves(sd)
+    rloss, _ = O.forward(rsd, batch, cfg, train=True)
+    rloss.backward()
+    assert abs(loss.item() - rloss.item()) <= 1e-2
+    errs = grad_errors(model, leaves)
+    s = summarize(errs)
+    report("train_sum_fusion", s)
+    assert not any(k.startswith("gate_net") for k in errs)
+    assert s["rest_max"] <= 5e-2, s      # 128 glyphs per BN batch: the CNN's forward noise reaches every gradient (see
+                                         # test_train_gpu.py::test_glyph_branch_and_full_arch3_backward)
