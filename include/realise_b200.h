@@ -16,10 +16,9 @@
  *     the optional device-resident dropout step counter are per-call arguments (`*_dtype`, `drop_counter`); the only
  *     statics are one-time cudaFuncSetAttribute flags, cached occupancy queries and the thread-local error string.
  *
- * 16-bit formats: every "bf16" tensor below may instead be IEEE fp16 when the call says so (RL_DT_F16).  tcgen05
- * kind::f16 multiplies bf16 and fp16 operands at the same rate and takes the format PER OPERAND, so the training path
- * keeps forward tensors (weights, activations) in fp16 — three more mantissa bits: logits land within the reference's
- * 1e-2 tolerance — and gradients in bf16 (range), mixing both inside one MMA (dW = dY^T X, dX = dY W).
+ * 16-bit formats: every "bf16" tensor below may instead be IEEE fp16 when the call says so (RL_DT_F16): same
+ * tensor-core rate, three more mantissa bits.  The two operands of one MMA must share ONE format: a tcgen05.mma
+ * kind::f16 whose descriptor mixes bf16 and fp16 raises "illegal instruction" on B200 (probed: tools/probe_mixed_mma.py).
  *
  * Dropout: masks are pure functions of (seed, site, element).  With a non-NULL `drop_counter` (device pointer) the
  * kernel uses seed + *drop_counter, read at run time: a captured CUDA graph of the whole train step draws fresh masks
@@ -101,8 +100,8 @@ typedef struct rl_gemm_desc {
   uint64_t drop_seed;  /* by the backward kernels.  drop_p = 0 disables it. */
   int32_t b_major;   /* 0: B stored [N, K].  1: B stored [K, N] with row stride ldb, e.g. B = W^T for a data
                         gradient straight from W [out, in], or B = X^T for a weight gradient */
-  int32_t a_dtype, b_dtype; /* RL_DT_BF16 or RL_DT_F16, independently (out_dtype / res_dtype take RL_DT_F16 too; out2
-                               shares out's 16-bit format) */
+  int32_t a_dtype, b_dtype; /* RL_DT_BF16 or RL_DT_F16, both the same (out_dtype / res_dtype take RL_DT_F16 too,
+                               independently; out2 shares out's 16-bit format) */
   const uint64_t* drop_counter; /* optional device step counter added to drop_seed at run time (NULL = plain seed) */
   int32_t tune_tile_n;  /* 0: the cost model picks the N tile.  64 / 128 / 256: force it (tuning and tests; results do
                            not depend on it) */
@@ -207,9 +206,10 @@ RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const vo
 
 /* ======================= training path (src/run.py:191-212) =========================================== */
 
-/* ---- attention backward: dqkv = [dQ | dK | dV] (bf16) from dctx (bf16), recomputing the probabilities ----
+/* ---- attention backward: dqkv = [dQ | dK | dV] from dctx, recomputing the probabilities ----
  * Differentiates BertSelfAttention.forward (modeling_bert.py:234-260) including its dropout on the probabilities.
- * qkv / ctx are the forward tensors (act_dtype: bf16 or fp16; ctx is needed for delta = rowsum(dO o O)); row_lse
+ * qkv / ctx are the forward tensors (ctx is needed for delta = rowsum(dO o O)); every 16-bit tensor of the call
+ * (qkv, ctx, dctx, dqkv) has the format act_dtype; row_lse
  * (optional) is the logsumexp saved by rl_attention_fwd: P = exp2(s - lse) is then recomputed in one pass over S.
  * seq_len <= 256. */
 RL_API int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,

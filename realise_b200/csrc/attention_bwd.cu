@@ -23,8 +23,8 @@ struct AttBwdParams {
   int heads;
   rl::DropSpec drop;
   const float* lse;           // optional [B, heads, L] log2-domain logsumexp saved by the forward: skips two passes over S
-  int f16;                    // forward tensors (Q/K/V, ctx, the recomputed P) are fp16; gradients (dO, dS, dqkv) stay bf16 —
-                              // tcgen05 kind::f16 takes the format per operand
+  int f16;                    // every 16-bit tensor of the call (Q/K/V, ctx, dO, dqkv, the P / dS tiles) is fp16 instead of
+                              // bf16: tcgen05 kind::f16 needs ONE format for both operands of an MMA (probed on B200)
 };
 
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -86,7 +86,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     rl::mbar_wait(bar_ld, 0);
     rl::tc_fence_after();
     const uint32_t idesc = rl::make_idesc_h(128, lkv16, 0, 0, p.f16, p.f16);      // S = Q K^T
-    const uint32_t idesc_dp = rl::make_idesc_h(128, lkv16, 0, 0, 0, p.f16);       // dP = dO (bf16) V^T
+    const uint32_t idesc_dp = rl::make_idesc_h(128, lkv16, 0, 0, p.f16, p.f16);   // dP = dO V^T
     const uint32_t qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK), va = rl::smem_u32(sV), da = rl::smem_u32(sDO);
 #pragma unroll
     for (int k = 0; k < 4; ++k)  // S = Q K^T
@@ -108,10 +108,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 a = o[i], c = g[i];
-      delta += rl::half_lo(a.x, p.f16) * rl::bf16_lo(c.x) + rl::half_hi(a.x, p.f16) * rl::bf16_hi(c.x) +
-               rl::half_lo(a.y, p.f16) * rl::bf16_lo(c.y) + rl::half_hi(a.y, p.f16) * rl::bf16_hi(c.y) +
-               rl::half_lo(a.z, p.f16) * rl::bf16_lo(c.z) + rl::half_hi(a.z, p.f16) * rl::bf16_hi(c.z) +
-               rl::half_lo(a.w, p.f16) * rl::bf16_lo(c.w) + rl::half_hi(a.w, p.f16) * rl::bf16_hi(c.w);
+      delta += rl::half_lo(a.x, p.f16) * rl::half_lo(c.x, p.f16) + rl::half_hi(a.x, p.f16) * rl::half_hi(c.x, p.f16) +
+               rl::half_lo(a.y, p.f16) * rl::half_lo(c.y, p.f16) + rl::half_hi(a.y, p.f16) * rl::half_hi(c.y, p.f16) +
+               rl::half_lo(a.z, p.f16) * rl::half_lo(c.z, p.f16) + rl::half_hi(a.z, p.f16) * rl::half_hi(c.z, p.f16) +
+               rl::half_lo(a.w, p.f16) * rl::half_lo(c.w, p.f16) + rl::half_hi(a.w, p.f16) * rl::half_hi(c.w, p.f16);
     }
   }
 
@@ -185,8 +185,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           make_uint4(rl::pack_h(pr[8 * g], pr[8 * g + 1], p.f16), rl::pack_h(pr[8 * g + 2], pr[8 * g + 3], p.f16),
                      rl::pack_h(pr[8 * g + 4], pr[8 * g + 5], p.f16), rl::pack_h(pr[8 * g + 6], pr[8 * g + 7], p.f16));
       *reinterpret_cast<uint4*>(td + piece) =
-          make_uint4(rl::pack_bf16(ds[8 * g], ds[8 * g + 1]), rl::pack_bf16(ds[8 * g + 2], ds[8 * g + 3]),
-                     rl::pack_bf16(ds[8 * g + 4], ds[8 * g + 5]), rl::pack_bf16(ds[8 * g + 6], ds[8 * g + 7]));
+          make_uint4(rl::pack_h(ds[8 * g], ds[8 * g + 1], p.f16), rl::pack_h(ds[8 * g + 2], ds[8 * g + 3], p.f16),
+                     rl::pack_h(ds[8 * g + 4], ds[8 * g + 5], p.f16), rl::pack_h(ds[8 * g + 6], ds[8 * g + 7], p.f16));
     }
   }
   if (nchunk < 2) {  // kv columns 32..63 of P tile 0 still hold V: clear them (their dV rows are never stored, but
@@ -204,8 +204,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t pa = rl::smem_u32(sV), dsa = rl::smem_u32(sDS), qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK),
                    da = rl::smem_u32(sDO);
     // dV[kv, d] = sum_q P[q, kv] dO[q, d] : A = P^T (MN-major: kv contiguous, 64-kv blocks one tile apart), B = dO^T
-    const uint32_t idesc_t = rl::make_idesc_h(128, HEAD_DIM, 1, 1, p.f16, 0);     // P (forward format) x dO (bf16)
-    const uint32_t idesc_k = rl::make_idesc_h(128, HEAD_DIM, 1, 1, 0, p.f16);     // dS (bf16) x Q
+    const uint32_t idesc_t = rl::make_idesc_h(128, HEAD_DIM, 1, 1, p.f16, p.f16);   // P^T dO
+    const uint32_t idesc_k = rl::make_idesc_h(128, HEAD_DIM, 1, 1, p.f16, p.f16);   // dS^T Q
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       rl::tc_mma_f16(tmem_base + COL_DV, rl::make_smem_desc_sw128(pa + k * 2048, 2 * T16K, 1024),  // P tiles: sV, sP1
@@ -216,7 +216,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       rl::tc_mma_f16(tmem_base + COL_DK, rl::make_smem_desc_sw128(dsa + k * 2048, T16K, 1024),
                      rl::make_smem_desc_sw128(qa + k * 2048, 1024, 1024), idesc_k, k != 0);
     // dQ[q, d] = sum_kv dS[q, kv] K[kv, d] : A = dS K-major over kv, B = K^T (MN-major)
-    const uint32_t idesc_q = rl::make_idesc_h(128, HEAD_DIM, 0, 1, 0, p.f16);     // dS (bf16) x K
+    const uint32_t idesc_q = rl::make_idesc_h(128, HEAD_DIM, 0, 1, p.f16, p.f16);   // dS K
     const int nk = lkv16 / 16;
     for (int k = 0; k < nk; ++k)
       rl::tc_mma_f16(tmem_base + COL_DQ, rl::make_smem_desc_sw128(dsa + (k >> 2) * T16K + (k & 3) * 32, 16, 1024),
@@ -241,10 +241,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint4* o = reinterpret_cast<uint4*>(base + t * p.H + c * 32);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            o[g] = make_uint4(rl::pack_bf16(__uint_as_float(v[8 * g]) * scl[t], __uint_as_float(v[8 * g + 1]) * scl[t]),
-                              rl::pack_bf16(__uint_as_float(v[8 * g + 2]) * scl[t], __uint_as_float(v[8 * g + 3]) * scl[t]),
-                              rl::pack_bf16(__uint_as_float(v[8 * g + 4]) * scl[t], __uint_as_float(v[8 * g + 5]) * scl[t]),
-                              rl::pack_bf16(__uint_as_float(v[8 * g + 6]) * scl[t], __uint_as_float(v[8 * g + 7]) * scl[t]));
+            o[g] = make_uint4(rl::pack_h(__uint_as_float(v[8 * g]) * scl[t], __uint_as_float(v[8 * g + 1]) * scl[t], p.f16),
+                              rl::pack_h(__uint_as_float(v[8 * g + 2]) * scl[t], __uint_as_float(v[8 * g + 3]) * scl[t], p.f16),
+                              rl::pack_h(__uint_as_float(v[8 * g + 4]) * scl[t], __uint_as_float(v[8 * g + 5]) * scl[t], p.f16),
+                              rl::pack_h(__uint_as_float(v[8 * g + 6]) * scl[t], __uint_as_float(v[8 * g + 7]) * scl[t], p.f16));
         }
       }
     }

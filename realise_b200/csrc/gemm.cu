@@ -824,6 +824,10 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.a_mode = d->a_mode;
   RL_REQUIRE((d->a_dtype == RL_DT_BF16 || d->a_dtype == RL_DT_F16) && (d->b_dtype == RL_DT_BF16 || d->b_dtype == RL_DT_F16),
              RL_EINVAL, "rl_gemm_bf16: a_dtype / b_dtype must be RL_DT_BF16 or RL_DT_F16");
+  // Probed on B200 (tools/probe_mixed_mma.py): an instruction descriptor whose a_format and b_format differ (bf16 x fp16)
+  // raises "illegal instruction" — kind::f16 multiplies two operands of ONE 16-bit format.
+  RL_REQUIRE(d->a_dtype == d->b_dtype, RL_EINVAL, "rl_gemm_bf16: A and B must share one 16-bit format (bf16 x fp16 is not "
+             "executable by tcgen05.mma kind::f16)");
   p.a_f16 = d->a_dtype == RL_DT_F16;
   p.b_f16 = d->b_dtype == RL_DT_F16;
   p.o_f16 = d->out_dtype == RL_DT_F16;

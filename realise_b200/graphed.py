@@ -40,6 +40,7 @@ class GraphedTrainStep:
         self._counter = torch.zeros(1, device=dev, dtype=torch.int64)   # dropout step counter (read as uint64)
         self._ones = torch.ones(1, device=dev, dtype=torch.float32)
         self._pool = None                 # graphs of different shapes replay one at a time: they share one memory pool
+        self._gen = None                  # model._prep_gen the cached graphs were captured against
         self.replays = 0
 
     # ---- batch plumbing --------------------------------------------------------------------------------------
@@ -89,10 +90,25 @@ class GraphedTrainStep:
             eng.seed, opt._step = seed0, step0     # recording a graph is not a training step
         return graph, static, loss
 
+    def _validate(self):
+        """A captured graph bakes in device pointers of the model's operand cache (16-bit weight copies, the optimizer's
+        shadow table).  model.eval() / .train() / .to() / load_state_dict / tie_cls_weight drop that cache: graphs
+        captured against an older generation must never be replayed (they would read and WRITE freed memory)."""
+        m = self.model
+        if m._prepared is None:
+            m.prepare()
+        if self._gen != m._prep_gen:
+            self._graphs.clear()
+            self._gen = m._prep_gen
+            self.opt._sig = None          # the shadow pointers in the optimizer table are stale too
+            if any(p.grad is not None for g in self.opt.param_groups for p in g["params"]):
+                self.opt._build()         # outside any capture (host-to-device copies)
+
     def __call__(self, batch):
         m = self.model
         if not m.training:
             raise RuntimeError("GraphedTrainStep: model.train() first")
+        self._validate()
         inputs = self._inputs(batch)
         key = tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items()))
         entry = self._graphs.get(key)

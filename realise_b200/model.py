@@ -166,16 +166,19 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         self.dropout = nn.Dropout(c.hidden_dropout_prob)
         self.classifier = nn.Linear(c.hidden_size, c.vocab_size)
         self.init_weights()
+        self._prep_gen = 0           # bumped whenever the operand cache is dropped or rebuilt: captured CUDA graphs (eval
+                                     # graphs here, realise_b200.graphed.GraphedTrainStep) hold pointers into it
         self._prepared = None
         self._ws = {}
         self._graphs = {}
+        self.max_eval_graphs = 8     # LRU bound of the per-shape eval graph cache (they share one memory pool)
+        self._graph_pool = None
         self.use_cuda_graph = True
         self.precise_classifier = False  # eval logits through the split-precision classifier (see prepare()): measured
                                          # to cut the logit error rms by only 15 % (the error is upstream), so off
         self.glyph_cache = False         # inference: replace the glyph CNN by a [vocab, 768] lookup built once (bit-identical;
                                          # off by default so that benchmarks time the CNN itself)
         self.eval_fp16 = True            # inference: fp16 (not bf16) operands for the transformer stacks, GRU and classifier
-        self.train_fp16 = True           # training: fp16 forward tensors, bf16 gradients (mixed-format MMAs); False = all bf16
         self._engine = None       # realise_b200.train.TrainEngine, built on the first train-mode forward
         self.fuse_block1 = True   # eval: glyph gather + whole res_block1 in one tcgen05 kernel
         self.collect = None  # tests set this to a dict to receive clones of the sub-module outputs
@@ -197,9 +200,23 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             if isinstance(m, nn.Linear) and m.bias is not None:
                 m.bias.data.zero_()
 
+    def _invalidate(self, workspaces=False):
+        self._prepared = None
+        self._prep_gen += 1
+        self._graphs = {}
+        if workspaces:
+            self._ws = {}
+
     def tie_cls_weight(self):
         self.classifier.weight = self.bert.embeddings.word_embeddings.weight
-        self._prepared = None
+        self._invalidate()
+
+    def zero_grad(self, set_to_none=True):
+        """src/run.py:211.  Gradients live in the train engine's flat buffer: dropping the .grad views also tells the
+        engine that the accumulated gradients were consumed (the next backward starts from zero)."""
+        super().zero_grad(set_to_none=set_to_none)
+        if self._engine is not None:
+            self._engine.grads_consumed()
 
     @staticmethod
     def build_batch(batch, tokenizer, pho_convertor=None):
@@ -234,22 +251,19 @@ class SpellBertPho2ResArch3Abla(nn.Module):
     def train(self, mode=True):
         # leaving train mode: the eval operand cache (folded BatchNorm, conv layouts) must be rebuilt from the
         # parameters / running statistics the training steps have changed
-        if bool(mode) != self.training:   # also: the two modes use different 16-bit operand formats (bf16 / fp16)
-            self._prepared = None
-            self._ws = {}
-            self._graphs = {}
+        if bool(mode) != self.training:   # (eval folds BatchNorm into the conv weights; training refreshes copies in place)
+            self._invalidate(workspaces=True)
         return super().train(mode)
 
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
-        self._prepared = None
+        self._invalidate()
         return out
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._prepared = None
-        self._ws = {}
-        self._graphs = {}
+        self._invalidate(workspaces=True)
+        self._engine = None          # its flat gradient buffer / views belong to the old parameter storage
         return out
 
     # ---- weight preparation (bf16 operand copies, fused / re-laid-out weights) -----------------
@@ -335,8 +349,30 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         torch.cuda.current_stream().synchronize()
         self._prepared = P
         self._shadow_bf16, self._shadow_f32 = sh16, sh32
+        self._shadow_params = {id(p): p for p in self.parameters() if id(p) in sh16 or id(p) in sh32}
+        self._shadow_versions = {i: p._version for i, p in self._shadow_params.items()}
         self._graphs = {}  # captured graphs hold pointers into the previous operand cache
+        self._prep_gen += 1
         return P
+
+    @torch.no_grad()
+    def refresh_stale_shadows(self):
+        """The GEMMs read 16-bit operand copies of the weights (and fused f32 bias vectors).  FusedAdamW(model=...)
+        refreshes them inside its update kernel; ANY other writer of p.data (the reference's vendored AdamW, a torch
+        optimizer, manual surgery) bumps the tensor's version counter instead — re-cast those copies in place (same
+        pointers: captured graphs and the optimizer table stay valid).  Returns the number of refreshed tensors."""
+        n = 0
+        for i, p in self._shadow_params.items():
+            if p._version != self._shadow_versions[i]:
+                if i in self._shadow_bf16:
+                    self._shadow_bf16[i].copy_(p.detach())
+                if i in self._shadow_f32:
+                    self._shadow_f32[i].copy_(p.detach())
+                self._shadow_versions[i] = p._version
+                n += 1
+        if n and not self.training:
+            self._invalidate()      # eval caches derived tensors too (GRU table, folded BatchNorm): rebuild them all
+        return n
 
     @staticmethod
     def _fold_bn(bn):
@@ -534,7 +570,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         input_ids = batch["src_idx"]
         if not input_ids.is_cuda:
             raise RuntimeError("realise_b200 has no CPU path: move the batch tensors to the model's CUDA device")
-        if self._prepared is None:
+        if self._prepared is None or self.refresh_stale_shadows() and self._prepared is None:
             self.prepare()
         dev = input_ids.device
         inputs = {"src_idx": input_ids.contiguous(), "masks": batch["masks"].contiguous()}
@@ -557,17 +593,22 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             return self._engine.run(inputs)
         if not self.use_cuda_graph or self.collect is not None:
             return self._run(inputs)
-        key = tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items()))
-        entry = self._graphs.get(key)
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items())) + (
+            self.glyph_cache, self.fuse_block1, self.precise_classifier, self.eval_fp16)
+        entry = self._graphs.pop(key, None)
         if entry is None:
+            while len(self._graphs) >= self.max_eval_graphs:      # least recently used shape goes first
+                self._graphs.pop(next(iter(self._graphs)))
             static = {k: v.clone() for k, v in inputs.items()}
             self._run(static)                      # eager warm-up: lazy init outside the capture
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(graph, pool=self._graph_pool):   # graphs replay one at a time: one shared pool
                 outs = self._run(static)
             entry = (graph, static, outs)
-            self._graphs[key] = entry
+        self._graphs[key] = entry                  # (re)insert as most recently used
         graph, static, outs = entry
         for k, v in inputs.items():
             static[k].copy_(v, non_blocking=True)
@@ -575,10 +616,10 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         return outs
 
     def _half_dtype(self):
-        """16-bit format of the FORWARD tensors (weights' operand copies, activations) of the transformer stacks, the GRU
-        and the classifier.  fp16 by default in both modes: tcgen05 takes the format per operand, so the training
-        backward multiplies bf16 gradients by fp16 forward tensors directly.  The glyph CNN stays bf16."""
-        return torch.float16 if (self.train_fp16 if self.training else self.eval_fp16) else torch.bfloat16
+        """16-bit format of the transformer stacks, the GRU and the classifier: fp16 for inference, bf16 for training
+        (gradient range).  One MMA cannot mix the two (include/realise_b200.h), so a mode uses one format throughout;
+        the glyph CNN stays bf16 in both."""
+        return torch.float16 if (self.eval_fp16 and not self.training) else torch.bfloat16
 
     def _run(self, inp):
         return self._run_impl(inp)

@@ -341,7 +341,7 @@ def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
 def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None, lse=None):
     for t, n in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, n)
-    assert ctx.dtype == qkv.dtype and dctx.dtype is torch.bfloat16 and dqkv.dtype is torch.bfloat16   # gradients stay bf16
+    assert ctx.dtype == qkv.dtype == dctx.dtype == dqkv.dtype
     with _Timed("attention_bwd", 14.0 * B * heads * L * L * 64):
         check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _ptr(lse), _c(B), _c(L),
                                      _c(heads), _c(64), _dt(qkv), *_drop(drop), _ctr(), _stream()), "rl_attention_bwd")
@@ -407,7 +407,7 @@ def gelu_bwd_colsum(t, u, dbias):
     _req(t, torch.bfloat16, "t")
     _req(u, torch.bfloat16, "u")
     rows, cols = t.shape
-    assert t.stride(1) == 1 and u.stride() == t.stride() and t.dtype is torch.bfloat16
+    assert t.stride(1) == 1 and u.stride() == t.stride()
     with _Timed("gelu_bwd_colsum", t.numel() * 6):
         check(lib().rl_gelu_bwd_colsum(_ptr(t), _ptr(u), _ptr(dbias), _c(rows), _c(cols), _c(t.stride(0)), _dt(u), _stream()),
               "rl_gelu_bwd_colsum")

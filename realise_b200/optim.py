@@ -24,6 +24,8 @@ CHUNK = 4096
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
                  correct_bias=True, model=None):
+        """model: the realise_b200 model whose 16-bit operand copies the update kernel refreshes in place.  Without it
+        the model notices the stale copies on its next forward (parameter version counters) and re-casts them."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.max_grad_norm = max_grad_norm
@@ -76,7 +78,14 @@ class FusedAdamW(torch.optim.Optimizer):
             grad_div = float(getattr(self.model, "grad_div", 1.0)) if self.model is not None else 1.0
         self._build()
         self._step += 1
+        eng = getattr(self.model, "_engine", None)
+        if eng is not None:
+            eng.grads_consumed()
         g0 = self.param_groups[0]
+        for g in self.param_groups[1:]:          # one launch updates every tensor: the groups may differ in weight decay only
+            if (g["lr"], tuple(g["betas"]), g["eps"]) != (g0["lr"], tuple(g0["betas"]), g0["eps"]):
+                raise ValueError("FusedAdamW: lr / betas / eps must agree across param groups (only weight_decay is per group, "
+                                 "as in src/run.py:146-152)")
         b1, b2 = g0["betas"]
         bc1 = 1.0 - b1 ** self._step if self.correct_bias else 1.0
         bc2 = 1.0 - b2 ** self._step if self.correct_bias else 1.0
@@ -93,6 +102,27 @@ class FusedAdamW(torch.optim.Optimizer):
             return
         check(lib().rl_mt_adamw(tab, ck, ctypes.c_int64(self._nchunks), ss, f(self.max_grad_norm or 0.0), f(g0["lr"]),
                                 f(b1), f(b2), f(g0["eps"]), f(bc1), f(bc2), f(grad_div), st), "rl_mt_adamw")
+
+    def state_dict(self):
+        """torch layout plus the shared step counter (bias correction resumes where it stopped); every state entry also
+        carries 'step' like the vendored AdamW's (transformers/optimization.py:136-140)."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p in self.state and "exp_avg" in self.state[p]:
+                    self.state[p]["step"] = self._step
+        sd = super().state_dict()
+        sd["fused_step"] = self._step
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        step = state_dict.pop("fused_step", None)
+        super().load_state_dict(state_dict)
+        if step is None:     # a vendored-AdamW / torch AdamW checkpoint: per-parameter 'step'
+            steps = [int(st["step"]) for st in self.state.values() if "step" in st]
+            step = max(steps) if steps else 0
+        self._step = int(step)
+        self._sig = None     # moment tensors were replaced: rebuild the device table
 
     def hyper_values(self, step):
         """{lr, 1 - beta1^t, 1 - beta2^t} of optimizer step `step` (1-based) for the device-resident schedule."""

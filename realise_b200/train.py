@@ -1,14 +1,15 @@
 """Training-mode forward + backward of the hot path on librealise_b200.so.
 
 `TrainEngine` runs the train-mode forward (saving the activations the backward needs) and the backward pass
-as a fixed sequence of C-ABI kernel calls; `torch.autograd` only sees ONE custom Function whose backward returns
+as a fixed sequence of C-ABI kernel calls; `torch.autograd` only sees ONE custom Function whose backward attaches
 the parameter gradients, so `loss.backward()` in the reference's loop (src/run.py:191-200) keeps working.
 
-Round-1 coverage: the semantic path (BertModel stacks, gated fusion, tied classifier, masked CE).  The pinyin GRU
-(BPTT) and CharResNet (conv / batch-stat BatchNorm backward) branches are not differentiated yet, so training is
-available for `with_pho='no', with_res='no'` configurations (src/models_abla.py) and raises otherwise.  Dropout must
-be 0 in this round (the Philox dropout kernels are not written yet): parity is checked against the oracle's
-autograd with dropout off, the protocol of SURVEY.md §8c.
+Coverage: every branch of SpellBertPho2ResArch3 / its ablations (src/models_abla.py) — the three BertModel stacks with
+counter-based dropout (hidden 0.1 / attention 0.1 as in the reference config), the pinyin GRU (backward through time),
+CharResNet with batch-statistics BatchNorm (running statistics updated like nn.BatchNorm2d), gated or sum fusion, the
+tied classifier and the masked CE.  Forward tensors are fp16 (or bf16), gradients bf16, accumulation / residual stream /
+LayerNorm / softmax / BatchNorm statistics fp32.  Gradients of successive backward() calls ACCUMULATE until the
+optimizer step or zero_grad() consumes them (src/run.py:193-205, gradient_accumulation_steps).
 """
 import torch
 
@@ -24,12 +25,17 @@ class _StepFn(torch.autograd.Function):
     def forward(ctx, engine, inputs, *params):
         loss, logits = engine.forward(inputs)
         ctx.engine = engine
+        ctx.saved = engine.saved          # the activations belong to THIS forward: a second forward before the backward
+        engine.saved = None               # (e.g. a train-mode loss probe) neither overwrites nor leaks them
         ctx.mark_non_differentiable(logits)
         return loss, logits
 
     @staticmethod
     def backward(ctx, gloss, _glogits):
         eng = ctx.engine
+        if ctx.saved is None:
+            raise RuntimeError("realise_b200: backward through the same forward twice (activations already released)")
+        eng.saved, ctx.saved = ctx.saved, None
         eng.backward_and_sync(gloss)
         return (None, None) + (None,) * len(eng.params)
 
@@ -41,6 +47,8 @@ class TrainEngine:
         if c.with_res == "yes" and c.num_fonts not in (1, 3):
             raise NotImplementedError("glyph kernels are built for 1 or 3 fonts")
         self.saved = None
+        self._pending = False         # gradients of an earlier backward() are still waiting for the optimizer
+        self._accum = None
         self.debug = None             # tests set a dict to receive intermediate gradients
         self._tap_idx = {}
         self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
@@ -108,15 +116,29 @@ class TrainEngine:
     def backward_and_sync(self, gloss):
         """Backward of the saved forward, the data-parallel gradient exchange, and .grad attachment.  Called by
         autograd (loss.backward()) or directly by realise_b200.graphed.GraphedTrainStep."""
+        # gradient accumulation (src/run.py:193-205): the kernels write / atomically add into a freshly zeroed flat
+        # buffer, so gradients that an earlier backward left for the optimizer are set aside and added back afterwards
+        accumulate = self._pending and any(p.grad is not None for p in self.params)
+        if accumulate:
+            if self._accum is None:
+                self._accum = torch.empty_like(self.flat)
+            self._accum.copy_(self.flat)
         self.backward(gloss)
         hook = getattr(self.m, "_post_backward", None)   # realise_b200.ddp.DataParallel: one all-reduce of self.flat
         if hook is not None:
             hook(self)
+        if accumulate:
+            self.flat.add_(self._accum)
+        self._pending = True
         # gradients live in persistent buffers (stable pointers for the fused optimizer); they are attached to the
         # parameters directly instead of being handed to autograd, which would copy or alias them
         for p, g in zip(self.params, self.grads):
             if g is not None:
                 p.grad = g
+
+    def grads_consumed(self):
+        """Called by FusedAdamW.step() and model.zero_grad(): the next backward starts from zero again."""
+        self._pending = False
 
     def set_seed(self, seed):
         self.seed = int(seed)
