@@ -136,7 +136,7 @@ def gru_final(sd, pho_idx, pho_lens):
     w_ih, w_hh = sd["pho_gru.weight_ih_l0"], sd["pho_gru.weight_hh_l0"]
     b_ih, b_hh = sd["pho_gru.bias_ih_l0"], sd["pho_gru.bias_hh_l0"]
     N, T, H = emb.shape
-    if FAST:
+    if FAST and not (w_ih.requires_grad or w_hh.requires_grad or emb.requires_grad):   # (the module path below cuts autograd)
         packed = torch.nn.utils.rnn.pack_padded_sequence(emb, pho_lens, batch_first=True, enforce_sorted=False)
         gru = torch.nn.GRU(H, H, num_layers=1, batch_first=True, device=emb.device)
         gru.weight_ih_l0, gru.weight_hh_l0 = torch.nn.Parameter(w_ih), torch.nn.Parameter(w_hh)

@@ -34,13 +34,21 @@ class DataParallel:
         optimizer.step()                               # FusedAdamW(model=model) reads model.grad_div
     """
 
-    def __init__(self, model, group=None):
-        self.model, self.group = model, group
-        model.grad_div = float(dist.get_world_size(group)) if dist.is_initialized() else 1.0
+    def __init__(self, model, group=None, average=False):
+        """average=False: gradients are SUMMED over ranks and FusedAdamW(model=model) divides by the world size inside
+        its update kernel (model.grad_div).  average=True: the buffer is scaled by 1/W right after the all-reduce, which
+        is what DistributedDataParallel leaves in p.grad — for optimizers that know nothing about grad_div (the
+        reference's vendored AdamW behind realise_b200.compat)."""
+        self.model, self.group, self.average = model, group, average
+        world = float(dist.get_world_size(group)) if dist.is_initialized() else 1.0
+        model.grad_div = 1.0 if average else world
+        self._inv_world = 1.0 / world
         model._post_backward = self.sync
 
     def sync(self, engine):
-        allreduce_sum_(engine.flat, self.group)
+        w = allreduce_sum_(engine.flat, self.group)
+        if self.average and w > 1:
+            engine.flat.mul_(self._inv_world)
 
     def broadcast_parameters(self, src=0):
         """DDP broadcasts rank-0 parameters/buffers at construction; do the same once."""

@@ -218,34 +218,73 @@ class SpellBertPho2ResArch3Abla(nn.Module):
         if self._engine is not None:
             self._engine.grads_consumed()
 
+    _pho_convertor = None
+
     @staticmethod
     def build_batch(batch, tokenizer, pho_convertor=None):
-        """src/models.py:797-804.  The pinyin convertor needs pypinyin (host-side, out of the
-        measured path); pass the reference's `pho2_convertor` or any object with .convert(chars)."""
+        """src/models.py:797-804.  Host-side pinyin conversion (out of the measured path): by default the reference's
+        own `Pinyin2` (src/utils.py:72-98, needs pypinyin) when this runs inside a reference checkout, else pass any
+        object with .convert(chars).  realise_b200.batch.PinyinTable is the device-side replacement."""
+        cls = SpellBertPho2ResArch3Abla
         if pho_convertor is None:
-            raise RuntimeError("build_batch needs a pinyin convertor (reference src/utils.py:Pinyin2)")
+            if cls._pho_convertor is None:
+                try:
+                    from utils import Pinyin2          # the reference's src/utils.py (src/ is the script directory)
+                    cls._pho_convertor = Pinyin2()
+                except Exception as e:  # noqa: BLE001
+                    raise RuntimeError("build_batch needs a pinyin convertor: run inside a ReaLiSe checkout (src/utils.py: "
+                                       "Pinyin2, pypinyin) or pass pho_convertor=") from e
+            pho_convertor = cls._pho_convertor
         src_idx = batch["src_idx"].flatten().tolist()
         chars = tokenizer.convert_ids_to_tokens(src_idx)
         batch["pho_idx"], batch["pho_lens"] = pho_convertor.convert(chars)
         return batch
 
+    def build_glyce_embed(self, vocab_dir, font_path, font_size=32):
+        """src/models.py:703-733 (src/run.py:435): rasterise vocab.txt with one font into char_images.weight."""
+        from . import glyphs
+        glyphs.build_glyce_embed(self, vocab_dir, font_path, font_size)
+
+    def build_glyce_embed_multifonts(self, vocab_dir, num_fonts, use_traditional_font, font_size=32, font_dir=".", s2t=None):
+        """src/models.py:735-761 (src/run.py:438): simhei / xiaozhuan / traditional-simhei planes of char_images_multifonts."""
+        from . import glyphs
+        glyphs.build_glyce_embed_multifonts(self, vocab_dir, num_fonts, use_traditional_font, font_size, font_dir, s2t)
+
+    @torch.no_grad()
+    def predict(self, batch):
+        """Token ids [B, L] (int64, on the device) = argmax over the vocabulary of forward(batch)'s logits, taken by a
+        kernel: replaces `logits.detach().cpu().numpy()` + `np.argmax` of src/test.py:140-145 / src/run.py:262-263, so
+        that B*L ids cross PCIe instead of B*L*21128 floats (692 MB at B64 x L128).  Ties resolve to the first maximum,
+        like np.argmax."""
+        logits = self.forward(batch)[-1]
+        B, L, V = logits.shape
+        out = torch.empty(B * L, dtype=torch.int64, device=logits.device)
+        ops.argmax_rows(logits.view(B * L, V), out)
+        return out.view(B, L)
+
     def save_pretrained(self, save_directory):
         """config.json + pytorch_model.bin, like PreTrainedModel.save_pretrained (modeling_utils.py:236-251)."""
         os.makedirs(save_directory, exist_ok=True)
         with open(os.path.join(save_directory, "config.json"), "w") as f:
-            json.dump(self.config.__dict__, f, indent=2, sort_keys=True)
+            json.dump(dict(self.config.__dict__, architectures=[type(self).__name__]), f, indent=2, sort_keys=True)
         torch.save(self.state_dict(), os.path.join(save_directory, "pytorch_model.bin"))
 
     @classmethod
     def from_pretrained(cls, path, config=None, **kw):
+        """PreTrainedModel.from_pretrained for a local directory (modeling_utils.py:254-492): config.json +
+        pytorch_model.bin.  Like the reference it loads non-strictly: a plain `bert-base-chinese` / roberta-wwm
+        checkpoint (keys `bert.*` only, `cls.*` heads ignored) initialises the semantic encoder and leaves the other
+        sub-modules at their init; `model.missing_keys` / `.unexpected_keys` record what happened.  Old-style LayerNorm
+        names (gamma / beta) are renamed (:429-444).  kw (cache_dir, ...) is accepted and ignored."""
         if config is None:
             with open(os.path.join(path, "config.json")) as f:
                 config = json.load(f)
         model = cls(config)
-        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
-        # old-checkpoint LayerNorm names (modeling_utils.py:429-444)
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
         sd = {k.replace(".gamma", ".weight").replace(".beta", ".bias"): v for k, v in sd.items()}
-        model.load_state_dict(sd, strict=False)
+        res = model.load_state_dict(sd, strict=False)
+        model.missing_keys, model.unexpected_keys = list(res.missing_keys), list(res.unexpected_keys)
+        model.eval()                 # modeling_utils.py:486: from_pretrained returns the model in eval mode
         return model
 
     def train(self, mode=True):

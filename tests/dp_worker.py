@@ -109,6 +109,12 @@ def main():
     model._post_backward = inner
     flat_params = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
     res["params_identical_after_3_eager_steps"] = all_equal_across_ranks(flat_params, world)
+    if not res["params_identical_after_3_eager_steps"]:
+        bad = []
+        for n, p in model.named_parameters():
+            if p.requires_grad and not all_equal_across_ranks(p.detach().reshape(-1).contiguous(), world):
+                bad.append(n)
+        res["differing_params"] = bad[:8] + [len(bad)]
     if own_gpu:       # the all-reduce inside a captured graph needs NCCL (gloo synchronises with the host)
         gstep = GraphedTrainStep(model, opt)
         for step in range(5):                                     # first call eager, second captures, then replays
@@ -137,7 +143,9 @@ def main():
     for (n, a), (_, b) in zip(m_dp.named_parameters(), m_one.named_parameters()):
         if a.grad is None or float(b.grad.norm()) < 1e-6 * gmax:
             continue
-        worst = max(worst, float((a.grad / world - b.grad).norm() / b.grad.norm()))
+        rel = float((a.grad / world - b.grad).norm() / b.grad.norm())
+        if rel > worst:
+            worst, res["w_ranks_vs_one_rank_worst_name"] = rel, n
     res["w_ranks_vs_one_rank_worst_rel_l2"] = worst
     ok = (res["sum_max_diff_rel"] <= (0.0 if world == 2 else 1e-6) and res["ranks_differ_before_sync"]
           and res["params_identical_after_3_eager_steps"] and worst <= 2e-2
