@@ -14,8 +14,10 @@ Synthetic batch (realise_b200.synth) and random-init weights of the full archite
 training-loop body (src/run.py:186-212) through the public API with a pinned HOST batch: H2D of the batch,
 model(batch) -> loss.backward() -> optimizer.step() -> loss.item() (D2H).  The forward-only configs[1] number
 (B=64, eval, CUDA graph) is reported as the secondary `forward_only` object.
-`--impl reference` / `cpu_baseline` time the CPU oracle port of the same train step (autograd + clip + AdamW
-as transformers/optimization.py:113-169) on the host cores on a bounded sample.  One JSON line (rank 0).
+`--impl reference` / `cpu_baseline` time the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.py:
+its SpellBertPho2ResArch3 and the loop body of src/run.py:186-212 with the vendored AdamW) on the host cores on a
+bounded sample (`kind: "reference"`; the oracle port is the fallback when baseline/_ref is absent).  `incumbent` = the
+same reference modules under torch eager on the B200 (fp32 and autocast-bf16), same batch.  One JSON line (rank 0).
 """
 import argparse
 import json
@@ -187,7 +189,8 @@ class CpuTrainStep:
 
 
 def cpu_train_rate(budget_s, max_steps, sample_b=4, warmup=1):
-    """sentences/s of the CPU train step on a bounded sample; returns (rate, steps, threads, sample text)."""
+    """sentences/s of the CPU oracle PORT's train step on a bounded sample (fallback when baseline/_ref is absent);
+    returns (rate, steps, threads, sample text, seconds)."""
     maxt = host_threads()
     torch.set_num_threads(min(maxt, 16))
     small = CpuTrainStep(1, SEQ_LEN)
@@ -209,22 +212,103 @@ def cpu_train_rate(budget_s, max_steps, sample_b=4, warmup=1):
     return n * sample_b / dt, n, torch.get_num_threads(), sample, dt
 
 
+def reference_cpu_rate(steps, warmup, budget_s):
+    """sentences/s of the UNMODIFIED reference (baseline/_ref: its SpellBertPho2ResArch3 + the loop body of
+    src/run.py:186-212 with clip_grad_norm_ and the vendored AdamW) on the host cores.  Each step is a bounded sample of
+    the BASELINE configs[2] workload: the largest batch in {4 .. 128} sentences x 128 tokens for which `warmup + steps`
+    steps fit the time budget.  Returns (rate, threads, sample text, seconds, sample batch)."""
+    from baseline import ref_model
+    from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
+    maxt = host_threads()
+    sd = synth_state_dict(ArchConfig(), seed=0)
+    model = ref_model.build(sd)
+    probe = ref_model.TrainStep(model, synth_batch(2, SEQ_LEN, seed=1, ragged=False))
+    torch.set_num_threads(min(maxt, 16))
+    probe()                                                        # page in, warm the allocator
+    pick_threads(probe, sorted({min(maxt, c) for c in (8, 16, 32, 64)}))
+    t0 = time.perf_counter()
+    probe()
+    t2 = time.perf_counter() - t0
+    probe.batch = synth_batch(4, SEQ_LEN, seed=1, ragged=False)
+    t0 = time.perf_counter()
+    probe()
+    t4 = time.perf_counter() - t0
+    per_sent = max((t4 - t2) / 2.0, 1e-3)
+    fixed = max(t2 - 2 * per_sent, 0.0)                            # optimizer + clip: independent of the batch
+    sample_b = 4
+    for b in (8, 16, 32, 64, 128):
+        if (steps + warmup) * (fixed + b * per_sent) <= budget_s:
+            sample_b = b
+    st = ref_model.TrainStep(model, synth_batch(sample_b, SEQ_LEN, seed=1, ragged=False))
+    st.opt = probe.opt
+    for _ in range(warmup):
+        st()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st()
+    dt = time.perf_counter() - t0
+    sample = (f"{steps} x the reference's own train step (SpellBertPho2ResArch3.forward + backward + clip_grad_norm_ + vendored "
+              f"AdamW, dropout 0.1, fp32; baseline/_ref) on {sample_b} sentences x {SEQ_LEN} tokens after {warmup} warm-up steps")
+    return steps * sample_b / dt, torch.get_num_threads(), sample, dt, sample_b
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    value, steps, threads, sample, dt = cpu_train_rate(budget_s=150.0, max_steps=args.steps, warmup=1)
+    from baseline import ref_model
+    if ref_model.available():
+        steps, warm = args.steps, args.warmup
+        value, threads, sample, dt, sample_b = reference_cpu_rate(steps, warm, budget_s=170.0)
+        kind = "reference"
+    else:
+        value, steps, threads, sample, dt = cpu_train_rate(budget_s=150.0, max_steps=args.steps, warmup=1)
+        kind, warm, sample_b = "port", 1, 4
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "sentences/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[2]: train step fwd+bwd+clip+AdamW of the full SpellBertPho2ResArch3, "
-                               "seq_len 128; each step = bounded sample of 4 sentences on the host CPU",
-                   "global_batch": 4, "seq_len": SEQ_LEN},
-        "cpu_baseline": {"value": value, "unit": "sentences/s", "cores": threads, "kind": "port", "sample": sample},
+                               f"seq_len 128; each step = bounded sample of {sample_b} sentences on the host CPU",
+                   "global_batch": sample_b, "seq_len": SEQ_LEN},
+        "cpu_baseline": {"value": value, "unit": "sentences/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def measure_incumbent(dev, steps=3):
+    """The comparator that means something for a GPU path: the UNCHANGED reference modules (baseline/_ref) under stock
+    torch eager on the same B200, same batch (B=128 x L=128), the reference's own loop body — in fp32 (its published
+    recipe) and under torch.autocast(bfloat16).  CUDA events, 1 warm-up + `steps` timed steps each."""
+    from baseline import ref_model
+    from realise_b200.synth import ArchConfig, synth_batch, synth_state_dict
+    if not ref_model.available():
+        return {"unavailable": "baseline/_ref not installed (baseline/install_ref.py)"}
+    out = {"workload": f"reference SpellBertPho2ResArch3 on the B200, torch {torch.__version__} eager, train step B={B_TRAIN} x "
+                       f"L={SEQ_LEN} (fwd+bwd+clip_grad_norm_+vendored AdamW), 1 warm-up + {steps} timed steps, CUDA events"}
+    host = synth_batch(B_TRAIN, SEQ_LEN, seed=4321, ragged=False, with_labels=True)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    for name, dt in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            model = ref_model.build(synth_state_dict(ArchConfig(), seed=0), device=dev)
+            st = ref_model.TrainStep(model, batch, autocast_dtype=dt)
+            st()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = st()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": B_TRAIN / (ms * 1e-3), "unit": "sentences/s", "ms_per_step": ms, "loss": float(loss.detach())}
+        except Exception as e:  # noqa: BLE001 — a comparator must never take the headline down
+            out[name] = {"error": repr(e)[:300]}
+        finally:
+            model = st = None
+            torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -471,6 +555,12 @@ def run_ours(args, rank, world, local_rank):
             fwd = measure_forward(args, dev, rank, world, dist, peaks)
         except Exception as e:  # noqa: BLE001 — the secondary object must never take the headline down
             fwd = {"error": repr(e)[:300]}
+    inc = None
+    if world == 1 and not args.no_incumbent:
+        inc = measure_incumbent(dev)
+        for k in ("fp32", "bf16_autocast"):
+            if isinstance(inc.get(k), dict) and "value" in inc[k]:
+                inc[k]["ours_over_incumbent"] = tr["value"] / inc[k]["value"]
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -478,8 +568,13 @@ def run_ours(args, rank, world, local_rank):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, reps, threads, sample, _ = cpu_train_rate(budget_s=20.0, max_steps=20, warmup=1)
-        cpu = {"value": rate, "unit": "sentences/s", "cores": threads, "kind": "port", "sample": sample}
+        from baseline import ref_model
+        if ref_model.available():
+            rate, threads, sample, _, _ = reference_cpu_rate(steps=3, warmup=1, budget_s=25.0)
+            cpu = {"value": rate, "unit": "sentences/s", "cores": threads, "kind": "reference", "sample": sample}
+        else:
+            rate, reps, threads, sample, _ = cpu_train_rate(budget_s=20.0, max_steps=20, warmup=1)
+            cpu = {"value": rate, "unit": "sentences/s", "cores": threads, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": tr["value"], "unit": "sentences/s", "n_gpus": world, "steps": args.steps,
         "warmup": tr["warmup"], "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
@@ -487,7 +582,7 @@ def run_ours(args, rank, world, local_rank):
         "config": tr["config"], "model_tflops_per_gpu": tr["model_tflops"],
         "roofline": tr["roofline"], "roofline_detail": tr["roofline_detail"],
         "cpu_baseline": cpu, "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"], "clocks": tr["clocks"],
-        "final_loss": tr["final_loss"], "peak_mem_gb": tr["peak_mem_gb"], "forward_only": fwd,
+        "final_loss": tr["final_loss"], "peak_mem_gb": tr["peak_mem_gb"], "forward_only": fwd, "incumbent": inc,
     }
     emit(line)
 
@@ -507,6 +602,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager Python loop instead of the CUDA-graph step")
     ap.add_argument("--no-forward", action="store_true", help="skip the secondary forward-only (configs[1]) measurement")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the reference-on-the-B200 (torch eager) comparator")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

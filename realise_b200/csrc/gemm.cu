@@ -134,7 +134,7 @@ __device__ __forceinline__ void epilogue_prefetch(const KParams& p, float* sb, i
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, uint8_t* stg_base,
                                               const float* sb, uint32_t taddr, int row0, int n0, int half, int lane,
-                                              float (&xr)[32]) {
+                                              float (&xr)[32], int& stg_sel) {
   constexpr int CH = BN / 64;  // 32-column chunks per half
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
@@ -206,8 +206,11 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
       }
       if (p.tma_store) {
-        // two swizzled staging tiles per warp: the TMA store issued two chunks ago must have finished reading
-        uint8_t* stg = stg_base + (cc & 1) * 4096;
+        // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (stg_sel lives in the tile loop: a
+        // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
+        // store was still reading): the TMA store issued two chunks ago must have finished reading
+        uint8_t* stg = stg_base + (stg_sel & 1) * 4096;
+        stg_sel ^= 1;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
         if (p.out_f32) {
@@ -458,6 +461,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
+    int stg_sel = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
@@ -470,7 +474,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
+      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr, stg_sel);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) rl::mbar_arrive(&tmem_empty[acc]);
@@ -733,6 +737,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
+    int stg_sel = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
@@ -745,7 +750,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr);
+      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr, stg_sel);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);

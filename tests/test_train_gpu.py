@@ -555,3 +555,21 @@ def test_stale_operand_copies_are_refreshed_for_foreign_optimizers():
     fresh.load_state_dict(model.state_dict())
     l1_fresh = fresh(b)[0].item()
     assert abs(l1 - l1_fresh) <= 1e-4
+
+
+def test_gemm_many_short_tiles_per_cta():
+    """Regression (found by the bench-shape parity tests): a persistent CTA that runs MANY one-chunk tiles back to back
+    (N = 64, K = 32: the training stem conv over 4.2 M pixels) reused its TMA-store staging tile while the previous
+    tile's store was still reading it."""
+    from realise_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for M, N, K, odt in [(1 << 19, 64, 32, torch.bfloat16), (1 << 18, 64, 32, torch.float32), (1 << 17, 128, 64, torch.bfloat16),
+                         (1 << 16, 64, 576, torch.bfloat16)]:
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=odt)
+        for _ in range(3):
+            ops.gemm(a, b, out)
+        ref = (a.float() @ b.float().t())
+        err = (out.float() - ref).abs().max().item()
+        assert err <= (0.13 if odt is torch.bfloat16 else 1e-3) * max(1.0, K / 64) ** 0.5, (M, N, K, err)
