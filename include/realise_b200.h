@@ -299,10 +299,13 @@ RL_API int rl_glyph_im2col(const float* glyphs, const int64_t* ids, void* col1, 
 /* ---- multi-tensor grad-norm and fused clip + AdamW (src/run.py:207 clip_grad_norm_,
  * transformers/optimization.py:113-169).  table: device array of {float* p; const float* g; float* m;
  * float* v; bf16* shadow; float* shadow32; int64 n; float wd; int shadow_f16 (the shadow is fp16, not bf16)}; chunks: device array of int2 {tensor, chunk} covering
- * every 4096-element block.  rl_mt_sumsq accumulates sum(g^2) into out (caller zeroes it);
+ * every 4096-element block.  rl_mt_sumsq writes sum(g^2) to out[0]: one partial per CTA into partials_ws (ws_floats >= 1;
+ * rl_workspace_bytes("mt_sumsq") gives the size that keeps every SM busy), then a fixed-order second stage — the result
+ * is bit-reproducible, so data-parallel replicas that hold identical gradients apply identical clip coefficients;
  * rl_mt_adamw applies g *= min(1, max_norm / (sqrt(sumsq)/grad_div + 1e-6)) / grad_div, then the AdamW update
  * with bias corrections bias_corr1 = 1-beta1^t, bias_corr2 = 1-beta2^t, and refreshes the bf16 shadow copy. */
-RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, void* stream);
+RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, float* partials_ws,
+                       int64_t ws_floats, void* stream);
 RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                        float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
                        float grad_div, void* stream);
@@ -328,7 +331,8 @@ RL_API int rl_mt_adamw_dev(const void* table, const void* chunks, int64_t num_ch
                            const float* hyper, float beta1, float beta2, float eps, float grad_div, void* stream);
 
 /* Scratch sizes (bytes) of the entry points that take a caller-owned workspace: op is one of "gate_fuse_fwd"
- * (mean_dot_ws), "gate_fuse_bwd" (ws), "masked_ce_fwd" (row_loss_ws).  Returns -1 for an unknown op. */
+ * (mean_dot_ws), "gate_fuse_bwd" (ws), "masked_ce_fwd" (row_loss_ws), "mt_sumsq" (partials_ws; B, L, H ignored).  Returns -1
+ * for an unknown op. */
 RL_API int64_t rl_workspace_bytes(const char* op, int64_t B, int64_t L, int64_t H);
 
 #endif /* REALISE_B200_H */

@@ -111,6 +111,7 @@ extern "C" int64_t rl_workspace_bytes(const char* op, int64_t B, int64_t L, int6
   if (s == "gate_fuse_fwd") return B * 3 * (int64_t)sizeof(float);
   if (s == "gate_fuse_bwd") return (B * L * 3 + 2 * B * H) * (int64_t)sizeof(float);
   if (s == "masked_ce_fwd") return B * L * (int64_t)sizeof(float);
+  if (s == "mt_sumsq") return 8LL * rl_num_sms() * (int64_t)sizeof(float);
   return -1;
 }
 

@@ -506,8 +506,23 @@ mt_sumsq_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ ch
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += sh[w];
-    atomicAdd(out, t);
+    out[blockIdx.x] = t;     // one partial per CTA, summed in a FIXED order below: float atomics would make the clip
+  }                          // coefficient — and after it every parameter — differ in the last bits between ranks
+}
+
+// deterministic second stage: total of the per-CTA partials (double accumulation, fixed strided order + fixed tree)
+__global__ void __launch_bounds__(256)
+mt_sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)partials[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) out[0] = (float)sh[0];
 }
 
 __global__ void __launch_bounds__(256)
@@ -679,12 +694,20 @@ extern "C" int rl_gate_fuse_bwd(const float* dhid, const float* m0, const float*
   return rl_check_launch("rl_gate_fuse_bwd");
 }
 
-extern "C" int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, void* stream) {
-  RL_REQUIRE(table && chunks && out, RL_EINVAL, "rl_mt_sumsq: null pointer");
-  if (num_chunks <= 0) return 0;
+extern "C" int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks, float* out, float* partials_ws,
+                           int64_t ws_floats, void* stream) {
+  RL_REQUIRE(table && chunks && out && partials_ws, RL_EINVAL, "rl_mt_sumsq: null pointer");
   long long grid = 8LL * rl_num_sms();
   if (grid > num_chunks) grid = num_chunks;
-  mt_sumsq_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, out, num_chunks);
+  if (grid > ws_floats) grid = ws_floats;          // fewer CTAs, same result up to fp32 partial rounding
+  RL_REQUIRE(num_chunks <= 0 || grid >= 1, RL_EINVAL, "rl_mt_sumsq: partials workspace is empty");
+  if (num_chunks <= 0) {
+    cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)stream);
+    return rl_check_launch("rl_mt_sumsq");
+  }
+  mt_sumsq_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const TensorEntry*)table, (const int2*)chunks, partials_ws,
+                                                                  num_chunks);
+  mt_sumsq_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials_ws, (int)grid, out);
   return rl_check_launch("rl_mt_sumsq");
 }
 

@@ -21,7 +21,15 @@ def allreduce_sum_(flat, group=None):
     """In-place sum over ranks of a flat gradient buffer (NCCL for CUDA tensors, gloo for the CPU tests)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 1
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if flat.is_cuda and dist.get_backend(group) != "nccl":
+        # gloo stages device tensors through host memory on its own streams: fence both sides so that the kernels that
+        # produced `flat` are done before it is read and the reduced values are in place before the optimizer runs
+        # (test-only path: two ranks sharing one GPU; NCCL is stream-ordered and needs none of this)
+        torch.cuda.synchronize()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.synchronize()
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return dist.get_world_size(group)
 
 

@@ -71,6 +71,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._chunks = torch.tensor(chunks, dtype=torch.int32).to(dev).contiguous()
         self._nchunks = len(chunks)
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        nws = int(lib().rl_workspace_bytes(b"mt_sumsq", ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0))) // 4
+        self._partials = torch.zeros(max(nws, 1), device=dev, dtype=torch.float32)
 
     @torch.no_grad()
     def step(self, closure=None, grad_div=None):
@@ -91,10 +93,10 @@ class FusedAdamW(torch.optim.Optimizer):
         bc2 = 1.0 - b2 ** self._step if self.correct_bias else 1.0
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         tab, ck = ctypes.c_void_p(self._table.data_ptr()), ctypes.c_void_p(self._chunks.data_ptr())
-        self._sumsq.zero_()
         ss = ctypes.c_void_p(self._sumsq.data_ptr())
         f = ctypes.c_float
-        check(lib().rl_mt_sumsq(tab, ck, ctypes.c_int64(self._nchunks), ss, st), "rl_mt_sumsq")
+        check(lib().rl_mt_sumsq(tab, ck, ctypes.c_int64(self._nchunks), ss, ctypes.c_void_p(self._partials.data_ptr()),
+                                ctypes.c_int64(self._partials.numel()), st), "rl_mt_sumsq")
         if self.device_hyper is not None:
             check(lib().rl_mt_adamw_dev(tab, ck, ctypes.c_int64(self._nchunks), ss, f(self.max_grad_norm or 0.0),
                                         ctypes.c_void_p(self.device_hyper.data_ptr()), f(b1), f(b2), f(g0["eps"]),

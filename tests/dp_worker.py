@@ -108,6 +108,11 @@ def main():
             res["sum_max_diff_rel"] = diff / max(scale, 1e-30)
             res["ranks_differ_before_sync"] = not torch.equal(pres[0], pres[-1])
         opt.step()
+        torch.cuda.synchronize()
+        chk = torch.stack([seen["post"].double().sum(), seen["post"].double().abs().sum(),
+                           torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad]).double().sum()])
+        res.setdefault("per_step_identical(grad_sum,grad_abs,param_sum)", []).append(
+            [bool(x) for x in (torch.stack(gather(chk, world))[0] == torch.stack(gather(chk, world))[-1])])
     model._post_backward = inner
     flat_params = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
     res["params_identical_after_3_eager_steps"] = all_equal_across_ranks(flat_params, world)

@@ -572,4 +572,5 @@ def test_gemm_many_short_tiles_per_cta():
             ops.gemm(a, b, out)
         ref = (a.float() @ b.float().t())
         err = (out.float() - ref).abs().max().item()
-        assert err <= (0.13 if odt is torch.bfloat16 else 1e-3) * max(1.0, K / 64) ** 0.5, (M, N, K, err)
+        tol = (2.0 ** -8 if odt is torch.bfloat16 else 1e-5) * ref.abs().max().item()      # one output rounding
+        assert err <= tol, (M, N, K, err, tol)
