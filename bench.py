@@ -258,7 +258,7 @@ def run_reference(args, rank, world):
     from baseline import ref_model
     if ref_model.available():
         steps, warm = args.steps, args.warmup
-        value, threads, sample, dt, sample_b = reference_cpu_rate(steps, warm, budget_s=170.0)
+        value, threads, sample, dt, sample_b = reference_cpu_rate(steps, warm, budget_s=args.ref_budget)
         kind = "reference"
     else:
         value, steps, threads, sample, dt = cpu_train_rate(budget_s=150.0, max_steps=args.steps, warmup=1)
@@ -602,6 +602,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager Python loop instead of the CUDA-graph step")
     ap.add_argument("--no-forward", action="store_true", help="skip the secondary forward-only (configs[1]) measurement")
+    ap.add_argument("--ref-budget", type=float, default=170.0,
+                    help="--impl reference: seconds the warm-up + timed CPU steps may take (sizes the bounded sample)")
     ap.add_argument("--no-incumbent", action="store_true", help="skip the reference-on-the-B200 (torch eager) comparator")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

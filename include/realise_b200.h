@@ -309,6 +309,14 @@ RL_API int rl_mt_sumsq(const void* table, const void* chunks, int64_t num_chunks
 RL_API int rl_mt_adamw(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,
                        float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2,
                        float grad_div, void* stream);
+/* Multi-tensor gather + cast in ONE launch: for every table entry {void* dst; const int32* map; int64 n; int32 dst_dtype;
+ * int32 pad} and i < n: dst[i] = cast(srcs[map[i] >> 24][map[i] & 0xFFFFFF]), or 0 where map[i] < 0.  srcs: device array of
+ * f32 pointers (<= 128 sources of < 2^24 elements each); chunks: device int2 {entry, 4096-element chunk}.  Used to
+ * re-derive the conv operand layouts (tap-major, transposed, parity-plane matrices) from the fp32 master weights after
+ * each optimizer step, and to scatter the tap-major weight-gradient GEMM outputs into the [cout, cin, kh, kw] gradients
+ * (src/char_cnn.py:15-29 weights). */
+RL_API int rl_mt_gather(const void* table, const void* chunks, int64_t num_chunks, const void* srcs, void* stream);
+
 /* out[r, :] = table[ids[r], :] for f32 rows of H (inference glyph cache: in eval mode CharResNet + its LayerNorm input
  * is a pure function of the token id, so a [vocab, 768] table replaces the CNN; src/models.py:829-838). */
 RL_API int rl_gather_rows_f32(const float* table, const int64_t* ids, float* out, int64_t rows, int64_t H, void* stream);

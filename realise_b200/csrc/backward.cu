@@ -565,6 +565,34 @@ mt_adamw_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ ch
   }
 }
 
+// ---- multi-tensor gather + cast: dst[i] = cast(srcs[map[i] >> 24][map[i] & 0xFFFFFF]) (0 where map[i] < 0) ----------
+// One launch re-derives every operand LAYOUT of the conv weights from the fp32 masters (tap-major / transposed /
+// parity-plane matrices, zero padded), and one more scatters the tap-major weight-gradient GEMM outputs back into the
+// parameters' [cout, cin, kh, kw] gradient layout — instead of ~100 cat / transpose / cast / index_put launches per step.
+struct GatherEntry {   // mirrored by realise_b200/train.py (ctypes) — keep in sync
+  void* dst;
+  const int* map;
+  long long n;
+  int dst_dtype;       // RL_DT_BF16 / RL_DT_F32 / RL_DT_F16
+  int pad;
+};
+
+__global__ void __launch_bounds__(256)
+mt_gather_kernel(const GatherEntry* __restrict__ tab, const int2* __restrict__ chunks, const float* const* __restrict__ srcs) {
+  const int2 ck = chunks[blockIdx.x];
+  const GatherEntry e = tab[ck.x];
+  const long long base = (long long)ck.y * OPT_CHUNK;
+  for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
+    const long long idx = base + i;
+    if (idx >= e.n) break;
+    const int m = __ldg(e.map + idx);
+    const float v = m < 0 ? 0.f : __ldg(srcs[m >> 24] + (m & 0xFFFFFF));
+    if (e.dst_dtype == RL_DT_F32) reinterpret_cast<float*>(e.dst)[idx] = v;
+    else if (e.dst_dtype == RL_DT_F16) reinterpret_cast<__half*>(e.dst)[idx] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(e.dst)[idx] = __float2bfloat16(v);
+  }
+}
+
 bool h_ok(int64_t H) { return H > 0 && H % 128 == 0 && H <= 128 * MAX_V4; }
 
 }  // namespace
@@ -720,6 +748,14 @@ extern "C" int rl_mt_adamw(const void* table, const void* chunks, int64_t num_ch
                                                                         max_norm, lr, beta1, beta2, eps, bias_corr1,
                                                                         bias_corr2, grad_div, nullptr);
   return rl_check_launch("rl_mt_adamw");
+}
+
+extern "C" int rl_mt_gather(const void* table, const void* chunks, int64_t num_chunks, const void* srcs, void* stream) {
+  RL_REQUIRE(table && chunks && srcs, RL_EINVAL, "rl_mt_gather: null pointer");
+  if (num_chunks <= 0) return 0;
+  mt_gather_kernel<<<(unsigned)num_chunks, 256, 0, (cudaStream_t)stream>>>((const GatherEntry*)table, (const int2*)chunks,
+                                                                         (const float* const*)srcs);
+  return rl_check_launch("rl_mt_gather");
 }
 
 extern "C" int rl_mt_adamw_dev(const void* table, const void* chunks, int64_t num_chunks, const float* sumsq, float max_norm,

@@ -528,6 +528,11 @@ def glyph_im2col(glyphs, ids, col1, colsc, n_img, C):
     _count()
 
 
+def mt_gather(table, chunks, n_chunks, srcs):
+    check(lib().rl_mt_gather(_ptr(table), _ptr(chunks), _c(n_chunks), _ptr(srcs), _stream()), "rl_mt_gather")
+    _count()
+
+
 def _wrap_untimed():
     """Give every wrapper without its own _Timed bracket one (work = 0), so a profiling pass sees the whole step."""
     import functools
@@ -542,7 +547,7 @@ def _wrap_untimed():
         return inner
 
     for name in ("colsum_bf16", "masked_ce_bwd", "embed_bwd", "gate_fuse_bwd", "gru_step_bwd", "gru_table_bwd",
-                 "gru_input_table", "bn_stats", "bn_finalize", "bn_apply", "bn_bwd", "im2col", "glyph_im2col"):
+                 "gru_input_table", "bn_stats", "bn_finalize", "bn_apply", "bn_bwd", "im2col", "glyph_im2col", "mt_gather"):
         globals()[name] = make(globals()[name], name)
 
 

@@ -11,6 +11,8 @@ tied classifier and the masked CE.  Forward tensors are fp16 (or bf16), gradient
 LayerNorm / softmax / BatchNorm statistics fp32.  Gradients of successive backward() calls ACCUMULATE until the
 optimizer step or zero_grad() consumes them (src/run.py:193-205, gradient_accumulation_steps).
 """
+import ctypes
+
 import torch
 
 from . import ops
@@ -40,6 +42,78 @@ class _StepFn(torch.autograd.Function):
         return (None, None) + (None,) * len(eng.params)
 
 
+class _GatherEntry(ctypes.Structure):
+    _fields_ = [("dst", ctypes.c_void_p), ("map", ctypes.c_void_p), ("n", ctypes.c_int64), ("dst_dtype", ctypes.c_int32),
+                ("pad", ctypes.c_int32)]
+
+
+class MultiGather:
+    """One rl_mt_gather launch: dst_k[i] = cast(src[map_k[i] >> 24][map_k[i] & 0xFFFFFF]) (0 where the map is negative)
+    for a fixed set of destination tensors.  Maps are built once on the host with ordinary torch indexing (the layout
+    code runs on tensors of element CODES instead of values), the launch replaces the per-step cat/transpose/cast chain."""
+    CHUNK = 4096
+
+    def __init__(self, device):
+        self.dev, self.srcs, self.entries, self._ready = device, [], [], False
+
+    def source(self, t):
+        """Register an f32 source tensor; returns an int32 tensor of its element codes, shaped like t."""
+        assert t.dtype is F32 and t.is_contiguous() and t.numel() < (1 << 24) and len(self.srcs) < 128
+        self.srcs.append(t)
+        return (torch.arange(t.numel(), dtype=torch.int32) + ((len(self.srcs) - 1) << 24)).view(t.shape)
+
+    def add(self, dst, codes):
+        assert dst.is_contiguous() and dst.numel() == codes.numel()
+        self.entries.append((dst, codes.reshape(-1).to(torch.int32).contiguous().to(self.dev)))
+
+    def run(self):
+        if not self.entries:
+            return
+        if not self._ready:
+            arr = (_GatherEntry * len(self.entries))()
+            chunks = []
+            for i, (dst, m) in enumerate(self.entries):
+                arr[i] = _GatherEntry(dst.data_ptr(), m.data_ptr(), dst.numel(), ops._DT[dst.dtype], 0)
+                chunks += [(i, c) for c in range((dst.numel() + self.CHUNK - 1) // self.CHUNK)]
+            self._table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+            self._chunks = torch.tensor(chunks, dtype=torch.int32).to(self.dev).contiguous()
+            self._srcs = torch.tensor([t.data_ptr() for t in self.srcs], dtype=torch.int64).to(self.dev)
+            self._ready = True
+        ops.mt_gather(self._table, self._chunks, self._chunks.shape[0], self._srcs)
+
+
+class ZeroPool:
+    """Scratch that must start at zero (split-K accumulators, BatchNorm sums, ...) comes out of ONE buffer cleared by ONE
+    memset per step instead of a fill kernel per tensor.  The first step of a shape records the sizes (and uses
+    torch.zeros); later steps hand out 256-byte aligned slices."""
+
+    def __init__(self, device):
+        self.dev, self.sizes, self.buf, self.key, self.off, self.recording = device, {}, None, None, 0, True
+
+    def begin(self, key):
+        self.key, self.off = key, 0
+        need = self.sizes.get(key)
+        self.recording = need is None
+        if not self.recording:
+            if self.buf is None or self.buf.numel() < need:
+                self.buf = torch.empty(need, device=self.dev, dtype=F32)
+            self.buf[:need].zero_()
+
+    def get(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        start, self.off = self.off, self.off + (n + 63) // 64 * 64
+        if self.recording:
+            self.sizes[self.key] = self.off
+            return torch.zeros(shape, device=self.dev, dtype=F32)
+        if self.off > self.sizes[self.key]:      # a different allocation sequence than the recorded one: re-record
+            self.recording = True
+            self.sizes[self.key] = self.off
+            return torch.zeros(shape, device=self.dev, dtype=F32)
+        return self.buf[start:start + n].view(shape)
+
+
 class TrainEngine:
     def __init__(self, model):
         self.m = model
@@ -50,7 +124,8 @@ class TrainEngine:
         self._pending = False         # gradients of an earlier backward() are still waiting for the optimizer
         self._accum = None
         self.debug = None             # tests set a dict to receive intermediate gradients
-        self._tap_idx = {}
+        self._res = None              # conv operand layouts + their refresh launch, built on the first training forward
+        self.zpool = ZeroPool(model.classifier.bias.device)
         self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
         # trainable parameters in a fixed order
@@ -163,8 +238,10 @@ class TrainEngine:
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _new(self, shape, dtype, zero=False):
-        dev = self.m.classifier.bias.device
-        return torch.zeros(shape, device=dev, dtype=dtype) if zero else torch.empty(shape, device=dev, dtype=dtype)
+        if zero:
+            assert dtype is F32
+            return self.zpool.get(tuple(shape))
+        return torch.empty(shape, device=self.m.classifier.bias.device, dtype=dtype)
 
     def _grad(self, p, zero=False):
         """Persistent fp32 gradient view of parameter p inside the flat buffer."""
@@ -232,64 +309,122 @@ class TrainEngine:
     def _s1_taps(S):
         return [(kw - 1, kh - 1, 0, kh, kw) for kh in range(3) for kw in range(3) if not (S == 1 and (kh != 1 or kw != 1))]
 
-    def _resnet_weights(self):
-        """bf16 operand layouts of the current conv weights (re-derived every step: pure layout + cast)."""
+    def _conv_layouts(self, w1, w2, wsc, b, cin, cout, S, pad):
+        """Operand layouts of one BasicBlock's conv weights as pure indexing of (w1 [cout,cin,3,3], w2 [cout,cout,3,3],
+        wsc [cout,cin]) — run once on tensors of element CODES (pad = -1 marks structural zeros) to obtain gather maps."""
+        def full(*shape):
+            return torch.full(shape, pad, dtype=w1.dtype)
+        e = {}
+        t2 = self._s1_taps(S)
+        e["w2f"] = torch.cat([w2[:, :, kh, kw] for (_, _, _, kh, kw) in t2], 1)
+        # data gradient of conv2: da1[h, w] = sum_taps dc2[h - dh, w - dw] W2[:, :, kh, kw]^T
+        e["w2t"] = torch.cat([w2[:, :, kh, kw].t() for (_, _, _, kh, kw) in t2], 1)
+        if b == 1:
+            w1g = full(cout, 32)
+            w1g[:, :9 * cin] = w1.reshape(cout, 9 * cin)
+            # the 1x1 stride-2 shortcut samples the centre tap of conv1's patch: same im2col matrix, weights on
+            # columns c*9 + 4 only (a K = 8 operand would make TMA fetch 16-byte rows)
+            wsg = full(cout, 32)
+            wsg[:, 4:9 * cin:9] = wsc
+            e["w1g"], e["wscg"] = w1g, wsg
+        else:
+            t1 = self._s2_taps(S)
+            e["w1f"] = torch.cat([w1[:, :, kh, kw] for (_, _, _, kh, kw) in t1], 1)
+            e["wscf"] = wsc.clone()
+            if S == 1:
+                # dx_in [N, 4*cin] = [dc1 | dcs] . Wbig^T, Wbig[p*cin+ci] = [W1[:, ci, 1+ph, 1+pw] | (p == 0) Wsc[:, ci]]
+                rows = []
+                for pl in range(4):
+                    a = w1[:, :, 1 + pl // 2, 1 + pl % 2].t()
+                    bsc = wsc.t() if pl == 0 else full(cin, cout)
+                    rows.append(torch.cat([a, bsc], 1))
+                e["wbig"] = torch.cat(rows, 0)                                        # [4*cin, 2*cout]
+            else:
+                for pl in range(4):
+                    ph, pw = pl // 2, pl % 2
+                    khs, kws = ([1] if ph == 0 else [0, 2]), ([1] if pw == 0 else [0, 2])
+                    cols = [w1[:, :, kh, kw].t() for kh in khs for kw in kws]         # [cin, cout] each
+                    if pl == 0:
+                        cols.append(wsc.t())                                          # the shortcut rides on tap (0, 0)
+                    e[f"dgrad{pl}"] = torch.cat(cols, 1)
+        return e
+
+    def _resnet_setup(self):
+        """Built once per engine: per block the static geometry (taps), persistent bf16 operand buffers in every layout
+        the forward / backward GEMMs read, ONE MultiGather that refreshes them all from the fp32 master weights, the
+        persistent tap-major weight-gradient accumulators and ONE MultiGather that scatters them into the parameters'
+        [cout, cin, kh, kw] gradients."""
         m, c = self.m, self.m.config
-        W = []
+        dev = m.classifier.bias.device
+        wg, gg = MultiGather(dev), MultiGather(dev)
+        blocks, wtmp_sizes = [], []
         cin = c.num_fonts
         for b in range(1, 6):
             blk = getattr(m.resnet, f"res_block{b}")
             conv1, bn1, _, conv2, bn2 = blk.residual_function
             convs, bns = blk.shortcut
             cout, S = self.RES_CH[b], 32 >> b
-            w1, w2, wsc = conv1.weight.detach(), conv2.weight.detach(), convs.weight.detach().reshape(cout, cin)
             e = {"S": S, "cin": cin, "cout": cout, "conv1": conv1, "conv2": conv2, "convs": convs, "bn1": bn1, "bn2": bn2,
-                 "bns": bns}
-            t2 = self._s1_taps(S)
-            e["taps2"] = t2
-            e["w2f"] = torch.cat([w2[:, :, kh, kw] for (_, _, _, kh, kw) in t2], 1).bfloat16().contiguous()
-            # data gradient of conv2: da1[h, w] = sum_taps dc2[h - dh, w - dw] W2[:, :, kh, kw]^T
-            e["w2t"] = torch.cat([w2[:, :, kh, kw].t() for (_, _, _, kh, kw) in t2], 1).bfloat16().contiguous()
-            e["taps2t"] = [(-dw, -dh, 0) for (dw, dh, _, _, _) in t2]
-            if b == 1:
-                w1g = torch.zeros(cout, 32, device=w1.device)
-                w1g[:, :9 * cin] = w1.reshape(cout, 9 * cin)
-                # the 1x1 stride-2 shortcut samples the centre tap of conv1's patch: same im2col matrix, weights on
-                # columns c*9 + 4 only (a K = 8 operand would make TMA fetch 16-byte rows)
-                wsg = torch.zeros(cout, 32, device=w1.device)
-                wsg[:, 4:9 * cin:9] = wsc
-                e["w1g"], e["wscg"] = w1g.bfloat16().contiguous(), wsg.bfloat16().contiguous()
-            else:
-                t1 = self._s2_taps(S)
-                e["taps1"] = t1
-                e["w1f"] = torch.cat([w1[:, :, kh, kw] for (_, _, _, kh, kw) in t1], 1).bfloat16().contiguous()
-                e["wscf"] = wsc.bfloat16().contiguous()
-                if S == 1:
-                    # dx_in [N, 4*cin] = [dc1 | dcs] . Wbig^T, Wbig[p*cin+ci] = [W1[:, ci, 1+ph, 1+pw] | (p == 0) Wsc[:, ci]]
-                    rows = []
-                    for pl in range(4):
-                        a = w1[:, :, 1 + pl // 2, 1 + pl % 2].t()
-                        bsc = wsc.t() if pl == 0 else torch.zeros_like(wsc.t())
-                        rows.append(torch.cat([a, bsc], 1))
-                    e["wbig"] = torch.cat(rows, 0).bfloat16().contiguous()          # [4*cin, 2*cout]
-                else:
-                    e["dgrad"] = []
+                 "bns": bns, "taps2": self._s1_taps(S)}
+            e["taps2t"] = [(-dw, -dh, 0) for (dw, dh, _, _, _) in e["taps2"]]
+            if b > 1:
+                e["taps1"] = self._s2_taps(S)
+                if S > 1:
+                    e["dgrad_taps"] = []
                     for pl in range(4):
                         ph, pw = pl // 2, pl % 2
                         khs, kws = ([1] if ph == 0 else [0, 2]), ([1] if pw == 0 else [0, 2])
-                        taps, cols = [], []
-                        for kh in khs:
-                            for kw in kws:
-                                dh = -1 if kh == 0 else 0
-                                dw = -1 if kw == 0 else 0
-                                taps.append((-dw, -dh, 0))
-                                cols.append(w1[:, :, kh, kw].t())                    # [cin, cout]
-                        if pl == 0:
-                            cols.append(wsc.t())                                     # the shortcut rides on tap (0, 0)
-                        e["dgrad"].append((taps, torch.cat(cols, 1).bfloat16().contiguous()))
-            W.append(e)
+                        e["dgrad_taps"].append([(-(-1 if kw == 0 else 0), -(-1 if kh == 0 else 0), 0) for kh in khs for kw in kws])
+            for conv in (conv1, conv2, convs):
+                assert conv.weight.is_contiguous() and conv.weight.dtype is F32
+            codes = self._conv_layouts(wg.source(conv1.weight.detach()), wg.source(conv2.weight.detach()),
+                                       wg.source(convs.weight.detach()).view(cout, cin), b, cin, cout, S, pad=-1)
+            for k, code in codes.items():
+                e[k] = torch.empty(code.shape, device=dev, dtype=BF16)
+                wg.add(e[k], code)
+            if b > 1 and S > 1:
+                e["dgrad"] = [(e["dgrad_taps"][pl], e[f"dgrad{pl}"]) for pl in range(4)]
+            # tap-major weight-gradient accumulators (f32, split-K adds into them) and their scatter into .grad layout
+            def wtmp(rows, cols):
+                wtmp_sizes.append((rows, cols))
+                return len(wtmp_sizes) - 1
+            e["tmp2"] = wtmp(cout, len(e["taps2"]) * cout)
+            e["tmp1"] = wtmp(2 * cout, 32) if b == 1 else wtmp(cout, len(e["taps1"]) * cin)
+            blocks.append(e)
             cin = cout
-        return W
+        total = sum((r * k + 63) // 64 * 64 for r, k in wtmp_sizes)
+        self._wtmp = torch.zeros(total, device=dev, dtype=F32)
+        views, off = [], 0
+        for r, k in wtmp_sizes:
+            views.append(self._wtmp[off:off + r * k].view(r, k))
+            off += (r * k + 63) // 64 * 64
+        for e in blocks:
+            cin, cout = e["cin"], e["cout"]
+            t2v, t1v = views[e["tmp2"]], views[e["tmp1"]]
+            e["tmp2"], e["tmp1"] = t2v, t1v
+            # conv2: tmp [cout, T2*cout] tap-major -> grad [cout, cout, 3, 3]
+            code2 = gg.source(t2v).view(cout, len(e["taps2"]), cout).permute(0, 2, 1)            # [co, ci, t]
+            m2 = torch.full((cout, cout, 9), -1, dtype=torch.int32)
+            m2[:, :, [kh * 3 + kw for (_, _, _, kh, kw) in e["taps2"]]] = code2
+            gg.add(self._grad(e["conv2"].weight), m2)
+            code1 = gg.source(t1v)
+            if e["S"] == 16:      # block 1: rows 0..cout-1 = dW1 over the 32-wide patch, rows cout.. = dWsc on the centre taps
+                gg.add(self._grad(e["conv1"].weight), code1[:cout, :9 * cin])
+                gg.add(self._grad(e["convs"].weight), code1[cout:, 4:9 * cin:9])
+            else:
+                t1 = e["taps1"]
+                c1 = code1.view(cout, len(t1), cin).permute(0, 2, 1)
+                m1 = torch.full((cout, cin, 9), -1, dtype=torch.int32)
+                m1[:, :, [kh * 3 + kw for (_, _, _, kh, kw) in t1]] = c1
+                gg.add(self._grad(e["conv1"].weight), m1)
+        self._res = {"blocks": blocks, "wgather": wg, "ggather": gg}
+
+    def _resnet_weights(self):
+        """bf16 operand layouts of the CURRENT conv weights: one gather launch over every layout of every conv."""
+        if self._res is None:
+            self._resnet_setup()
+        self._res["wgather"].run()
+        return self._res["blocks"]
 
     def _bn_train(self, raw, bn, M):
         """Batch statistics of a raw conv output -> (scale, shift, mean, rstd); updates the running stats."""
@@ -349,27 +484,18 @@ class TrainEngine:
         sv["res"] = blocks
         return x   # f32 [N, 768]
 
-    def _conv_wgrad(self, dy, col, weight, taps, cout, cin, conv=None):
-        """dW[co, t, ci] = dy^T col (split-K GEMM, tap-major) -> the parameter's [co, ci, kh, kw] gradient view.
+    def _conv_wgrad(self, dy, col, tmp, taps, conv=None):
+        """tmp[co, t*cin + ci] += dy^T col (split-K GEMM, tap-major accumulator; scattered into the parameter's
+        [co, ci, kh, kw] gradient by the engine's gradient MultiGather at the end of the CNN backward).
         conv = (x, nimg, S, planes): the im2col matrix is implicit (gathered by TMA inside the GEMM), col is None."""
-        T = len(taps)
-        tmp = self._new((cout, T * cin), F32, zero=True)
         if conv is not None:
             x, nimg, S, planes = conv
             ops.conv_wgrad(dy, x, tmp, nimg=nimg, H=S, W=S, planes=planes, taps=[t[:3] for t in taps])
         else:
             ops.gemm(dy, col, tmp, a_t=True, b_t=True, split_k=-1)
-        gw = self._grad(weight).view(cout, cin, 9)
-        if T == 9:
-            gw.copy_(tmp.view(cout, 9, cin).permute(0, 2, 1))
-        else:
-            key = tuple(kh * 3 + kw for (_, _, _, kh, kw) in taps)
-            idx = self._tap_idx.get(key)
-            if idx is None:   # built once: a host->device copy here would synchronise every step (and break graph capture)
-                idx = self._tap_idx[key] = torch.tensor(key, device=tmp.device)
-            gw[:, :, idx] = tmp.view(cout, T, cin).permute(0, 2, 1)
 
     def _resnet_bwd(self, sv, dout, N):
+        self._wtmp.zero_()                                   # every tap-major accumulator at once
         for bi in range(4, -1, -1):
             s = sv["res"][bi]
             if self.debug is not None:
@@ -391,34 +517,31 @@ class TrainEngine:
             # conv2 weight gradient (reference layout [cout, cin, kh, kw]) and data gradient
             T2 = len(e["taps2"])
             if T2 == 9:
-                self._conv_wgrad(dc2, None, e["conv2"].weight, e["taps2"], cout, cout, conv=(s["a1"], N, S, 1))
+                self._conv_wgrad(dc2, None, e["tmp2"], e["taps2"], conv=(s["a1"], N, S, 1))
                 da1 = self._new((M, cout), BF16)
                 ops.conv_gemm(dc2.view(N, 1, S, S, cout), e["w2t"], da1, nimg=N, H=S, W=S, planes=1, taps=e["taps2t"])
             else:  # 1x1 map: only the centre tap touched data
-                self._conv_wgrad(dc2, s["a1"], e["conv2"].weight, e["taps2"], cout, cout)
+                self._conv_wgrad(dc2, s["a1"], e["tmp2"], e["taps2"])
                 da1 = self._new((M, cout), BF16)
                 ops.gemm(dc2, e["w2f"], da1, b_t=True)
             # a1 = relu(bn1(c1))
             ops.bn_bwd(da1, s["a1"], s["c1"], s["bn1"][2], s["bn1"][3], e["bn1"].weight.detach(), g(e["bn1"].bias),
                        g(e["bn1"].weight), dcat[:, :cout])
             dc1, dcs = dcat[:, :cout], dcat[:, cout:]
-            gw1, gws = g(e["conv1"].weight), g(e["convs"].weight)
+            gws = g(e["convs"].weight)
             if bi == 0:
                 # [dc1 | dcs]^T col1 in ONE split-K GEMM (a full 128-row tile): rows 0..63 = dW1, rows 64..127 = dWsc
-                tmp = self._new((2 * cout, 32), F32, zero=True)
-                ops.gemm(dcat, s["col1"], tmp, a_t=True, b_t=True, split_k=-1)
-                gw1.view(cout, 9 * cin).copy_(tmp[:cout, :9 * cin])
-                gws.view(cout, cin).copy_(tmp[cout:, 4:9 * cin:9])
-                return
+                ops.gemm(dcat, s["col1"], e["tmp1"], a_t=True, b_t=True, split_k=-1)
+                break
             x_in = s["x_in"]
             t1 = e["taps1"]
             if S >= 2:   # parity-split block input gathered inside the GEMM (implicit im2col)
-                self._conv_wgrad(dc1, None, e["conv1"].weight, t1, cout, cin, conv=(x_in, N, S, 4))
+                self._conv_wgrad(dc1, None, e["tmp1"], t1, conv=(x_in, N, S, 4))
                 ops.conv_wgrad(dcs, x_in, gws.view(cout, cin), nimg=N, H=S, W=S, planes=4, taps=[(0, 0, 0)])
             else:        # 1x1 map: the 4 parity planes of the input are 4 column blocks of one row
                 col = self._new((M, cin * len(t1)), BF16)
                 ops.im2col(x_in, col, N, cin, S, S, 4, [t[:3] for t in t1])
-                self._conv_wgrad(dc1, col, e["conv1"].weight, t1, cout, cin)
+                self._conv_wgrad(dc1, col, e["tmp1"], t1)
                 colsc = self._new((M, cin), BF16)
                 ops.im2col(x_in, colsc, N, cin, S, S, 4, [(0, 0, 0)])
                 ops.gemm(dcs, colsc, gws.view(cout, cin), a_t=True, b_t=True, split_k=-1)
@@ -433,6 +556,7 @@ class TrainEngine:
                     ops.conv_gemm(dview, wp, dx, nimg=N, H=S, W=S, planes=1, taps=taps, out_remap=2, remap_plane=pl,
                                   c_use=cu)
             dout = dx
+        self._res["ggather"].run()                           # tap-major accumulators -> [cout, cin, kh, kw] gradients
 
     # ---- pinyin GRU (train): every step's state is kept for the backward-through-time ---------------
     def _gru_fwd(self, P, pho_idx, lens_dev, N, sv):
@@ -492,7 +616,8 @@ class TrainEngine:
         N, H, V = B * L, c.hidden_size, c.vocab_size
         if L > 128:
             raise NotImplementedError("attention backward kernel supports seq_len <= 128")
-        self.act16 = P["half"]       # forward tensors: fp16 (default) or bf16; gradients are always bf16
+        self.act16 = P["half"]       # 16-bit format of activations and gradients (bf16 in training)
+        self.zpool.begin((B, L, inp["pho_idx"].shape[1] if "pho_idx" in inp else 0))
         self.step_seed = self.seed
         self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         sv = {"B": B, "L": L, "mask": mask, "inp": inp, "seed": self.step_seed}
@@ -574,12 +699,11 @@ class TrainEngine:
         # embeddings: x0 = LN(e),  e = word[ids] (or inputs_embeds) + pos + type0
         e = mod.embeddings
         de = self._new((N, H), F32)
-        dtype_sum = self._new((H,), F32, zero=True)
-        ops.layernorm_bwd(dx, sv["e_pre"], P["ln_w"], None, de, None, self._grad(e.LayerNorm.weight, True),
-                          self._grad(e.LayerNorm.bias, True), dtype_sum, c.layer_norm_eps, drop_p=hp, drop_seed=seed,
-                          site_in=self.site(name, 0, 9) if hp > 0 else 0)
+        # every token has type 0 (modeling_bert.py:183): the column sum of de IS row 0 of the token-type gradient
         gtype = self._grad(e.token_type_embeddings.weight, True)
-        gtype[0].copy_(dtype_sum)
+        ops.layernorm_bwd(dx, sv["e_pre"], P["ln_w"], None, de, None, self._grad(e.LayerNorm.weight, True),
+                          self._grad(e.LayerNorm.bias, True), gtype[0], c.layer_norm_eps, drop_p=hp, drop_seed=seed,
+                          site_in=self.site(name, 0, 9) if hp > 0 else 0)
         dpos = self._grad(e.position_embeddings.weight, True)
         if sv["from_embeds"]:
             ops.embed_bwd(de, None, None, dpos, N, L, H, sv["pos_mode"])

@@ -1,4 +1,4 @@
-"""CPU: the reference arm of bench.py (the oracle's train step on the host cores) prints ONE JSON line on stdout with
+"""CPU: the reference arm of bench.py (the reference's own train step on the host cores) prints ONE JSON line on stdout with
 the keys the driver reads; bench.py's module-level constants name the BASELINE metric."""
 import json
 import os
@@ -10,7 +10,8 @@ from conftest import ROOT
 
 def test_reference_arm_prints_one_json_line():
     env = dict(os.environ, OMP_NUM_THREADS="8")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-budget", "12"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
@@ -20,5 +21,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
     assert "fwd+bwd" in d["metric"] and d["config"]["seq_len"] == 128 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "train step" in cb["sample"]
+    # "reference" = the unmodified reference from baseline/_ref (installed by baseline/install_ref.py), "port" = the oracle
+    # restatement when that install is absent
+    want = "reference" if os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "src", "models.py")) else "port"
+    assert cb["kind"] == want and cb["cores"] >= 1 and cb["value"] == d["value"] and "train step" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
