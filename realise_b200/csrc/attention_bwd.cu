@@ -259,6 +259,242 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 constexpr int ATT_BWD_SMEM = 7 * T16K + 128 * 4 + 3 * 8 + 16;   // 115,240 B: two CTAs per SM
 
+// ------------------------------------------------------------------------------------------------------------------
+// 128 < seq_len <= 256: the same algebra blocked 128 x 128.  One CTA per (sentence, head) keeps both q tiles and both kv
+// tiles of Q / K / V / dO resident (8 x 16 KB) and walks the four (kv tile j, q tile i) blocks:
+//     S_ij = Q_i K_j^T, dP_ij = dO_i V_j^T  ->  P_ij, dS_ij (smem)  ->  dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j
+// dQ_0 / dQ_1 accumulate over j, dK_j / dV_j over i — all in TMEM (512 columns, nothing aliased); the saved logsumexp of
+// the forward is required (P = exp2(s - lse) in one pass).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_bwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const AttBwdParams p) {
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;   // dQ_i at COL_DQ + 64 i
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((rl::smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* sQ = smem;                 // [2][128 x 64]
+  uint8_t* sK = sQ + 2 * T16K;
+  uint8_t* sV = sK + 2 * T16K;
+  uint8_t* sDO = sV + 2 * T16K;
+  uint8_t* sP = sDO + 2 * T16K;       // P block: two [128 q x 64 kv] tiles
+  uint8_t* sDS = sP + 2 * T16K;       // dS block
+  float* s_mask = reinterpret_cast<float*>(sDS + 2 * T16K);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 256);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bar_ld = &bars[0];
+  uint64_t* bar_s = &bars[1];
+  uint64_t* bar_o = &bars[2];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int L = p.L;
+  const int row0 = b * L;
+
+  if (tid == 0) {
+    rl::tma_prefetch_desc(&tmQ);
+    rl::tma_prefetch_desc(&tmDO);
+    rl::mbar_init(bar_ld, 1);
+    rl::mbar_init(bar_s, 1);
+    rl::mbar_init(bar_o, 1);
+    rl::fence_barrier_init();
+  }
+  if (warp == 0) rl::tmem_alloc(tmem_ptr, 512);
+  for (int j = tid; j < 256; j += ATT_THREADS) {
+    float m = -INFINITY;
+    if (j < L) m = (1.0f - (float)p.mask[(long long)b * L + j]) * -10000.0f * 1.4426950408889634f;
+    s_mask[j] = m;
+  }
+  for (int i = tid; i < 4 * T16K / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  rl::fence_proxy_async();
+  rl::tc_fence_before();
+  __syncthreads();
+  rl::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (tid == 0) {
+    rl::mbar_expect_tx(bar_ld, 8 * T16K);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {   // rows beyond the tensor read zeros; rows of the next sentence are masked out below
+      rl::tma_load_2d(sQ + t * T16K, &tmQ, bar_ld, head * HEAD_DIM, row0 + t * 128);
+      rl::tma_load_2d(sK + t * T16K, &tmQ, bar_ld, p.H + head * HEAD_DIM, row0 + t * 128);
+      rl::tma_load_2d(sV + t * T16K, &tmQ, bar_ld, 2 * p.H + head * HEAD_DIM, row0 + t * 128);
+      rl::tma_load_2d(sDO + t * T16K, &tmDO, bar_ld, head * HEAD_DIM, row0 + t * 128);
+    }
+  }
+  // per-row constants of both q tiles: delta = rowsum(dO o O), lse
+  float delta[2], lse[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = i * 128 + tid;
+    delta[i] = 0.f;
+    lse[i] = INFINITY;               // rows beyond the sentence: P = 0
+    if (q < L) {
+      lse[i] = p.lse[((long long)b * p.heads + head) * L + q];
+      const uint4* o = reinterpret_cast<const uint4*>(p.ctx + (long long)(row0 + q) * p.H + head * HEAD_DIM);
+      const uint4* g = reinterpret_cast<const uint4*>(p.dctx + (long long)(row0 + q) * p.H + head * HEAD_DIM);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 a = o[k], c = g[k];
+        delta[i] += rl::half_lo(a.x, p.f16) * rl::half_lo(c.x, p.f16) + rl::half_hi(a.x, p.f16) * rl::half_hi(c.x, p.f16) +
+                    rl::half_lo(a.y, p.f16) * rl::half_lo(c.y, p.f16) + rl::half_hi(a.y, p.f16) * rl::half_hi(c.y, p.f16) +
+                    rl::half_lo(a.z, p.f16) * rl::half_lo(c.z, p.f16) + rl::half_hi(a.z, p.f16) * rl::half_hi(c.z, p.f16) +
+                    rl::half_lo(a.w, p.f16) * rl::half_lo(c.w, p.f16) + rl::half_hi(a.w, p.f16) * rl::half_hi(c.w, p.f16);
+      }
+    }
+  }
+  rl::DropSpec dsp = p.drop;
+  rl::drop_resolve(dsp);
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t qa = rl::smem_u32(sQ), ka = rl::smem_u32(sK), va = rl::smem_u32(sV), da = rl::smem_u32(sDO),
+                 pa = rl::smem_u32(sP), dsa = rl::smem_u32(sDS);
+  const uint32_t idesc_s = rl::make_idesc_h(128, 128, 0, 0, p.f16, p.f16);
+  const uint32_t idesc_t = rl::make_idesc_h(128, HEAD_DIM, 1, 1, p.f16, p.f16);
+  const uint32_t idesc_q = rl::make_idesc_h(128, HEAD_DIM, 0, 1, p.f16, p.f16);
+  uint32_t ph_s = 0, ph_o = 0;
+  const int r = tid;
+  int blk = 0;
+  for (int j = 0; j < 2; ++j) {
+    for (int i = 0; i < 2; ++i, ++blk) {
+      if (tid == 0) {
+        if (blk == 0) {
+          rl::mbar_wait(bar_ld, 0);
+        }
+        rl::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S = Q_i K_j^T
+          rl::tc_mma_f16(tmem_base + COL_S, rl::make_smem_desc_sw128(qa + i * T16K + k * 32, 16, 1024),
+                         rl::make_smem_desc_sw128(ka + j * T16K + k * 32, 16, 1024), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP = dO_i V_j^T
+          rl::tc_mma_f16(tmem_base + COL_DP, rl::make_smem_desc_sw128(da + i * T16K + k * 32, 16, 1024),
+                         rl::make_smem_desc_sw128(va + j * T16K + k * 32, 16, 1024), idesc_s, k != 0);
+        rl::tc_commit(bar_s);
+      }
+      rl::mbar_wait(bar_s, ph_s);
+      ph_s ^= 1;
+      rl::tc_fence_after();
+      const int q = i * 128 + r;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32], w[32];
+        rl::tmem_ld_32x32(t_row + COL_S + c * 32, v);
+        rl::tmem_ld_32x32(t_row + COL_DP + c * 32, w);
+        rl::tmem_ld_wait();
+        float pr[32], ds[32];
+        unsigned int keep_bits = 0xFFFFFFFFu;
+        const int col0 = j * 128 + c * 32;
+        if (dsp.thresh && q < L)
+          keep_bits = rl::drop_bits32(dsp, (((unsigned long long)b * p.heads + head) * L + q) * L + col0);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int col = col0 + jj;
+          const float sc = col < L ? fmaf(__uint_as_float(v[jj]), p.scale_log2, s_mask[col]) : -INFINITY;
+          pr[jj] = rl::ex2(sc - lse[i]);
+          float dp = __uint_as_float(w[jj]);
+          if (p.drop.thresh) {
+            const bool keep = (keep_bits >> jj) & 1u;
+            dp = keep ? dp * p.drop.scale : 0.f;
+            ds[jj] = col < L ? pr[jj] * (dp - delta[i]) : 0.f;
+            pr[jj] = keep ? pr[jj] * p.drop.scale : 0.f;
+          } else {
+            ds[jj] = col < L ? pr[jj] * (dp - delta[i]) : 0.f;
+          }
+        }
+        uint8_t* tp = sP + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
+        uint8_t* td = sDS + (c >> 1) * T16K + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int piece = (((c & 1) * 4 + g) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(tp + piece) =
+              make_uint4(rl::pack_h(pr[8 * g], pr[8 * g + 1], p.f16), rl::pack_h(pr[8 * g + 2], pr[8 * g + 3], p.f16),
+                         rl::pack_h(pr[8 * g + 4], pr[8 * g + 5], p.f16), rl::pack_h(pr[8 * g + 6], pr[8 * g + 7], p.f16));
+          *reinterpret_cast<uint4*>(td + piece) =
+              make_uint4(rl::pack_h(ds[8 * g], ds[8 * g + 1], p.f16), rl::pack_h(ds[8 * g + 2], ds[8 * g + 3], p.f16),
+                         rl::pack_h(ds[8 * g + 4], ds[8 * g + 5], p.f16), rl::pack_h(ds[8 * g + 6], ds[8 * g + 7], p.f16));
+        }
+      }
+      rl::fence_proxy_async();
+      rl::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        rl::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV_j[kv, d] (+)= sum_q P[q, kv] dO_i[q, d]
+          rl::tc_mma_f16(tmem_base + COL_DV, rl::make_smem_desc_sw128(pa + k * 2048, T16K, 1024),
+                         rl::make_smem_desc_sw128(da + i * T16K + k * 2048, 1024, 1024), idesc_t, (i != 0 || k != 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK_j[kv, d] (+)= sum_q dS[q, kv] Q_i[q, d]
+          rl::tc_mma_f16(tmem_base + COL_DK, rl::make_smem_desc_sw128(dsa + k * 2048, T16K, 1024),
+                         rl::make_smem_desc_sw128(qa + i * T16K + k * 2048, 1024, 1024), idesc_t, (i != 0 || k != 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_i[q, d] (+)= sum_kv dS[q, kv] K_j[kv, d]
+          rl::tc_mma_f16(tmem_base + COL_DQ + i * 64, rl::make_smem_desc_sw128(dsa + (k >> 2) * T16K + (k & 3) * 32, 16, 1024),
+                         rl::make_smem_desc_sw128(ka + j * T16K + k * 2048, 1024, 1024), idesc_q, (j != 0 || k != 0));
+        rl::tc_commit(bar_o);
+      }
+      // the next block overwrites S / dP (TMEM) and the P / dS tiles (smem): its MMAs and stores wait for this commit
+      rl::mbar_wait(bar_o, ph_o);
+      ph_o ^= 1;
+      rl::tc_fence_after();
+    }
+    // dK_j, dV_j complete: rows kv = j*128 + r
+    {
+      const int kv = j * 128 + r;
+      unsigned short* base = reinterpret_cast<unsigned short*>(p.dqkv) + (long long)(row0 + kv) * 3 * p.H + head * HEAD_DIM;
+      const uint32_t cols[2] = {COL_DK, COL_DV};
+      const float scl[2] = {0.125f, 1.0f};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          rl::tmem_ld_32x32(t_row + cols[t] + c * 32, v);
+          rl::tmem_ld_wait();
+          if (kv < L) {
+            uint4* o = reinterpret_cast<uint4*>(base + (t + 1) * p.H + c * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              o[g] = make_uint4(rl::pack_h(__uint_as_float(v[8 * g]) * scl[t], __uint_as_float(v[8 * g + 1]) * scl[t], p.f16),
+                                rl::pack_h(__uint_as_float(v[8 * g + 2]) * scl[t], __uint_as_float(v[8 * g + 3]) * scl[t], p.f16),
+                                rl::pack_h(__uint_as_float(v[8 * g + 4]) * scl[t], __uint_as_float(v[8 * g + 5]) * scl[t], p.f16),
+                                rl::pack_h(__uint_as_float(v[8 * g + 6]) * scl[t], __uint_as_float(v[8 * g + 7]) * scl[t], p.f16));
+          }
+        }
+      }
+      rl::tc_fence_before();
+      __syncthreads();   // every thread has read dK_j / dV_j before the next j's MMAs overwrite them
+      rl::tc_fence_after();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = i * 128 + r;
+    unsigned short* base = reinterpret_cast<unsigned short*>(p.dqkv) + (long long)(row0 + q) * 3 * p.H + head * HEAD_DIM;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      rl::tmem_ld_32x32(t_row + COL_DQ + i * 64 + c * 32, v);
+      rl::tmem_ld_wait();
+      if (q < L) {
+        uint4* o = reinterpret_cast<uint4*>(base + c * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          o[g] = make_uint4(rl::pack_h(__uint_as_float(v[8 * g]) * 0.125f, __uint_as_float(v[8 * g + 1]) * 0.125f, p.f16),
+                            rl::pack_h(__uint_as_float(v[8 * g + 2]) * 0.125f, __uint_as_float(v[8 * g + 3]) * 0.125f, p.f16),
+                            rl::pack_h(__uint_as_float(v[8 * g + 4]) * 0.125f, __uint_as_float(v[8 * g + 5]) * 0.125f, p.f16),
+                            rl::pack_h(__uint_as_float(v[8 * g + 6]) * 0.125f, __uint_as_float(v[8 * g + 7]) * 0.125f, p.f16));
+      }
+    }
+  }
+  rl::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    rl::tc_fence_after();
+    rl::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr int ATT_BWD256_SMEM = 12 * T16K + 256 * 4 + 3 * 8 + 16;   // 197,672 B: one CTA per SM
+
 }  // namespace
 
 extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
@@ -267,14 +503,15 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
                                 void* stream) {
   RL_REQUIRE(qkv && mask && ctx && dctx && dqkv, RL_EINVAL, "rl_attention_bwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_bwd: head_dim must be 64");
-  RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 128, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..128", (long long)L);
+  RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 256, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..256", (long long)L);
+  RL_REQUIRE(L <= 128 || row_lse, RL_EINVAL, "rl_attention_bwd: seq_len > 128 needs the row_lse saved by rl_attention_fwd");
   const int H = (int)(heads * head_dim);
   const int lkv16 = (int)((L + 15) / 16 * 16);
   CUtensorMap tq, tkv, tdo;
   uint64_t dims[2] = {(uint64_t)(3 * H), (uint64_t)(B * L)};
   uint64_t strides[1] = {(uint64_t)(3 * H) * 2};
   uint32_t boxq[2] = {64, 128};
-  uint32_t boxkv[2] = {64, (uint32_t)lkv16};
+  uint32_t boxkv[2] = {64, (uint32_t)(lkv16 <= 128 ? lkv16 : 128)};
   int rc = rl_make_tmap_bf16(&tq, qkv, 2, dims, strides, boxq);
   if (rc) return rc;
   rc = rl_make_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv);
@@ -283,6 +520,32 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
   uint64_t strideso[1] = {(uint64_t)H * 2};
   rc = rl_make_tmap_bf16(&tdo, dctx, 2, dimso, strideso, boxq);
   if (rc) return rc;
+  if (L > 128) {
+    static std::atomic<bool> configured256{false};
+    if (!configured256) {
+      cudaError_t e = cudaFuncSetAttribute(attention_bwd256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD256_SMEM);
+      if (e != cudaSuccess) {
+        rl_set_error("rl_attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+      configured256 = true;
+    }
+    AttBwdParams p;
+    p.mask = reinterpret_cast<const long long*>(mask);
+    p.ctx = reinterpret_cast<const __nv_bfloat16*>(ctx);
+    p.dctx = reinterpret_cast<const __nv_bfloat16*>(dctx);
+    p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+    p.L = (int)L;
+    p.H = H;
+    p.lkv16 = lkv16;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    p.heads = (int)heads;
+    p.drop = rl::make_drop(drop_p, drop_seed, drop_site, drop_counter);
+    p.f16 = act_dtype == RL_DT_F16;
+    p.lse = row_lse;
+    attention_bwd256_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD256_SMEM, (cudaStream_t)stream>>>(tq, tdo, p);
+    return rl_check_launch("rl_attention_bwd(256)");
+  }
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);

@@ -99,6 +99,7 @@ class GraphedTrainStep:
             m.prepare()
         if self._gen != m._prep_gen:
             self._graphs.clear()
+            self._pool = None             # a memory pool dies with its last graph: never hand a stale handle to a capture
             self._gen = m._prep_gen
             self.opt._sig = None          # the shadow pointers in the optimizer table are stale too
             if any(p.grad is not None for g in self.opt.param_groups for p in g["params"]):

@@ -642,7 +642,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             self._run(static)                      # eager warm-up: lazy init outside the capture
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            if self._graph_pool is None:
+            if self._graph_pool is None or not self._graphs:     # (a pool dies with its last graph: take a fresh handle)
                 self._graph_pool = torch.cuda.graph_pool_handle()
             with torch.cuda.graph(graph, pool=self._graph_pool):   # graphs replay one at a time: one shared pool
                 outs = self._run(static)

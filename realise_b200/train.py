@@ -614,8 +614,8 @@ class TrainEngine:
         input_ids, mask = inp["src_idx"], inp["masks"]
         B, L = input_ids.shape
         N, H, V = B * L, c.hidden_size, c.vocab_size
-        if L > 128:
-            raise NotImplementedError("attention backward kernel supports seq_len <= 128")
+        if L > 256:
+            raise NotImplementedError("the attention kernels support seq_len <= 256")
         self.act16 = P["half"]       # 16-bit format of activations and gradients (bf16 in training)
         self.zpool.begin((B, L, inp["pho_idx"].shape[1] if "pho_idx" in inp else 0))
         self.step_seed = self.seed

@@ -46,7 +46,7 @@ def _oracle_grads(sd, batch, cfg):
     return loss, logits, leaves
 
 
-@pytest.mark.parametrize("B,L,seed", [(2, 16, 5), (3, 40, 6), (1, 128, 7)])
+@pytest.mark.parametrize("B,L,seed", [(2, 16, 5), (3, 40, 6), (1, 128, 7), (2, 200, 8), (1, 256, 9)])
 def test_backward_matches_oracle_autograd(B, L, seed):
     cfg, sd, model = _setup()
     batch = synth_batch(B, L, seed=seed)
@@ -226,14 +226,16 @@ def test_train_mode_guards():
     db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
     with pytest.raises(RuntimeError, match="tgt_idx"):
         m(db)
-    long = synth_batch(1, 160, seed=1)
+    long = synth_batch(1, 300, seed=1)
     with pytest.raises(NotImplementedError, match="seq_len"):
         m({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in long.items()})
 
 
-def test_dropout_training_parity_with_exported_masks():
+@pytest.mark.parametrize("B,L", [(3, 40), (2, 192)])
+def test_dropout_training_parity_with_exported_masks(B, L):
     """p = 0.1 everywhere (the reference config): the kernels' counter-based masks are exported with
-    rl_dropout_mask and installed in the oracle, so both sides drop exactly the same elements."""
+    rl_dropout_mask and installed in the oracle, so both sides drop exactly the same elements.  L = 192 runs the
+    128 x 128-blocked attention backward (seq_len > 128)."""
     from oracle import realise_oracle as O
     from realise_b200 import ops
     from realise_b200.model import SpellBertPho2ResArch3Abla
@@ -248,7 +250,7 @@ def test_dropout_training_parity_with_exported_masks():
     model.train().cuda()
     model._engine = TrainEngine(model)
     model._engine.set_seed(4242)
-    batch = synth_batch(3, 40, seed=6)
+    batch = synth_batch(B, L, seed=6)
     db = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
     loss, logits = model(db)
     loss.backward()
