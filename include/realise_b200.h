@@ -105,7 +105,9 @@ typedef struct rl_gemm_desc {
   const uint64_t* drop_counter; /* optional device step counter added to drop_seed at run time (NULL = plain seed) */
   int32_t tune_tile_n;  /* 0: the cost model picks the N tile.  64 / 128 / 256: force it (tuning and tests; results do
                            not depend on it) */
-  int32_t tune_no_pair; /* 1: never use the CTA-pair (cta_group::2) kernel */
+  int32_t tune_no_pair; /* 0: cost model.  1: never use the CTA-pair (cta_group::2) kernels.  2: pairs but no 4-CTA
+                           clusters (two pairs sharing the B tile through TMA multicast).  3: 4-CTA clusters whenever
+                           eligible (M >= 512, 256-wide tiles, plain B).  Results do not depend on it. */
   int32_t b_mode;    /* 0: B is a 2-D matrix.  1 (needs b_major = 1, a_mode = 0): B is the im2col matrix of the conv
                         activation `b` ([NIMG, P, H, W, C], geometry / taps in the conv_* fields), never materialised:
                         B[k = output pixel (img, oh, ow), n = tap * Cuse + c] = x[img, plane_t, oh+dh_t, ow+dw_t, c],

@@ -37,6 +37,9 @@ struct KParams {
   int out_remap;
   int remap_plane;  // out_remap == 2: rows (img, h, w) of the GEMM go to plane `remap_plane` of a parity-split tensor
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
+  int tma_res;    // residual tiles arrive through tmR (TMA load into the staging tile the result leaves from): per-thread
+                  // row loads touch 32 cache lines per instruction and made the f32-residual epilogues L1-bound
+  int tma_out2;   // GELU_SAVE: the pre-activation tile leaves through tmC2 from the upper half of the staging tile
   int vec_store;  // direct path may use 16-byte stores
   rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
   int a_f16, b_f16;   // operand formats of the MMA: IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either, per operand)
@@ -127,14 +130,27 @@ __device__ __forceinline__ void epilogue_prefetch(const KParams& p, float* sb, i
     sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
     sb[128 + i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
   }
-  load_residual(p, row0 + lane, row0 + lane < p.M, c0, xr);
+  if (!p.tma_res) load_residual(p, row0 + lane, row0 + lane < p.M, c0, xr);
   __syncwarp();
 }
 
+struct EpiState {
+  int stg_sel;       // staging tile of the next chunk (alternates per chunk ACROSS tiles)
+  uint32_t rphase;   // bit b: phase of the residual-arrival barrier of staging tile b
+};
+
+// lane 0: fetch the residual tile of the chunk at column nb into staging tile `buf` (its previous TMA store must be done)
+__device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorMap* tmR_ptr, uint8_t* stg_base,
+                                               uint64_t* rbar, int buf, int nb, int row0) {
+  rl::mbar_expect_tx(&rbar[buf], p.res_f32 ? 4096u : 2048u);
+  rl::tma_load_2d(stg_base + buf * 4096, tmR_ptr, &rbar[buf], nb, row0);
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, uint8_t* stg_base,
+__device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, const CUtensorMap* tmC2_ptr,
+                                              const CUtensorMap* tmR_ptr, uint8_t* stg_base, uint64_t* rbar,
                                               const float* sb, uint32_t taddr, int row0, int n0, int half, int lane,
-                                              float (&xr)[32], int& stg_sel) {
+                                              float (&xr)[32], EpiState& st) {
   constexpr int CH = BN / 64;  // 32-column chunks per half
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
@@ -143,24 +159,57 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
   for (int cc = 0; cc < CH; ++cc) {
     const int c = half * CH + cc;
     const int nb = n0 + c * 32;
+    const bool live = nb < p.N && row0 < p.M;  // warp-uniform
     uint32_t v[32];
     rl::tmem_ld_32x32(taddr + c * 32, v);
     float xn[32];
-    if (cc + 1 < CH) load_residual(p, row, row_ok, nb + 32, xn);  // overlaps the TMEM load and this chunk's math
+    if (p.tma_res) {
+      // residual of THIS chunk: TMA delivered it into the staging tile the result will leave from (issued one chunk
+      // ahead); read my row, then prefetch the next chunk's tile into the other staging tile
+      const int buf = st.stg_sel & 1;
+      if (live) {
+        if (cc + 1 < CH && nb + 32 < p.N && lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that last read tile buf^1
+          issue_residual(p, tmR_ptr, stg_base, rbar, buf ^ 1, nb + 32, row0);
+        }
+        rl::mbar_wait(&rbar[buf], (st.rphase >> buf) & 1u);
+        st.rphase ^= 1u << buf;
+        const uint8_t* rt = stg_base + buf * 4096;
+        if (p.res_f32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(rt + lane * 128 + ((g ^ (lane & 7)) << 4));
+            xr[4 * g] = t.x; xr[4 * g + 1] = t.y; xr[4 * g + 2] = t.z; xr[4 * g + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 t = *reinterpret_cast<const uint4*>(rt + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+            xr[8 * g] = rl::half_lo(t.x, p.r_f16); xr[8 * g + 1] = rl::half_hi(t.x, p.r_f16);
+            xr[8 * g + 2] = rl::half_lo(t.y, p.r_f16); xr[8 * g + 3] = rl::half_hi(t.y, p.r_f16);
+            xr[8 * g + 4] = rl::half_lo(t.z, p.r_f16); xr[8 * g + 5] = rl::half_hi(t.z, p.r_f16);
+            xr[8 * g + 6] = rl::half_lo(t.w, p.r_f16); xr[8 * g + 7] = rl::half_hi(t.w, p.r_f16);
+          }
+        }
+        __syncwarp();   // every lane has its residual row in registers before anyone overwrites the tile with results
+      }
+    } else if (cc + 1 < CH) {
+      load_residual(p, row, row_ok, nb + 32, xn);  // overlaps the TMEM load and this chunk's math
+    }
     rl::tmem_ld_wait();
-    const bool live = nb < p.N && row0 < p.M;  // warp-uniform
     if (live) {
       float x[32];
       if (p.act == RL_ACT_GELU_GRAD) {
         // data gradient through GELU: the `res` operand carries the saved pre-activation u
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 32; j += 4) {   // packed f32x2 polynomial (FFMA2 / FMUL2): half the issue slots of the scalar form
           const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
           const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
-          x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x) * gelu_grad(xr[j]);
-          x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y) * gelu_grad(xr[j + 1]);
-          x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z) * gelu_grad(xr[j + 2]);
-          x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w) * gelu_grad(xr[j + 3]);
+          const rl::f2 g0 = rl::gelu_grad2(rl::f2{xr[j], xr[j + 1]}), g1 = rl::gelu_grad2(rl::f2{xr[j + 2], xr[j + 3]});
+          x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x) * g0.x;
+          x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y) * g0.y;
+          x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z) * g1.x;
+          x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w) * g1.y;
         }
       } else {
 #pragma unroll
@@ -181,7 +230,26 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] += xr[j];
       }
-      if (p.act == RL_ACT_GELU_SAVE && row_ok && p.out2) {
+      uint8_t* stg = nullptr;
+      if (p.tma_store) {
+        // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (st.stg_sel lives in the tile loop: a
+        // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
+        // store was still reading): the TMA store issued two chunks ago must have finished reading
+        stg = stg_base + (st.stg_sel & 1) * 4096;
+        st.stg_sel ^= 1;
+        if (!p.tma_res) {   // (with tma_res the tile's previous store was drained before the residual was fetched into it)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+      }
+      if (p.act == RL_ACT_GELU_SAVE && p.tma_out2) {
+        // training forward: the pre-activation tile (16-bit) goes to the upper half of the staging tile
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(stg + 2048 + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], p.o_f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], p.o_f16),
+                         rl::pack_h(x[8 * g + 4], x[8 * g + 5], p.o_f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], p.o_f16));
+      } else if (p.act == RL_ACT_GELU_SAVE && row_ok && p.out2) {
         // training forward: keep the pre-activation (bf16) for the backward pass, then activate
         if (nb + 32 <= p.N && p.vec_store) {
           uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
@@ -197,7 +265,11 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
       }
       if (p.act == RL_ACT_GELU || p.act == RL_ACT_GELU_SAVE) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f * (1.0f + fast_erf(x[j] * 0.70710678118654752440f));
+        for (int j = 0; j < 32; j += 2) {
+          const rl::f2 g = rl::gelu_erf2(rl::f2{x[j], x[j + 1]});
+          x[j] = g.x;
+          x[j + 1] = g.y;
+        }
       } else if (p.act == RL_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
@@ -206,13 +278,6 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
       }
       if (p.tma_store) {
-        // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (stg_sel lives in the tile loop: a
-        // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
-        // store was still reading): the TMA store issued two chunks ago must have finished reading
-        uint8_t* stg = stg_base + (stg_sel & 1) * 4096;
-        stg_sel ^= 1;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
         if (p.out_f32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -237,6 +302,11 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(tmC_ptr)),
                          "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
+                         : "memory");
+          if (p.tma_out2)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(tmC2_ptr)),
+                         "r"(rl::smem_u32(stg + 2048)), "r"(nb), "r"(row0)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -288,7 +358,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         }
       }
     }
-    if (cc + 1 < CH) {
+    if (cc + 1 < CH && !p.tma_res) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) xr[j] = xn[j];
     }
@@ -298,7 +368,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const KParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                 const __grid_constant__ CUtensorMap tmR, const KParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
@@ -313,6 +384,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // [8 epilogue warps][2 staging tiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -322,6 +394,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     rl::tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 16; ++s) rl::mbar_init(&res_bar[s], 1);
     for (int s = 0; s < STAGES; ++s) {
       rl::mbar_init(&full_bar[s], 1);
       rl::mbar_init(&empty_bar[s], 1);
@@ -461,7 +534,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    int stg_sel = 0;
+    EpiState est{0, 0u};
+    uint64_t* rbar = res_bar + ew * 2;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
@@ -471,10 +545,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
+      if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
+        // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+      }
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr, stg_sel);
+      epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) rl::mbar_arrive(&tmem_empty[acc]);
@@ -494,12 +573,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (A_BYTES + BN * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  return STAGES * (A_BYTES + BN * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 128 + 1024;
 }
 
 template <int BN, int STAGES>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
-                cudaStream_t st) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
@@ -513,7 +592,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   }
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = tiles < rl_num_sms() ? tiles : rl_num_sms();
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);
+  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16");
 }
 
@@ -550,11 +629,20 @@ __device__ __forceinline__ void tma2_load_5d(void* dst, const void* tmap, uint64
       "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {  // arrive on the same barrier in both CTAs
+// 2-D tile load delivered to the same CTA-relative smem offset of every CTA in `mask` (multicast through the cluster);
+// the bytes are credited to the full barrier of each destination's pair leader
+__device__ __forceinline__ void tma2_load_2d_mc(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(rl::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(rl::smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar, uint16_t mask = 3) {  // arrive on the same barrier in every CTA of mask
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           rl::smem_u32(bar)),
-      "h"((uint16_t)3)
+      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void tc2_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -570,11 +658,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // from eit
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rl::smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-template <int BN, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const KParams p) {
+// CL = CTAs per cluster: 2 = one pair; 4 = two pairs stacked along M that SHARE the B tile: each CTA fetches only a
+// quarter of it and multicasts the quarter to its counterpart in the other pair, so a CTA pulls 24 KB instead of 32 KB
+// through L2 per 64-deep k-block (the pair kernel is bound by L2 -> SM bytes, not by the tensor pipe).
+template <int BN, int STAGES, int CL>
+__device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                           const CUtensorMap& tmC2, const CUtensorMap& tmR, const KParams& p) {
   constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
+  constexpr int PAIRS = CL / 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -586,11 +677,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // [8 epilogue warps][2 staging tiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();   // 0 .. CL-1
+  const uint32_t rank = crank & 1;            // rank inside the CTA pair
+  const uint32_t pair = crank >> 1;           // pair inside the cluster (0 when CL == 2)
   const bool leader = rank == 0;
+  const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+  const uint16_t bcast_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));   // CL == 4: my counterpart in the other pair
 
   if (warp == 0 && lane == 0) {
     rl::tma_prefetch_desc(&tmA);
@@ -598,9 +695,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     rl::tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 16; ++s) rl::mbar_init(&res_bar[s], 1);
     for (int s = 0; s < STAGES; ++s) {
       rl::mbar_init(&full_bar[s], 1);
-      rl::mbar_init(&empty_bar[s], 1);
+      rl::mbar_init(&empty_bar[s], PAIRS);   // a stage is free once EVERY pair that reads it (own A, shared B) has consumed it
     }
     for (int s = 0; s < 2; ++s) {
       rl::mbar_init(&tmem_full[s], 1);
@@ -619,9 +717,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   rl::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;  // tiles_m counts 256-row pair tiles here
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;  // tiles_m counts (CL * 128)-row cluster tiles here
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -635,7 +733,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m_blk = mn / p.tiles_n;
         const int n_blk = mn - m_blk * p.tiles_n;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-        const int m0 = m_blk * 2 * BM + (int)rank * BM;
+        const int m0 = m_blk * CL * BM + (int)crank * BM;
         const int n0 = n_blk * BN + (int)rank * (BN / 2);
         int img0 = 0, h0 = 0;
         if (p.a_mode == 1) {
@@ -673,6 +771,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               else
                 tma2_load_5d(smem_b + stage * BH_BYTES + b * 8192, &tmB, &full_bar[stage], 0, 0, 0, 0, p.nimg);
             }
+          } else if (CL == 4) {
+            // quarter `pair` of this half of B (64 n-rows / n-columns = 8 KB), delivered to both pairs
+            if (p.b_mn)
+              tma2_load_2d_mc(smem_b + stage * BH_BYTES + pair * 8192, &tmB, &full_bar[stage], n0 + (int)pair * 64, kb * BK,
+                              bcast_mask);
+            else
+              tma2_load_2d_mc(smem_b + stage * BH_BYTES + pair * 8192, &tmB, &full_bar[stage], kb * BK, n0 + (int)pair * 64,
+                              bcast_mask);
           } else if (p.b_mn) {
 #pragma unroll
             for (int b = 0; b < BN / 128; ++b)
@@ -715,7 +821,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               tc2_mma_f16(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            tc2_commit_mc(&empty_bar[stage]);
+            tc2_commit_mc(&empty_bar[stage], all_mask);
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -723,7 +829,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             phase ^= 1;
           }
         }
-        if (rl::elect_one()) tc2_commit_mc(&tmem_full[acc]);
+        if (rl::elect_one()) tc2_commit_mc(&tmem_full[acc], pair_mask);
         __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -737,20 +843,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    int stg_sel = 0;
+    EpiState est{0, 0u};
+    uint64_t* rbar = res_bar + ew * 2;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
       const int m_blk = mn / p.tiles_n;
       const int n_blk = mn - m_blk * p.tiles_n;
-      const int row0 = m_blk * 2 * BM + (int)rank * BM + q * 32;
+      const int row0 = m_blk * CL * BM + (int)crank * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
+      if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
+        // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+      }
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tmC, stg, sb, taddr, row0, n0, half, lane, xr, stg_sel);
+      epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -769,13 +881,29 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <int BN, int STAGES>
-constexpr int gemm2_smem_bytes() {
-  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                  const __grid_constant__ CUtensorMap tmR, const KParams p) {
+  gemm2_body<BN, STAGES, 2>(tmA, tmB, tmC, tmC2, tmR, p);
 }
 
 template <int BN, int STAGES>
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
-                 cudaStream_t st) {
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm4_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                  const __grid_constant__ CUtensorMap tmR, const KParams p) {
+  gemm2_body<BN, STAGES, 4>(tmA, tmB, tmC, tmC2, tmR, p);
+}
+
+template <int BN, int STAGES>
+constexpr int gemm2_smem_bytes() {
+  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 128 + 1024;
+}
+
+template <int BN, int STAGES>
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                 const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
   constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
@@ -789,8 +917,47 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int max_clusters = rl_num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_bf16_kernel<BN, STAGES><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, p);
+  gemm2_bf16_kernel<BN, STAGES><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16(cta_group::2)");
+}
+
+// co-resident 4-CTA clusters of the quad kernel (a cluster must sit inside one GPC: fewer than SMs / 4 may fit)
+template <int BN, int STAGES>
+int gemm4_max_clusters() {
+  static std::atomic<int> cached{-1};
+  int v = cached.load();
+  if (v >= 0) return v;
+  constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
+  cudaFuncSetAttribute(gemm4_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(rl_num_sms() / 4 * 4), 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 4;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm4_bf16_kernel<BN, STAGES>, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 0;   // no device / query failed: the quad kernel is never selected
+  }
+  cached.store(n);
+  return n;
+}
+
+template <int BN, int STAGES>
+int launch_gemm4(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                 const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
+  constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
+  const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
+  const int max_clusters = gemm4_max_clusters<BN, STAGES>();
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm4_bf16_kernel<BN, STAGES><<<4 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  return rl_check_launch("rl_gemm_bf16(4-CTA cluster)");
 }
 
 int ilog2_exact(int v) {
@@ -864,7 +1031,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   int bn = 256;
   int pair = 0;
   const int g_force_bn = d->tune_tile_n;          // 0 = cost model; 64 / 128 / 256 force the N tile (tuning, tests)
-  const int g_pair_mode = d->tune_no_pair ? 0 : 1;  // tune_no_pair: never use the cta_group::2 kernel
+  const int g_pair_mode = d->tune_no_pair == 1 ? 0 : 1;  // tune_no_pair 1: never use the cta_group::2 kernels
   {
     const int sms = rl_num_sms();
     double best = 1e30;
@@ -902,7 +1069,32 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
       pair = 0;
     }
   }
-  if (pair) p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  // 4-CTA clusters (two pairs sharing the B tile through TMA multicast): same cost model, 24 KB instead of 32 KB per
+  // CTA and k-block, but only as many clusters as fit the GPCs and 512-row tiles
+  int quad = 0;
+  if (pair && bn == 256 && d->b_mode == 0 && d->tune_no_pair != 2 && p.M >= 4 * BM) {
+    const int maxc4 = gemm4_max_clusters<256, 4>();
+    if (maxc4 > 0) {
+      const long long tn = (p.N + 255) / 256;
+      const long long t2 = ((p.M + 2 * BM - 1) / (2 * BM)) * tn, t4 = ((p.M + 4 * BM - 1) / (4 * BM)) * tn;
+      const long long u2 = rl_num_sms() / 2, u4 = maxc4;
+      const double kb2 = (A_BYTES + 128 * BK * 2.0) / 42.6, kb4_l2 = (A_BYTES + 64 * BK * 2.0) / 42.6;
+      const double kb4 = kb4_l2 > 512.0 ? kb4_l2 : 512.0;
+      double c2, c4;
+      if (d->split_k != 0) {   // split-K fills whole waves: compare machine-wide throughput
+        c2 = (double)t2 * kb2 / (double)u2;
+        c4 = (double)t4 * kb4 / (double)u4;
+      } else {
+        c2 = (double)((t2 + u2 - 1) / u2) * (kb2 * p.num_kb + 1500.0);
+        c4 = (double)((t4 + u4 - 1) / u4) * (kb4 * p.num_kb + 1500.0);
+      }
+      (void)c2; (void)c4;
+      // Measured (tools/gemm_bench.py, profiles/): the 4-CTA kernel is correct but NOT faster — multicast cuts L2 reads, the
+      // bytes entering each SM stay the same — so the cost model never picks it; tune_no_pair = 3 forces it (tests, bench).
+      quad = d->tune_no_pair == 3 ? 1 : 0;
+    }
+  }
+  if (pair) p.tiles_m = quad ? (p.M + 4 * BM - 1) / (4 * BM) : (p.M + 2 * BM - 1) / (2 * BM);
   p.tiles_n = (p.N + bn - 1) / bn;
   // split-K (weight gradients: few output tiles, K = tokens / pixels): ~2 CTAs per SM worth of tiles, >= 8 k-blocks each
   p.k_splits = 1;
@@ -917,7 +1109,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     // epilogue, ~10 k-blocks' worth), e.g. 27 tiles on 74 pairs: 8 splits (3 full waves of 32 k-blocks) beat 6
     // (3 ragged waves of 43).
     const long long tiles = (long long)p.tiles_m * p.tiles_n;
-    const long long units = pair ? rl_num_sms() / 2 : rl_num_sms();
+    const long long units = quad ? gemm4_max_clusters<256, 4>() : pair ? rl_num_sms() / 2 : rl_num_sms();
     int maxs = p.num_kb / 8;
     if (maxs < 1) maxs = 1;
     int want = 1;
@@ -1046,14 +1238,17 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   } else {
     uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->ldb * 2};
-    uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};
+    uint32_t box[2] = {BK, (uint32_t)(quad ? bn / 4 : pair ? bn / 2 : bn)};
     rc = rl_make_tmap_bf16(&tmB, d->b, 2, dims, strides, box);
     if (rc) return rc;
   }
   // output path: TMA store for plain row-major outputs with 16-byte aligned rows
   const int oelt = p.out_f32 ? 4 : 2;
   const bool aligned16 = ((uintptr_t)d->out & 15) == 0 && (d->ldo * oelt) % 16 == 0;
-  p.tma_store = (d->out_remap == 0 && d->out2 == nullptr && aligned16) ? 1 : 0;  // else direct stores / scalar atomics
+  const bool out2_tma = d->out2 != nullptr && d->act == RL_ACT_GELU_SAVE && !p.out_f32 && ((uintptr_t)d->out2 & 15) == 0 &&
+                        (d->ldo2 * 2) % 16 == 0;
+  p.tma_store = (d->out_remap == 0 && (d->out2 == nullptr || out2_tma) && aligned16) ? 1 : 0;  // else direct stores / scalar atomics
+  p.tma_out2 = (p.tma_store && out2_tma) ? 1 : 0;
   // (split-K with a TMA-able output: the per-chunk store becomes a cp.reduce.async.bulk .add — no per-element atomics)
   p.vec_store = (aligned16 && (d->out2 == nullptr || (((uintptr_t)d->out2 & 15) == 0 && d->ldo2 % 8 == 0))) ? 1 : 0;
   if (d->res) {
@@ -1069,12 +1264,31 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     rc = rl_make_tmap(&tmC, d->out, p.out_f32 ? RL_TMAP_F32 : RL_TMAP_BF16, p.out_f32 ? 128 : 64, 2, dims, strides, box);
     if (rc) return rc;
   }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (pair) {
-    if (bn == 256) return launch_gemm2<256, 4>(tmA, tmB, tmC, p, st);
-    return launch_gemm2<128, 6>(tmA, tmB, tmC, p, st);
+  CUtensorMap tmC2 = tmB, tmR = tmB;
+  if (p.tma_out2) {
+    uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+    uint64_t strides[1] = {(uint64_t)d->ldo2 * 2};
+    uint32_t box[2] = {32, 32};
+    rc = rl_make_tmap(&tmC2, d->out2, RL_TMAP_BF16, 64, 2, dims, strides, box);
+    if (rc) return rc;
   }
-  if (bn == 256) return launch_gemm<256, 3>(tmA, tmB, tmC, p, st);
-  if (bn == 64) return launch_gemm<64, 6>(tmA, tmB, tmC, p, st);
-  return launch_gemm<128, 4>(tmA, tmB, tmC, p, st);
+  // residual tiles by TMA: plain row-major result leaving by TMA, residual rows 16-byte aligned (checked above), and the
+  // residual tile must fit the staging tile the result leaves from (f32 residual -> f32 result)
+  p.tma_res = (d->res && p.tma_store && !p.atomic_out && !p.tma_out2 && (p.out_f32 || !p.res_f32)) ? 1 : 0;
+  if (p.tma_res) {
+    uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+    uint64_t strides[1] = {(uint64_t)d->ldr * (p.res_f32 ? 4 : 2)};
+    uint32_t box[2] = {32, 32};
+    rc = rl_make_tmap(&tmR, d->res, p.res_f32 ? RL_TMAP_F32 : RL_TMAP_BF16, p.res_f32 ? 128 : 64, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (quad) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  if (pair) {
+    if (bn == 256) return launch_gemm2<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    return launch_gemm2<128, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  }
+  if (bn == 256) return launch_gemm<256, 3>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  if (bn == 64) return launch_gemm<64, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  return launch_gemm<128, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
 }

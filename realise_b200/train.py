@@ -277,8 +277,9 @@ class TrainEngine:
             x1, s["x1b"] = self._new((N, H), F32), self._new((N, H), A16)
             ops.layernorm(s["y1"], lw["ln1_w"], lw["ln1_b"], x1, s["x1b"], c.layer_norm_eps)
             s["u"], s["h"] = self._new((N, I), A16), self._new((N, I), A16)
-            ops.gemm(s["x1b"], lw["w_1"], s["u"], bias=lw["b_1"])
-            ops.gelu(s["u"], s["h"])       # stand-alone pass: cheaper than erf in the epilogue of a K = 768 GEMM
+            # h = gelu(u), u kept for the backward: both tiles leave the GEMM epilogue through TMA (packed f32x2 erf
+            # polynomial on the 8 epilogue warps, hidden behind the next tile's MMAs)
+            ops.gemm(s["x1b"], lw["w_1"], s["h"], bias=lw["b_1"], act=ops.ACT_GELU_SAVE, out2=s["u"])
             s["y2"] = self._new((N, H), F32)
             ops.gemm(s["h"], lw["w_2"], s["y2"], bias=lw["b_2"], res=x1, drop=self.hdrop(self.site(name, li, 3)))
             x, xb = self._new((N, H), F32), self._new((N, H), A16)
