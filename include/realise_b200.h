@@ -108,6 +108,10 @@ typedef struct rl_gemm_desc {
   int32_t tune_no_pair; /* 0: cost model.  1: never use the CTA-pair (cta_group::2) kernels.  2: pairs but no 4-CTA
                            clusters (two pairs sharing the B tile through TMA multicast).  3: 4-CTA clusters whenever
                            eligible (M >= 512, 256-wide tiles, plain B).  Results do not depend on it. */
+  float* colsum;     /* optional f32 [N], ACCUMULATED into: sum over the M rows of the final result (after act): the bias
+                        gradient of the layer below comes out of the data-gradient GEMM, BatchNorm's batch sum out of the
+                        conv GEMM.  Needs split_k = 0. */
+  float* colsumsq;   /* optional f32 [N], accumulated: sum over rows of result^2 (BatchNorm batch statistics) */
   int32_t b_mode;    /* 0: B is a 2-D matrix.  1 (needs b_major = 1, a_mode = 0): B is the im2col matrix of the conv
                         activation `b` ([NIMG, P, H, W, C], geometry / taps in the conv_* fields), never materialised:
                         B[k = output pixel (img, oh, ow), n = tap * Cuse + c] = x[img, plane_t, oh+dh_t, ow+dw_t, c],

@@ -33,6 +33,7 @@ class GemmDesc(ctypes.Structure):
         ("a_dtype", ctypes.c_int32), ("b_dtype", ctypes.c_int32),
         ("drop_counter", ctypes.c_void_p),
         ("tune_tile_n", ctypes.c_int32), ("tune_no_pair", ctypes.c_int32),
+        ("colsum", ctypes.c_void_p), ("colsumsq", ctypes.c_void_p),
         ("b_mode", ctypes.c_int32),
     ]
 

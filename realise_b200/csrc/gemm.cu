@@ -40,6 +40,8 @@ struct KParams {
   int tma_res;    // residual tiles arrive through tmR (TMA load into the staging tile the result leaves from): per-thread
                   // row loads touch 32 cache lines per instruction and made the f32-residual epilogues L1-bound
   int tma_out2;   // GELU_SAVE: the pre-activation tile leaves through tmC2 from the upper half of the staging tile
+  float* colsum;    // optional [N]: += sum over rows of the result (bias gradients; BatchNorm batch statistics)
+  float* colsumsq;  // optional [N]: += sum over rows of result^2
   int vec_store;  // direct path may use 16-byte stores
   rl::DropSpec drop;  // dropout on the linear output before the residual add (BertSelfOutput / BertOutput)
   int a_f16, b_f16;   // operand formats of the MMA: IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either, per operand)
@@ -137,7 +139,44 @@ __device__ __forceinline__ void epilogue_prefetch(const KParams& p, float* sb, i
 struct EpiState {
   int stg_sel;       // staging tile of the next chunk (alternates per chunk ACROSS tiles)
   uint32_t rphase;   // bit b: phase of the residual-arrival barrier of staging tile b
+  // column reductions (p.colsum / p.colsumsq): lane l accumulates column l of each of this warp's chunks across the
+  // tiles of the persistent loop and flushes with one atomic per column when the column block changes (a conv GEMM
+  // with one N tile flushes ONCE per CTA — per-tile atomics on 64 addresses would serialise in L2)
+  float cs[4], cq[4];
+  int cs_n0;
 };
+
+// per-column sum over the 32 rows held by the warp (lane = row, v[c] = column c): butterfly transpose-reduce, 31 shuffles;
+// on return lane l holds the total of column l in v[0]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = upper ? v[i] : v[i + w];
+      const float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+template <int CH>
+__device__ __forceinline__ void colsum_flush(const KParams& p, EpiState& st, int half, int lane) {
+  if (st.cs_n0 < 0) return;
+#pragma unroll
+  for (int cc = 0; cc < CH; ++cc) {
+    const int col = st.cs_n0 + (half * CH + cc) * 32 + lane;
+    if (col < p.N) {
+      if (p.colsum) atomicAdd(p.colsum + col, st.cs[cc]);
+      if (p.colsumsq) atomicAdd(p.colsumsq + col, st.cq[cc]);
+    }
+    st.cs[cc] = 0.f;
+    st.cq[cc] = 0.f;
+  }
+  st.cs_n0 = -1;
+}
 
 // lane 0: fetch the residual tile of the chunk at column nb into staging tile `buf` (its previous TMA store must be done)
 __device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorMap* tmR_ptr, uint8_t* stg_base,
@@ -146,7 +185,7 @@ __device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorM
   rl::tma_load_2d(stg_base + buf * 4096, tmR_ptr, &rbar[buf], nb, row0);
 }
 
-template <int BN>
+template <int BN, bool COLS>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, const CUtensorMap* tmC2_ptr,
                                               const CUtensorMap* tmR_ptr, uint8_t* stg_base, uint64_t* rbar,
                                               const float* sb, uint32_t taddr, int row0, int n0, int half, int lane,
@@ -277,6 +316,29 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
       }
+      if (COLS) {
+        if (st.cs_n0 != n0) {
+          colsum_flush<CH>(p, st, half, lane);
+          st.cs_n0 = n0;
+        }
+        float t[32];
+        if (p.colsum) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = row_ok ? x[j] : 0.f;
+          const float tot = warp_colsum32(t, lane);
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (k == cc) st.cs[k] += tot;
+        }
+        if (p.colsumsq) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = row_ok ? x[j] * x[j] : 0.f;
+          const float tot = warp_colsum32(t, lane);
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (k == cc) st.cq[k] += tot;
+        }
+      }
       if (p.tma_store) {
         if (p.out_f32) {
 #pragma unroll
@@ -365,7 +427,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COLS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -534,7 +596,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    EpiState est{0, 0u};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
     uint64_t* rbar = res_bar + ew * 2;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -553,13 +615,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
+      epilogue_tile<BN, COLS>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) rl::mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (COLS) colsum_flush<BN / 64>(p, est, half, lane);
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
@@ -576,13 +639,13 @@ constexpr int gemm_smem_bytes() {
   return STAGES * (A_BYTES + BN * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 128 + 1024;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COLS = false>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                 const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, COLS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -592,7 +655,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   }
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = tiles < rl_num_sms() ? tiles : rl_num_sms();
-  gemm_bf16_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm_bf16_kernel<BN, STAGES, COLS><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16");
 }
 
@@ -661,7 +724,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // from eit
 // CL = CTAs per cluster: 2 = one pair; 4 = two pairs stacked along M that SHARE the B tile: each CTA fetches only a
 // quarter of it and multicasts the quarter to its counterpart in the other pair, so a CTA pulls 24 KB instead of 32 KB
 // through L2 per 64-deep k-block (the pair kernel is bound by L2 -> SM bytes, not by the tensor pipe).
-template <int BN, int STAGES, int CL>
+template <int BN, int STAGES, int CL, bool COLS>
 __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                            const CUtensorMap& tmC2, const CUtensorMap& tmR, const KParams& p) {
   constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
@@ -843,7 +906,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    EpiState est{0, 0u};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
     uint64_t* rbar = res_bar + ew * 2;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -862,13 +925,14 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
+      epilogue_tile<BN, COLS>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (COLS) colsum_flush<BN / 64>(p, est, half, lane);
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
@@ -880,12 +944,12 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COLS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                   const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  gemm2_body<BN, STAGES, 2>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_body<BN, STAGES, 2, COLS>(tmA, tmB, tmC, tmC2, tmR, p);
 }
 
 template <int BN, int STAGES>
@@ -893,7 +957,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm4_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                   const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  gemm2_body<BN, STAGES, 4>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_body<BN, STAGES, 4, false>(tmA, tmB, tmC, tmC2, tmR, p);
 }
 
 template <int BN, int STAGES>
@@ -901,13 +965,13 @@ constexpr int gemm2_smem_bytes() {
   return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 128 + 1024;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COLS = false>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                  const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
   constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -917,7 +981,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int max_clusters = rl_num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_bf16_kernel<BN, STAGES><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_bf16_kernel<BN, STAGES, COLS><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16(cta_group::2)");
 }
 
@@ -1024,6 +1088,9 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.out_remap = d->out_remap;
   p.remap_plane = d->remap_plane;
   p.drop = rl::make_drop(d->drop_p, d->drop_seed, d->drop_site, d->drop_counter);
+  p.colsum = d->colsum;
+  p.colsumsq = d->colsumsq;
+  RL_REQUIRE(!(d->colsum || d->colsumsq) || d->split_k == 0, RL_EINVAL, "rl_gemm_bf16: colsum / colsumsq need split_k = 0");
 
   // Tile / kernel selection.  Cost model per 64-deep k-block of one CTA tile (cycles): the tensor pipe needs
   // 2*bn, the operand bytes need bytes / 42.6 (measured L2->SM ingress per SM, ~6.3 KB/clk chip-wide);
@@ -1283,12 +1350,14 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (quad) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  const bool cols = d->colsum || d->colsumsq;   // separate instantiations: the reductions cost registers in the epilogue
+  if (quad && !cols) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
   if (pair) {
-    if (bn == 256) return launch_gemm2<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
-    return launch_gemm2<128, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (bn == 256) return cols ? launch_gemm2<256, 4, true>(tmA, tmB, tmC, tmC2, tmR, p, st)
+                               : launch_gemm2<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    return cols ? launch_gemm2<128, 6, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm2<128, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
   }
-  if (bn == 256) return launch_gemm<256, 3>(tmA, tmB, tmC, tmC2, tmR, p, st);
-  if (bn == 64) return launch_gemm<64, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
-  return launch_gemm<128, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  if (bn == 256) return cols ? launch_gemm<256, 3, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm<256, 3>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  if (bn == 64) return cols ? launch_gemm<64, 6, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm<64, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  return cols ? launch_gemm<128, 4, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm<128, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
 }

@@ -92,7 +92,7 @@ def _req(t, dtype, name):
 
 
 def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None, a_t=False, b_t=False, drop=None,
-         split_k=0):
+         split_k=0, colsum=None, colsumsq=None):
     """out[M,N] = act((A @ B^T) * scale + bias + res) with A = a [M,K] (or a^T when a_t: a is stored [K,M],
     MN-major operand) and B = b [N,K] (or b^T when b_t: b is stored [K,N]).  a, b bf16; out bf16 or f32."""
     _req(a, torch.bfloat16, "a")
@@ -113,6 +113,7 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
         d.drop_counter = _COUNTER.data_ptr() if _COUNTER is not None else None
     d.split_k = split_k
     d.a_mode = 0
+    _fill_colsums(d, colsum, colsumsq, N)
     _fill_epilogue(d, out, scale, bias, res, act, out2, 0)
     with _Timed("gemm", 2.0 * M * N * K, (M, N, K, int(a_t), int(b_t), split_k, act, str(out.dtype)[6:], res is not None,
                                           drop is not None)):
@@ -121,8 +122,16 @@ def gemm(a, b, out, *, scale=None, bias=None, res=None, act=ACT_NONE, out2=None,
     return out
 
 
+def _fill_colsums(d, colsum, colsumsq, N):
+    for name, t in (("colsum", colsum), ("colsumsq", colsumsq)):
+        if t is not None:
+            _req(t, torch.float32, name)
+            assert t.is_contiguous() and t.numel() == N
+            setattr(d, name, t.data_ptr())
+
+
 def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res=None,
-              act=ACT_NONE, out_remap=0, remap_plane=0, c_use=0):
+              act=ACT_NONE, out_remap=0, remap_plane=0, c_use=0, colsum=None, colsumsq=None):
     """Implicit-GEMM convolution.  x: bf16 activation [nimg, planes, H, W, C] (contiguous);
     w: bf16 [Cout, ntaps*C] tap-major; taps: list of (dw, dh, plane); output rows are (img, oh, ow)
     over an H x W map; out_remap=1 writes rows parity-split for a following stride-2 conv."""
@@ -145,6 +154,7 @@ def conv_gemm(x, w, out, *, nimg, H, W, planes, taps, scale=None, bias=None, res
     d.remap_plane = remap_plane
     for i, (dw, dh, pl) in enumerate(taps):
         d.tap_dw[i], d.tap_dh[i], d.tap_plane[i] = dw, dh, pl
+    _fill_colsums(d, colsum, colsumsq, N)
     _fill_epilogue(d, out, scale, bias, res, act, None, out_remap)
     with _Timed("conv_gemm", 2.0 * M * N * K, (M, N, K, "conv", len(taps), out_remap, act, str(out.dtype)[6:], res is not None, False)):
         check(lib().rl_gemm_bf16(ctypes.byref(d), _stream()), "rl_gemm_bf16(conv)")
