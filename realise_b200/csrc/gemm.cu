@@ -39,6 +39,7 @@ struct KParams {
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int tma_res;    // residual tiles arrive through tmR (TMA load into the staging tile the result leaves from): per-thread
                   // row loads touch 32 cache lines per instruction and made the f32-residual epilogues L1-bound
+  int res_all;    // tma_res with 16-bit residual AND result: every chunk of a tile has its own 2 KB staging tile (see issue_residual)
   int tma_out2;   // GELU_SAVE: the pre-activation tile leaves through tmC2 from the upper half of the staging tile
   float* colsum;    // optional [N]: += sum over rows of the result (bias gradients; BatchNorm batch statistics)
   float* colsumsq;  // optional [N]: += sum over rows of result^2
@@ -179,10 +180,14 @@ __device__ __forceinline__ void colsum_flush(const KParams& p, EpiState& st, int
 }
 
 // lane 0: fetch the residual tile of the chunk at column nb into staging tile `buf` (its previous TMA store must be done)
+// Two schemes: (a) 4 KB tiles (f32 residual / f32 result): two tiles, the next chunk's residual is fetched while this chunk
+// is processed; (b) all-16-bit (p.res_all): the tile's CH <= 4 residual chunks fit the 8 KB staging region as 2 KB tiles and
+// are ALL fetched when the warp starts on the tile, a whole main loop before they are needed (one chunk of lead does not
+// cover the ~1 us TMA latency).
 __device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorMap* tmR_ptr, uint8_t* stg_base,
                                                uint64_t* rbar, int buf, int nb, int row0) {
   rl::mbar_expect_tx(&rbar[buf], p.res_f32 ? 4096u : 2048u);
-  rl::tma_load_2d(stg_base + buf * 4096, tmR_ptr, &rbar[buf], nb, row0);
+  rl::tma_load_2d(stg_base + buf * (p.res_all ? 2048 : 4096), tmR_ptr, &rbar[buf], nb, row0);
 }
 
 template <int BN, bool COLS>
@@ -205,15 +210,15 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
     if (p.tma_res) {
       // residual of THIS chunk: TMA delivered it into the staging tile the result will leave from (issued one chunk
       // ahead); read my row, then prefetch the next chunk's tile into the other staging tile
-      const int buf = st.stg_sel & 1;
+      const int buf = p.res_all ? cc : (st.stg_sel & 1);
       if (live) {
-        if (cc + 1 < CH && nb + 32 < p.N && lane == 0) {
+        if (!p.res_all && cc + 1 < CH && nb + 32 < p.N && lane == 0) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that last read tile buf^1
           issue_residual(p, tmR_ptr, stg_base, rbar, buf ^ 1, nb + 32, row0);
         }
         rl::mbar_wait(&rbar[buf], (st.rphase >> buf) & 1u);
         st.rphase ^= 1u << buf;
-        const uint8_t* rt = stg_base + buf * 4096;
+        const uint8_t* rt = stg_base + buf * (p.res_all ? 2048 : 4096);
         if (p.res_f32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -274,7 +279,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (st.stg_sel lives in the tile loop: a
         // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
         // store was still reading): the TMA store issued two chunks ago must have finished reading
-        stg = stg_base + (st.stg_sel & 1) * 4096;
+        stg = p.res_all ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
         st.stg_sel ^= 1;
         if (!p.tma_res) {   // (with tma_res the tile's previous store was drained before the residual was fetched into it)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -446,7 +451,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // [8 epilogue warps][2 staging tiles]
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // [8 epilogue warps][up to 4 staging tiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -456,7 +461,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     rl::tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 16; ++s) rl::mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 32; ++s) rl::mbar_init(&res_bar[s], 1);
     for (int s = 0; s < STAGES; ++s) {
       rl::mbar_init(&full_bar[s], 1);
       rl::mbar_init(&empty_bar[s], 1);
@@ -597,7 +602,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
     EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
-    uint64_t* rbar = res_bar + ew * 2;
+    uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
@@ -608,9 +613,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
       if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
-        // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+        if (p.res_all) {
+          // every residual chunk of this output tile, now: the stores of the previous tile have long drained
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll
+          for (int cc = 0; cc < BN / 64; ++cc)
+            if (n0 + half * (BN / 2) + cc * 32 < p.N) issue_residual(p, &tmR, stg, rbar, cc, n0 + half * (BN / 2) + cc * 32, row0);
+        } else {
+          // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+        }
       }
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
@@ -636,7 +649,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (A_BYTES + BN * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 128 + 1024;
+  return STAGES * (A_BYTES + BN * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 + 1024;
 }
 
 template <int BN, int STAGES, bool COLS = false>
@@ -740,7 +753,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // [8 epilogue warps][2 staging tiles]
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // [8 epilogue warps][up to 4 staging tiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -758,7 +771,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     rl::tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 16; ++s) rl::mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 32; ++s) rl::mbar_init(&res_bar[s], 1);
     for (int s = 0; s < STAGES; ++s) {
       rl::mbar_init(&full_bar[s], 1);
       rl::mbar_init(&empty_bar[s], PAIRS);   // a stage is free once EVERY pair that reads it (own A, shared B) has consumed it
@@ -907,7 +920,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
     EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
-    uint64_t* rbar = res_bar + ew * 2;
+    uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = p.ks_major ? tile % (p.tiles_m * p.tiles_n) : tile / p.k_splits;
@@ -918,9 +931,17 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
       if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
-        // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+        if (p.res_all) {
+          // every residual chunk of this output tile, now: the stores of the previous tile have long drained
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll
+          for (int cc = 0; cc < BN / 64; ++cc)
+            if (n0 + half * (BN / 2) + cc * 32 < p.N) issue_residual(p, &tmR, stg, rbar, cc, n0 + half * (BN / 2) + cc * 32, row0);
+        } else {
+          // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+        }
       }
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
@@ -962,7 +983,7 @@ gemm4_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <int BN, int STAGES>
 constexpr int gemm2_smem_bytes() {
-  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 128 + 1024;
+  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 + 1024;
 }
 
 template <int BN, int STAGES, bool COLS = false>
@@ -1342,6 +1363,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   // residual tiles by TMA: plain row-major result leaving by TMA, residual rows 16-byte aligned (checked above), and the
   // residual tile must fit the staging tile the result leaves from (f32 residual -> f32 result)
   p.tma_res = (d->res && p.tma_store && !p.atomic_out && !p.tma_out2 && (p.out_f32 || !p.res_f32)) ? 1 : 0;
+  p.res_all = (p.tma_res && !p.res_f32 && !p.out_f32) ? 1 : 0;
   if (p.tma_res) {
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
     uint64_t strides[1] = {(uint64_t)d->ldr * (p.res_f32 ? 4 : 2)};

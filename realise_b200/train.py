@@ -125,6 +125,8 @@ class TrainEngine:
         self._accum = None
         self.debug = None             # tests set a dict to receive intermediate gradients
         self._res = None              # conv operand layouts + their refresh launch, built on the first training forward
+        self.multistream = True       # the three encoders (and their backward passes) run on three CUDA streams: the HBM-bound
+        self._streams = None          # CNN passes and the latency-bound GRU steps fill the wave tails of the BERT GEMMs
         self.zpool = ZeroPool(model.classifier.bias.device)
         self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
@@ -210,6 +212,28 @@ class TrainEngine:
         for p, g in zip(self.params, self.grads):
             if g is not None:
                 p.grad = g
+
+    def _side_streams(self):
+        if not self.multistream:
+            return None, None
+        if self._streams is None:
+            dev = self.m.classifier.bias.device
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        main = torch.cuda.current_stream()
+        for st in self._streams:
+            st.wait_stream(main)          # fork: everything issued so far (inputs, zeroed scratch) is visible to the branches
+        return self._streams
+
+    def _join(self, *streams):
+        main = torch.cuda.current_stream()
+        for st in streams:
+            if st is not None:
+                main.wait_stream(st)
+
+    @staticmethod
+    def _on(stream):
+        import contextlib
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
 
     def grads_consumed(self):
         """Called by FusedAdamW.step() and model.zero_grad(): the next backward starts from zero again."""
@@ -627,17 +651,25 @@ class TrainEngine:
         self.step_seed = self.seed
         self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         sv = {"B": B, "L": L, "mask": mask, "inp": inp, "seed": self.step_seed}
+        # the three encoders are independent until the fusion: issue them on three streams (fork / join; inside a captured
+        # graph these become parallel branches)
+        s_pho, s_res = self._side_streams() if (c.with_pho == "yes" or c.with_res == "yes") else (None, None)
+        if c.with_res == "yes":     # issued first: the longest HBM-bound chain
+            with self._on(s_res):
+                res_raw = self._resnet_fwd(P, input_ids.view(-1), N, sv)
+                sv["res_raw"] = res_raw
+                res_h = self._new((N, H), F32)
+                ops.layernorm(res_raw, P["res_ln_w"], P["res_ln_b"], res_h, None, c.layer_norm_eps)
+        if c.with_pho == "yes":
+            with self._on(s_pho):
+                pho_gru = self._gru_fwd(P, inp["pho_idx"], inp["pho_lens"], N, sv)
+                pho_h, _, sv["pho"] = self._stack_fwd("pho", m.pho_model, P["pho_model"], mask, B, L, inputs_embeds=pho_gru)
         bert_h, _, sv["bert"] = self._stack_fwd("bert", m.bert, P["bert"], mask, B, L, ids=input_ids.view(-1))
+        self._join(s_pho, s_res)
         mods = [bert_h]
         if c.with_pho == "yes":
-            pho_gru = self._gru_fwd(P, inp["pho_idx"], inp["pho_lens"], N, sv)
-            pho_h, _, sv["pho"] = self._stack_fwd("pho", m.pho_model, P["pho_model"], mask, B, L, inputs_embeds=pho_gru)
             mods.append(pho_h)
         if c.with_res == "yes":
-            res_raw = self._resnet_fwd(P, input_ids.view(-1), N, sv)
-            sv["res_raw"] = res_raw
-            res_h = self._new((N, H), F32)
-            ops.layernorm(res_raw, P["res_ln_w"], P["res_ln_b"], res_h, None, c.layer_norm_eps)
             mods.append(res_h)
         sv["mods"] = mods
         fused = self._new((N, H), F32)
@@ -680,9 +712,10 @@ class TrainEngine:
                               site_out=self.site(name, li, 3) if hp > 0 else 0)
             ops.gemm(dy2b, s["h"], self._grad(out.dense.weight), a_t=True, b_t=True, split_k=-1)              # dW2 = dy2^T h
             du = self._new((N, I), BF16)
-            # du = (dy2 W2) o gelu'(u) with u arriving as TMA tiles in the epilogue; db1 = column sums of the fp32 products
-            ops.gemm(dy2b, lw["w_2"], du, b_t=True, res=s["u"], act=ops.ACT_GELU_GRAD,
-                     colsum=self._grad(lyr.intermediate.dense.bias, True))
+            ops.gemm(dy2b, lw["w_2"], du, b_t=True)
+            # du = (dy2 W2) o gelu'(u) and db1 as one element-wise pass: measured faster than the fused epilogue (ACT_GELU_GRAD
+            # + colsum), whose erf' polynomial on 8 epilogue warps outlasts a K = 768 main loop (tools/gemm_bench.py)
+            ops.gelu_bwd_colsum(du, s["u"], self._grad(lyr.intermediate.dense.bias, True))
             ops.gemm(du, s["x1b"], self._grad(lyr.intermediate.dense.weight), a_t=True, b_t=True, split_k=-1)  # dW1 = du^T x1
             dx1 = self._new((N, H), F32)
             ops.gemm(du, lw["w_1"], dx1, b_t=True, res=dy2)                                         # dx1 = du W1 + dy2
@@ -747,17 +780,21 @@ class TrainEngine:
         else:
             dms = [dfused] * nm
         dm0 = dms[0]
-        if c.with_pho == "yes":
-            dgru = self._stack_bwd(sv["pho"], dms[1], mask, B, L)
-            self._gru_bwd(P, sv, dgru, N)
+        s_pho, s_res = self._side_streams() if (c.with_pho == "yes" or c.with_res == "yes") else (None, None)
         if c.with_res == "yes":
-            dres = self._new((N, H), F32)
-            ops.layernorm_bwd(dms[-1], sv["res_raw"], P["res_ln_w"], None, dres, None, self._grad(m.resnet_layernorm.weight),
-                              self._grad(m.resnet_layernorm.bias), None, c.layer_norm_eps)
-            if self.debug is not None:
-                self.debug["dres"] = dres.clone()
-            self._resnet_bwd(sv, dres, N)
+            with self._on(s_res):
+                dres = self._new((N, H), F32)
+                ops.layernorm_bwd(dms[-1], sv["res_raw"], P["res_ln_w"], None, dres, None, self._grad(m.resnet_layernorm.weight),
+                                  self._grad(m.resnet_layernorm.bias), None, c.layer_norm_eps)
+                if self.debug is not None:
+                    self.debug["dres"] = dres.clone()
+                self._resnet_bwd(sv, dres, N)
+        if c.with_pho == "yes":
+            with self._on(s_pho):
+                dgru = self._stack_bwd(sv["pho"], dms[1], mask, B, L)
+                self._gru_bwd(P, sv, dgru, N)
         self._stack_bwd(sv["bert"], dm0, mask, B, L)   # scatter-adds the embedding rows into the (tied) dE buffer
+        self._join(s_pho, s_res)
         self.saved = None
         # parameters that never receive a gradient (poolers, unused word embeddings of output_block) -> None
         return self.grads
