@@ -125,8 +125,9 @@ class TrainEngine:
         self._accum = None
         self.debug = None             # tests set a dict to receive intermediate gradients
         self._res = None              # conv operand layouts + their refresh launch, built on the first training forward
-        self.multistream = True       # the three encoders (and their backward passes) run on three CUDA streams: the HBM-bound
-        self._streams = None          # CNN passes and the latency-bound GRU steps fill the wave tails of the BERT GEMMs
+        self.multistream = False      # experiment (off): the three encoders (and their backward passes) on three CUDA streams.
+        self._streams = None          # Measured on B200: no gain — the persistent GEMMs hold every SM's register file, so the
+                                      # other branches' kernels only fill wave tails (42.8 vs 42.0 ms/step within clock noise)
         self.zpool = ZeroPool(model.classifier.bias.device)
         self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
