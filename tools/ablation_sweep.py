@@ -1,6 +1,6 @@
 """BASELINE configs[4]: ablation sweep on 1 GPU — semantic-only / +glyph / +pinyin / full (src/models_abla.py) at
 seq_len 64 / 128 / 256.  Forward-only (eval, CUDA graph, fp16 operands) for every cell; the training step (fwd + bwd +
-clip + AdamW as one CUDA-graph replay) where the backward kernels support the length (seq_len <= 128).
+clip + AdamW as one CUDA-graph replay) for every cell too (batch 64 at seq_len 256).
 Prints one JSON object per cell and a summary table; random-init weights, synthetic batches (realise_b200.synth)."""
 import json
 import sys
@@ -46,7 +46,7 @@ for name, pho, res in (("semantic-only", "no", "no"), ("+glyph", "no", "yes"), (
         cell["fwd_ms"] = round(ms, 3)
         cell["fwd_sentences_per_s"] = round(B / ms * 1e3, 1)
         # ---- train step ----
-        if L <= 128:
+        if True:
             model.train()
             if opt is None:
                 opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=5e-5, max_grad_norm=1.0, model=model)
@@ -65,8 +65,6 @@ for name, pho, res in (("semantic-only", "no", "no"), ("+glyph", "no", "yes"), (
             cell["train_sentences_per_s"] = round(B / ms * 1e3, 1)
             del step
             model._engine = None
-        else:
-            cell["train_ms"] = None   # attention backward kernel covers seq_len <= 128 this round
         torch.cuda.empty_cache()
         rows.append(cell)
         print(json.dumps(cell), flush=True)
