@@ -576,3 +576,21 @@ def test_gemm_many_short_tiles_per_cta():
         err = (out.float() - ref).abs().max().item()
         tol = (2.0 ** -8 if odt is torch.bfloat16 else 1e-5) * ref.abs().max().item()      # one output rounding
         assert err <= tol, (M, N, K, err, tol)
+
+
+def test_gemm_epilogue_column_reductions():
+    """rl_gemm_desc.colsum / colsumsq: per-column sum and sum of squares of the fp32 results, accumulated across tiles
+    (one N tile: flushed once per CTA; several: per tile) — bias gradients / BatchNorm batch statistics."""
+    from realise_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    for M, N, K in [(70000, 64, 32), (5000, 128, 576), (3000, 768, 768), (1000, 200, 64)]:
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        b = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
+        bias = torch.randn(N, device="cuda", generator=g)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        cs, cq = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+        ops.gemm(a, b, out, bias=bias, colsum=cs, colsumsq=cq)
+        ref = a.float() @ b.float().t() + bias
+        assert (out.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item()
+        assert torch.allclose(cs, ref.sum(0), rtol=1e-3, atol=1e-3 * ref.sum(0).abs().max().item()), (M, N, K)
+        assert torch.allclose(cq, (ref * ref).sum(0), rtol=1e-3), (M, N, K)
