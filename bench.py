@@ -59,12 +59,13 @@ def load_peaks():
 
 
 def load_traffic():
-    p = os.path.join(ROOT, "profiles", "r01_train_traffic.json")
-    try:
-        with open(p) as f:
-            return float(json.load(f)["gemm_dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+    for name in ("r02_train_traffic.json", "r01_train_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["gemm_dram_bytes_per_launch"])
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 class ClockSampler:
@@ -449,7 +450,7 @@ def measure_train(args, dev, rank, world, dist, peaks):
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tf / peaks["tf_sustained"],
                      # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, from the committed ncu pass over one
-                     # train step (profiles/r01_train_traffic.json); null when that file is absent
+                     # train step (profiles/r02_train_traffic.json); null when that file is absent
                      "traffic": load_traffic(),
                      "kernel": "gemm_bf16_kernel / gemm2_bf16_kernel (tcgen05 GEMM, implicit-GEMM conv, split-K wgrad): "
                                f"executed 2*M*N*K over CUDA-event time of its {gn} launches in one train step",

@@ -39,7 +39,11 @@ struct KParams {
   int tma_store;  // epilogue writes through tmC (plain row-major outputs)
   int tma_res;    // residual tiles arrive through tmR (TMA load into the staging tile the result leaves from): per-thread
                   // row loads touch 32 cache lines per instruction and made the f32-residual epilogues L1-bound
-  int res_all;    // tma_res with 16-bit residual AND result: every chunk of a tile has its own 2 KB staging tile (see issue_residual)
+  int deep;       // 16-bit result leaving by TMA: every chunk of a tile has its OWN 2 KB staging tile, the stores are issued
+                  // back to back and only drained when the warp starts its NEXT tile (a whole main loop later).  With two
+                  // alternating tiles each chunk waited for the TMA store of two chunks earlier to finish READING its tile —
+                  // behind the main loop's loads that takes thousands of cycles and made every K = 768 GEMM epilogue-bound.
+  int res_all;    // deep + tma_res (16-bit residual AND result): every chunk of a tile has its own 2 KB staging tile (see issue_residual)
   int tma_out2;   // GELU_SAVE: the pre-activation tile leaves through tmC2 from the upper half of the staging tile
   float* colsum;    // optional [N]: += sum over rows of the result (bias gradients; BatchNorm batch statistics)
   float* colsumsq;  // optional [N]: += sum over rows of result^2
@@ -279,9 +283,9 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (st.stg_sel lives in the tile loop: a
         // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
         // store was still reading): the TMA store issued two chunks ago must have finished reading
-        stg = p.res_all ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
+        stg = p.deep ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
         st.stg_sel ^= 1;
-        if (!p.tma_res) {   // (with tma_res the tile's previous store was drained before the residual was fetched into it)
+        if (!p.tma_res && !p.deep) {   // (tma_res / deep: the tile's previous store was drained earlier)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
@@ -612,6 +616,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
+      if (p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
       if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
         if (p.res_all) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
@@ -930,6 +938,10 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
+      if (p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
       if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
         if (p.res_all) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
@@ -1363,7 +1375,8 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   // residual tiles by TMA: plain row-major result leaving by TMA, residual rows 16-byte aligned (checked above), and the
   // residual tile must fit the staging tile the result leaves from (f32 residual -> f32 result)
   p.tma_res = (d->res && p.tma_store && !p.atomic_out && !p.tma_out2 && (p.out_f32 || !p.res_f32)) ? 1 : 0;
-  p.res_all = (p.tma_res && !p.res_f32 && !p.out_f32) ? 1 : 0;
+  p.deep = (p.tma_store && !p.out_f32 && !p.tma_out2 && !p.atomic_out) ? 1 : 0;
+  p.res_all = (p.deep && p.tma_res) ? 1 : 0;
   if (p.tma_res) {
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
     uint64_t strides[1] = {(uint64_t)d->ldr * (p.res_f32 ? 4 : 2)};

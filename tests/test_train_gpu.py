@@ -531,7 +531,7 @@ def test_gradient_accumulation_and_probe_forward():
     l1 = model(b1)[0]
     model(b2)                                # probe forward in between: must not disturb l1's saved activations
     l1.backward()
-    assert torch.allclose(p.grad, g1, rtol=1e-3, atol=1e-6 * g1.abs().max().item())
+    assert ((p.grad - g1).norm() / g1.norm()).item() <= 1e-3        # (split-K atomics reorder fp32 sums run to run)
     model(b2)[0].backward()                  # no zero_grad: accumulates
     ref = g1 + g2
     assert ((p.grad - ref).norm() / ref.norm()).item() <= 1e-3
