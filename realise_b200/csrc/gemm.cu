@@ -194,7 +194,7 @@ __device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorM
   rl::tma_load_2d(stg_base + buf * (p.res_all ? 2048 : 4096), tmR_ptr, &rbar[buf], nb, row0);
 }
 
-template <int BN, bool COLS>
+template <int BN, bool COLS, int NSTG = 2>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, const CUtensorMap* tmC2_ptr,
                                               const CUtensorMap* tmR_ptr, uint8_t* stg_base, uint64_t* rbar,
                                               const float* sb, uint32_t taddr, int row0, int n0, int half, int lane,
@@ -214,9 +214,16 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
     if (p.tma_res) {
       // residual of THIS chunk: TMA delivered it into the staging tile the result will leave from (issued one chunk
       // ahead); read my row, then prefetch the next chunk's tile into the other staging tile
-      const int buf = p.res_all ? cc : (st.stg_sel & 1);
+      const int buf = NSTG == 1 ? 0 : p.res_all ? cc : (st.stg_sel & 1);
       if (live) {
-        if (!p.res_all && cc + 1 < CH && nb + 32 < p.N && lane == 0) {
+        if (NSTG == 1) {
+          // single staging tile: fetch THIS chunk's residual once the previous chunk's store has drained (the latency is
+          // hidden behind the >= 24 k-block main loop of the next tile)
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue_residual(p, tmR_ptr, stg_base, rbar, 0, nb, row0);
+          }
+        } else if (!p.res_all && cc + 1 < CH && nb + 32 < p.N && lane == 0) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that last read tile buf^1
           issue_residual(p, tmR_ptr, stg_base, rbar, buf ^ 1, nb + 32, row0);
         }
@@ -283,9 +290,14 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (st.stg_sel lives in the tile loop: a
         // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
         // store was still reading): the TMA store issued two chunks ago must have finished reading
-        stg = p.deep ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
+        stg = NSTG == 1 ? stg_base : p.deep ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
         st.stg_sel ^= 1;
-        if (!p.tma_res && !p.deep) {   // (tma_res / deep: the tile's previous store was drained earlier)
+        if (NSTG == 1) {
+          if (!p.tma_res) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+        } else if (!p.tma_res && !p.deep) {   // (tma_res / deep: the tile's previous store was drained earlier)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
@@ -745,7 +757,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // from eit
 // CL = CTAs per cluster: 2 = one pair; 4 = two pairs stacked along M that SHARE the B tile: each CTA fetches only a
 // quarter of it and multicasts the quarter to its counterpart in the other pair, so a CTA pulls 24 KB instead of 32 KB
 // through L2 per 64-deep k-block (the pair kernel is bound by L2 -> SM bytes, not by the tensor pipe).
-template <int BN, int STAGES, int CL, bool COLS>
+// NSTG = 32x32 fp32 staging tiles per epilogue warp: 2 (default), or 1 for the LONG-K variant, which spends the shared
+// memory on a fifth pipeline stage instead: ncu shows the main loop bound by bytes in flight (4 x 32 KB per SM at ~2 us of
+// TMA latency = 900 clk per k-block, 57 % tensor-pipe), and behind >= 24 k-blocks a serialised epilogue is invisible.
+template <int BN, int STAGES, int CL, bool COLS, int NSTG = 2>
 __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                            const CUtensorMap& tmC2, const CUtensorMap& tmR, const KParams& p) {
   constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
@@ -756,7 +771,8 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint8_t* smem_stage = smem_b + STAGES * BH_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + STAGE_BYTES);
+  constexpr int WARP_STG = NSTG * 4096 + 1024;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + 8 * WARP_STG);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -924,8 +940,8 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     const int ew = warp - 4;
     const int q = warp & 3;
     const int half = ew >> 2;
-    uint8_t* stg = smem_stage + ew * (8192 + 1024);
-    float* sb = reinterpret_cast<float*>(stg + 8192);
+    uint8_t* stg = smem_stage + ew * WARP_STG;
+    float* sb = reinterpret_cast<float*>(stg + NSTG * 4096);
     int acc = 0;
     EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
     uint64_t* rbar = res_bar + ew * 4;
@@ -938,11 +954,11 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
-      if (p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
+      if (NSTG == 2 && p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
-      if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
+      if (NSTG == 2 && p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
         if (p.res_all) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -958,7 +974,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN, COLS>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
+      epilogue_tile<BN, COLS, NSTG>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
       rl::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -977,12 +993,12 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   }
 }
 
-template <int BN, int STAGES, bool COLS>
+template <int BN, int STAGES, bool COLS, int NSTG = 2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                   const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  gemm2_body<BN, STAGES, 2, COLS>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_body<BN, STAGES, 2, COLS, NSTG>(tmA, tmB, tmC, tmC2, tmR, p);
 }
 
 template <int BN, int STAGES>
@@ -993,18 +1009,19 @@ gemm4_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   gemm2_body<BN, STAGES, 4, false>(tmA, tmB, tmC, tmC2, tmR, p);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NSTG = 2>
 constexpr int gemm2_smem_bytes() {
-  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 + 1024;
+  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + 8 * (NSTG * 4096 + 1024) + (2 * STAGES + 4) * 8 + 16 + 256 + 1024;
 }
 
-template <int BN, int STAGES, bool COLS = false>
+template <int BN, int STAGES, bool COLS = false, int NSTG = 2>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                  const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
-  constexpr int smem = gemm2_smem_bytes<BN, STAGES>();
+  constexpr int smem = gemm2_smem_bytes<BN, STAGES, NSTG>();
+  static_assert(smem <= 232448, "dynamic shared memory of the pair kernel exceeds 227 KB");
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES, COLS, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1014,7 +1031,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int max_clusters = rl_num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_bf16_kernel<BN, STAGES, COLS><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_bf16_kernel<BN, STAGES, COLS, NSTG><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16(cta_group::2)");
 }
 
@@ -1375,7 +1392,8 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   // residual tiles by TMA: plain row-major result leaving by TMA, residual rows 16-byte aligned (checked above), and the
   // residual tile must fit the staging tile the result leaves from (f32 residual -> f32 result)
   p.tma_res = (d->res && p.tma_store && !p.atomic_out && !p.tma_out2 && (p.out_f32 || !p.res_f32)) ? 1 : 0;
-  p.deep = (p.tma_store && !p.out_f32 && !p.tma_out2 && !p.atomic_out) ? 1 : 0;
+  const bool long_k = pair && bn == 256 && !(d->colsum || d->colsumsq) && !p.tma_out2 && p.kb_per_split >= 24 && d->tune_no_pair != 4;
+  p.deep = (p.tma_store && !p.out_f32 && !p.tma_out2 && !p.atomic_out && !long_k) ? 1 : 0;
   p.res_all = (p.deep && p.tma_res) ? 1 : 0;
   if (p.tma_res) {
     uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
@@ -1388,6 +1406,9 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   const bool cols = d->colsum || d->colsumsq;   // separate instantiations: the reductions cost registers in the epilogue
   if (quad && !cols) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
   if (pair) {
+    // long-K variant (5 stages, one staging tile per epilogue warp): >= 24 k-blocks per work item
+    if (bn == 256 && !cols && !p.tma_out2 && p.kb_per_split >= 24 && d->tune_no_pair != 4)
+      return launch_gemm2<256, 5, false, 1>(tmA, tmB, tmC, tmC2, tmR, p, st);
     if (bn == 256) return cols ? launch_gemm2<256, 4, true>(tmA, tmB, tmC, tmC2, tmR, p, st)
                                : launch_gemm2<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
     return cols ? launch_gemm2<128, 6, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm2<128, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);

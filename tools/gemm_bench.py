@@ -49,7 +49,7 @@ for name, (m, n, k), a_t, b_t, sk, odt, res in cases:
     if r is not None:
         ref = ref + r
     row = [name, f"{m}x{n}x{k}"]
-    for mode in (0,):
+    for mode in (4, 0):
         ops.TUNE_NO_PAIR = mode
         out = torch.zeros(m, n, device=dev, dtype=odt)
 
