@@ -544,6 +544,36 @@ mt_adamw_kernel(const TensorEntry* __restrict__ tab, const int2* __restrict__ ch
     if (c < 1.0f) coef *= c;
   }
   const float step_size = lr * sqrtf(bc2) / bc1;
+  // full, 16-byte aligned chunks: float4 / 8-byte 16-bit stores (28 B per parameter of pure streaming)
+  const bool vec = base + OPT_CHUNK <= e.n &&
+                   (((reinterpret_cast<uintptr_t>(e.p + base) | reinterpret_cast<uintptr_t>(e.g + base) |
+                      reinterpret_cast<uintptr_t>(e.m + base) | reinterpret_cast<uintptr_t>(e.v + base) |
+                      (e.shadow32 ? reinterpret_cast<uintptr_t>(e.shadow32 + base) : 0)) & 15) == 0) &&
+                   (!e.shadow || (reinterpret_cast<uintptr_t>(e.shadow + base) & 7) == 0);
+  if (vec) {
+#pragma unroll
+    for (int it = 0; it < OPT_CHUNK / 4 / 256; ++it) {
+      const long long i4 = base / 4 + it * 256 + threadIdx.x;
+      const float4 g4 = reinterpret_cast<const float4*>(e.g)[i4];
+      float4 m4 = reinterpret_cast<float4*>(e.m)[i4], v4 = reinterpret_cast<float4*>(e.v)[i4], p4 = reinterpret_cast<float4*>(e.p)[i4];
+      float gg[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mm[k] = beta1 * mm[k] + (1.0f - beta1) * gg[k];
+        vv[k] = beta2 * vv[k] + (1.0f - beta2) * gg[k] * gg[k];
+        pp[k] -= step_size * mm[k] / (sqrtf(vv[k]) + eps);
+        if (e.wd > 0.f) pp[k] -= lr * e.wd * pp[k];
+      }
+      reinterpret_cast<float4*>(e.m)[i4] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(e.v)[i4] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      reinterpret_cast<float4*>(e.p)[i4] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      if (e.shadow)
+        reinterpret_cast<uint2*>(e.shadow)[i4] = make_uint2(rl::pack_h(pp[0], pp[1], e.shadow_f16), rl::pack_h(pp[2], pp[3], e.shadow_f16));
+      if (e.shadow32) reinterpret_cast<float4*>(e.shadow32)[i4] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
     const long long idx = base + i;
     if (idx < e.n) {

@@ -126,13 +126,13 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
 }
 
 // scale/bias of this warp's BN/2 columns -> sb[0..BN/2) and sb[128..128+BN/2); first residual chunk -> xr
-template <int BN>
+template <int BN, int NSTG = 2>
 __device__ __forceinline__ void epilogue_prefetch(const KParams& p, float* sb, int row0, int n0, int half, int lane,
                                                   float (&xr)[32]) {
   constexpr int HC = BN / 2;
   const int c0 = n0 + half * HC;
   __syncwarp();
-  for (int i = lane; i < HC; i += 32) {
+  for (int i = lane; NSTG != 1 && i < HC; i += 32) {
     const int n = c0 + i;
     sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
     sb[128 + i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
@@ -192,6 +192,34 @@ __device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorM
                                                uint64_t* rbar, int buf, int nb, int row0) {
   rl::mbar_expect_tx(&rbar[buf], p.res_f32 ? 4096u : 2048u);
   rl::tma_load_2d(stg_base + buf * (p.res_all ? 2048 : 4096), tmR_ptr, &rbar[buf], nb, row0);
+}
+
+// scale / bias of 4 consecutive columns: from the warp's shared-memory table, or (NSTG == 1: the long-K variant has no
+// table — its shared memory went into pipeline stages) straight from global memory (warp-uniform addresses, L1 hits)
+template <int NSTG>
+__device__ __forceinline__ void load_scale_bias(const KParams& p, const float* sb, int cc, int j, int nb, float4& sc, float4& bi) {
+  if (NSTG == 1) {
+    sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    bi = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = nb + j;
+    if (n + 4 <= p.N) {
+      if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+      if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    } else {
+      float s4[4] = {1.f, 1.f, 1.f, 1.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (n + k < p.N) {
+          if (p.scale) s4[k] = __ldg(p.scale + n + k);
+          if (p.bias) b4[k] = __ldg(p.bias + n + k);
+        }
+      sc = make_float4(s4[0], s4[1], s4[2], s4[3]);
+      bi = make_float4(b4[0], b4[1], b4[2], b4[3]);
+    }
+  } else {
+    sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
+    bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+  }
 }
 
 template <int BN, bool COLS, int NSTG = 2>
@@ -258,8 +286,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         // data gradient through GELU: the `res` operand carries the saved pre-activation u
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {   // packed f32x2 polynomial (FFMA2 / FMUL2): half the issue slots of the scalar form
-          const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
-          const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+          float4 sc, bi;
+          load_scale_bias<NSTG>(p, sb, cc, j, nb, sc, bi);
           const rl::f2 g0 = rl::gelu_grad2(rl::f2{xr[j], xr[j + 1]}), g1 = rl::gelu_grad2(rl::f2{xr[j + 2], xr[j + 3]});
           x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x) * g0.x;
           x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y) * g0.y;
@@ -269,8 +297,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
-          const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+          float4 sc, bi;
+          load_scale_bias<NSTG>(p, sb, cc, j, nb, sc, bi);
           x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
           x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
           x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
@@ -766,12 +794,15 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   constexpr int PAIRS = CL / 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // NSTG == 2: pad to 1024 B by pointer arithmetic.  NSTG == 1 (long-K variant) has no slack to pad with: the dynamic
+  // shared-memory window of a kernel without static shared memory starts 1024-byte aligned (trap if it ever does not)
+  uint8_t* smem = smem_raw + (NSTG == 1 ? 0u : ((1024u - (rl::smem_u32(smem_raw) & 1023u)) & 1023u));
+  if (NSTG == 1 && (rl::smem_u32(smem_raw) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint8_t* smem_stage = smem_b + STAGES * BH_BYTES;
-  constexpr int WARP_STG = NSTG * 4096 + 1024;
+  constexpr int WARP_STG = NSTG == 1 ? 4096 : NSTG * 4096 + 1024;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + 8 * WARP_STG);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -953,7 +984,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       const int row0 = m_blk * CL * BM + (int)crank * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
-      epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
+      epilogue_prefetch<BN, NSTG>(p, sb, row0, n0, half, lane, xr);
       if (NSTG == 2 && p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
@@ -1011,7 +1042,7 @@ gemm4_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <int BN, int STAGES, int NSTG = 2>
 constexpr int gemm2_smem_bytes() {
-  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + 8 * (NSTG * 4096 + 1024) + (2 * STAGES + 4) * 8 + 16 + 256 + 1024;
+  return STAGES * (A_BYTES + (BN / 2) * BK * 2) + (NSTG == 1 ? 8 * 4096 : 8 * (NSTG * 4096 + 1024) + 1024) + (2 * STAGES + 4) * 8 + 16 + 256;
 }
 
 template <int BN, int STAGES, bool COLS = false, int NSTG = 2>
@@ -1406,7 +1437,10 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   const bool cols = d->colsum || d->colsumsq;   // separate instantiations: the reductions cost registers in the epilogue
   if (quad && !cols) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
   if (pair) {
-    // long-K variant (5 stages, one staging tile per epilogue warp): >= 24 k-blocks per work item
+    // long-K variant (5 stages; one staging tile per epilogue warp, no scale/bias table): >= 24 k-blocks per work item.
+    // Measured (tools/gemm_bench.py): 4 -> 5 stages = -5..10 % on K >= 2304 GEMMs and split-K weight gradients, 5 -> 6 nothing
+    // more: ~750 clk per k-block is what 32 KB per k-block costs at the ~81 GB/s an SM can ingest (68 % tensor-pipe ceiling
+    // of 256x256 pair tiles)
     if (bn == 256 && !cols && !p.tma_out2 && p.kb_per_split >= 24 && d->tune_no_pair != 4)
       return launch_gemm2<256, 5, false, 1>(tmA, tmB, tmC, tmC2, tmR, p, st);
     if (bn == 256) return cols ? launch_gemm2<256, 4, true>(tmA, tmB, tmC, tmC2, tmR, p, st)
