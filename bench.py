@@ -442,6 +442,29 @@ def measure_train(args, dev, rank, world, dist, peaks):
     e2e_value = world * B * args.steps / t.item()
     peak_mem = torch.cuda.max_memory_allocated(dev) / 1e9
     att, attb = agg.get("attention"), agg.get("attention_bwd")
+    # BertSelfAttention (modeling_bert.py:220-263) = fused QKV projection + attention core, forward and fwd+bwd: the
+    # "attention-GEMM roofline" north_star asks for (3.932 MFLOP/token/layer forward)
+    N_tok, H3, Hd = B * L, 3 * 768, 768
+    qkv_f = [0.0, 0.0]
+    qkv_b = [0.0, 0.0]
+    for kind, work, e0_, e1_, detail in prof:
+        if kind != "gemm" or not detail:
+            continue
+        m_, n_, k_ = detail[0], detail[1], detail[2]
+        dt_ = e0_.elapsed_time(e1_) * 1e-3
+        if (m_, n_, k_) == (N_tok, H3, Hd):
+            qkv_f[0] += work; qkv_f[1] += dt_
+        elif (m_, n_, k_) in ((N_tok, Hd, H3), (H3, Hd, N_tok)):
+            qkv_b[0] += work; qkv_b[1] += dt_
+    bsa = None
+    if att and attb and qkv_f[1] > 0:
+        f_w, f_t = qkv_f[0] + att[0], qkv_f[1] + att[1]
+        a_w, a_t = f_w + qkv_b[0] + attb[0], f_t + qkv_b[1] + attb[1]
+        bsa = {"forward_tflops": f_w / f_t / 1e12, "forward_frac_of_peak": f_w / f_t / 1e12 / peaks["tf_sustained"],
+               "fwd_bwd_tflops": a_w / a_t / 1e12, "fwd_bwd_frac_of_peak": a_w / a_t / 1e12 / peaks["tf_sustained"],
+               "ms_per_step": a_t * 1e3,
+               "what": "fused QKV GEMM + attention core (19 layers), executed FLOPs over CUDA-event time, against the measured "
+                       "sustained bf16 peak; ncu tensor-pipe-active per kernel: profiles/r02_ncu_full_kernels.json"}
     out = {
         "value": value, "ms_per_step": total_ms / args.steps, "warmup": W, "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "sentences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -459,6 +482,7 @@ def measure_train(args, dev, rank, world, dist, peaks):
             "gemm_ms_per_step": gt * 1e3,
             "attention_fwd_tflops": None if not att else att[0] / att[1] / 1e12,
             "attention_bwd_tflops": None if not attb else attb[0] / attb[1] / 1e12,
+            "bert_self_attention": bsa,
             "per_kernel_ms_per_step": {k: round(v[1] * 1e3, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
             "timed_kernels_ms": round(sum(v[1] for v in agg.values()) * 1e3, 3),
         },

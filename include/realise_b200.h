@@ -112,6 +112,9 @@ typedef struct rl_gemm_desc {
                         gradient of the layer below comes out of the data-gradient GEMM, BatchNorm's batch sum out of the
                         conv GEMM.  Needs split_k = 0. */
   float* colsumsq;   /* optional f32 [N], accumulated: sum over rows of result^2 (BatchNorm batch statistics) */
+  int32_t sm_reserve; /* SMs this (persistent, one-CTA-per-SM) launch leaves free: the grid, the wave model and the split-K
+                         chooser work with num_SMs - sm_reserve.  Data parallelism sets it while an NCCL all-reduce of a
+                         gradient bucket runs concurrently with the rest of the backward (src/run.py:165-167, :200). */
   int32_t b_mode;    /* 0: B is a 2-D matrix.  1 (needs b_major = 1, a_mode = 0): B is the im2col matrix of the conv
                         activation `b` ([NIMG, P, H, W, C], geometry / taps in the conv_* fields), never materialised:
                         B[k = output pixel (img, oh, ow), n = tap * Cuse + c] = x[img, plane_t, oh+dh_t, ow+dw_t, c],

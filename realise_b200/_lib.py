@@ -34,6 +34,7 @@ class GemmDesc(ctypes.Structure):
         ("drop_counter", ctypes.c_void_p),
         ("tune_tile_n", ctypes.c_int32), ("tune_no_pair", ctypes.c_int32),
         ("colsum", ctypes.c_void_p), ("colsumsq", ctypes.c_void_p),
+        ("sm_reserve", ctypes.c_int32),
         ("b_mode", ctypes.c_int32),
     ]
 

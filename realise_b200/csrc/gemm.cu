@@ -45,6 +45,7 @@ struct KParams {
                   // behind the main loop's loads that takes thousands of cycles and made every K = 768 GEMM epilogue-bound.
   int res_all;    // deep + tma_res (16-bit residual AND result): every chunk of a tile has its own 2 KB staging tile (see issue_residual)
   int tma_out2;   // GELU_SAVE: the pre-activation tile leaves through tmC2 from the upper half of the staging tile
+  int sms;          // SMs this launch may occupy (num_SMs - sm_reserve)
   float* colsum;    // optional [N]: += sum over rows of the result (bias gradients; BatchNorm batch statistics)
   float* colsumsq;  // optional [N]: += sum over rows of result^2
   int vec_store;  // direct path may use 16-byte stores
@@ -715,7 +716,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     configured = true;
   }
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
-  const int grid = tiles < rl_num_sms() ? tiles : rl_num_sms();
+  const int grid = tiles < p.sms ? tiles : p.sms;
   gemm_bf16_kernel<BN, STAGES, COLS><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16");
 }
@@ -1060,7 +1061,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     configured = true;
   }
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
-  const int max_clusters = rl_num_sms() / 2;
+  const int max_clusters = p.sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   gemm2_bf16_kernel<BN, STAGES, COLS, NSTG><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16(cta_group::2)");
@@ -1169,6 +1170,8 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   p.out_remap = d->out_remap;
   p.remap_plane = d->remap_plane;
   p.drop = rl::make_drop(d->drop_p, d->drop_seed, d->drop_site, d->drop_counter);
+  RL_REQUIRE(d->sm_reserve >= 0 && d->sm_reserve < rl_num_sms() - 1, RL_EINVAL, "rl_gemm_bf16: sm_reserve %d out of range", d->sm_reserve);
+  p.sms = (rl_num_sms() - d->sm_reserve) & ~1;   // an even number: CTA pairs
   p.colsum = d->colsum;
   p.colsumsq = d->colsumsq;
   RL_REQUIRE(!(d->colsum || d->colsumsq) || d->split_k == 0, RL_EINVAL, "rl_gemm_bf16: colsum / colsumsq need split_k = 0");
@@ -1181,7 +1184,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   const int g_force_bn = d->tune_tile_n;          // 0 = cost model; 64 / 128 / 256 force the N tile (tuning, tests)
   const int g_pair_mode = d->tune_no_pair == 1 ? 0 : 1;  // tune_no_pair 1: never use the cta_group::2 kernels
   {
-    const int sms = rl_num_sms();
+    const int sms = p.sms;
     double best = 1e30;
     for (int mode = 0; mode < 2; ++mode) {
       if (mode == 1 && (!g_pair_mode || d->M <= BM)) continue;
@@ -1225,7 +1228,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     if (maxc4 > 0) {
       const long long tn = (p.N + 255) / 256;
       const long long t2 = ((p.M + 2 * BM - 1) / (2 * BM)) * tn, t4 = ((p.M + 4 * BM - 1) / (4 * BM)) * tn;
-      const long long u2 = rl_num_sms() / 2, u4 = maxc4;
+      const long long u2 = p.sms / 2, u4 = maxc4;
       const double kb2 = (A_BYTES + 128 * BK * 2.0) / 42.6, kb4_l2 = (A_BYTES + 64 * BK * 2.0) / 42.6;
       const double kb4 = kb4_l2 > 512.0 ? kb4_l2 : 512.0;
       double c2, c4;
@@ -1257,7 +1260,7 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     // epilogue, ~10 k-blocks' worth), e.g. 27 tiles on 74 pairs: 8 splits (3 full waves of 32 k-blocks) beat 6
     // (3 ragged waves of 43).
     const long long tiles = (long long)p.tiles_m * p.tiles_n;
-    const long long units = quad ? gemm4_max_clusters<256, 4>() : pair ? rl_num_sms() / 2 : rl_num_sms();
+    const long long units = quad ? gemm4_max_clusters<256, 4>() : pair ? p.sms / 2 : p.sms;
     int maxs = p.num_kb / 8;
     if (maxs < 1) maxs = 1;
     int want = 1;

@@ -7,6 +7,8 @@ ranks see the same count), the model is wrapped in DistributedDataParallel, and 
 NVSwitch on the 8xB200 box — and the division by W is folded into the fused clip+AdamW kernel (grad_div).
 BatchNorm statistics stay per-rank (plain BatchNorm2d in the reference, no SyncBN).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -42,7 +44,7 @@ class DataParallel:
         optimizer.step()                               # FusedAdamW(model=model) reads model.grad_div
     """
 
-    def __init__(self, model, group=None, average=False):
+    def __init__(self, model, group=None, average=False, overlap=None, sm_reserve=16):
         """average=False: gradients are SUMMED over ranks and FusedAdamW(model=model) divides by the world size inside
         its update kernel (model.grad_div).  average=True: the buffer is scaled by 1/W right after the all-reduce, which
         is what DistributedDataParallel leaves in p.grad — for optimizers that know nothing about grad_div (the
@@ -52,9 +54,40 @@ class DataParallel:
         model.grad_div = 1.0 if average else world
         self._inv_world = 1.0 / world
         model._post_backward = self.sync
+        # overlap (default with NCCL and more than one rank): the flat buffer is laid out in backward-completion order
+        # (TrainEngine.buckets); each bucket is all-reduced on a communication stream as soon as the backward has issued
+        # its last gradient kernel, behind the remaining backward.  The persistent GEMMs normally take every SM, which
+        # would leave NCCL's CTAs waiting (or a GEMM's last CTAs waiting for NCCL): while a reduction may be in flight
+        # the GEMMs are launched on `sm_reserve` fewer SMs.
+        if overlap is None:      # RL_DP_OVERLAP=0: one all-reduce of the whole buffer after the backward (A/B measurements)
+            overlap = world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("RL_DP_OVERLAP", "1") != "0"
+        self.overlap, self.sm_reserve, self._comm, self._pending = bool(overlap), int(sm_reserve), None, False
+        if self.overlap:
+            model._bucket_ready = self.bucket_ready
+
+    def bucket_ready(self, engine, k):
+        from . import ops
+        a, b = engine.buckets[k]
+        if b <= a:
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(engine.flat.device)
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)                     # the bucket's gradient kernels were issued on `main`
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(engine.flat[a:b], op=dist.ReduceOp.SUM, group=self.group)
+        self._pending = True
+        ops.SM_RESERVE = self.sm_reserve                 # GEMMs of the remaining backward leave SMs to NCCL
 
     def sync(self, engine):
-        w = allreduce_sum_(engine.flat, self.group)
+        if self.overlap and self._pending:
+            from . import ops
+            torch.cuda.current_stream().wait_stream(self._comm)     # join: every bucket has been reduced
+            ops.SM_RESERVE = 0
+            self._pending = False
+            w = dist.get_world_size(self.group)
+        else:
+            w = allreduce_sum_(engine.flat, self.group)
         if self.average and w > 1:
             engine.flat.mul_(self._inv_world)
 

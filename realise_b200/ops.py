@@ -43,6 +43,7 @@ _H16 = (torch.bfloat16, torch.float16)
 # tuning knobs of the GEMM (per call through the descriptor; the library keeps no global switches)
 TUNE_TILE_N = 0
 TUNE_NO_PAIR = 0
+SM_RESERVE = 0      # SMs the persistent GEMMs leave free (realise_b200.ddp sets it while a gradient all-reduce is in flight)
 
 # Device-resident dropout step counter (int64 tensor of one element) handed to every dropout-bearing kernel while set:
 # the kernels then use seed + *counter, read at run time (realise_b200.graphed bumps it inside the captured graph).
@@ -196,7 +197,7 @@ def _fill_epilogue(d, out, scale, bias, res, act, out2, out_remap):
     if not out.is_cuda or out.dtype not in _DT:
         raise RuntimeError("out must be a CUDA bf16/f32 tensor")
     d.out, d.ldo, d.out_dtype = out.data_ptr(), out.stride(0), _DT[out.dtype]
-    d.tune_tile_n, d.tune_no_pair = TUNE_TILE_N, TUNE_NO_PAIR
+    d.tune_tile_n, d.tune_no_pair, d.sm_reserve = TUNE_TILE_N, TUNE_NO_PAIR, SM_RESERVE
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")
         assert out2.dtype == out.dtype, "out2 shares out's 16-bit format"

@@ -137,47 +137,79 @@ class TrainEngine:
         self._layout()
 
     def _layout(self):
-        """All gradients live in ONE flat fp32 buffer (stable pointers for the fused optimizer, one NCCL all-reduce
-        for data parallelism): [ accumulated-into region (zeroed every step) | overwritten-by-GEMM region ].
-        The q/k/v weights (biases) of a layer are adjacent so that the fused [3H, H] wgrad GEMM ([3H] column sum)
-        writes them in one go.  Parameters that never receive a gradient (poolers, the unused word embeddings of
-        pho_model / output_block) are left out, like autograd leaves their .grad at None in the reference."""
+        """All gradients live in ONE flat fp32 buffer (stable pointers for the fused optimizer, NCCL all-reduce straight
+        out of it), zeroed once per step and written by split-K GEMMs / column-sum kernels.  Blocks are laid out in the
+        order in which the BACKWARD pass completes them — output_block + gate, pinyin branch, glyph branch, bert layers
+        11..0, bert embeddings (the tied classifier / word-embedding matrix is finished last, by the embedding
+        scatter) — so that data parallelism can all-reduce contiguous BUCKETS while the rest of the backward still runs
+        (`self.buckets`, realise_b200.ddp.DataParallel(overlap=True)).  The q/k/v weights (biases) of a layer are
+        adjacent so that the fused [3H, H] wgrad GEMM ([3H] column sum) writes them in one go.  Parameters that never
+        receive a gradient (poolers, the unused word embeddings of pho_model / output_block) are left out, like autograd
+        leaves their .grad at None in the reference."""
         m = self.m
         H = m.config.hidden_size
         dev = m.classifier.bias.device
         no_grad = set()
-        for stack in [m.bert, m.output_block] + ([m.pho_model] if hasattr(m, "pho_model") else []):
+        stacks = [m.bert, m.output_block] + ([m.pho_model] if hasattr(m, "pho_model") else [])
+        for stack in stacks:
             no_grad.update(id(p) for p in stack.pooler.parameters())
             if stack is not m.bert:
                 no_grad.add(id(stack.embeddings.word_embeddings.weight))
         tied = m.classifier.weight is m.bert.embeddings.word_embeddings.weight
-        over_ids, order_zero, order_over, seen = set(), [], [], set()
         self._fused = {}
-        stacks = [m.bert, m.output_block] + ([m.pho_model] if hasattr(m, "pho_model") else [])
-        for stack in stacks:
-            for lyr in stack.encoder.layer:
-                sa = lyr.attention.self
-                order_over.append(("qkv_w", lyr.attention, [sa.query.weight, sa.key.weight, sa.value.weight]))
-                order_zero.append(("qkv_b", lyr.attention, [sa.query.bias, sa.key.bias, sa.value.bias]))
-                for p in (sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias):
-                    seen.add(id(p))
-                for lin in (lyr.attention.output.dense, lyr.intermediate.dense, lyr.output.dense):
-                    over_ids.add(id(lin.weight))
-        over_ids.add(id(m.classifier.weight))
-        for p in self.params:
-            if id(p) in seen or id(p) in no_grad:
-                continue
-            (order_over if id(p) in over_ids else order_zero).append(("p", None, [p]))
+        trainable = {id(p) for p in self.params}
+        entries, placed = [], set()          # (kind, attention module, [params])
+
+        def add(ps, kind="p", att=None):
+            ps = [p for p in ps if id(p) in trainable and id(p) not in no_grad and id(p) not in placed]
+            if ps:
+                placed.update(id(p) for p in ps)
+                entries.append((kind, att, ps))
+
+        def add_layer(lyr):
+            sa = lyr.attention.self
+            add([sa.query.weight, sa.key.weight, sa.value.weight], "qkv_w", lyr.attention)
+            add([sa.query.bias, sa.key.bias, sa.value.bias], "qkv_b", lyr.attention)
+            add(list(lyr.parameters()))
+
+        def add_stack(stack, layers=None):
+            for lyr in reversed(list(stack.encoder.layer) if layers is None else layers):
+                add_layer(lyr)
+
+        marks = []                           # entry counts at the bucket boundaries
+        word = m.bert.embeddings.word_embeddings.weight
+        placed.add(id(word))                 # finished last (classifier dE at the start, embedding scatter at the end)
+        add([m.classifier.bias] + ([] if tied else [m.classifier.weight]))
+        add_stack(m.output_block)
+        add(list(m.output_block.embeddings.parameters()))
+        if hasattr(m, "gate_net"):
+            add(list(m.gate_net.parameters()))
+        if hasattr(m, "pho_model"):
+            add_stack(m.pho_model)
+            add(list(m.pho_model.embeddings.parameters()) + list(m.pho_gru.parameters()) + list(m.pho_embeddings.parameters()))
+        if hasattr(m, "resnet"):
+            add(list(m.resnet_layernorm.parameters()))
+            for b in range(5, 0, -1):
+                add(list(getattr(m.resnet, f"res_block{b}").parameters()))
+        marks.append(len(entries))
+        bert_layers = list(m.bert.encoder.layer)
+        half = len(bert_layers) // 2
+        add_stack(m.bert, bert_layers[half:])
+        marks.append(len(entries))
+        add_stack(m.bert, bert_layers[:half])
+        placed.discard(id(word))
+        add(list(m.bert.embeddings.parameters()))
+        add([p for p in self.params])        # anything not named above (none for the shipped classes)
+        marks.append(len(entries))
+
         def padded(n):  # every block starts 256-byte aligned (float4 atomics, TMA stores, vector loads)
             return (n + 63) // 64 * 64
 
-        n_zero = sum(padded(sum(p.numel() for p in ps)) for _, _, ps in order_zero)
-        n_over = sum(padded(sum(p.numel() for p in ps)) for _, _, ps in order_over)
-        self.flat = torch.zeros(n_zero + n_over, device=dev, dtype=F32)
-        self.flat_zero = self.flat[:n_zero]
+        total = sum(padded(sum(p.numel() for p in ps)) for _, _, ps in entries)
+        self.flat = torch.zeros(total, device=dev, dtype=F32)
         self.grads = [None] * len(self.params)
-        off = 0
-        for kind, att, ps in order_zero + order_over:
+        off, bounds = 0, [0]
+        for ei, (kind, att, ps) in enumerate(entries):
             start = off = padded(off)
             for p in ps:
                 self.grads[self.index[id(p)]] = self.flat[off:off + p.numel()].view(p.shape)
@@ -186,6 +218,11 @@ class TrainEngine:
                 self._fused.setdefault(id(att), {})["w"] = self.flat[start:off].view(3 * H, H)
             elif kind == "qkv_b":
                 self._fused.setdefault(id(att), {})["b"] = self.flat[start:off]
+            if ei + 1 in marks:
+                bounds.append(padded(off))
+        bounds[-1] = total
+        self.buckets = list(zip(bounds[:-1], bounds[1:]))        # [(start, end)] element offsets; may contain empty ranges
+        self.bert_split = half               # bucket 1 is complete once bert layer `half` has been differentiated
         self.tied = tied
 
     def run(self, inputs):
@@ -202,8 +239,8 @@ class TrainEngine:
                 self._accum = torch.empty_like(self.flat)
             self._accum.copy_(self.flat)
         self.backward(gloss)
-        hook = getattr(self.m, "_post_backward", None)   # realise_b200.ddp.DataParallel: one all-reduce of self.flat
-        if hook is not None:
+        hook = getattr(self.m, "_post_backward", None)   # realise_b200.ddp.DataParallel: all-reduce of self.flat (or the
+        if hook is not None:                             # join of the bucketed all-reduces issued during the backward)
             hook(self)
         if accumulate:
             self.flat.add_(self._accum)
@@ -235,6 +272,13 @@ class TrainEngine:
     def _on(stream):
         import contextlib
         return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def _bucket_done(self, k):
+        """Every gradient of flat-buffer bucket k has been issued on the current stream: data parallelism may start
+        reducing it while the rest of the backward runs (no-op without an overlapping DataParallel)."""
+        hook = getattr(self.m, "_bucket_ready", None)
+        if hook is not None and k < len(self.buckets):
+            hook(self, k)
 
     def grads_consumed(self):
         """Called by FusedAdamW.step() and model.zero_grad(): the next backward starts from zero again."""
@@ -734,6 +778,8 @@ class TrainEngine:
             dxin = self._new((N, H), F32)
             ops.gemm(dqkv, lw["w_qkv"], dxin, b_t=True, res=dy1)                                    # dx = dqkv Wqkv + dy1
             dx = dxin
+            if name == "bert" and li == self.bert_split:
+                self._bucket_done(1)                   # the upper half of the bert layers is complete
         # embeddings: x0 = LN(e),  e = word[ids] (or inputs_embeds) + pos + type0
         e = mod.embeddings
         de = self._new((N, H), F32)
@@ -791,7 +837,11 @@ class TrainEngine:
             with self._on(s_pho):
                 dgru = self._stack_bwd(sv["pho"], dms[1], mask, B, L)
                 self._gru_bwd(P, sv, dgru, N)
+        if getattr(m, "_bucket_ready", None) is not None:
+            self._join(s_pho, s_res)
+            self._bucket_done(0)                       # output_block, gate, pinyin and glyph gradients are complete
         self._stack_bwd(sv["bert"], dm0, mask, B, L)   # scatter-adds the embedding rows into the (tied) dE buffer
+        self._bucket_done(2)
         self._join(s_pho, s_res)
         self.saved = None
         # parameters that never receive a gradient (poolers, unused word embeddings of output_block) -> None

@@ -1,8 +1,8 @@
 """Worker of tests/test_ddp_gpu.py — one process per rank (torchrun).  Checks the data-parallel training path on
 hardware against the reference's DDP semantics (src/run.py:165-167, :200):
 
-  1. the buffer every rank holds after the exchange is exactly the SUM of the per-rank gradient buffers (the optimizer
-     divides by W: mean of per-rank gradients, as DistributedDataParallel does);
+  1. the buffer every rank holds after the (bucketed, overlapped) exchange is the SUM of the per-rank gradient buffers
+     (the optimizer divides by W: mean of per-rank gradients, as DistributedDataParallel does);
   2. parameters are bit-identical across ranks after 3 eager steps and after 4 more CUDA-graph steps (the all-reduce
      captured inside the graph);
   3. W ranks x (global batch / W) gives the W=1 gradient of the global batch (model without BatchNorm: statistics are
@@ -83,37 +83,41 @@ def main():
     opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, max_grad_norm=1.0, model=model)
     flat_params = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
     res["params_identical_after_broadcast"] = all_equal_across_ranks(flat_params, world)
-    seen = {}
-    inner = model._post_backward
-
-    def spy(engine):
-        seen["pre"] = engine.flat.clone()
-        inner(engine)
-        seen["post"] = engine.flat.clone()
-
-    model._post_backward = spy
+    from realise_b200.train import TrainEngine
+    eng = model._engine = TrainEngine(model)
+    res["overlap"] = bool(dp.overlap)
+    res["buckets_mb"] = [round((b - a) * 4 / 1e6, 1) for a, b in eng.buckets]
     for step in range(3):
         g = synth_batch(per * world, L, seed=100 + step, ragged=False)
         local = rows(g, torch.tensor(shard_examples(list(range(per * world)), rank, world)), L)
+        if step == 0:
+            # this rank's own gradient: the same step (same dropout seed) with the data-parallel hooks taken off
+            hooks = {k: model.__dict__.pop(k) for k in ("_post_backward", "_bucket_ready") if k in model.__dict__}
+            eng.set_seed(77)
+            model(to_dev(local, dev))[0].backward()
+            mine = eng.flat.clone()
+            model.zero_grad()
+            model.__dict__.update(hooks)
+            eng.set_seed(77)
         loss = model(to_dev(local, dev))[0]
         loss.backward()
+        torch.cuda.synchronize()
+        post = eng.flat.clone()
         if step == 0:
-            pres = gather(seen["pre"], world)
+            pres = gather(mine, world)
             total = pres[0].clone()
             for p in pres[1:]:
                 total += p
-            diff = float((seen["post"] - total).abs().max())
+            diff = float((post - total).abs().max())
             scale = float(total.abs().max())
-            res["sum_exact"] = bool(torch.equal(seen["post"], total))
-            res["sum_max_diff_rel"] = diff / max(scale, 1e-30)
+            res["sum_max_diff_rel"] = diff / max(scale, 1e-30)      # (split-K atomics reorder fp32 sums between the two runs)
             res["ranks_differ_before_sync"] = not torch.equal(pres[0], pres[-1])
         opt.step()
         torch.cuda.synchronize()
-        chk = torch.stack([seen["post"].double().sum(), seen["post"].double().abs().sum(),
+        chk = torch.stack([post.double().sum(), post.double().abs().sum(),
                            torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad]).double().sum()])
         res.setdefault("per_step_identical(grad_sum,grad_abs,param_sum)", []).append(
             [bool(x) for x in (torch.stack(gather(chk, world))[0] == torch.stack(gather(chk, world))[-1])])
-    model._post_backward = inner
     flat_params = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
     res["params_identical_after_3_eager_steps"] = all_equal_across_ranks(flat_params, world)
     if not res["params_identical_after_3_eager_steps"]:
@@ -154,7 +158,7 @@ def main():
         if rel > worst:
             worst, res["w_ranks_vs_one_rank_worst_name"] = rel, n
     res["w_ranks_vs_one_rank_worst_rel_l2"] = worst
-    ok = (res["params_identical_after_broadcast"] and res["sum_max_diff_rel"] <= (0.0 if world == 2 else 1e-6) and res["ranks_differ_before_sync"]
+    ok = (res["params_identical_after_broadcast"] and res["sum_max_diff_rel"] <= 1e-5 and res["ranks_differ_before_sync"]
           and res["params_identical_after_3_eager_steps"] and worst <= 2e-2
           and (not own_gpu or (res["params_identical_after_graph_steps"] and res["graph_replays"] >= 3)))
     res["ok"] = bool(ok)

@@ -89,3 +89,37 @@ def test_flat_gradient_layout_on_cpu():
     assert eng._grad(att.self.key.weight).data_ptr() == w.data_ptr() + 768 * 768 * 4
     assert eng._grad(att.self.value.bias).data_ptr() == b.data_ptr() + 2 * 768 * 4
     assert (w.data_ptr() - base) % 256 == 0 and (b.data_ptr() - base) % 256 == 0
+
+
+def test_flat_buffer_buckets_follow_backward_completion_order():
+    """The flat gradient buffer is laid out in the order the backward completes it, in three contiguous buckets that data
+    parallelism all-reduces behind the remaining backward: [output_block, gate, pinyin, glyph | upper bert layers |
+    lower bert layers + embeddings (the tied classifier matrix is finished last, by the embedding scatter)]."""
+    from realise_b200.train import TrainEngine
+    m = SpellBertPho2ResArch3Abla(ArchConfig(num_hidden_layers=4))
+    m.tie_cls_weight()
+    eng = TrainEngine(m)
+    assert len(eng.buckets) == 3 and eng.buckets[0][0] == 0 and eng.buckets[-1][1] == eng.flat.numel()
+    assert all(a[1] == b[0] for a, b in zip(eng.buckets, eng.buckets[1:])) and eng.bert_split == 2
+    base = eng.flat.data_ptr()
+
+    def bucket_of(p):
+        off = (eng._grad(p).data_ptr() - base) // 4
+        return next(k for k, (a, b) in enumerate(eng.buckets) if a <= off < b)
+
+    named = dict(m.named_parameters())
+    for n, p in named.items():
+        if not p.requires_grad or eng.grads[eng.index[id(p)]] is None:
+            continue
+        k = bucket_of(p)
+        if n.startswith(("output_block.", "gate_net.", "pho_", "resnet", "classifier.bias")):
+            assert k == 0, n
+        elif n.startswith(("bert.encoder.layer.2.", "bert.encoder.layer.3.")):
+            assert k == 1, n
+        elif n.startswith("bert."):
+            assert k == 2, n
+    assert bucket_of(m.classifier.weight) == 2              # tied to bert.embeddings.word_embeddings
+    # within bucket 1 the later layer comes first (it is differentiated first)
+    l3 = eng._grad(named["bert.encoder.layer.3.output.dense.weight"]).data_ptr()
+    l2 = eng._grad(named["bert.encoder.layer.2.output.dense.weight"]).data_ptr()
+    assert l3 < l2
