@@ -54,13 +54,16 @@ class DataParallel:
         model.grad_div = 1.0 if average else world
         self._inv_world = 1.0 / world
         model._post_backward = self.sync
-        # overlap (default with NCCL and more than one rank): the flat buffer is laid out in backward-completion order
+        # overlap (opt-in: overlap=True or RL_DP_OVERLAP=1): the flat buffer is laid out in backward-completion order
         # (TrainEngine.buckets); each bucket is all-reduced on a communication stream as soon as the backward has issued
         # its last gradient kernel, behind the remaining backward.  The persistent GEMMs normally take every SM, which
         # would leave NCCL's CTAs waiting (or a GEMM's last CTAs waiting for NCCL): while a reduction may be in flight
         # the GEMMs are launched on `sm_reserve` fewer SMs.
-        if overlap is None:      # RL_DP_OVERLAP=0: one all-reduce of the whole buffer after the backward (A/B measurements)
-            overlap = world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("RL_DP_OVERLAP", "1") != "0"
+        # MEASURED on 8 x B200 (profiles/r02_bench_train_n8*.json): 45.98 ms/step with the overlap vs 45.63 ms with one
+        # all-reduce after the backward, 43.96 vs 43.90 at N = 2 — the SMs lent to NCCL cost the GEMMs what the overlap
+        # hides of a 1.3 ms exchange, so the single all-reduce stays the default.
+        if overlap is None:
+            overlap = world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("RL_DP_OVERLAP", "0") == "1"
         self.overlap, self.sm_reserve, self._comm, self._pending = bool(overlap), int(sm_reserve), None, False
         if self.overlap:
             model._bucket_ready = self.bucket_ready
