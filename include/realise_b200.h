@@ -166,9 +166,10 @@ RL_API int rl_gate_fuse_fwd(const float* m0, const float* m1, const float* m2, i
 
 /* ---- masked CrossEntropyLoss (src/models.py:862-868) -----------------------------------------
  * loss = mean over rows with loss_mask == 1 of (logsumexp(logits[row]) - logits[row, tgt[row]]).
- * logits f32 [rows, V] with row stride ld; row_loss_ws f32 [rows] scratch; loss f32 [1]. */
-RL_API int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask,
-                            float* row_loss_ws, float* loss, float* row_lse_out /* optional [rows] */,
+ * logits f32 (or fp16: the train step's choice — half the bytes written by the classifier GEMM and re-read here and by
+ * the backward) [rows, V] with row stride ld (elements); row_loss_ws f32 [rows] scratch; loss f32 [1]. */
+RL_API int rl_masked_ce_fwd(const void* logits, int32_t logits_dtype /* RL_DT_F32 or RL_DT_F16 */, const int64_t* tgt,
+                            const int64_t* loss_mask, float* row_loss_ws, float* loss, float* row_lse_out /* optional [rows] */,
                             float* count_out /* optional [1] */, int64_t rows, int64_t V, int64_t ld,
                             void* stream);
 
@@ -243,9 +244,9 @@ RL_API int rl_colsum_bf16(const void* x, float* out, int64_t rows, int64_t cols,
 
 /* ---- masked CE backward: dlogits (bf16 [rows, ldd], columns >= V zeroed) from the logits, the per-row
  * logsumexp and the active-row count saved by rl_masked_ce_fwd; gscale = d(loss) (device scalar, may be NULL). */
-RL_API int rl_masked_ce_bwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, const float* row_lse,
-                            const float* count, const float* gscale, void* dlogits, int64_t rows, int64_t V,
-                            int64_t ld, int64_t ldd, void* stream);
+RL_API int rl_masked_ce_bwd(const void* logits, int32_t logits_dtype, const int64_t* tgt, const int64_t* loss_mask,
+                            const float* row_lse, const float* count, const float* gscale, void* dlogits, int64_t rows,
+                            int64_t V, int64_t ld, int64_t ldd, void* stream);
 
 /* ---- BertEmbeddings backward: dword[ids[row]] += de[row], dpos[position(row)] += de[row] (vector atomics) ---- */
 RL_API int rl_embed_bwd(const float* de, const int64_t* ids, float* dword, float* dpos, int64_t rows, int64_t L,

@@ -270,8 +270,9 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
 // masked CE backward: dlogits[r, j] = gscale * mask_r / count * (exp(logit_rj - lse_r) - [j == tgt_r]), bf16,
 // columns [V, ldd) zero (K padding of the following GEMMs).
 // ---------------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(256)
-ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
+ce_bwd_kernel(const void* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
               const float* __restrict__ row_lse, const float* __restrict__ count, const float* __restrict__ gscale,
               __nv_bfloat16* __restrict__ dlogits, int V, long long ld, long long ldd) {
   const long long row = blockIdx.x;
@@ -283,13 +284,20 @@ ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
   const float coef = (gscale ? gscale[0] : 1.0f) / count[0];
   const float lse = row_lse[row];
   const int t = (int)tgt[row];
-  const float* x = logits + row * ld;
+  const char* x = reinterpret_cast<const char*>(logits) + row * ld * (F16 ? 2 : 4);
   int j0 = 0;
-  if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {   // 8 logits -> one 16-byte bf16 store
+  if ((ld & 7) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {   // 8 logits -> one 16-byte bf16 store
     const int V8 = V >> 3;
     for (int g = threadIdx.x; g < V8; g += blockDim.x) {
-      const float4 a = reinterpret_cast<const float4*>(x)[2 * g], b = reinterpret_cast<const float4*>(x)[2 * g + 1];
-      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float v[8];
+      if (F16) {
+        const uint4 a = reinterpret_cast<const uint4*>(x)[g];
+        v[0] = rl::half_lo(a.x, 1); v[1] = rl::half_hi(a.x, 1); v[2] = rl::half_lo(a.y, 1); v[3] = rl::half_hi(a.y, 1);
+        v[4] = rl::half_lo(a.z, 1); v[5] = rl::half_hi(a.z, 1); v[6] = rl::half_lo(a.w, 1); v[7] = rl::half_hi(a.w, 1);
+      } else {
+        const float4 a = reinterpret_cast<const float4*>(x)[2 * g], b = reinterpret_cast<const float4*>(x)[2 * g + 1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = coef * __expf(v[k] - lse);
       if ((t >> 3) == g) v[t & 7] -= coef;
@@ -300,7 +308,10 @@ ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
   }
   for (int j = j0 + threadIdx.x; j < (int)ldd; j += blockDim.x) {
     float v = 0.f;
-    if (j < V) v = coef * (__expf(x[j] - lse) - (j == t ? 1.0f : 0.0f));
+    if (j < V) {
+      const float xj = F16 ? __half2float(reinterpret_cast<const __half*>(x)[j]) : reinterpret_cast<const float*>(x)[j];
+      v = coef * (__expf(xj - lse) - (j == t ? 1.0f : 0.0f));
+    }
     d[j] = __float2bfloat16(v);
   }
 }
@@ -705,14 +716,19 @@ extern "C" int rl_gelu_bwd_colsum(void* t, const void* u, float* dbias, int64_t 
   return rl_check_launch("rl_gelu_bwd_colsum");
 }
 
-extern "C" int rl_masked_ce_bwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, const float* row_lse,
-                                const float* count, const float* gscale, void* dlogits, int64_t rows, int64_t V,
-                                int64_t ld, int64_t ldd, void* stream) {
+extern "C" int rl_masked_ce_bwd(const void* logits, int32_t logits_dtype, const int64_t* tgt, const int64_t* loss_mask,
+                                const float* row_lse, const float* count, const float* gscale, void* dlogits, int64_t rows,
+                                int64_t V, int64_t ld, int64_t ldd, void* stream) {
   RL_REQUIRE(logits && tgt && loss_mask && row_lse && count && dlogits, RL_EINVAL, "rl_masked_ce_bwd: null pointer");
   RL_REQUIRE(ldd >= V && ldd % 8 == 0 && ((uintptr_t)dlogits & 15) == 0, RL_EALIGN, "rl_masked_ce_bwd: ldd must be >= V, %%8");
   if (rows <= 0) return 0;
-  ce_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)tgt, (const long long*)loss_mask,
-                                                                 row_lse, count, gscale, (__nv_bfloat16*)dlogits, (int)V, ld, ldd);
+  RL_REQUIRE(logits_dtype == RL_DT_F32 || logits_dtype == RL_DT_F16, RL_EINVAL, "rl_masked_ce_bwd: logits must be f32 or fp16");
+  if (logits_dtype == RL_DT_F16)
+    ce_bwd_kernel<true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)tgt, (const long long*)loss_mask,
+                                                                         row_lse, count, gscale, (__nv_bfloat16*)dlogits, (int)V, ld, ldd);
+  else
+    ce_bwd_kernel<false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, (const long long*)tgt, (const long long*)loss_mask,
+                                                                          row_lse, count, gscale, (__nv_bfloat16*)dlogits, (int)V, ld, ldd);
   return rl_check_launch("rl_masked_ce_bwd");
 }
 

@@ -284,7 +284,7 @@ extern "C" int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, cons
                                    const float* t2s, void* out, int64_t n_img, int32_t C, void* stream) {
   RL_REQUIRE(glyphs && ids && w1_packed && wsc_packed && w2_packed && t1 && t2s && out, RL_EINVAL,
              "rl_glyph_block1_fwd: null pointer");
-  RL_REQUIRE(C == 1 || C == 3, RL_EINVAL, "rl_glyph_block1_fwd: num_fonts must be 1 or 3 (got %d)", C);
+  RL_REQUIRE(C >= 1 && C <= 3, RL_EINVAL, "rl_glyph_block1_fwd: num_fonts must be 1, 2 or 3 (got %d: 9*C taps must fit K = 32)", C);
   RL_REQUIRE(((uintptr_t)glyphs & 15) == 0 && ((uintptr_t)out & 15) == 0, RL_EALIGN, "rl_glyph_block1_fwd: alignment");
   if (n_img <= 0) return 0;
   CUtensorMap m1, msc, m2;
@@ -312,5 +312,5 @@ extern "C" int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, cons
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.n_img = (int)n_img;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return C == 3 ? launch_b1<3>(m1, msc, m2, p, st) : launch_b1<1>(m1, msc, m2, p, st);
+  return C == 3 ? launch_b1<3>(m1, msc, m2, p, st) : C == 2 ? launch_b1<2>(m1, msc, m2, p, st) : launch_b1<1>(m1, msc, m2, p, st);
 }

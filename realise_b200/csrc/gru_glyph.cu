@@ -349,13 +349,16 @@ extern "C" int rl_glyph_stem_fwd(const float* glyphs, const int64_t* ids, const 
                                  const float* shift_sc, void* y1, void* ysc, int64_t n_img, int32_t C, void* stream) {
   RL_REQUIRE(glyphs && ids && w1 && wsc && scale1 && shift1 && scale_sc && shift_sc && y1 && ysc, RL_EINVAL,
              "rl_glyph_stem_fwd: null pointer");
-  RL_REQUIRE(C == 1 || C == 3, RL_EINVAL, "rl_glyph_stem_fwd: num_fonts must be 1 or 3 (got %d)", C);
+  RL_REQUIRE(C >= 1 && C <= 3, RL_EINVAL, "rl_glyph_stem_fwd: num_fonts must be 1, 2 or 3 (got %d)", C);
   RL_REQUIRE(((uintptr_t)glyphs & 15) == 0 && ((uintptr_t)y1 & 15) == 0 && ((uintptr_t)ysc & 15) == 0, RL_EALIGN,
              "rl_glyph_stem_fwd: alignment");
   if (n_img <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 3)
     glyph_stem_kernel<3><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, w1, wsc, scale1, shift1,
+                                                         scale_sc, shift_sc, (__nv_bfloat16*)y1, (__nv_bfloat16*)ysc);
+  else if (C == 2)
+    glyph_stem_kernel<2><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, w1, wsc, scale1, shift1,
                                                          scale_sc, shift_sc, (__nv_bfloat16*)y1, (__nv_bfloat16*)ysc);
   else
     glyph_stem_kernel<1><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, w1, wsc, scale1, shift1,

@@ -787,11 +787,13 @@ extern "C" int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C
 
 extern "C" int rl_glyph_im2col(const float* glyphs, const int64_t* ids, void* col1, void* colsc, int64_t n_img, int32_t C,
                                void* stream) {
-  RL_REQUIRE(glyphs && ids && col1 && (C == 1 || C == 3), RL_EINVAL, "rl_glyph_im2col: bad arguments");  // colsc optional
+  RL_REQUIRE(glyphs && ids && col1 && C >= 1 && C <= 3, RL_EINVAL, "rl_glyph_im2col: bad arguments (num_fonts 1..3)");  // colsc optional
   if (n_img <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 3)
     glyph_im2col_kernel<3><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, (__nv_bfloat16*)col1, (__nv_bfloat16*)colsc);
+  else if (C == 2)
+    glyph_im2col_kernel<2><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, (__nv_bfloat16*)col1, (__nv_bfloat16*)colsc);
   else
     glyph_im2col_kernel<1><<<(unsigned)n_img, 256, 0, st>>>(glyphs, (const long long*)ids, (__nv_bfloat16*)col1, (__nv_bfloat16*)colsc);
   return rl_check_launch("rl_glyph_im2col");

@@ -193,32 +193,54 @@ gate_fuse_kernel(const float* __restrict__ m0, const float* __restrict__ m1, con
 }
 
 // ---- masked cross entropy (src/models.py:862-868): mean over loss_mask==1 of lse - logit[tgt] ----
+// logits may be f32 or IEEE fp16 (F16: the train step keeps its [tokens, vocab] logits in fp16 — 0.69 GB instead of
+// 1.38 GB written by the classifier GEMM and read again here and by the backward; nobody reads train-mode logits at
+// f32 precision, and 11 mantissa bits put 2^-12 relative error on exp(x - lse), far below the bf16 rounding of dlogits)
+template <bool F16>
+__device__ __forceinline__ float ce_ld(const void* x, long long i) {
+  return F16 ? __half2float(reinterpret_cast<const __half*>(x)[i]) : reinterpret_cast<const float*>(x)[i];
+}
+// 8 consecutive logits starting at element 8*g of a 16-byte aligned row
+template <bool F16>
+__device__ __forceinline__ void ce_ld8(const void* x, int g, float (&v)[8]) {
+  if (F16) {
+    const uint4 a = reinterpret_cast<const uint4*>(x)[g];
+    v[0] = rl::half_lo(a.x, 1); v[1] = rl::half_hi(a.x, 1); v[2] = rl::half_lo(a.y, 1); v[3] = rl::half_hi(a.y, 1);
+    v[4] = rl::half_lo(a.z, 1); v[5] = rl::half_hi(a.z, 1); v[6] = rl::half_lo(a.w, 1); v[7] = rl::half_hi(a.w, 1);
+  } else {
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * g], b = reinterpret_cast<const float4*>(x)[2 * g + 1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(256)
-ce_row_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
+ce_row_kernel(const void* __restrict__ logits, const long long* __restrict__ tgt, const long long* __restrict__ loss_mask,
               float* __restrict__ row_loss, float* __restrict__ row_lse, long long rows, int V, long long ld) {
   const long long row = blockIdx.x;
   __shared__ float s_red[8];
-  __shared__ float s_bc;
   if (loss_mask[row] != 1) {
     if (threadIdx.x == 0) row_loss[row] = 0.f;
     return;
   }
-  const float* x = logits + row * ld;
-  // one pass, online softmax: running (max, sum of exp) per thread, float4 loads when the row is 16-byte aligned
+  const void* x = reinterpret_cast<const char*>(logits) + row * ld * (F16 ? 2 : 4);
+  // one pass, online softmax: running (max, sum of exp) per thread, 8 logits per step when the row is 16-byte aligned
   float mx = -INFINITY, s = 0.f;
-  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
-  const int V4 = vec ? (V >> 2) : 0;
-  for (int i = threadIdx.x; i < V4; i += blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
-    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-    if (m4 > mx) {
-      s *= __expf(mx - m4);
-      mx = m4;
+  const bool vec = ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int V8 = vec ? (V >> 3) : 0;
+  for (int i = threadIdx.x; i < V8; i += blockDim.x) {
+    float v[8];
+    ce_ld8<F16>(x, i, v);
+    const float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+    if (m8 > mx) {
+      s *= __expf(mx - m8);
+      mx = m8;
     }
-    s += (__expf(v.x - mx) + __expf(v.y - mx)) + (__expf(v.z - mx) + __expf(v.w - mx));
+    s += ((__expf(v[0] - mx) + __expf(v[1] - mx)) + (__expf(v[2] - mx) + __expf(v[3] - mx))) +
+         ((__expf(v[4] - mx) + __expf(v[5] - mx)) + (__expf(v[6] - mx) + __expf(v[7] - mx)));
   }
-  for (int i = V4 * 4 + threadIdx.x; i < V; i += blockDim.x) {
-    const float v = x[i];
+  for (int i = V8 * 8 + threadIdx.x; i < V; i += blockDim.x) {
+    const float v = ce_ld<F16>(x, i);
     if (v > mx) {
       s *= __expf(mx - v);
       mx = v;
@@ -246,8 +268,7 @@ ce_row_kernel(const float* __restrict__ logits, const long long* __restrict__ tg
     for (int w = 0; w < 8; ++w) t += s_red[w] == -INFINITY ? 0.f : s_sum[w] * __expf(s_red[w] - m);
     const float lse = logf(t) + m;
     if (row_lse) row_lse[row] = lse;
-    row_loss[row] = lse - x[tgt[row]];
-    s_bc = lse;
+    row_loss[row] = lse - ce_ld<F16>(x, tgt[row]);
   }
 }
 
@@ -384,14 +405,19 @@ extern "C" int rl_gate_fuse_fwd(const float* m0, const float* m1, const float* m
   return rl_check_launch("rl_gate_fuse_fwd");
 }
 
-extern "C" int rl_masked_ce_fwd(const float* logits, const int64_t* tgt, const int64_t* loss_mask, float* row_loss_ws,
-                                float* loss, float* row_lse_out, float* count_out, int64_t rows, int64_t V, int64_t ld,
-                                void* stream) {
+extern "C" int rl_masked_ce_fwd(const void* logits, int32_t logits_dtype, const int64_t* tgt, const int64_t* loss_mask,
+                                float* row_loss_ws, float* loss, float* row_lse_out, float* count_out, int64_t rows, int64_t V,
+                                int64_t ld, void* stream) {
   RL_REQUIRE(logits && tgt && loss_mask && row_loss_ws && loss, RL_EINVAL, "rl_masked_ce_fwd: null pointer");
   RL_REQUIRE(rows > 0 && V > 0 && ld >= V, RL_EINVAL, "rl_masked_ce_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  ce_row_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, (const long long*)tgt, (const long long*)loss_mask, row_loss_ws,
-                                                row_lse_out, rows, (int)V, ld);
+  RL_REQUIRE(logits_dtype == RL_DT_F32 || logits_dtype == RL_DT_F16, RL_EINVAL, "rl_masked_ce_fwd: logits must be f32 or fp16");
+  if (logits_dtype == RL_DT_F16)
+    ce_row_kernel<true><<<(unsigned)rows, 256, 0, st>>>(logits, (const long long*)tgt, (const long long*)loss_mask, row_loss_ws,
+                                                        row_lse_out, rows, (int)V, ld);
+  else
+    ce_row_kernel<false><<<(unsigned)rows, 256, 0, st>>>(logits, (const long long*)tgt, (const long long*)loss_mask, row_loss_ws,
+                                                         row_lse_out, rows, (int)V, ld);
   int rc = rl_check_launch("rl_masked_ce_fwd(rows)");
   if (rc) return rc;
   ce_reduce_kernel<<<1, 1024, 0, st>>>(row_loss_ws, (const long long*)loss_mask, loss, count_out, rows);

@@ -281,12 +281,12 @@ def gate_fuse(mods, sum_mode, mask, gate_w, gate_b, ws, out, gates_out, B, L, H)
 
 
 def masked_ce(logits, tgt, loss_mask, row_ws, loss, row_lse=None, count=None):
-    _req(logits, torch.float32, "logits")
+    assert logits.is_cuda and logits.dtype in (torch.float32, torch.float16)
     _req(tgt, torch.int64, "tgt")
     _req(loss_mask, torch.int64, "loss_mask")
     rows, V = logits.shape
-    with _Timed("masked_ce", rows * V * 4):
-        check(lib().rl_masked_ce_fwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _ptr(row_lse),
+    with _Timed("masked_ce", rows * V * logits.element_size()):
+        check(lib().rl_masked_ce_fwd(_ptr(logits), _dt(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_ws), _ptr(loss), _ptr(row_lse),
                                      _ptr(count), _c(rows), _c(V), _c(logits.stride(0)), _stream()), "rl_masked_ce_fwd")
     _count(2)
 
@@ -428,7 +428,8 @@ def gelu_bwd_colsum(t, u, dbias):
 def masked_ce_bwd(logits, tgt, loss_mask, row_lse, count, gscale, dlogits):
     rows, V = logits.shape
     _req(dlogits, torch.bfloat16, "dlogits")
-    check(lib().rl_masked_ce_bwd(_ptr(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_lse), _ptr(count), _ptr(gscale),
+    assert logits.dtype in (torch.float32, torch.float16)
+    check(lib().rl_masked_ce_bwd(_ptr(logits), _dt(logits), _ptr(tgt), _ptr(loss_mask), _ptr(row_lse), _ptr(count), _ptr(gscale),
                                  _ptr(dlogits), _c(rows), _c(V), _c(logits.stride(0)), _c(dlogits.stride(0)), _stream()),
           "rl_masked_ce_bwd")
     _count()

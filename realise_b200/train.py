@@ -118,8 +118,8 @@ class TrainEngine:
     def __init__(self, model):
         self.m = model
         c = model.config
-        if c.with_res == "yes" and c.num_fonts not in (1, 3):
-            raise NotImplementedError("glyph kernels are built for 1 or 3 fonts")
+        if c.with_res == "yes" and not 1 <= c.num_fonts <= 3:
+            raise NotImplementedError("glyph kernels are built for 1..3 fonts (src/run.py --num_fonts; 9 taps x C <= 32)")
         self.saved = None
         self._pending = False         # gradients of an earlier backward() are still waiting for the optimizer
         self._accum = None
@@ -723,7 +723,10 @@ class TrainEngine:
         _, seq_b, sv["out"] = self._stack_fwd("out", m.output_block, P["output_block"], mask, B, L, inputs_embeds=fused,
                                               pos_mode=1, last_drop=True)
         sv["seq_b"] = seq_b
-        logits = self._new((N, V), F32)
+        # train-mode logits live in fp16 (independent of the bf16 operand format: the epilogue packs what it is told):
+        # half the bytes written here and re-read by the CE forward and backward; the reference's loop only reads
+        # outputs[0] in training (src/run.py:191), callers that want them get an fp16 [B, L, V] tensor
+        logits = self._new((N, V), torch.float16)
         ops.gemm(seq_b, P["cls_w"], logits, bias=P["cls_b"])
         loss = self._new((1,), F32)
         sv["lse"], sv["count"] = self._new((N,), F32), self._new((1,), F32)

@@ -94,9 +94,12 @@ def test_cuda_path_matches_oracle_on_fresh_inputs():
         assert (logits.reshape(B * L, -1).argmax(-1).cpu()[safe] == rlogits.reshape(B * L, -1).argmax(-1)[safe]).all()
 
 
-def test_single_font_glyph_table():
+@pytest.mark.parametrize("num_fonts", [1, 2])
+def test_one_and_two_font_glyph_tables(num_fonts):
+    """--num_fonts 1 (char_images Embedding [vocab, 1024]) and 2 (char_images_multifonts [vocab, 2, 32, 32]); the
+    reference takes any count (src/models.py:674-679), the kernels 1..3 (9 taps x C <= 32)."""
     from oracle import realise_oracle as O
-    cfg = ArchConfig(num_hidden_layers=1, num_fonts=1, vocab_size=21128)
+    cfg = ArchConfig(num_hidden_layers=1, num_fonts=num_fonts, vocab_size=21128)
     sd = cached_state_dict(cfg, 2)
     model = build(cfg, 2)
     batch = synth_batch(2, 16, seed=3)

@@ -594,3 +594,29 @@ def test_gemm_epilogue_column_reductions():
         assert (out.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item()
         assert torch.allclose(cs, ref.sum(0), rtol=1e-3, atol=1e-3 * ref.sum(0).abs().max().item()), (M, N, K)
         assert torch.allclose(cq, (ref * ref).sum(0), rtol=1e-3), (M, N, K)
+
+
+def test_two_font_training_step():
+    """num_fonts = 2 through the training stem (glyph_im2col<2>, K = 18 of 32) against the oracle's autograd."""
+    from oracle import realise_oracle as O
+    cfg = ArchConfig(num_hidden_layers=1, with_pho="no", num_fonts=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = _small_model(cfg, 14)
+    sd = cached_state_dict(cfg, 14)
+    batch = synth_batch(4, 32, seed=15)
+    loss, _ = model(_dev(batch))
+    loss.backward()
+    rsd = {k: v.clone() for k, v in sd.items()}
+    rsd["classifier.weight"] = rsd["bert.embeddings.word_embeddings.weight"]
+    leaves = {}
+    for k, v in rsd.items():
+        if v.dtype.is_floating_point and "running" not in k and not k.startswith("char_images"):
+            v.requires_grad_(True)
+            leaves[k] = v
+    rloss, _ = O.forward(rsd, batch, cfg, train=True)
+    rloss.backward()
+    assert abs(loss.item() - rloss.item()) <= 1e-2
+    for name in ("bert.encoder.layer.0.output.dense.weight", "gate_net.weight", "resnet_layernorm.weight"):
+        g, rg = dict(model.named_parameters())[name].grad.float().cpu(), leaves[name].grad
+        assert ((g - rg).norm() / rg.norm()).item() <= 5e-2, name
+    g = model.resnet.res_block1.residual_function[0].weight.grad
+    assert g.shape == (64, 2, 3, 3) and torch.isfinite(g).all() and float(g.abs().max()) > 0
