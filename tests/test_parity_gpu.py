@@ -187,3 +187,24 @@ def test_glyph_cache_and_device_batch_builder_are_exact():
         l1 = model(b1)[1].clone()
         l2 = model(b2)[1].clone()
     assert b2["pho_idx"].shape[1] == MAX_PHO_LEN and torch.equal(l1, l2)
+
+
+def test_predict_is_the_device_argmax_of_forward():
+    """model.predict(batch): token ids [B, L] taken on the device (rl_argmax_rows) == np.argmax of the logits the
+    reference ships to the host (src/test.py:140-145); first maximum wins on ties, like np.argmax."""
+    from realise_b200 import ops
+    cfg = ArchConfig(num_hidden_layers=1)
+    model = build(cfg, 21)
+    batch = to_dev(synth_batch(5, 23, seed=32, with_labels=False))
+    with torch.no_grad():
+        (logits,) = model(batch)
+        ref = logits.float().cpu().numpy().argmax(-1)
+        ids = model.predict(batch)
+    assert ids.dtype == torch.int64 and tuple(ids.shape) == (5, 23) and ids.is_cuda
+    assert (ids.cpu().numpy() == ref).all()
+    tie = torch.zeros(3, 21128, device="cuda")
+    tie[0, 7] = tie[0, 9000] = 2.0          # two equal maxima: the first index wins
+    tie[1, 21127] = 1.0
+    out = torch.empty(3, dtype=torch.int64, device="cuda")
+    ops.argmax_rows(tie, out)
+    assert out.tolist() == [7, 21127, 0]
