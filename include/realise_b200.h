@@ -107,7 +107,8 @@ typedef struct rl_gemm_desc {
                            not depend on it) */
   int32_t tune_no_pair; /* 0: cost model.  1: never use the CTA-pair (cta_group::2) kernels.  2: pairs but no 4-CTA
                            clusters (two pairs sharing the B tile through TMA multicast).  3: 4-CTA clusters whenever
-                           eligible (M >= 512, 256-wide tiles, plain B).  Results do not depend on it. */
+                           eligible (M >= 512, 256-wide tiles, plain B).  4: no long-K (5-stage) variant.  5: no compile-time
+                           specialised epilogues.  Results do not depend on it. */
   float* colsum;     /* optional f32 [N], ACCUMULATED into: sum over the M rows of the final result (after act): the bias
                         gradient of the layer below comes out of the data-gradient GEMM, BatchNorm's batch sum out of the
                         conv GEMM.  Needs split_k = 0. */

@@ -57,7 +57,25 @@ struct KParams {
   int nimg;       // conv: number of images (an image index >= nimg makes a TMA box read zeros)
   int ntaps;
   int a_mn, b_mn; // operand stored MN-major: A as [K, M] (M contiguous), B as [K, N] (N contiguous)
+  uint32_t eflags; // the epilogue's mode switches packed into one word (EF_* below; host: pack_eflags)
 };
+
+// Epilogue mode bits.  The per-chunk code of an epilogue warp used to test ~25 KParams fields, each an LDC -> ISETP -> BRA
+// chain of 30-90 cycles that two warps per scheduler cannot hide: warp-state sampling of the K = 768 GEMMs (QKV, 16384 x
+// 2304 x 768) showed 3.2 k cycles per 32-column chunk for ~260 instructions, the epilogue outlasting the 9 k-cycle main
+// loop and the MMA warp blocked on tmem_empty 19 % of the kernel.  The switches now live in ONE register (EpiState::flags,
+// loaded once per warp), and the hottest configurations of the 256 x 256 pair kernel are compiled with the word as a
+// template constant (SPEC != 0), which folds every test and frees the registers of the paths not taken.
+enum : uint32_t {
+  EF_TMA_RES = 1u << 0, EF_RES_F32 = 1u << 1, EF_R_F16 = 1u << 2, EF_DROP = 1u << 3, EF_TMA_STORE = 1u << 4,
+  EF_DEEP = 1u << 5, EF_RES_ALL = 1u << 6, EF_TMA_OUT2 = 1u << 7, EF_OUT_F32 = 1u << 8, EF_O_F16 = 1u << 9,
+  EF_ATOMIC = 1u << 10, EF_SCALE = 1u << 11, EF_RES = 1u << 12, EF_OUT2 = 1u << 13, EF_VEC = 1u << 14,
+  EF_COLSUM = 1u << 15, EF_COLSUMSQ = 1u << 16, EF_ACT_SHIFT = 24, EF_VALID = 1u << 31
+};
+// compile-time specialisations of the pair kernel (training formats: bf16 operands and results)
+constexpr uint32_t SPEC_OUT16 = EF_VALID | EF_TMA_STORE | EF_DEEP | EF_VEC;                  // (bias) -> bf16: QKV, dgrads
+constexpr uint32_t SPEC_GELU_SAVE = EF_VALID | EF_TMA_STORE | EF_TMA_OUT2 | EF_OUT2 | EF_VEC | ((uint32_t)RL_ACT_GELU_SAVE << EF_ACT_SHIFT);
+constexpr uint32_t SPEC_RES32 = EF_VALID | EF_TMA_STORE | EF_TMA_RES | EF_RES | EF_RES_F32 | EF_OUT_F32 | EF_DROP | EF_VEC;  // bias + dropout + f32 residual -> f32
 
 using rl::fast_erf;
 using rl::gelu_grad;
@@ -90,10 +108,11 @@ __device__ __forceinline__ long long remap_row(const KParams& p, int row) {
 // registers BEFORE the warp waits for the MMAs of the tile; the residual of chunk c+1 is loaded while chunk c
 // is being computed.  Results leave through a swizzled 32x32 smem tile + one TMA store per chunk (coalesced,
 // clips the M/N tails) or, for remapped / oddly aligned outputs, through direct row stores.
-__device__ __forceinline__ void load_residual(const KParams& p, int row, bool row_ok, int nb, float (&x)[32]) {
-  if (p.res && row_ok && nb < p.N) {
+__device__ __forceinline__ void load_residual(const KParams& p, uint32_t F, int row, bool row_ok, int nb, float (&x)[32]) {
+  const bool r_f16 = F & EF_R_F16;
+  if ((F & EF_RES) && row_ok && nb < p.N) {
     if (nb + 32 <= p.N) {
-      if (p.res_f32) {
+      if (F & EF_RES_F32) {
         const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + (long long)row * p.ldr + nb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -105,10 +124,10 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 t = r[j];
-          x[8 * j] = rl::half_lo(t.x, p.r_f16); x[8 * j + 1] = rl::half_hi(t.x, p.r_f16);
-          x[8 * j + 2] = rl::half_lo(t.y, p.r_f16); x[8 * j + 3] = rl::half_hi(t.y, p.r_f16);
-          x[8 * j + 4] = rl::half_lo(t.z, p.r_f16); x[8 * j + 5] = rl::half_hi(t.z, p.r_f16);
-          x[8 * j + 6] = rl::half_lo(t.w, p.r_f16); x[8 * j + 7] = rl::half_hi(t.w, p.r_f16);
+          x[8 * j] = rl::half_lo(t.x, r_f16); x[8 * j + 1] = rl::half_hi(t.x, r_f16);
+          x[8 * j + 2] = rl::half_lo(t.y, r_f16); x[8 * j + 3] = rl::half_hi(t.y, r_f16);
+          x[8 * j + 4] = rl::half_lo(t.z, r_f16); x[8 * j + 5] = rl::half_hi(t.z, r_f16);
+          x[8 * j + 6] = rl::half_lo(t.w, r_f16); x[8 * j + 7] = rl::half_hi(t.w, r_f16);
         }
       }
     } else {
@@ -116,8 +135,8 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
       for (int j = 0; j < 32; ++j) {
         x[j] = 0.f;
         if (nb + j < p.N)
-          x[j] = p.res_f32 ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + nb + j]
-                           : rl::half_lo((uint32_t)reinterpret_cast<const unsigned short*>(p.res)[(long long)row * p.ldr + nb + j], p.r_f16);
+          x[j] = (F & EF_RES_F32) ? reinterpret_cast<const float*>(p.res)[(long long)row * p.ldr + nb + j]
+                                  : rl::half_lo((uint32_t)reinterpret_cast<const unsigned short*>(p.res)[(long long)row * p.ldr + nb + j], r_f16);
       }
     }
   } else {
@@ -126,19 +145,31 @@ __device__ __forceinline__ void load_residual(const KParams& p, int row, bool ro
   }
 }
 
-// scale/bias of this warp's BN/2 columns -> sb[0..BN/2) and sb[128..128+BN/2); first residual chunk -> xr
+// scale/bias of this warp's BN/2 columns -> sb[0..BN/2) and sb[128..128+BN/2); first residual chunk -> xr.
+// All global loads are issued before the first shared store: the rolled loop this replaces paid one global-load latency
+// per 32 columns (4 x ~500 cycles per 256-wide tile, 14 % of the epilogue warps' time in the K = 768 GEMMs).
 template <int BN, int NSTG = 2>
-__device__ __forceinline__ void epilogue_prefetch(const KParams& p, float* sb, int row0, int n0, int half, int lane,
+__device__ __forceinline__ void epilogue_prefetch(const KParams& p, uint32_t F, float* sb, int row0, int n0, int half, int lane,
                                                   float (&xr)[32]) {
   constexpr int HC = BN / 2;
   const int c0 = n0 + half * HC;
   __syncwarp();
-  for (int i = lane; NSTG != 1 && i < HC; i += 32) {
-    const int n = c0 + i;
-    sb[i] = (p.scale && n < p.N) ? __ldg(p.scale + n) : 1.0f;
-    sb[128 + i] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+  if (NSTG != 1) {
+    float sv[HC / 32], bv[HC / 32];
+    const float* bias = p.bias;
+#pragma unroll
+    for (int k = 0; k < HC / 32; ++k) {
+      const int n = c0 + lane + 32 * k;
+      sv[k] = ((F & EF_SCALE) && n < p.N) ? __ldg(p.scale + n) : 1.0f;
+      bv[k] = (bias && n < p.N) ? __ldg(bias + n) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < HC / 32; ++k) {
+      if (F & EF_SCALE) sb[lane + 32 * k] = sv[k];
+      sb[128 + lane + 32 * k] = bv[k];
+    }
   }
-  if (!p.tma_res) load_residual(p, row0 + lane, row0 + lane < p.M, c0, xr);
+  if (!(F & EF_TMA_RES)) load_residual(p, F, row0 + lane, row0 + lane < p.M, c0, xr);
   __syncwarp();
 }
 
@@ -150,7 +181,15 @@ struct EpiState {
   // with one N tile flushes ONCE per CTA — per-tile atomics on 64 addresses would serialise in L2)
   float cs[4], cq[4];
   int cs_n0;
+  uint32_t flags;    // KParams::eflags in a register (see EF_*)
 };
+
+// KParams::eflags as an opaque register value: the compiler may not re-derive it from constant memory at each use
+__device__ __forceinline__ uint32_t load_eflags(const KParams& p) {
+  uint32_t f = p.eflags;
+  asm volatile("mov.b32 %0, %0;" : "+r"(f));
+  return f;
+}
 
 // per-column sum over the 32 rows held by the warp (lane = row, v[c] = column c): butterfly transpose-reduce, 31 shuffles;
 // on return lane l holds the total of column l in v[0]
@@ -186,49 +225,81 @@ __device__ __forceinline__ void colsum_flush(const KParams& p, EpiState& st, int
 
 // lane 0: fetch the residual tile of the chunk at column nb into staging tile `buf` (its previous TMA store must be done)
 // Two schemes: (a) 4 KB tiles (f32 residual / f32 result): two tiles, the next chunk's residual is fetched while this chunk
-// is processed; (b) all-16-bit (p.res_all): the tile's CH <= 4 residual chunks fit the 8 KB staging region as 2 KB tiles and
+// is processed; (b) all-16-bit (EF_RES_ALL): the tile's CH <= 4 residual chunks fit the 8 KB staging region as 2 KB tiles and
 // are ALL fetched when the warp starts on the tile, a whole main loop before they are needed (one chunk of lead does not
 // cover the ~1 us TMA latency).
-__device__ __forceinline__ void issue_residual(const KParams& p, const CUtensorMap* tmR_ptr, uint8_t* stg_base,
+__device__ __forceinline__ void issue_residual(uint32_t F, const CUtensorMap* tmR_ptr, uint8_t* stg_base,
                                                uint64_t* rbar, int buf, int nb, int row0) {
-  rl::mbar_expect_tx(&rbar[buf], p.res_f32 ? 4096u : 2048u);
-  rl::tma_load_2d(stg_base + buf * (p.res_all ? 2048 : 4096), tmR_ptr, &rbar[buf], nb, row0);
+  rl::mbar_expect_tx(&rbar[buf], (F & EF_RES_F32) ? 4096u : 2048u);
+  rl::tma_load_2d(stg_base + buf * ((F & EF_RES_ALL) ? 2048 : 4096), tmR_ptr, &rbar[buf], nb, row0);
 }
 
-// scale / bias of 4 consecutive columns: from the warp's shared-memory table, or (NSTG == 1: the long-K variant has no
-// table — its shared memory went into pipeline stages) straight from global memory (warp-uniform addresses, L1 hits)
+// x = acc * scale + bias for the 32 columns of a chunk.  Scale/bias come from the warp's shared-memory table, or (NSTG == 1:
+// the long-K variant has no table — its shared memory went into pipeline stages) straight from global memory
+// (warp-uniform addresses, L1 hits).  Without a scale vector (everything but the BatchNorm-folded convs) it is one add.
 template <int NSTG>
-__device__ __forceinline__ void load_scale_bias(const KParams& p, const float* sb, int cc, int j, int nb, float4& sc, float4& bi) {
+__device__ __forceinline__ void affine32(const KParams& p, uint32_t F, const float* sb, int cc, int nb,
+                                         const uint32_t (&v)[32], float (&x)[32]) {
   if (NSTG == 1) {
-    sc = make_float4(1.f, 1.f, 1.f, 1.f);
-    bi = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int n = nb + j;
-    if (n + 4 <= p.N) {
-      if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-      if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    } else {
-      float s4[4] = {1.f, 1.f, 1.f, 1.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (n + k < p.N) {
-          if (p.scale) s4[k] = __ldg(p.scale + n + k);
-          if (p.bias) b4[k] = __ldg(p.bias + n + k);
-        }
-      sc = make_float4(s4[0], s4[1], s4[2], s4[3]);
-      bi = make_float4(b4[0], b4[1], b4[2], b4[3]);
+    for (int j = 0; j < 32; j += 4) {
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int n = nb + j;
+      if (n + 4 <= p.N) {
+        if (F & EF_SCALE) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+        if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      } else {
+        float s4[4] = {1.f, 1.f, 1.f, 1.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (n + k < p.N) {
+            if (F & EF_SCALE) s4[k] = __ldg(p.scale + n + k);
+            if (p.bias) b4[k] = __ldg(p.bias + n + k);
+          }
+        sc = make_float4(s4[0], s4[1], s4[2], s4[3]);
+        bi = make_float4(b4[0], b4[1], b4[2], b4[3]);
+      }
+      x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+      x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+      x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+      x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+    }
+  } else if (F & EF_SCALE) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
+      const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+      x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
+      x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+      x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+      x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
     }
   } else {
-    sc = *reinterpret_cast<const float4*>(sb + cc * 32 + j);
-    bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bi = *reinterpret_cast<const float4*>(sb + 128 + cc * 32 + j);
+      x[j] = __uint_as_float(v[j]) + bi.x;
+      x[j + 1] = __uint_as_float(v[j + 1]) + bi.y;
+      x[j + 2] = __uint_as_float(v[j + 2]) + bi.z;
+      x[j + 3] = __uint_as_float(v[j + 3]) + bi.w;
+    }
   }
 }
 
-template <int BN, bool COLS, int NSTG = 2>
+// One output tile of an epilogue warp.  SPEC != 0: the mode word is a compile-time constant (see EF_*).  `release()` hands
+// the accumulator buffer back to the MMA warp; it is called as soon as the LAST chunk has left TMEM, so the math and the
+// stores of that chunk overlap the MMAs of the tile after next.
+template <int BN, bool COLS, int NSTG = 2, uint32_t SPEC = 0, class Release>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMap* tmC_ptr, const CUtensorMap* tmC2_ptr,
                                               const CUtensorMap* tmR_ptr, uint8_t* stg_base, uint64_t* rbar,
                                               const float* sb, uint32_t taddr, int row0, int n0, int half, int lane,
-                                              float (&xr)[32], EpiState& st) {
+                                              float (&xr)[32], EpiState& st, Release release) {
   constexpr int CH = BN / 64;  // 32-column chunks per half
+  const uint32_t F = SPEC ? SPEC : st.flags;
+  const int act = (int)((F >> EF_ACT_SHIFT) & 7u);
+  const bool tma_res = F & EF_TMA_RES, res_all = F & EF_RES_ALL, deep = F & EF_DEEP, tma_store = F & EF_TMA_STORE;
+  const bool tma_out2 = F & EF_TMA_OUT2, out_f32 = F & EF_OUT_F32, o_f16 = F & EF_O_F16, r_f16 = F & EF_R_F16;
+  const bool atomic_out = F & EF_ATOMIC, vec_store = F & EF_VEC, has_out2 = F & EF_OUT2, has_res = F & EF_RES;
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const long long orow = remap_row(p, row);
@@ -240,26 +311,26 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
     uint32_t v[32];
     rl::tmem_ld_32x32(taddr + c * 32, v);
     float xn[32];
-    if (p.tma_res) {
+    if (tma_res) {
       // residual of THIS chunk: TMA delivered it into the staging tile the result will leave from (issued one chunk
       // ahead); read my row, then prefetch the next chunk's tile into the other staging tile
-      const int buf = NSTG == 1 ? 0 : p.res_all ? cc : (st.stg_sel & 1);
+      const int buf = NSTG == 1 ? 0 : res_all ? cc : (st.stg_sel & 1);
       if (live) {
         if (NSTG == 1) {
           // single staging tile: fetch THIS chunk's residual once the previous chunk's store has drained (the latency is
           // hidden behind the >= 24 k-block main loop of the next tile)
           if (lane == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            issue_residual(p, tmR_ptr, stg_base, rbar, 0, nb, row0);
+            issue_residual(F, tmR_ptr, stg_base, rbar, 0, nb, row0);
           }
-        } else if (!p.res_all && cc + 1 < CH && nb + 32 < p.N && lane == 0) {
+        } else if (!res_all && cc + 1 < CH && nb + 32 < p.N && lane == 0) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store that last read tile buf^1
-          issue_residual(p, tmR_ptr, stg_base, rbar, buf ^ 1, nb + 32, row0);
+          issue_residual(F, tmR_ptr, stg_base, rbar, buf ^ 1, nb + 32, row0);
         }
         rl::mbar_wait(&rbar[buf], (st.rphase >> buf) & 1u);
         st.rphase ^= 1u << buf;
-        const uint8_t* rt = stg_base + buf * (p.res_all ? 2048 : 4096);
-        if (p.res_f32) {
+        const uint8_t* rt = stg_base + buf * (res_all ? 2048 : 4096);
+        if (F & EF_RES_F32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 t = *reinterpret_cast<const float4*>(rt + lane * 128 + ((g ^ (lane & 7)) << 4));
@@ -269,100 +340,95 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint4 t = *reinterpret_cast<const uint4*>(rt + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
-            xr[8 * g] = rl::half_lo(t.x, p.r_f16); xr[8 * g + 1] = rl::half_hi(t.x, p.r_f16);
-            xr[8 * g + 2] = rl::half_lo(t.y, p.r_f16); xr[8 * g + 3] = rl::half_hi(t.y, p.r_f16);
-            xr[8 * g + 4] = rl::half_lo(t.z, p.r_f16); xr[8 * g + 5] = rl::half_hi(t.z, p.r_f16);
-            xr[8 * g + 6] = rl::half_lo(t.w, p.r_f16); xr[8 * g + 7] = rl::half_hi(t.w, p.r_f16);
+            xr[8 * g] = rl::half_lo(t.x, r_f16); xr[8 * g + 1] = rl::half_hi(t.x, r_f16);
+            xr[8 * g + 2] = rl::half_lo(t.y, r_f16); xr[8 * g + 3] = rl::half_hi(t.y, r_f16);
+            xr[8 * g + 4] = rl::half_lo(t.z, r_f16); xr[8 * g + 5] = rl::half_hi(t.z, r_f16);
+            xr[8 * g + 6] = rl::half_lo(t.w, r_f16); xr[8 * g + 7] = rl::half_hi(t.w, r_f16);
           }
         }
         __syncwarp();   // every lane has its residual row in registers before anyone overwrites the tile with results
       }
-    } else if (cc + 1 < CH) {
-      load_residual(p, row, row_ok, nb + 32, xn);  // overlaps the TMEM load and this chunk's math
+    } else if (has_res && cc + 1 < CH) {
+      load_residual(p, F, row, row_ok, nb + 32, xn);  // overlaps the TMEM load and this chunk's math
     }
     rl::tmem_ld_wait();
+    if (cc == CH - 1) {   // the tile has left TMEM: the MMA warp may start the tile after next on this buffer
+      rl::tc_fence_before();
+      __syncwarp();
+      release();
+    }
     if (live) {
       float x[32];
-      if (p.act == RL_ACT_GELU_GRAD) {
+      affine32<NSTG>(p, F, sb, cc, nb, v, x);
+      if (act == RL_ACT_GELU_GRAD) {
         // data gradient through GELU: the `res` operand carries the saved pre-activation u
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {   // packed f32x2 polynomial (FFMA2 / FMUL2): half the issue slots of the scalar form
-          float4 sc, bi;
-          load_scale_bias<NSTG>(p, sb, cc, j, nb, sc, bi);
-          const rl::f2 g0 = rl::gelu_grad2(rl::f2{xr[j], xr[j + 1]}), g1 = rl::gelu_grad2(rl::f2{xr[j + 2], xr[j + 3]});
-          x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x) * g0.x;
-          x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y) * g0.y;
-          x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z) * g1.x;
-          x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w) * g1.y;
+        for (int j = 0; j < 32; j += 2) {   // packed f32x2 polynomial (FFMA2 / FMUL2): half the issue slots of the scalar form
+          const rl::f2 g = rl::gelu_grad2(rl::f2{xr[j], xr[j + 1]});
+          x[j] *= g.x;
+          x[j + 1] *= g.y;
         }
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 sc, bi;
-          load_scale_bias<NSTG>(p, sb, cc, j, nb, sc, bi);
-          x[j] = fmaf(__uint_as_float(v[j]), sc.x, bi.x);
-          x[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-          x[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-          x[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
-        }
-        if (p.drop.thresh) {
+        if (F & EF_DROP) {
           const unsigned long long e0 = (unsigned long long)row * p.N + nb;
           rl::DropSpec dsp = p.drop;
           rl::drop_resolve(dsp);
           rl::drop_apply32(dsp, e0, x);
         }
+        if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] += xr[j];
+          for (int j = 0; j < 32; ++j) x[j] += xr[j];
+        }
       }
       uint8_t* stg = nullptr;
-      if (p.tma_store) {
+      if (tma_store) {
         // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (st.stg_sel lives in the tile loop: a
         // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
         // store was still reading): the TMA store issued two chunks ago must have finished reading
-        stg = NSTG == 1 ? stg_base : p.deep ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
+        stg = NSTG == 1 ? stg_base : deep ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
         st.stg_sel ^= 1;
         if (NSTG == 1) {
-          if (!p.tma_res) {
+          if (!tma_res) {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
-        } else if (!p.tma_res && !p.deep) {   // (tma_res / deep: the tile's previous store was drained earlier)
+        } else if (!tma_res && !deep) {   // (tma_res / deep: the tile's previous store was drained earlier)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
       }
-      if (p.act == RL_ACT_GELU_SAVE && p.tma_out2) {
+      if (act == RL_ACT_GELU_SAVE && tma_out2) {
         // training forward: the pre-activation tile (16-bit) goes to the upper half of the staging tile
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<uint4*>(stg + 2048 + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-              make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], p.o_f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], p.o_f16),
-                         rl::pack_h(x[8 * g + 4], x[8 * g + 5], p.o_f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], p.o_f16));
-      } else if (p.act == RL_ACT_GELU_SAVE && row_ok && p.out2) {
+              make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], o_f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], o_f16),
+                         rl::pack_h(x[8 * g + 4], x[8 * g + 5], o_f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], o_f16));
+      } else if (act == RL_ACT_GELU_SAVE && row_ok && has_out2) {
         // training forward: keep the pre-activation (bf16) for the backward pass, then activate
-        if (nb + 32 <= p.N && p.vec_store) {
+        if (nb + 32 <= p.N && vec_store) {
           uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.o_f16),
-                              rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.o_f16));
+            o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], o_f16),
+                              rl::pack_h(x[8 * j + 4], x[8 * j + 5], o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], o_f16));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.o_f16) & 0xFFFFu);
+            if (nb + j < p.N) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, o_f16) & 0xFFFFu);
         }
       }
-      if (p.act == RL_ACT_GELU || p.act == RL_ACT_GELU_SAVE) {
+      if (act == RL_ACT_GELU || act == RL_ACT_GELU_SAVE) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const rl::f2 g = rl::gelu_erf2(rl::f2{x[j], x[j + 1]});
           x[j] = g.x;
           x[j + 1] = g.y;
         }
-      } else if (p.act == RL_ACT_RELU) {
+      } else if (act == RL_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-      } else if (p.act == RL_ACT_TANH) {
+      } else if (act == RL_ACT_TANH) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
       }
@@ -372,7 +438,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
           st.cs_n0 = n0;
         }
         float t[32];
-        if (p.colsum) {
+        if (F & EF_COLSUM) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) t[j] = row_ok ? x[j] : 0.f;
           const float tot = warp_colsum32(t, lane);
@@ -380,7 +446,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
           for (int k = 0; k < CH; ++k)
             if (k == cc) st.cs[k] += tot;
         }
-        if (p.colsumsq) {
+        if (F & EF_COLSUMSQ) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) t[j] = row_ok ? x[j] * x[j] : 0.f;
           const float tot = warp_colsum32(t, lane);
@@ -389,8 +455,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
             if (k == cc) st.cq[k] += tot;
         }
       }
-      if (p.tma_store) {
-        if (p.out_f32) {
+      if (tma_store) {
+        if (out_f32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<float4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
@@ -399,13 +465,13 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], p.o_f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], p.o_f16),
-                           rl::pack_h(x[8 * g + 4], x[8 * g + 5], p.o_f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], p.o_f16));
+                make_uint4(rl::pack_h(x[8 * g], x[8 * g + 1], o_f16), rl::pack_h(x[8 * g + 2], x[8 * g + 3], o_f16),
+                           rl::pack_h(x[8 * g + 4], x[8 * g + 5], o_f16), rl::pack_h(x[8 * g + 6], x[8 * g + 7], o_f16));
         }
         rl::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.atomic_out)  // split-K: the tile is ADDED to the (zero-initialised) f32 output by the TMA unit itself
+          if (atomic_out)  // split-K: the tile is ADDED to the (zero-initialised) f32 output by the TMA unit itself
             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(tmC_ptr)),
                          "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
@@ -415,18 +481,18 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
                              reinterpret_cast<uint64_t>(tmC_ptr)),
                          "r"(rl::smem_u32(stg)), "r"(nb), "r"(row0)
                          : "memory");
-          if (p.tma_out2)
+          if (tma_out2)
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(tmC2_ptr)),
                          "r"(rl::smem_u32(stg + 2048)), "r"(nb), "r"(row0)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-      } else if (p.atomic_out) {
+      } else if (atomic_out) {
         // split-K: partial sums of the different K ranges meet in the (zero-initialised) f32 output
         if (row_ok) {
           float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + nb;
-          if (nb + 32 <= p.N && p.vec_store) {
+          if (nb + 32 <= p.N && vec_store) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
@@ -437,8 +503,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
           }
         }
       } else if (row_ok) {
-        if (nb + 32 <= p.N && p.vec_store) {
-          if (p.out_f32) {
+        if (nb + 32 <= p.N && vec_store) {
+          if (out_f32) {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + nb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
@@ -446,31 +512,31 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
             uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.o_f16),
-                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.o_f16));
+              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], o_f16),
+                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], o_f16));
           }
-          if (p.out2 && p.act != RL_ACT_GELU_SAVE) {
+          if (has_out2 && act != RL_ACT_GELU_SAVE) {
             uint4* o = reinterpret_cast<uint4*>(p.out2 + orow * p.ldo2 + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], p.o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], p.o_f16),
-                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], p.o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], p.o_f16));
+              o[j] = make_uint4(rl::pack_h(x[8 * j], x[8 * j + 1], o_f16), rl::pack_h(x[8 * j + 2], x[8 * j + 3], o_f16),
+                                rl::pack_h(x[8 * j + 4], x[8 * j + 5], o_f16), rl::pack_h(x[8 * j + 6], x[8 * j + 7], o_f16));
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (nb + j < p.N) {
-              if (p.out_f32)
+              if (out_f32)
                 reinterpret_cast<float*>(p.out)[orow * p.ldo + nb + j] = x[j];
               else
-                reinterpret_cast<unsigned short*>(p.out)[orow * p.ldo + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.o_f16) & 0xFFFFu);
-              if (p.out2 && p.act != RL_ACT_GELU_SAVE) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, p.o_f16) & 0xFFFFu);
+                reinterpret_cast<unsigned short*>(p.out)[orow * p.ldo + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, o_f16) & 0xFFFFu);
+              if (has_out2 && act != RL_ACT_GELU_SAVE) reinterpret_cast<unsigned short*>(p.out2)[orow * p.ldo2 + nb + j] = (unsigned short)(rl::pack_h(x[j], 0.f, o_f16) & 0xFFFFu);
             }
           }
         }
       }
     }
-    if (cc + 1 < CH && !p.tma_res) {
+    if (has_res && cc + 1 < CH && !tma_res) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) xr[j] = xn[j];
     }
@@ -646,7 +712,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, load_eflags(p)};
+    const uint32_t F = est.flags;
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -656,36 +723,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
-      epilogue_prefetch<BN>(p, sb, row0, n0, half, lane, xr);
-      if (p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
+      epilogue_prefetch<BN>(p, F, sb, row0, n0, half, lane, xr);
+      if ((F & EF_DEEP) && !(F & EF_TMA_RES)) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
-      if (p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
-        if (p.res_all) {
+      if ((F & EF_TMA_RES) && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
+        if (F & EF_RES_ALL) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #pragma unroll
           for (int cc = 0; cc < BN / 64; ++cc)
-            if (n0 + half * (BN / 2) + cc * 32 < p.N) issue_residual(p, &tmR, stg, rbar, cc, n0 + half * (BN / 2) + cc * 32, row0);
+            if (n0 + half * (BN / 2) + cc * 32 < p.N) issue_residual(F, &tmR, stg, rbar, cc, n0 + half * (BN / 2) + cc * 32, row0);
         } else {
           // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+          issue_residual(F, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
         }
       }
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN, COLS>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
-      rl::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) rl::mbar_arrive(&tmem_empty[acc]);
+      uint64_t* done = &tmem_empty[acc];
+      epilogue_tile<BN, COLS>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est,
+                              [done, lane] { if (lane == 0) rl::mbar_arrive(done); });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (COLS) colsum_flush<BN / 64>(p, est, half, lane);
-    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if ((F & EF_TMA_STORE) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   rl::tc_fence_before();
@@ -789,7 +855,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // from eit
 // NSTG = 32x32 fp32 staging tiles per epilogue warp: 2 (default), or 1 for the LONG-K variant, which spends the shared
 // memory on a fifth pipeline stage instead: ncu shows the main loop bound by bytes in flight (4 x 32 KB per SM at ~2 us of
 // TMA latency = 900 clk per k-block, 57 % tensor-pipe), and behind >= 24 k-blocks a serialised epilogue is invisible.
-template <int BN, int STAGES, int CL, bool COLS, int NSTG = 2>
+// SPEC != 0: the epilogue's mode word as a compile-time constant (EF_*, SPEC_*).
+template <int BN, int STAGES, int CL, bool COLS, int NSTG = 2, uint32_t SPEC = 0>
 __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                            const CUtensorMap& tmC2, const CUtensorMap& tmR, const KParams& p) {
   constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
@@ -975,7 +1042,8 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     uint8_t* stg = smem_stage + ew * WARP_STG;
     float* sb = reinterpret_cast<float*>(stg + NSTG * 4096);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC ? SPEC : load_eflags(p)};
+    const uint32_t F = SPEC ? SPEC : est.flags;
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -985,36 +1053,35 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       const int row0 = m_blk * CL * BM + (int)crank * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
-      epilogue_prefetch<BN, NSTG>(p, sb, row0, n0, half, lane, xr);
-      if (NSTG == 2 && p.deep && !p.tma_res) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
+      epilogue_prefetch<BN, NSTG>(p, F, sb, row0, n0, half, lane, xr);
+      if (NSTG == 2 && (F & EF_DEEP) && !(F & EF_TMA_RES)) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
-      if (NSTG == 2 && p.tma_res && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
-        if (p.res_all) {
+      if (NSTG == 2 && (F & EF_TMA_RES) && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
+        if (F & EF_RES_ALL) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #pragma unroll
           for (int cc = 0; cc < BN / 64; ++cc)
-            if (n0 + half * (BN / 2) + cc * 32 < p.N) issue_residual(p, &tmR, stg, rbar, cc, n0 + half * (BN / 2) + cc * 32, row0);
+            if (n0 + half * (BN / 2) + cc * 32 < p.N) issue_residual(F, &tmR, stg, rbar, cc, n0 + half * (BN / 2) + cc * 32, row0);
         } else {
           // first residual tile of this output tile: its staging tile was last read by the store two chunks ago
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          issue_residual(p, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
+          issue_residual(F, &tmR, stg, rbar, est.stg_sel & 1, n0 + half * (BN / 2), row0);
         }
       }
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN, COLS, NSTG>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est);
-      rl::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      uint64_t* done = &tmem_empty[acc];
+      epilogue_tile<BN, COLS, NSTG, SPEC>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est,
+                                          [done, lane] { if (lane == 0) mbar_arrive_leader(done); });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (COLS) colsum_flush<BN / 64>(p, est, half, lane);
-    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if ((F & EF_TMA_STORE) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   rl::tc_fence_before();
@@ -1025,12 +1092,12 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   }
 }
 
-template <int BN, int STAGES, bool COLS, int NSTG = 2>
+template <int BN, int STAGES, bool COLS, int NSTG = 2, uint32_t SPEC = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                   const __grid_constant__ CUtensorMap tmR, const KParams p) {
-  gemm2_body<BN, STAGES, 2, COLS, NSTG>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_body<BN, STAGES, 2, COLS, NSTG, SPEC>(tmA, tmB, tmC, tmC2, tmR, p);
 }
 
 template <int BN, int STAGES>
@@ -1046,14 +1113,14 @@ constexpr int gemm2_smem_bytes() {
   return STAGES * (A_BYTES + (BN / 2) * BK * 2) + (NSTG == 1 ? 8 * 4096 : 8 * (NSTG * 4096 + 1024) + 1024) + (2 * STAGES + 4) * 8 + 16 + 256;
 }
 
-template <int BN, int STAGES, bool COLS = false, int NSTG = 2>
+template <int BN, int STAGES, bool COLS = false, int NSTG = 2, uint32_t SPEC = 0>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                  const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
   constexpr int smem = gemm2_smem_bytes<BN, STAGES, NSTG>();
   static_assert(smem <= 232448, "dynamic shared memory of the pair kernel exceeds 227 KB");
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES, COLS, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<BN, STAGES, COLS, NSTG, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -1063,7 +1130,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int max_clusters = p.sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_bf16_kernel<BN, STAGES, COLS, NSTG><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm2_bf16_kernel<BN, STAGES, COLS, NSTG, SPEC><<<2 * clusters, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16(cta_group::2)");
 }
 
@@ -1438,7 +1505,19 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool cols = d->colsum || d->colsumsq;   // separate instantiations: the reductions cost registers in the epilogue
+  p.eflags = EF_VALID | (p.tma_res ? EF_TMA_RES : 0u) | (p.res && p.res_f32 ? EF_RES_F32 : 0u) | (p.res && p.r_f16 ? EF_R_F16 : 0u) |
+             (p.drop.thresh ? EF_DROP : 0u) | (p.tma_store ? EF_TMA_STORE : 0u) | (p.deep ? EF_DEEP : 0u) |
+             (p.res_all ? EF_RES_ALL : 0u) | (p.tma_out2 ? EF_TMA_OUT2 : 0u) | (p.out_f32 ? EF_OUT_F32 : 0u) |
+             (p.o_f16 ? EF_O_F16 : 0u) | (p.atomic_out ? EF_ATOMIC : 0u) | (p.scale ? EF_SCALE : 0u) | (p.res ? EF_RES : 0u) |
+             (p.out2 ? EF_OUT2 : 0u) | (p.vec_store ? EF_VEC : 0u) | (p.colsum ? EF_COLSUM : 0u) |
+             (p.colsumsq ? EF_COLSUMSQ : 0u) | ((uint32_t)p.act << EF_ACT_SHIFT);
   if (quad && !cols) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  if (pair && bn == 256 && !cols && !long_k && d->tune_no_pair != 5) {
+    // the hot short-K configurations of a train step, with the epilogue's mode word folded at compile time
+    if (p.eflags == SPEC_OUT16) return launch_gemm2<256, 4, false, 2, SPEC_OUT16>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (p.eflags == SPEC_GELU_SAVE) return launch_gemm2<256, 4, false, 2, SPEC_GELU_SAVE>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (p.eflags == SPEC_RES32) return launch_gemm2<256, 4, false, 2, SPEC_RES32>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  }
   if (pair) {
     // long-K variant (5 stages; one staging tile per epilogue warp, no scale/bias table): >= 24 k-blocks per work item.
     // Measured (tools/gemm_bench.py): 4 -> 5 stages = -5..10 % on K >= 2304 GEMMs and split-K weight gradients, 5 -> 6 nothing
