@@ -72,7 +72,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // additive mask, exactly the reference's (1 - mask) * -10000 (modeling_bert.py:696-697), in log2 units
   for (int j = tid; j < LKV_MAX; j += ATT_THREADS) {
     float m = -INFINITY;
-    if (j < L) m = (1.0f - (float)p.mask[(long long)b * L + j]) * -10000.0f * 1.4426950408889634f;
+    if (j < L) m = p.mask[(long long)b * L + j] != 0 ? 0.0f : -10000.0f * 1.4426950408889634f;   // attention masks are 0 / 1 (no I2F.S64)
     s_mask[j] = m;
   }
   rl::tc_fence_before();

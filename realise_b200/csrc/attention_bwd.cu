@@ -29,7 +29,8 @@ struct AttBwdParams {
 
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                     const __grid_constant__ CUtensorMap tmDO, const AttBwdParams p) {
+                     const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmO,
+                     const __grid_constant__ CUtensorMap tmDQKV, const AttBwdParams p) {
   // Two CTAs per SM: 256 TMEM columns and 7 x 16 KB of shared memory each.  S / dP (phase 1) are dead once every
   // thread has turned them into the bf16 P / dS tiles, so the phase-2 accumulators dV / dK / dQ reuse their columns;
   // V is dead once dP = dO V^T has completed (bar_s), so kv-tile 0 of P overwrites it.
@@ -58,6 +59,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     rl::tma_prefetch_desc(&tmQ);
     rl::tma_prefetch_desc(&tmKV);
     rl::tma_prefetch_desc(&tmDO);
+    rl::tma_prefetch_desc(&tmO);
+    rl::tma_prefetch_desc(&tmDQKV);
     rl::mbar_init(bar_ld, 1);
     rl::mbar_init(bar_s, 1);
     rl::mbar_init(bar_o, 1);
@@ -66,11 +69,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 0) rl::tmem_alloc(tmem_ptr, 256);
   for (int j = tid; j < 128; j += ATT_THREADS) {
     float m = -INFINITY;
-    if (j < L) m = (1.0f - (float)p.mask[(long long)b * L + j]) * -10000.0f * 1.4426950408889634f;
+    if (j < L) m = p.mask[(long long)b * L + j] != 0 ? 0.0f : -10000.0f * 1.4426950408889634f;   // attention masks are 0 / 1
     s_mask[j] = m;
   }
-  // zero the P / dS tiles once: chunk tiles or rows that are never written must not feed NaNs into the MMAs
-  for (int i = tid; i < 3 * T16K / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP1)[i] = make_uint4(0, 0, 0, 0);
+  // zero P tile 1 and dS tile 1 once: chunk tiles or rows that are never written must not feed NaNs into the MMAs
+  // (dS tile 0 first receives the O tile; every thread clears its own row there once it has read it)
+  for (int i = tid; i < T16K / 16; i += ATT_THREADS) {
+    reinterpret_cast<uint4*>(sP1)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(sDS + T16K)[i] = make_uint4(0, 0, 0, 0);
+  }
   rl::fence_proxy_async();
   rl::tc_fence_before();
   __syncthreads();
@@ -78,7 +85,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (tid == 0) {
-    rl::mbar_expect_tx(bar_ld, 2 * T16K + 2 * lkv16 * 128);
+    rl::mbar_expect_tx(bar_ld, 3 * T16K + 2 * lkv16 * 128);
+    rl::tma_load_2d(sDS, &tmO, bar_ld, head * HEAD_DIM, row0);   // O, for delta: lives in dS tile 0 until the rows are read
     rl::tma_load_2d(sQ, &tmQ, bar_ld, head * HEAD_DIM, row0);
     rl::tma_load_2d(sK, &tmKV, bar_ld, p.H + head * HEAD_DIM, row0);
     rl::tma_load_2d(sV, &tmKV, bar_ld, 2 * p.H + head * HEAD_DIM, row0);
@@ -99,21 +107,30 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     rl::tc_commit(bar_s);
   }
 
-  // delta = rowsum(dO o O) for this thread's query row (global reads overlap the loads / MMAs above)
+  // delta = rowsum(dO o O) for this thread's query row, from the two TMA-loaded tiles (row-strided global loads cost 32
+  // cache lines per instruction and were 19 % of the kernel's stall samples).  Row r of a SWIZZLE_128B tile: 16-byte piece g
+  // sits at ((g ^ (r & 7)) << 4) of the 128-byte row.
   const int r = tid;
   float delta = 0.f;
-  if (r < L) {
-    const uint4* o = reinterpret_cast<const uint4*>(p.ctx + (long long)(row0 + r) * p.H + head * HEAD_DIM);
-    const uint4* g = reinterpret_cast<const uint4*>(p.dctx + (long long)(row0 + r) * p.H + head * HEAD_DIM);
+  if (tid != 0) rl::mbar_wait(bar_ld, 0);   // (thread 0 has waited above)
+  {
+    const uint8_t* orow = sDS + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint8_t* grow = sDO + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint4 a = o[i], c = g[i];
+      const uint4 a = *reinterpret_cast<const uint4*>(orow + ((i ^ (r & 7)) << 4));
+      const uint4 c = *reinterpret_cast<const uint4*>(grow + ((i ^ (r & 7)) << 4));
       delta += rl::half_lo(a.x, p.f16) * rl::half_lo(c.x, p.f16) + rl::half_hi(a.x, p.f16) * rl::half_hi(c.x, p.f16) +
                rl::half_lo(a.y, p.f16) * rl::half_lo(c.y, p.f16) + rl::half_hi(a.y, p.f16) * rl::half_hi(c.y, p.f16) +
                rl::half_lo(a.z, p.f16) * rl::half_lo(c.z, p.f16) + rl::half_hi(a.z, p.f16) * rl::half_hi(c.z, p.f16) +
                rl::half_lo(a.w, p.f16) * rl::half_lo(c.w, p.f16) + rl::half_hi(a.w, p.f16) * rl::half_hi(c.w, p.f16);
     }
+    // my row of dS tile 0 held O: clear it (kv chunks this sentence does not reach stay zero)
+    uint8_t* zrow = sDS + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(zrow + (i << 4)) = make_uint4(0, 0, 0, 0);
   }
+  if (r >= L) delta = 0.f;
 
   rl::mbar_wait(bar_s, 0);
   rl::tc_fence_after();
@@ -226,32 +243,46 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   rl::mbar_wait(bar_o, 0);
   rl::tc_fence_after();
   {
-    // tcgen05.ld is warp-collective: every lane loads, only rows inside the sentence store
-    __nv_bfloat16* base = p.dqkv + (long long)(row0 + r) * 3 * p.H + head * HEAD_DIM;
+    // dQ / dK / dV leave through the dead Q / K / dO tiles (SWIZZLE_128B rows) and one TMA store each; the 3-D map
+    // [B][L][3H] clips the rows beyond the sentence.  (Row-strided 16-byte global stores were 18 % of the stall samples.)
+    uint8_t* stage[3] = {sQ, sK, sDO};
     const uint32_t cols[3] = {COL_DQ, COL_DK, COL_DV};
     const float scl[3] = {0.125f, 0.125f, 1.0f};
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
+      uint8_t* srow = stage[t] + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         rl::tmem_ld_32x32(t_row + cols[t] + c * 32, v);
         rl::tmem_ld_wait();
-        if (r < L) {
-          uint4* o = reinterpret_cast<uint4*>(base + t * p.H + c * 32);
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            o[g] = make_uint4(rl::pack_h(__uint_as_float(v[8 * g]) * scl[t], __uint_as_float(v[8 * g + 1]) * scl[t], p.f16),
-                              rl::pack_h(__uint_as_float(v[8 * g + 2]) * scl[t], __uint_as_float(v[8 * g + 3]) * scl[t], p.f16),
-                              rl::pack_h(__uint_as_float(v[8 * g + 4]) * scl[t], __uint_as_float(v[8 * g + 5]) * scl[t], p.f16),
-                              rl::pack_h(__uint_as_float(v[8 * g + 6]) * scl[t], __uint_as_float(v[8 * g + 7]) * scl[t], p.f16));
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(srow + (((c * 4 + g) ^ (r & 7)) << 4)) =
+              make_uint4(rl::pack_h(__uint_as_float(v[8 * g]) * scl[t], __uint_as_float(v[8 * g + 1]) * scl[t], p.f16),
+                         rl::pack_h(__uint_as_float(v[8 * g + 2]) * scl[t], __uint_as_float(v[8 * g + 3]) * scl[t], p.f16),
+                         rl::pack_h(__uint_as_float(v[8 * g + 4]) * scl[t], __uint_as_float(v[8 * g + 5]) * scl[t], p.f16),
+                         rl::pack_h(__uint_as_float(v[8 * g + 6]) * scl[t], __uint_as_float(v[8 * g + 7]) * scl[t], p.f16));
       }
     }
   }
+  rl::fence_proxy_async();
   rl::tc_fence_before();
   __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const uint8_t* src = t == 0 ? sQ : t == 1 ? sK : sDO;
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(&tmDQKV)),
+                   "r"(rl::smem_u32(src)), "r"(t * p.H + head * HEAD_DIM), "r"(0), "r"(b)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tiles are read before the CTA's smem goes away
+  }
   if (warp == 0) {
+    __syncwarp();
     rl::tc_fence_after();
     rl::tmem_dealloc(tmem_base, 256);
   }
@@ -300,7 +331,7 @@ attention_bwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (warp == 0) rl::tmem_alloc(tmem_ptr, 512);
   for (int j = tid; j < 256; j += ATT_THREADS) {
     float m = -INFINITY;
-    if (j < L) m = (1.0f - (float)p.mask[(long long)b * L + j]) * -10000.0f * 1.4426950408889634f;
+    if (j < L) m = p.mask[(long long)b * L + j] != 0 ? 0.0f : -10000.0f * 1.4426950408889634f;   // attention masks are 0 / 1 (no I2F.S64)
     s_mask[j] = m;
   }
   for (int i = tid; i < 4 * T16K / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
@@ -555,6 +586,16 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
     }
     configured = true;
   }
+  CUtensorMap to, tdq;
+  rc = rl_make_tmap_bf16(&to, ctx, 2, dimso, strideso, boxq);
+  if (rc) return rc;
+  {
+    uint64_t dims3[3] = {(uint64_t)(3 * H), (uint64_t)L, (uint64_t)B};
+    uint64_t strides3[2] = {(uint64_t)(3 * H) * 2, (uint64_t)L * (3 * H) * 2};
+    uint32_t box3[3] = {64, 128, 1};
+    rc = rl_make_tmap_bf16(&tdq, dqkv, 3, dims3, strides3, box3);
+    if (rc) return rc;
+  }
   AttBwdParams p;
   p.mask = reinterpret_cast<const long long*>(mask);
   p.ctx = reinterpret_cast<const __nv_bfloat16*>(ctx);
@@ -568,6 +609,6 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
   p.drop = rl::make_drop(drop_p, drop_seed, drop_site, drop_counter);
   p.f16 = act_dtype == RL_DT_F16;
   p.lse = row_lse;
-  attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, p);
+  attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, to, tdq, p);
   return rl_check_launch("rl_attention_bwd");
 }

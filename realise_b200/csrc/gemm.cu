@@ -75,6 +75,9 @@ enum : uint32_t {
 // compile-time specialisations of the pair kernel (training formats: bf16 operands and results)
 constexpr uint32_t SPEC_OUT16 = EF_VALID | EF_TMA_STORE | EF_DEEP | EF_VEC;                  // (bias) -> bf16: QKV, dgrads
 constexpr uint32_t SPEC_GELU_SAVE = EF_VALID | EF_TMA_STORE | EF_TMA_OUT2 | EF_OUT2 | EF_VEC | ((uint32_t)RL_ACT_GELU_SAVE << EF_ACT_SHIFT);
+constexpr uint32_t SPEC_GELU_GRAD = EF_VALID | EF_TMA_STORE | EF_DEEP | EF_TMA_RES | EF_RES_ALL | EF_RES | EF_VEC |
+                                    ((uint32_t)RL_ACT_GELU_GRAD << EF_ACT_SHIFT);          // du = (dy W2) o gelu'(u) -> bf16
+constexpr uint32_t SPEC_GELU_GRAD_CS = SPEC_GELU_GRAD | EF_COLSUM;                          // ... and db1 = column sums of du
 constexpr uint32_t SPEC_RES32 = EF_VALID | EF_TMA_STORE | EF_TMA_RES | EF_RES | EF_RES_F32 | EF_OUT_F32 | EF_DROP | EF_VEC;  // bias + dropout + f32 residual -> f32
 
 using rl::fast_erf;
@@ -1517,7 +1520,10 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     if (p.eflags == SPEC_OUT16) return launch_gemm2<256, 4, false, 2, SPEC_OUT16>(tmA, tmB, tmC, tmC2, tmR, p, st);
     if (p.eflags == SPEC_GELU_SAVE) return launch_gemm2<256, 4, false, 2, SPEC_GELU_SAVE>(tmA, tmB, tmC, tmC2, tmR, p, st);
     if (p.eflags == SPEC_RES32) return launch_gemm2<256, 4, false, 2, SPEC_RES32>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (p.eflags == SPEC_GELU_GRAD) return launch_gemm2<256, 4, false, 2, SPEC_GELU_GRAD>(tmA, tmB, tmC, tmC2, tmR, p, st);
   }
+  if (pair && bn == 256 && cols && d->tune_no_pair != 5 && p.eflags == SPEC_GELU_GRAD_CS)
+    return launch_gemm2<256, 4, true, 2, SPEC_GELU_GRAD_CS>(tmA, tmB, tmC, tmC2, tmR, p, st);
   if (pair) {
     // long-K variant (5 stages; one staging tile per epilogue warp, no scale/bias table): >= 24 k-blocks per work item.
     // Measured (tools/gemm_bench.py): 4 -> 5 stages = -5..10 % on K >= 2304 GEMMs and split-K weight gradients, 5 -> 6 nothing

@@ -12,6 +12,7 @@ LayerNorm / softmax / BatchNorm statistics fp32.  Gradients of successive backwa
 optimizer step or zero_grad() consumes them (src/run.py:193-205, gradient_accumulation_steps).
 """
 import ctypes
+import os
 
 import torch
 
@@ -128,6 +129,7 @@ class TrainEngine:
         self.multistream = False      # experiment (off): the three encoders (and their backward passes) on three CUDA streams.
         self._streams = None          # Measured on B200: no gain — the persistent GEMMs hold every SM's register file, so the
                                       # other branches' kernels only fill wave tails (42.8 vs 42.0 ms/step within clock noise)
+        self.fused_gelu_grad = os.environ.get("RL_FUSED_GELU_GRAD", "0") == "1"   # du and db1 out of the dgrad GEMM's epilogue
         self.zpool = ZeroPool(model.classifier.bias.device)
         self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
@@ -757,10 +759,13 @@ class TrainEngine:
                               site_out=self.site(name, li, 3) if hp > 0 else 0)
             ops.gemm(dy2b, s["h"], self._grad(out.dense.weight), a_t=True, b_t=True, split_k=-1)              # dW2 = dy2^T h
             du = self._new((N, I), BF16)
-            ops.gemm(dy2b, lw["w_2"], du, b_t=True)
-            # du = (dy2 W2) o gelu'(u) and db1 as one element-wise pass: measured faster than the fused epilogue (ACT_GELU_GRAD
-            # + colsum), whose erf' polynomial on 8 epilogue warps outlasts a K = 768 main loop (tools/gemm_bench.py)
-            ops.gelu_bwd_colsum(du, s["u"], self._grad(lyr.intermediate.dense.bias, True))
+            if self.fused_gelu_grad:
+                ops.gemm(dy2b, lw["w_2"], du, b_t=True, res=s["u"], act=ops.ACT_GELU_GRAD,
+                         colsum=self._grad(lyr.intermediate.dense.bias, True))
+            else:
+                ops.gemm(dy2b, lw["w_2"], du, b_t=True)
+                # du = (dy2 W2) o gelu'(u) and db1 as one element-wise pass
+                ops.gelu_bwd_colsum(du, s["u"], self._grad(lyr.intermediate.dense.bias, True))
             ops.gemm(du, s["x1b"], self._grad(lyr.intermediate.dense.weight), a_t=True, b_t=True, split_k=-1)  # dW1 = du^T x1
             dx1 = self._new((N, H), F32)
             ops.gemm(du, lw["w_1"], dx1, b_t=True, res=dy2)                                         # dx1 = du W1 + dy2
