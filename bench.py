@@ -380,6 +380,10 @@ def measure_train(args, dev, rank, world, dist, peaks):
     eager_step()
     torch.cuda.synchronize()
     prof, ops._prof = ops._prof, None
+    if args.dump_prof and rank == 0:
+        with open(args.dump_prof, "w") as fh:
+            json.dump([{"kind": k, "detail": list(d) if d else None, "us": round(e0.elapsed_time(e1) * 1e3, 2), "work": w}
+                       for k, w, e0, e1, d in prof], fh)
     try:
         for _ in range(W):
             step()                                         # first call of the shape is eager, the second captures
@@ -630,6 +634,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=170.0,
                     help="--impl reference: seconds the warm-up + timed CPU steps may take (sizes the bounded sample)")
     ap.add_argument("--no-incumbent", action="store_true", help="skip the reference-on-the-B200 (torch eager) comparator")
+    ap.add_argument("--dump-prof", default=None, help="write the per-call timeline of the eager profiling pass (kind, shape key, "
+                    "us, executed work) of one train step to this JSON file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -279,6 +279,9 @@ RL_API int rl_gru_table_bwd(const float* dtable, const float* emb, const float* 
  * rl_bn_apply: out = [relu](x1*scale1 + shift1 [+ x2*scale2 + shift2]); remap = 1 writes parity-split rows.
  * rl_bn_bwd: BatchNorm backward for dy (f32/bf16; rows parity-split when remap) optionally masked by the ReLU that
  *   followed (act_out > 0); dbeta/dgamma accumulated, dx written as bf16 with row stride ldx.
+ *   fwd_scale / fwd_shift (optional, the rl_bn_finalize outputs the forward applied): the ReLU mask is re-derived from the
+ *   raw conv outputs as (x*scale + shift [+ x2*scale2 + shift2]) > 0 — rl_bn_apply's own arithmetic, so the same bits —
+ *   and act_out is not read at all (one tensor-sized HBM stream less in each of the two passes).
  * rl_im2col_bf16: col[m, t*C + ci] = x[img, plane_t, oh+dh_t, ow+dw_t, ci] so that a conv weight gradient
  *   dW[co, t, ci] is ONE split-K rl_gemm_bf16 (A = dY MN-major, B = col MN-major).
  * rl_glyph_im2col: the same for res_block1 straight from the glyph table: col1 [n*256, 32] (27 used), colsc [n*256, 8]
@@ -292,7 +295,8 @@ RL_API int rl_bn_apply(const void* x1, const float* scale1, const float* shift1,
                        int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream);
 RL_API int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const void* x,
                      int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
-                     int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream);
+                     int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, const float* fwd_scale,
+                     const float* fwd_shift, void* stream);
 /* Two BatchNorms that fed the same ReLU (out = relu(bn2(c2) + bn_s(cs)), src/char_cnn.py:31-32) differentiated in one
  * reduce + one apply pass: dy / act_out are read once for both branches.  x2 == NULL: single branch (== rl_bn_bwd).
  * x1 / x2 are f32 or bf16 (x_dtype; res_block1-2 keep their raw conv outputs in bf16 to halve the BatchNorm traffic).  C must be 8*2^k (< 256) or a multiple of 256; all pointers 16-byte aligned. */
@@ -300,7 +304,8 @@ RL_API int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out, int
                       const float* mean1, const float* rstd1, const float* gamma1, float* dbeta1, float* dgamma1, void* dx1,
                       int64_t ldx1, const void* x2, const float* mean2, const float* rstd2, const float* gamma2,
                       float* dbeta2, float* dgamma2, void* dx2, int64_t ldx2, int64_t M, int64_t C, int32_t remap,
-                      int32_t map_h, int32_t map_w, void* stream);
+                      int32_t map_h, int32_t map_w, const float* fwd_scale1, const float* fwd_shift1,
+                      const float* fwd_scale2, const float* fwd_shift2, void* stream);
 RL_API int rl_im2col_bf16(const void* x, void* col, int64_t n_img, int32_t C, int32_t W, int32_t H, int32_t P,
                           int32_t ntaps, const int8_t* tap_dw, const int8_t* tap_dh, const int8_t* tap_plane,
                           void* stream);

@@ -78,6 +78,8 @@ constexpr uint32_t SPEC_GELU_SAVE = EF_VALID | EF_TMA_STORE | EF_TMA_OUT2 | EF_O
 constexpr uint32_t SPEC_GELU_GRAD = EF_VALID | EF_TMA_STORE | EF_DEEP | EF_TMA_RES | EF_RES_ALL | EF_RES | EF_VEC |
                                     ((uint32_t)RL_ACT_GELU_GRAD << EF_ACT_SHIFT);          // du = (dy W2) o gelu'(u) -> bf16
 constexpr uint32_t SPEC_GELU_GRAD_CS = SPEC_GELU_GRAD | EF_COLSUM;                          // ... and db1 = column sums of du
+constexpr uint32_t SPEC_RES32_ND = EF_VALID | EF_TMA_STORE | EF_TMA_RES | EF_RES | EF_RES_F32 | EF_OUT_F32 | EF_VEC;   // f32 residual -> f32, no dropout (dgrads)
+constexpr uint32_t SPEC_SPLITK = EF_VALID | EF_TMA_STORE | EF_OUT_F32 | EF_ATOMIC | EF_VEC;     // split-K weight gradients (TMA reduce-add)
 constexpr uint32_t SPEC_RES32 = EF_VALID | EF_TMA_STORE | EF_TMA_RES | EF_RES | EF_RES_F32 | EF_OUT_F32 | EF_DROP | EF_VEC;  // bias + dropout + f32 residual -> f32
 
 using rl::fast_erf;
@@ -148,16 +150,30 @@ __device__ __forceinline__ void load_residual(const KParams& p, uint32_t F, int 
   }
 }
 
+struct EpiState {
+  int stg_sel;       // staging tile of the next chunk (alternates per chunk ACROSS tiles)
+  uint32_t rphase;   // bit b: phase of the residual-arrival barrier of staging tile b
+  // column reductions (p.colsum / p.colsumsq): lane l accumulates column l of each of this warp's chunks across the
+  // tiles of the persistent loop and flushes with one atomic per column when the column block changes (a conv GEMM
+  // with one N tile flushes ONCE per CTA — per-tile atomics on 64 addresses would serialise in L2)
+  float cs[4], cq[4];
+  int cs_n0;
+  uint32_t flags;    // KParams::eflags in a register (see EF_*)
+  int sb_n0;         // column block whose scale/bias the warp's table holds (-1: none): a GEMM with ONE N tile (the convs)
+                     // fills it once per CTA instead of paying a global-load latency on every 128-row tile
+};
+
 // scale/bias of this warp's BN/2 columns -> sb[0..BN/2) and sb[128..128+BN/2); first residual chunk -> xr.
 // All global loads are issued before the first shared store: the rolled loop this replaces paid one global-load latency
 // per 32 columns (4 x ~500 cycles per 256-wide tile, 14 % of the epilogue warps' time in the K = 768 GEMMs).
 template <int BN, int NSTG = 2>
 __device__ __forceinline__ void epilogue_prefetch(const KParams& p, uint32_t F, float* sb, int row0, int n0, int half, int lane,
-                                                  float (&xr)[32]) {
+                                                  float (&xr)[32], EpiState& st) {
   constexpr int HC = BN / 2;
   const int c0 = n0 + half * HC;
   __syncwarp();
-  if (NSTG != 1) {
+  if (NSTG != 1 && st.sb_n0 != n0) {
+    st.sb_n0 = n0;
     float sv[HC / 32], bv[HC / 32];
     const float* bias = p.bias;
 #pragma unroll
@@ -176,16 +192,6 @@ __device__ __forceinline__ void epilogue_prefetch(const KParams& p, uint32_t F, 
   __syncwarp();
 }
 
-struct EpiState {
-  int stg_sel;       // staging tile of the next chunk (alternates per chunk ACROSS tiles)
-  uint32_t rphase;   // bit b: phase of the residual-arrival barrier of staging tile b
-  // column reductions (p.colsum / p.colsumsq): lane l accumulates column l of each of this warp's chunks across the
-  // tiles of the persistent loop and flushes with one atomic per column when the column block changes (a conv GEMM
-  // with one N tile flushes ONCE per CTA — per-tile atomics on 64 addresses would serialise in L2)
-  float cs[4], cq[4];
-  int cs_n0;
-  uint32_t flags;    // KParams::eflags in a register (see EF_*)
-};
 
 // KParams::eflags as an opaque register value: the compiler may not re-derive it from constant memory at each use
 __device__ __forceinline__ uint32_t load_eflags(const KParams& p) {
@@ -715,7 +721,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, load_eflags(p)};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, load_eflags(p), -1};
     const uint32_t F = est.flags;
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
@@ -726,7 +732,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
-      epilogue_prefetch<BN>(p, F, sb, row0, n0, half, lane, xr);
+      epilogue_prefetch<BN>(p, F, sb, row0, n0, half, lane, xr, est);
       if ((F & EF_DEEP) && !(F & EF_TMA_RES)) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
@@ -1045,7 +1051,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     uint8_t* stg = smem_stage + ew * WARP_STG;
     float* sb = reinterpret_cast<float*>(stg + NSTG * 4096);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC ? SPEC : load_eflags(p)};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC ? SPEC : load_eflags(p), -1};
     const uint32_t F = SPEC ? SPEC : est.flags;
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
@@ -1056,7 +1062,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       const int row0 = m_blk * CL * BM + (int)crank * BM + q * 32;
       const int n0 = n_blk * BN;
       float xr[32];
-      epilogue_prefetch<BN, NSTG>(p, F, sb, row0, n0, half, lane, xr);
+      epilogue_prefetch<BN, NSTG>(p, F, sb, row0, n0, half, lane, xr, est);
       if (NSTG == 2 && (F & EF_DEEP) && !(F & EF_TMA_RES)) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
@@ -1529,8 +1535,14 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     // Measured (tools/gemm_bench.py): 4 -> 5 stages = -5..10 % on K >= 2304 GEMMs and split-K weight gradients, 5 -> 6 nothing
     // more: ~750 clk per k-block is what 32 KB per k-block costs at the ~81 GB/s an SM can ingest (68 % tensor-pipe ceiling
     // of 256x256 pair tiles)
-    if (bn == 256 && !cols && !p.tma_out2 && p.kb_per_split >= 24 && d->tune_no_pair != 4)
+    if (bn == 256 && !cols && !p.tma_out2 && p.kb_per_split >= 24 && d->tune_no_pair != 4) {
+      if (d->tune_no_pair != 5) {
+        if (p.eflags == SPEC_RES32) return launch_gemm2<256, 5, false, 1, SPEC_RES32>(tmA, tmB, tmC, tmC2, tmR, p, st);
+        if (p.eflags == SPEC_RES32_ND) return launch_gemm2<256, 5, false, 1, SPEC_RES32_ND>(tmA, tmB, tmC, tmC2, tmR, p, st);
+        if (p.eflags == SPEC_SPLITK) return launch_gemm2<256, 5, false, 1, SPEC_SPLITK>(tmA, tmB, tmC, tmC2, tmR, p, st);
+      }
       return launch_gemm2<256, 5, false, 1>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    }
     if (bn == 256) return cols ? launch_gemm2<256, 4, true>(tmA, tmB, tmC, tmC2, tmR, p, st)
                                : launch_gemm2<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
     return cols ? launch_gemm2<128, 6, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm2<128, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);

@@ -263,7 +263,43 @@ struct BnBranch {          // one BatchNorm whose output fed the (shared) ReLU
   float* dgamma;
   __nv_bfloat16* dx;       // [M, ldx] bf16, plain rows
   long long ldx;
+  const float* sc;         // optional: the forward's scale / shift (rl_bn_finalize).  When branch 0 carries them the ReLU mask
+  const float* sh;         // is re-derived as (x*sc + sh [+ x2*sc2 + sh2]) > 0 — rl_bn_apply's arithmetic — and act_out is not read
 };
+
+// ReLU mask of 8 channels from the raw conv outputs (same fmaf / add order as bn_apply_vec_kernel)
+template <int NB>
+__device__ __forceinline__ void relu_mask8(const float (&x0)[8], const float (&x1)[8], const float* s_m, int lc, float (&g)[8]) {
+  float a[8], b[8], y[8];
+  *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(s_m + lc);
+  *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(s_m + lc + 4);
+  *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(s_m + 256 + lc);
+  *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(s_m + 256 + lc + 4);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = fmaf(x0[j], a[j], b[j]);
+  if (NB == 2) {
+    *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(s_m + 512 + lc);
+    *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(s_m + 512 + lc + 4);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(s_m + 768 + lc);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(s_m + 768 + lc + 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] += fmaf(x1[j], a[j], b[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = y[j] > 0.f ? g[j] : 0.f;
+}
+
+// the forward scale / shift of the CTA's 256-column block -> s_m[NB][2][256]
+template <int NB>
+__device__ __forceinline__ void fill_mask_coef(float* s_m, const BnBranch& b0, const BnBranch& b1, int C) {
+  const int ct = blockIdx.x * 256 + threadIdx.x;
+  s_m[threadIdx.x] = ct < C ? b0.sc[ct] : 0.f;
+  s_m[256 + threadIdx.x] = ct < C ? b0.sh[ct] : 0.f;
+  if (NB == 2) {
+    s_m[512 + threadIdx.x] = ct < C ? b1.sc[ct] : 0.f;
+    s_m[768 + threadIdx.x] = ct < C ? b1.sh[ct] : 0.f;
+  }
+}
 
 // reduce: dbeta = sum g, dgamma = rstd * (sum g*x - mean * sum g) — mean/rstd are applied once at the end, so the loop
 // carries only 8 * (1 + NB) accumulators (4 CTAs per SM); two row groups in flight per warp.
@@ -287,6 +323,50 @@ bn_bwd_reduce_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __
   }
   const int step = 8 * rpw;
   long long r = r0 + warp * rpw + (lane >> lpr_shift);
+  __shared__ __align__(16) float s_m[NB * 2 * 256];
+  const bool recompute = b0.sc != nullptr;      // kernel-uniform
+  const int lc = (lane & (lpr - 1)) * 8;
+  if (recompute) {
+    fill_mask_coef<NB>(s_m, b0, b1, C);
+    __syncthreads();
+    // mask from the raw conv outputs: three (two) streams instead of four (three), two row groups in flight
+    constexpr int U2 = 2;
+    for (; r + (U2 - 1) * step < r1; r += U2 * step) {
+      float g[U2][8], x0[U2][8], x1[U2][8];
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        const long long rr = r + u * step;
+        const long long dr = remap ? split_row(rr, hw_shift, w_shift) : rr;
+        load8(dy, dy_f32, dr * C + col, g[u]);
+        load_raw8(b0.x, b0.x_f32, rr * C + col, x0[u]);
+        if (NB == 2) load_raw8(b1.x, b1.x_f32, rr * C + col, x1[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        relu_mask8<NB>(x0[u], x1[u], s_m, lc, g[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sg[j] += g[u][j];
+          sx[0][j] = fmaf(g[u][j], x0[u][j], sx[0][j]);
+          if (NB == 2) sx[NB - 1][j] = fmaf(g[u][j], x1[u][j], sx[NB - 1][j]);
+        }
+      }
+    }
+    for (; r < r1; r += step) {
+      const long long dr = remap ? split_row(r, hw_shift, w_shift) : r;
+      float g[8], x0[8], x1[8];
+      load8(dy, dy_f32, dr * C + col, g);
+      load_raw8(b0.x, b0.x_f32, r * C + col, x0);
+      if (NB == 2) load_raw8(b1.x, b1.x_f32, r * C + col, x1);
+      relu_mask8<NB>(x0, x1, s_m, lc, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sg[j] += g[j];
+        sx[0][j] = fmaf(g[j], x0[j], sx[0][j]);
+        if (NB == 2) sx[NB - 1][j] = fmaf(g[j], x1[j], sx[NB - 1][j]);
+      }
+    }
+  }
   constexpr int U = 4;   // row groups in flight per warp (bf16 rows are only 16 B per lane and tensor)
   for (; r + (U - 1) * step < r1; r += U * step) {
     float g[U][8], xv[U][8];
@@ -377,8 +457,11 @@ __global__ void __launch_bounds__(256, NB == 2 ? 2 : 3)
 bn_bwd_apply_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ act_out, int act_f32, BnBranch b0,
                         BnBranch b1, long long M, int C, int lpr_shift, int rows_per_cta, int remap, int hw_shift, int w_shift) {
   __shared__ __align__(16) float s_coef[NB][3][256];
+  __shared__ __align__(16) float s_m[NB * 2 * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpr = 1 << lpr_shift, rpw = 32 >> lpr_shift;
+  const bool recompute = b0.sc != nullptr;      // kernel-uniform
+  if (recompute) fill_mask_coef<NB>(s_m, b0, b1, C);
   {
     const int ct = blockIdx.x * 256 + threadIdx.x;
     const float invM = 1.0f / (float)M;
@@ -420,7 +503,10 @@ bn_bwd_apply_vec_kernel(const void* __restrict__ dy, int dy_f32, const void* __r
       load_raw8(b1.x, b1.x_f32, r * C + col, xv[0][NB - 1]);
       load_raw8(b1.x, b1.x_f32, xb_row * C + col, xv[1][NB - 1]);
     }
-    if (act_out) {
+    if (recompute) {
+      relu_mask8<NB>(xv[0][0], xv[0][NB - 1], s_m, lc, g[0]);
+      relu_mask8<NB>(xv[1][0], xv[1][NB - 1], s_m, lc, g[1]);
+    } else if (act_out) {
       float a0[8], a1[8];
       load8(act_out, act_f32, da * C + col, a0);
       load8(act_out, act_f32, db * C + col, a1);
@@ -697,7 +783,10 @@ extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out,
                           const float* mean1, const float* rstd1, const float* gamma1, float* dbeta1, float* dgamma1, void* dx1,
                           int64_t ldx1, const void* x2, const float* mean2, const float* rstd2, const float* gamma2,
                           float* dbeta2, float* dgamma2, void* dx2, int64_t ldx2, int64_t M, int64_t C, int32_t remap,
-                          int32_t map_h, int32_t map_w, void* stream) {
+                          int32_t map_h, int32_t map_w, const float* fwd_scale1, const float* fwd_shift1,
+                          const float* fwd_scale2, const float* fwd_shift2, void* stream) {
+  RL_REQUIRE(!fwd_scale1 || (fwd_shift1 && (!x2 || (fwd_scale2 && fwd_shift2))), RL_EINVAL,
+             "rl_bn_bwd2: the mask is re-derived from the forward scale AND shift of every branch");
   RL_REQUIRE(dy && x1 && mean1 && rstd1 && gamma1 && dbeta1 && dgamma1 && dx1 && M > 0 && C > 0 && ldx1 >= C && ldx1 % 8 == 0,
              RL_EINVAL, "rl_bn_bwd2: bad arguments");
   RL_REQUIRE(!x2 || (mean2 && rstd2 && gamma2 && dbeta2 && dgamma2 && dx2 && ldx2 >= C && ldx2 % 8 == 0), RL_EINVAL,
@@ -714,8 +803,8 @@ extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out,
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int xf = x_dtype == RL_DT_F32;
-  BnBranch b0{x1, xf, mean1, rstd1, gamma1, dbeta1, dgamma1, (__nv_bfloat16*)dx1, ldx1};
-  BnBranch b1{x2, xf, mean2, rstd2, gamma2, dbeta2, dgamma2, (__nv_bfloat16*)dx2, ldx2};
+  BnBranch b0{x1, xf, mean1, rstd1, gamma1, dbeta1, dgamma1, (__nv_bfloat16*)dx1, ldx1, fwd_scale1, fwd_shift1};
+  BnBranch b1{x2, xf, mean2, rstd2, gamma2, dbeta2, dgamma2, (__nv_bfloat16*)dx2, ldx2, fwd_scale2, fwd_shift2};
   dim3 vg, va;
   int rpc, rpa;
   vec_grid(M, C, ls, &vg, &rpc, x2 ? (const void*)bn_bwd_reduce_vec_kernel<2> : (const void*)bn_bwd_reduce_vec_kernel<1>);
@@ -737,7 +826,8 @@ extern "C" int rl_bn_bwd2(const void* dy, int32_t dy_dtype, const void* act_out,
 
 extern "C" int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, int32_t act_dtype, const void* x,
                          int32_t x_dtype, const float* mean, const float* rstd, const float* gamma, float* dbeta, float* dgamma, void* dx,
-                         int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, void* stream) {
+                         int64_t ldx, int64_t M, int64_t C, int32_t remap, int32_t map_h, int32_t map_w, const float* fwd_scale,
+                         const float* fwd_shift, void* stream) {
   RL_REQUIRE(dy && x && mean && rstd && gamma && dbeta && dgamma && dx && M > 0 && C > 0 && C % 8 == 0 && ldx >= C, RL_EINVAL,
              "rl_bn_bwd: bad arguments");
   int hs = 0, ws = 0;
@@ -750,7 +840,9 @@ extern "C" int rl_bn_bwd(const void* dy, int32_t dy_dtype, const void* act_out, 
   if (vec_lpr_shift(C) >= 0 && ldx % 8 == 0 && (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0 &&
       (!act_out || ((uintptr_t)act_out & 15) == 0))
     return rl_bn_bwd2(dy, dy_dtype, act_out, act_dtype, x_dtype, x, mean, rstd, gamma, dbeta, dgamma, dx, ldx, nullptr, nullptr,
-                      nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, remap, map_h, map_w, stream);
+                      nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, remap, map_h, map_w, fwd_scale,
+                      fwd_scale ? fwd_shift : nullptr, nullptr, nullptr, stream);
+  RL_REQUIRE(act_out || !fwd_scale, RL_EINVAL, "rl_bn_bwd: the scalar fallback path masks with act_out (pass it too)");
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((M + 2047) / 2048));
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, dy_dtype == RL_DT_F32, act_out, act_dtype == RL_DT_F32, x, x_dtype == RL_DT_F32,
                                              mean, rstd, dbeta, dgamma, M, (int)C, remap, hs + ws, ws);

@@ -498,30 +498,37 @@ def bn_apply(x1, sc1, sh1, x2, sc2, sh2, out, relu, remap=False, map_hw=(1, 1)):
     _count()
 
 
-def bn_bwd(dy, act_out, x, mean, rstd, gamma, dbeta, dgamma, dx, remap=False, map_hw=(1, 1)):
+def bn_bwd(dy, act_out, x, mean, rstd, gamma, dbeta, dgamma, dx, remap=False, map_hw=(1, 1), fwd=None):
+    """fwd = (scale, shift) the forward applied (bn_finalize): the ReLU mask is re-derived from x and act_out is not read."""
     M, C = x.shape
-    check(lib().rl_bn_bwd(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out),
-                          ctypes.c_int32(_DT[act_out.dtype] if act_out is not None else 0), _ptr(x),
-                          ctypes.c_int32(_DT[x.dtype]), _ptr(mean), _ptr(rstd),
-                          _ptr(gamma), _ptr(dbeta), _ptr(dgamma), _ptr(dx), _c(dx.stride(0)), _c(M), _c(C),
-                          ctypes.c_int32(int(remap)), ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), _stream()),
-          "rl_bn_bwd")
+    sc, sh = fwd if fwd is not None else (None, None)
+    with _Timed("bn_bwd", 0):
+        check(lib().rl_bn_bwd(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out),
+                              ctypes.c_int32(_DT[act_out.dtype] if act_out is not None else 0), _ptr(x),
+                              ctypes.c_int32(_DT[x.dtype]), _ptr(mean), _ptr(rstd),
+                              _ptr(gamma), _ptr(dbeta), _ptr(dgamma), _ptr(dx), _c(dx.stride(0)), _c(M), _c(C),
+                              ctypes.c_int32(int(remap)), ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), _ptr(sc), _ptr(sh),
+                              _stream()), "rl_bn_bwd")
     _count(2)
 
 
-def bn_bwd2(dy, act_out, br1, br2, M, C, remap=False, map_hw=(1, 1)):
+def bn_bwd2(dy, act_out, br1, br2, M, C, remap=False, map_hw=(1, 1), fwd=None):
     """Backward of out = relu(bn_a(x_a) + bn_b(x_b)) for both branches in one reduce + one apply pass.
-    br = (x f32 or bf16 [M,C], mean, rstd, gamma, dbeta, dgamma, dx bf16 view with row stride)."""
+    br = (x f32 or bf16 [M,C], mean, rstd, gamma, dbeta, dgamma, dx bf16 view with row stride).
+    fwd = ((scale_a, shift_a), (scale_b, shift_b)) of the forward: the ReLU mask is re-derived from x_a, x_b (the same
+    fmaf arithmetic as bn_apply) and act_out is not read."""
     args = []
     for br in (br1, br2):
         x, mean, rstd, gamma, dbeta, dgamma, dx = br
         assert x.is_cuda and x.dtype == br1[0].dtype and x.dtype in _DT
         _req(dx, torch.bfloat16, "dx")
         args += [_ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dbeta), _ptr(dgamma), _ptr(dx), _c(dx.stride(0))]
+    f = [_ptr(t) for pair in (fwd if fwd is not None else ((None, None), (None, None))) for t in pair]
     with _Timed("bn_bwd", 0):
-        check(lib().rl_bn_bwd2(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out), ctypes.c_int32(_DT[act_out.dtype]),
+        check(lib().rl_bn_bwd2(_ptr(dy), ctypes.c_int32(_DT[dy.dtype]), _ptr(act_out),
+                               ctypes.c_int32(_DT[act_out.dtype] if act_out is not None else 0),
                                ctypes.c_int32(_DT[br1[0].dtype]), *args, _c(M), _c(C), ctypes.c_int32(int(remap)),
-                               ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), _stream()), "rl_bn_bwd2")
+                               ctypes.c_int32(map_hw[0]), ctypes.c_int32(map_hw[1]), *f, _stream()), "rl_bn_bwd2")
     _count(2)
 
 

@@ -130,6 +130,8 @@ class TrainEngine:
         self._streams = None          # Measured on B200: no gain — the persistent GEMMs hold every SM's register file, so the
                                       # other branches' kernels only fill wave tails (42.8 vs 42.0 ms/step within clock noise)
         self.fused_gelu_grad = os.environ.get("RL_FUSED_GELU_GRAD", "0") == "1"   # du and db1 out of the dgrad GEMM's epilogue
+        # BatchNorm backward re-derives the ReLU mask from the raw conv outputs instead of reading the activation
+        self.bn_mask_recompute = os.environ.get("RL_BN_MASK_RECOMPUTE", "1") == "1"
         self.zpool = ZeroPool(model.classifier.bias.device)
         self.raw_bf16 = True          # res_block1-2 keep raw conv outputs in bf16 (see _resnet_fwd)
         self.seed = 0x5EED            # dropout seed of the next step; advanced every forward (set_seed to pin it)
@@ -587,7 +589,8 @@ class TrainEngine:
             ops.bn_bwd2(dout, s["out"],
                         (s["c2"], s["bn2"][2], s["bn2"][3], e["bn2"].weight.detach(), g(e["bn2"].bias), g(e["bn2"].weight), dc2),
                         (s["cs"], s["bns"][2], s["bns"][3], e["bns"].weight.detach(), g(e["bns"].bias), g(e["bns"].weight),
-                         dcat[:, cout:]), M, cout, remap=remap, map_hw=(S, S))
+                         dcat[:, cout:]), M, cout, remap=remap, map_hw=(S, S),
+                        fwd=(s["bn2"][:2], s["bns"][:2]) if self.bn_mask_recompute else None)
             # conv2 weight gradient (reference layout [cout, cin, kh, kw]) and data gradient
             T2 = len(e["taps2"])
             if T2 == 9:
@@ -600,7 +603,7 @@ class TrainEngine:
                 ops.gemm(dc2, e["w2f"], da1, b_t=True)
             # a1 = relu(bn1(c1))
             ops.bn_bwd(da1, s["a1"], s["c1"], s["bn1"][2], s["bn1"][3], e["bn1"].weight.detach(), g(e["bn1"].bias),
-                       g(e["bn1"].weight), dcat[:, :cout])
+                       g(e["bn1"].weight), dcat[:, :cout], fwd=s["bn1"][:2] if self.bn_mask_recompute else None)
             dc1, dcs = dcat[:, :cout], dcat[:, cout:]
             gws = g(e["convs"].weight)
             if bi == 0:

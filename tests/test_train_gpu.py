@@ -360,6 +360,20 @@ def test_colsum_and_bn_kernels_match_torch():
         for got, ref in ((dx1, xs[0].grad), (dcat[:, C:], xs[1].grad)):
             rel = (got.float() - ref).norm().item() / ref.norm().item()
             assert rel <= 1e-2, (M, C, rel)
+        # the same with the ReLU mask re-derived from the raw conv outputs (fwd = the forward's scale / shift): act_out unread
+        fwd = [(ga * st[1], be - st[0] * ga * st[1]) for ga, be, st in zip(gam, bet, stats)]
+        dcat_r = torch.zeros_like(dcat); dx1_r = torch.zeros_like(dx1)
+        db_r = [torch.zeros(C, device="cuda") for _ in range(2)]
+        dg_r = [torch.zeros(C, device="cuda") for _ in range(2)]
+        ops.bn_bwd2(dperm, None, (x1, stats[0][0], stats[0][1], gam[0], db_r[0], dg_r[0], dx1_r),
+                    (x2, stats[1][0], stats[1][1], gam[1], db_r[1], dg_r[1], dcat_r[:, C:]), M, C, remap=remap, map_hw=(S, S),
+                    fwd=fwd)
+        for i in range(2):
+            assert torch.allclose(db_r[i], bl[i].grad, rtol=2e-3, atol=2e-2), (M, C, i)
+            assert torch.allclose(dg_r[i], gl[i].grad, rtol=2e-3, atol=2e-2), (M, C, i)
+        for got, ref in ((dx1_r, xs[0].grad), (dcat_r[:, C:], xs[1].grad)):
+            rel = (got.float() - ref).norm().item() / ref.norm().item()
+            assert rel <= 1e-2, (M, C, rel)
 
 
 def test_dropout_counter_offsets_the_seed():
