@@ -58,6 +58,7 @@ struct KParams {
   int ntaps;
   int a_mn, b_mn; // operand stored MN-major: A as [K, M] (M contiguous), B as [K, N] (N contiguous)
   uint32_t eflags; // the epilogue's mode switches packed into one word (EF_* below; host: pack_eflags)
+  int8_t halo_t[12]; // conv64_halo_kernel: weight tap block of (dw + 1) * 3 + (dh + 1)
 };
 
 // Epilogue mode bits.  The per-chunk code of an epilogue warp used to test ~25 KParams fields, each an LDC -> ISETP -> BRA
@@ -797,6 +798,180 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3x3 convolution, 64 -> 64 channels on 16 x 16 maps, stride 1 (res_block1.conv2 and its data gradient: 4.19 M output
+// pixels per train step, the two longest launches of the step).  As nine-tap implicit GEMM through the generic kernel
+// every 128-pixel tile pulled 9 x 16 KB of (overlapping) activation windows and 9 x 8 KB of weights through L2 — 216 KB
+// per tile at the ~5 KB/clk the L2 delivers chip-wide, 3x the HBM time of the layer.  Here
+//   * the weights (72 KB) are loaded ONCE per CTA and stay in shared memory;
+//   * per dw in {-1, 0, +1} ONE TMA box of 10 image rows (h0-1 .. h0+8) x 16 pixels x 64 channels (20 KB) lands in a stage,
+//     and the three dh taps are the SAME buffer read through UMMA descriptors offset by dh * 16 pixels * 128 B = 2 KB
+//     (a multiple of the 1 KB swizzle period, so the plain SWIZZLE_128B K-major descriptor applies);
+// 60 KB per tile instead of 216 KB.  Image borders are TMA out-of-bounds zeros, as in the generic conv path.
+// Roles and epilogue are those of gemm_bf16_kernel (BN = 64; results leave as 16-bit tiles through TMA: SPEC_OUT16).
+constexpr int CH_STAGES = 6;
+constexpr int CH_A_BYTES = 160 * 128;
+constexpr int CH_B_BYTES = 9 * 64 * 128;
+constexpr int CH_WARP_STG = 4096;   // per epilogue warp: 2 KB result tile + 1 KB scale/bias table
+constexpr int CONV_HALO_SMEM = CH_B_BYTES + CH_STAGES * CH_A_BYTES + 8 * CH_WARP_STG + (2 * CH_STAGES + 5) * 8 + 16 + 32 * 8;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, const KParams p) {
+  constexpr int BN = 64;
+  constexpr uint32_t SPEC = SPEC_OUT16;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((rl::smem_u32(smem_raw) & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles need 1 KB alignment (no slack is budgeted)
+  uint8_t* smem_b = smem_raw;
+  uint8_t* smem_a = smem_b + CH_B_BYTES;
+  uint8_t* smem_stage = smem_a + CH_STAGES * CH_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + 8 * CH_WARP_STG);
+  uint64_t* empty_bar = full_bar + CH_STAGES;
+  uint64_t* tmem_full = empty_bar + CH_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* b_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_bar + 1);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);   // (unused by this epilogue mode; the interface wants it)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    rl::tma_prefetch_desc(&tmA);
+    rl::tma_prefetch_desc(&tmB);
+    rl::tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) {
+      rl::mbar_init(&full_bar[s], 1);
+      rl::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      rl::mbar_init(&tmem_full[s], 1);
+      rl::mbar_init(&tmem_empty[s], 8);
+    }
+    rl::mbar_init(b_bar, 1);
+    rl::fence_barrier_init();
+  }
+  if (warp == 2) rl::tmem_alloc(tmem_ptr, 128);
+  rl::tc_fence_before();
+  __syncthreads();
+  rl::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int num_tiles = p.tiles_m;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      rl::mbar_expect_tx(b_bar, CH_B_BYTES);
+      for (int t = 0; t < 9; ++t) rl::tma_load_2d(smem_b + t * 8192, &tmB, b_bar, t * BK, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        const int img0 = m0 >> 8, h0 = (m0 & 255) >> 4;
+        for (int dwi = 0; dwi < 3; ++dwi) {
+          rl::mbar_wait(&empty_bar[stage], phase ^ 1);
+          rl::mbar_expect_tx(&full_bar[stage], CH_A_BYTES);
+          rl::tma_load_5d(smem_a + stage * CH_A_BYTES, &tmA, &full_bar[stage], 0, dwi - 1, h0 - 1, 0, img0);
+          if (++stage == CH_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = rl::make_idesc_h(BM, BN, 0, 0, p.a_f16, p.b_f16);
+    const uint32_t a_base = rl::smem_u32(smem_a), b_base = rl::smem_u32(smem_b);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    rl::mbar_wait(b_bar, 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      rl::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      rl::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int dwi = 0; dwi < 3; ++dwi) {
+        rl::mbar_wait(&full_bar[stage], phase);
+        rl::tc_fence_after();
+        if (rl::elect_one()) {
+#pragma unroll
+          for (int dhi = 0; dhi < 3; ++dhi) {
+            const int t = p.halo_t[dwi * 3 + dhi];
+            const uint64_t adesc = rl::make_smem_desc_sw128(a_base + stage * CH_A_BYTES + dhi * 2048, 16, 1024);
+            const uint64_t bdesc = rl::make_smem_desc_sw128(b_base + t * 8192, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              rl::tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dwi > 0 || dhi > 0 || k > 0) ? 1u : 0u);
+          }
+          rl::tc_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == CH_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (rl::elect_one()) rl::tc_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    uint8_t* stg = smem_stage + ew * CH_WARP_STG;
+    float* sb = reinterpret_cast<float*>(stg + 2048);
+    int acc = 0;
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC, -1};
+    uint64_t* rbar = res_bar + ew * 4;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int row0 = tile * BM + q * 32;
+      float xr[32];
+      epilogue_prefetch<BN>(p, SPEC, sb, row0, 0, half, lane, xr, est);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's store has read the staging tile
+      __syncwarp();
+      rl::mbar_wait(&tmem_full[acc], acc_phase);
+      rl::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      uint64_t* done = &tmem_empty[acc];
+      epilogue_tile<BN, false, 2, SPEC>(p, &tmC, &tmC, &tmC, stg, rbar, sb, taddr, row0, 0, half, lane, xr, est,
+                                        [done, lane] { if (lane == 0) rl::mbar_arrive(done); });
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  rl::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    rl::tc_fence_after();
+    rl::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+int launch_conv64_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p, cudaStream_t st) {
+  static_assert(CONV_HALO_SMEM <= 232448, "dynamic shared memory of conv64_halo_kernel exceeds 227 KB");
+  static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv64_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_HALO_SMEM);
+    if (e != cudaSuccess) {
+      rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int grid = p.tiles_m < p.sms ? p.tiles_m : p.sms;
+  conv64_halo_kernel<<<grid, GEMM_THREADS, CONV_HALO_SMEM, st>>>(tmA, tmB, tmC, p);
+  return rl_check_launch("rl_gemm_bf16(conv 3x3 c64 halo)");
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA stages its own
 // 128 rows of A and HALF of the B tile, the leader's single thread issues M=256 tcgen05.mma that read both
 // CTAs' shared memory and write 128 accumulator lanes in each CTA's TMEM.  Per SM this cuts the operand bytes
@@ -1520,6 +1695,27 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
              (p.o_f16 ? EF_O_F16 : 0u) | (p.atomic_out ? EF_ATOMIC : 0u) | (p.scale ? EF_SCALE : 0u) | (p.res ? EF_RES : 0u) |
              (p.out2 ? EF_OUT2 : 0u) | (p.vec_store ? EF_VEC : 0u) | (p.colsum ? EF_COLSUM : 0u) |
              (p.colsumsq ? EF_COLSUMSQ : 0u) | ((uint32_t)p.act << EF_ACT_SHIFT);
+  // res_block1's 3x3 / 64-channel / 16x16 convolution (forward conv2 and its data gradient): resident weights + row-halo A
+  if (d->a_mode == 1 && d->ntaps == 9 && d->conv_C == 64 && (d->conv_Cuse == 0 || d->conv_Cuse == 64) && d->conv_W == 16 &&
+      d->conv_H == 16 && d->conv_P == 1 && p.N == 64 && d->K == 576 && bn == 64 && !pair && !cols && d->split_k == 0 &&
+      d->b_major == 0 && d->b_mode == 0 && p.M % BM == 0 && p.eflags == SPEC_OUT16 && d->tune_no_pair != 5) {
+    bool ok = true;
+    for (int i = 0; i < 9; ++i) p.halo_t[i] = -1;
+    for (int t = 0; t < 9 && ok; ++t) {
+      const int dw = d->tap_dw[t], dh = d->tap_dh[t];
+      ok = dw >= -1 && dw <= 1 && dh >= -1 && dh <= 1 && d->tap_plane[t] == 0 && p.halo_t[(dw + 1) * 3 + dh + 1] < 0;
+      if (ok) p.halo_t[(dw + 1) * 3 + dh + 1] = (int8_t)t;
+    }
+    if (ok) {
+      CUtensorMap tmH;
+      uint32_t box[5] = {BK, 16, 10, 1, 1};
+      uint64_t dims[5] = {64, 16, 16, 1, (uint64_t)d->conv_NIMG};
+      uint64_t strides[4] = {64 * 2, 64 * 16 * 2, 64 * 16 * 16 * 2, 64 * 16 * 16 * 2};
+      rc = rl_make_tmap_bf16(&tmH, d->a, 5, dims, strides, box);
+      if (rc) return rc;
+      return launch_conv64_halo(tmH, tmB, tmC, p, st);
+    }
+  }
   if (quad && !cols) return launch_gemm4<256, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
   if (pair && bn == 256 && !cols && !long_k && d->tune_no_pair != 5) {
     // the hot short-K configurations of a train step, with the epilogue's mode word folded at compile time

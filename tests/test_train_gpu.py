@@ -634,3 +634,37 @@ def test_two_font_training_step():
         assert ((g - rg).norm() / rg.norm()).item() <= 5e-2, name
     g = model.resnet.res_block1.residual_function[0].weight.grad
     assert g.shape == (64, 2, 3, 3) and torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+def test_conv3x3_c64_halo_kernel_matches_generic_path_and_torch():
+    """res_block1.conv2 shape (64 -> 64 channels, 16x16 maps, 9 taps): the resident-weight / row-halo kernel against the
+    generic nine-tap implicit GEMM (tune_no_pair = 5 keeps the generic path) and against torch conv2d, for the forward tap
+    order, the mirrored order of the data gradient, a bias vector, and an image count that leaves a partial last wave."""
+    import torch.nn.functional as F
+    from realise_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for n_img, mirrored, with_bias in [(3, False, False), (150, True, True), (37, False, True)]:
+        x = torch.randn(n_img, 16, 16, 64, device="cuda", generator=g).bfloat16()
+        w4 = (torch.randn(64, 64, 3, 3, device="cuda", generator=g) * 0.05).bfloat16()       # [co, ci, kh, kw]
+        bias = torch.randn(64, device="cuda", generator=g) * 0.1 if with_bias else None
+        taps = [(kw - 1, kh - 1, 0) for kh in range(3) for kw in range(3)]
+        wk = w4.permute(0, 2, 3, 1).reshape(64, 576).contiguous()                              # tap-major [co, (kh, kw), ci]
+        if mirrored:   # any order / sign convention of the nine taps must work: the kernel maps (dw, dh) -> weight block
+            order = list(reversed(range(9)))
+            taps = [taps[i] for i in order]
+            wk = wk.view(64, 9, 64)[:, order].reshape(64, 576).contiguous()
+        outs = []
+        for mode in (5, 0):
+            ops.TUNE_NO_PAIR = mode
+            try:
+                out = torch.empty(n_img * 256, 64, device="cuda", dtype=torch.bfloat16)
+                ops.conv_gemm(x.view(n_img, 1, 16, 16, 64), wk, out, nimg=n_img, H=16, W=16, planes=1, taps=taps, bias=bias)
+            finally:
+                ops.TUNE_NO_PAIR = 0
+            outs.append(out.float())
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), bias=bias, padding=1).permute(0, 2, 3, 1).reshape(-1, 64)
+        scale = ref.abs().max().item()
+        assert (outs[1] - ref).abs().max().item() <= 1e-2 * scale, (n_img, mirrored)
+        # same products, different summation order of the nine taps: at most a bf16 rounding step apart
+        assert (outs[0] - outs[1]).abs().max().item() <= 1.6e-2 * scale, (n_img, mirrored)
+        assert ((outs[0] - outs[1]).abs() > 0).float().mean().item() < 0.2
