@@ -162,7 +162,31 @@ struct EpiState {
   uint32_t flags;    // KParams::eflags in a register (see EF_*)
   int sb_n0;         // column block whose scale/bias the warp's table holds (-1: none): a GEMM with ONE N tile (the convs)
                      // fills it once per CTA instead of paying a global-load latency on every 128-row tile
+  int deep_set;      // EF_DEEP with fewer than 4 chunks per warp and tile (BN = 64 / 128): which SET of 2 KB staging tiles this
+                     // tile uses.  Rotating over 4 / CH sets lets a tile start while the TMA stores of the previous ones are
+                     // still reading shared memory; waiting for them (wait_group.read 0) serialised every 128-row tile of
+                     // the short-K conv GEMMs behind a store round trip (~2.5 k cycles per tile, 3.5 TB/s on an HBM-bound layer)
 };
+
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// before a tile reuses its staging set: the stores of every earlier tile that used this set have been read
+template <int CH>
+__device__ __forceinline__ void deep_tile_begin(bool rotate, int lane) {
+  constexpr int SETS = 4 / CH;
+  if (lane == 0) {
+    if (rotate) bulk_wait_read<(SETS - 1) * CH>();
+    else bulk_wait_read<0>();
+  }
+  __syncwarp();
+}
+template <int CH>
+__device__ __forceinline__ void deep_tile_end(bool rotate, EpiState& st) {
+  constexpr int SETS = 4 / CH;
+  if (rotate) st.deep_set = (st.deep_set + 1) & (SETS - 1);
+}
 
 // scale/bias of this warp's BN/2 columns -> sb[0..BN/2) and sb[128..128+BN/2); first residual chunk -> xr.
 // All global loads are issued before the first shared store: the rolled loop this replaces paid one global-load latency
@@ -395,7 +419,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
         // two swizzled staging tiles per warp, alternated per CHUNK ACROSS TILES (st.stg_sel lives in the tile loop: a
         // BN = 64 tile has one chunk per warp, so alternating on the chunk index alone reused the tile the previous
         // store was still reading): the TMA store issued two chunks ago must have finished reading
-        stg = NSTG == 1 ? stg_base : deep ? stg_base + cc * 2048 : stg_base + (st.stg_sel & 1) * 4096;
+        stg = NSTG == 1 ? stg_base : deep ? stg_base + (st.deep_set * CH + cc) * 2048 : stg_base + (st.stg_sel & 1) * 4096;
         st.stg_sel ^= 1;
         if (NSTG == 1) {
           if (!tma_res) {
@@ -553,7 +577,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const CUtensorMa
   }
 }
 
-template <int BN, int STAGES, bool COLS>
+template <int BN, int STAGES, bool COLS, uint32_t SPEC = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -722,8 +746,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = smem_stage + ew * (8192 + 1024);
     float* sb = reinterpret_cast<float*>(stg + 8192);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, load_eflags(p), -1};
-    const uint32_t F = est.flags;
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC ? SPEC : load_eflags(p), -1, 0};
+    const uint32_t F = SPEC ? SPEC : est.flags;
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -734,10 +758,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN>(p, F, sb, row0, n0, half, lane, xr, est);
-      if ((F & EF_DEEP) && !(F & EF_TMA_RES)) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-      }
+      // staging-set rotation (see EpiState::deep_set): every chunk of every tile must issue a store, i.e. no N tail
+      const bool rotate = BN < 256 && (F & EF_DEEP) && !(F & EF_TMA_RES) && p.N % BN == 0 && p.M % BM == 0;
+      if ((F & EF_DEEP) && !(F & EF_TMA_RES)) deep_tile_begin<BN / 64>(rotate, lane);   // the staging tiles about to be reused have been read
       if ((F & EF_TMA_RES) && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
         if (F & EF_RES_ALL) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
@@ -755,8 +778,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       rl::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       uint64_t* done = &tmem_empty[acc];
-      epilogue_tile<BN, COLS>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est,
-                              [done, lane] { if (lane == 0) rl::mbar_arrive(done); });
+      epilogue_tile<BN, COLS, 2, SPEC>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est,
+                                       [done, lane] { if (lane == 0) rl::mbar_arrive(done); });
+      deep_tile_end<BN / 64>(rotate, est);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -777,13 +801,13 @@ constexpr int gemm_smem_bytes() {
   return STAGES * (A_BYTES + BN * BK * 2) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 + 1024;
 }
 
-template <int BN, int STAGES, bool COLS = false>
+template <int BN, int STAGES, bool COLS = false, uint32_t SPEC = 0>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                 const CUtensorMap& tmR, const KParams& p, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   static std::atomic<bool> configured{false};  // idempotent attribute set: a second thread racing here only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, COLS>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, COLS, SPEC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       rl_set_error("rl_gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -793,7 +817,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   }
   const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
   const int grid = tiles < p.sms ? tiles : p.sms;
-  gemm_bf16_kernel<BN, STAGES, COLS><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
+  gemm_bf16_kernel<BN, STAGES, COLS, SPEC><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, tmR, p);
   return rl_check_launch("rl_gemm_bf16");
 }
 
@@ -808,10 +832,10 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 //     (a multiple of the 1 KB swizzle period, so the plain SWIZZLE_128B K-major descriptor applies);
 // 60 KB per tile instead of 216 KB.  Image borders are TMA out-of-bounds zeros, as in the generic conv path.
 // Roles and epilogue are those of gemm_bf16_kernel (BN = 64; results leave as 16-bit tiles through TMA: SPEC_OUT16).
-constexpr int CH_STAGES = 6;
+constexpr int CH_STAGES = 5;
 constexpr int CH_A_BYTES = 160 * 128;
 constexpr int CH_B_BYTES = 9 * 64 * 128;
-constexpr int CH_WARP_STG = 4096;   // per epilogue warp: 2 KB result tile + 1 KB scale/bias table
+constexpr int CH_WARP_STG = 5120;   // per epilogue warp: two 2 KB result tiles (alternating per tile) + 1 KB scale/bias table
 constexpr int CONV_HALO_SMEM = CH_B_BYTES + CH_STAGES * CH_A_BYTES + 8 * CH_WARP_STG + (2 * CH_STAGES + 5) * 8 + 16 + 32 * 8;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -924,16 +948,16 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;
     const int half = ew >> 2;
     uint8_t* stg = smem_stage + ew * CH_WARP_STG;
-    float* sb = reinterpret_cast<float*>(stg + 2048);
+    float* sb = reinterpret_cast<float*>(stg + 4096);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC, -1};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC, -1, 0};
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int row0 = tile * BM + q * 32;
       float xr[32];
       epilogue_prefetch<BN>(p, SPEC, sb, row0, 0, half, lane, xr, est);
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's store has read the staging tile
+      if (lane == 0) bulk_wait_read<1>();   // the store of the tile before the previous one has read this staging tile
       __syncwarp();
       rl::mbar_wait(&tmem_full[acc], acc_phase);
       rl::tc_fence_after();
@@ -941,6 +965,7 @@ conv64_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint64_t* done = &tmem_empty[acc];
       epilogue_tile<BN, false, 2, SPEC>(p, &tmC, &tmC, &tmC, stg, rbar, sb, taddr, row0, 0, half, lane, xr, est,
                                         [done, lane] { if (lane == 0) rl::mbar_arrive(done); });
+      est.deep_set ^= 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -1226,7 +1251,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
     uint8_t* stg = smem_stage + ew * WARP_STG;
     float* sb = reinterpret_cast<float*>(stg + NSTG * 4096);
     int acc = 0;
-    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC ? SPEC : load_eflags(p), -1};
+    EpiState est{0, 0u, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, -1, SPEC ? SPEC : load_eflags(p), -1, 0};
     const uint32_t F = SPEC ? SPEC : est.flags;
     uint64_t* rbar = res_bar + ew * 4;
     uint32_t acc_phase = 0;
@@ -1238,10 +1263,8 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       const int n0 = n_blk * BN;
       float xr[32];
       epilogue_prefetch<BN, NSTG>(p, F, sb, row0, n0, half, lane, xr, est);
-      if (NSTG == 2 && (F & EF_DEEP) && !(F & EF_TMA_RES)) {   // drain the previous tile's stores (issued a main loop ago) before its staging tiles are reused
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-      }
+      const bool rotate = NSTG == 2 && BN < 256 && (F & EF_DEEP) && !(F & EF_TMA_RES) && p.N % BN == 0 && p.M % (CL * BM) == 0;
+      if (NSTG == 2 && (F & EF_DEEP) && !(F & EF_TMA_RES)) deep_tile_begin<BN / 64>(rotate, lane);
       if (NSTG == 2 && (F & EF_TMA_RES) && lane == 0 && row0 < p.M && n0 + half * (BN / 2) < p.N) {
         if (F & EF_RES_ALL) {
           // every residual chunk of this output tile, now: the stores of the previous tile have long drained
@@ -1261,6 +1284,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
       uint64_t* done = &tmem_empty[acc];
       epilogue_tile<BN, COLS, NSTG, SPEC>(p, &tmC, &tmC2, &tmR, stg, rbar, sb, taddr, row0, n0, half, lane, xr, est,
                                           [done, lane] { if (lane == 0) mbar_arrive_leader(done); });
+      deep_tile_end<BN / 64>(rotate, est);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -1744,6 +1768,8 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     return cols ? launch_gemm2<128, 6, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm2<128, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
   }
   if (bn == 256) return cols ? launch_gemm<256, 3, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm<256, 3>(tmA, tmB, tmC, tmC2, tmR, p, st);
+  if (bn == 64 && !cols && p.eflags == SPEC_OUT16 && d->tune_no_pair != 5)   // the glyph stem convs: one chunk per warp and tile, epilogue-bound
+    return launch_gemm<64, 6, false, SPEC_OUT16>(tmA, tmB, tmC, tmC2, tmR, p, st);
   if (bn == 64) return cols ? launch_gemm<64, 6, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm<64, 6>(tmA, tmB, tmC, tmC2, tmR, p, st);
   return cols ? launch_gemm<128, 4, true>(tmA, tmB, tmC, tmC2, tmR, p, st) : launch_gemm<128, 4>(tmA, tmB, tmC, tmC2, tmR, p, st);
 }
