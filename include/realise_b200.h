@@ -222,9 +222,12 @@ RL_API int rl_glyph_block1_fwd(const float* glyphs, const int64_t* ids, const vo
  * qkv / ctx are the forward tensors (ctx is needed for delta = rowsum(dO o O)); every 16-bit tensor of the call
  * (qkv, ctx, dctx, dqkv) has the format act_dtype; row_lse
  * (optional) is the logsumexp saved by rl_attention_fwd: P = exp2(s - lse) is then recomputed in one pass over S.
+ * dbias (optional, seq_len <= 128): f32 [3*heads*64], ACCUMULATED into — the column sums of dqkv, i.e. the bias gradient of
+ * the fused query/key/value projection (BertSelfAttention.query/key/value.bias), summed from the staged 16-bit tiles while
+ * their TMA stores are in flight; saves a separate pass over dqkv.
  * seq_len <= 256. */
 RL_API int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                            const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t act_dtype,
+                            float* dbias, const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t act_dtype,
                             float drop_p, uint64_t drop_seed, uint32_t drop_site, const uint64_t* drop_counter,
                             void* stream);
 

@@ -23,6 +23,7 @@ struct AttBwdParams {
   int heads;
   rl::DropSpec drop;
   const float* lse;           // optional [B, heads, L] log2-domain logsumexp saved by the forward: skips two passes over S
+  float* dbias;               // optional [3H] f32, accumulated: column sums of dqkv (the fused q/k/v bias gradient)
   int f16;                    // every 16-bit tensor of the call (Q/K/V, ctx, dO, dqkv, the P / dS tiles) is fp16 instead of
                               // bf16: tcgen05 kind::f16 needs ONE format for both operands of an MMA (probed on B200)
 };
@@ -269,6 +270,24 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   rl::fence_proxy_async();
   rl::tc_fence_before();
   __syncthreads();
+  if (p.dbias && tid >= 32) {
+    // bias gradient of the fused QKV projection = column sums of the three staged tiles (rows beyond the sentence are exact
+    // zeros).  Warps 1-3 take one tile each, a lane two adjacent columns (one conflict-free 4-byte word per row), while
+    // thread 0 issues the TMA stores of the same tiles; 192 atomics per CTA.  (A 31-shuffle butterfly per 32-column chunk
+    // before the staging cost the kernel 12 %; this costs ~2 %.)
+    const int t = (tid >> 5) - 1, cp = tid & 31;
+    const uint8_t* src = (t == 0 ? sQ : t == 1 ? sK : sDO) + (cp & 3) * 4;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int row = 0; row < 128; ++row) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(src + (row >> 3) * 1024 + (row & 7) * 128 + (((cp >> 2) ^ (row & 7)) << 4));
+      s0 += rl::half_lo(w, p.f16);
+      s1 += rl::half_hi(w, p.f16);
+    }
+    float* o = p.dbias + t * p.H + head * HEAD_DIM + 2 * cp;
+    atomicAdd(o, s0);
+    atomicAdd(o + 1, s1);
+  }
   if (tid == 0) {
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
@@ -529,13 +548,14 @@ constexpr int ATT_BWD256_SMEM = 12 * T16K + 256 * 4 + 3 * 8 + 16;   // 197,672 B
 }  // namespace
 
 extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void* ctx, const void* dctx, void* dqkv,
-                                const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t act_dtype,
+                                float* dbias, const float* row_lse, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t act_dtype,
                                 float drop_p, uint64_t drop_seed, uint32_t drop_site, const uint64_t* drop_counter,
                                 void* stream) {
   RL_REQUIRE(qkv && mask && ctx && dctx && dqkv, RL_EINVAL, "rl_attention_bwd: null pointer");
   RL_REQUIRE(head_dim == HEAD_DIM, RL_EINVAL, "rl_attention_bwd: head_dim must be 64");
   RL_REQUIRE(B > 0 && heads > 0 && L > 0 && L <= 256, RL_EINVAL, "rl_attention_bwd: seq_len %lld not in 1..256", (long long)L);
   RL_REQUIRE(L <= 128 || row_lse, RL_EINVAL, "rl_attention_bwd: seq_len > 128 needs the row_lse saved by rl_attention_fwd");
+  RL_REQUIRE(L <= 128 || !dbias, RL_EINVAL, "rl_attention_bwd: the fused bias gradient (dbias) is built for seq_len <= 128");
   const int H = (int)(heads * head_dim);
   const int lkv16 = (int)((L + 15) / 16 * 16);
   CUtensorMap tq, tkv, tdo;
@@ -574,6 +594,7 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
     p.drop = rl::make_drop(drop_p, drop_seed, drop_site, drop_counter);
     p.f16 = act_dtype == RL_DT_F16;
     p.lse = row_lse;
+    p.dbias = nullptr;
     attention_bwd256_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD256_SMEM, (cudaStream_t)stream>>>(tq, tdo, p);
     return rl_check_launch("rl_attention_bwd(256)");
   }
@@ -609,6 +630,7 @@ extern "C" int rl_attention_bwd(const void* qkv, const int64_t* mask, const void
   p.drop = rl::make_drop(drop_p, drop_seed, drop_site, drop_counter);
   p.f16 = act_dtype == RL_DT_F16;
   p.lse = row_lse;
+  p.dbias = dbias;
   attention_bwd_kernel<<<dim3((unsigned)heads, (unsigned)B), ATT_THREADS, ATT_BWD_SMEM, (cudaStream_t)stream>>>(tq, tkv, tdo, to, tdq, p);
   return rl_check_launch("rl_attention_bwd");
 }

@@ -360,6 +360,22 @@ __device__ __forceinline__ unsigned int drop_bits32(const DropSpec& d, unsigned 
   return bits;
 }
 
+// per-column sum over the 32 rows held by the warp (lane = row, v[c] = column c): butterfly transpose-reduce, 31 shuffles;
+// on return lane l holds the total of column l in v[0]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = upper ? v[i] : v[i + w];
+      const float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
 // erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result)
 __device__ __forceinline__ float fast_erf(float x) {
   const float ax = fabsf(x);

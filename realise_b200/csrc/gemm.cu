@@ -225,21 +225,7 @@ __device__ __forceinline__ uint32_t load_eflags(const KParams& p) {
   return f;
 }
 
-// per-column sum over the 32 rows held by the warp (lane = row, v[c] = column c): butterfly transpose-reduce, 31 shuffles;
-// on return lane l holds the total of column l in v[0]
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int w = 16; w >= 1; w >>= 1) {
-    const bool upper = (lane & w) != 0;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float send = upper ? v[i] : v[i + w];
-      const float keep = upper ? v[i + w] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-    }
-  }
-  return v[0];
-}
+using rl::warp_colsum32;
 
 template <int CH>
 __device__ __forceinline__ void colsum_flush(const KParams& p, EpiState& st, int half, int lane) {

@@ -349,12 +349,16 @@ def glyph_block1(glyphs, ids, w1p, wscp, w2p, t1, t2s, out, n_img, C):
 # ---------------------------------------------------------------------------------------------------------
 # training path
 # ---------------------------------------------------------------------------------------------------------
-def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None, lse=None):
+def attention_bwd(qkv, mask, ctx, dctx, dqkv, B, L, heads, drop=None, lse=None, dbias=None):
+    """dbias (optional f32 [3*heads*64], L <= 128): += column sums of dqkv (the fused q/k/v bias gradient)."""
     for t, n in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, n)
     assert ctx.dtype == qkv.dtype == dctx.dtype == dqkv.dtype
+    if dbias is not None:
+        _req(dbias, torch.float32, "dbias")
+        assert dbias.numel() == 3 * heads * 64 and dbias.is_contiguous()
     with _Timed("attention_bwd", 14.0 * B * heads * L * L * 64):
-        check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _ptr(lse), _c(B), _c(L),
+        check(lib().rl_attention_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(dctx), _ptr(dqkv), _ptr(dbias), _ptr(lse), _c(B), _c(L),
                                      _c(heads), _c(64), _dt(qkv), *_drop(drop), _ctr(), _stream()), "rl_attention_bwd")
     _count()
 

@@ -781,10 +781,12 @@ class TrainEngine:
             dctx = self._new((N, H), BF16)
             ops.gemm(dy1b, lw["w_o"], dctx, b_t=True)
             dqkv = self._new((N, 3 * H), BF16)
-            ops.attention_bwd(s["qkv"], mask, s["ctx"], dctx, dqkv, B, L, c.num_attention_heads,
-                              drop=self.adrop(self.site(name, li, 1)), lse=s["lse"])
             dw, db = self._qkv_grads(att, H)
-            ops.colsum_bf16(dqkv, db)
+            fused_db = L <= 128      # the q/k/v bias gradient comes out of the attention backward's epilogue
+            ops.attention_bwd(s["qkv"], mask, s["ctx"], dctx, dqkv, B, L, c.num_attention_heads,
+                              drop=self.adrop(self.site(name, li, 1)), lse=s["lse"], dbias=db if fused_db else None)
+            if not fused_db:
+                ops.colsum_bf16(dqkv, db)
             ops.gemm(dqkv, s["xb"], dw, a_t=True, b_t=True, split_k=-1)                                         # dWqkv = dqkv^T x
             dxin = self._new((N, H), F32)
             ops.gemm(dqkv, lw["w_qkv"], dxin, b_t=True, res=dy1)                                    # dx = dqkv Wqkv + dy1

@@ -36,7 +36,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     i64, i32, f32, u64, u32 = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32
     assert lib.rl_attention_fwd(None, None, None, None, i64(1), i64(1), i64(1), i64(64), i32(0), f32(0), u64(0), u32(0), None,
                                 None) < 0
-    assert lib.rl_attention_bwd(None, None, None, None, None, None, i64(1), i64(1), i64(1), i64(64), i32(2), f32(0), u64(0),
+    assert lib.rl_attention_bwd(None, None, None, None, None, None, None, i64(1), i64(1), i64(1), i64(64), i32(2), f32(0), u64(0),
                                 u32(0), None, None) < 0
     assert lib.rl_layernorm_fwd(None, None, None, None, None, i64(1), i64(768), f32(1e-12), f32(0), u64(0), u32(0), None, i32(0),
                                 i32(0), None) < 0

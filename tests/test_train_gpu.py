@@ -668,3 +668,28 @@ def test_conv3x3_c64_halo_kernel_matches_generic_path_and_torch():
         # same products, different summation order of the nine taps: at most a bf16 rounding step apart
         assert (outs[0] - outs[1]).abs().max().item() <= 1.6e-2 * scale, (n_img, mirrored)
         assert ((outs[0] - outs[1]).abs() > 0).float().mean().item() < 0.2
+
+
+def test_attention_bwd_fused_bias_gradient_equals_column_sums_of_dqkv():
+    """rl_attention_bwd's optional dbias output (the fused q/k/v bias gradient) against the column sums of the dqkv it wrote,
+    with ragged sentence lengths (rows beyond a sentence must contribute exact zeros) and dropout on the probabilities."""
+    from realise_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for B, L, heads in [(3, 23, 2), (5, 128, 12), (2, 100, 4)]:
+        H = heads * 64
+        qkv = (torch.randn(B * L, 3 * H, device="cuda", generator=g) * 0.5).bfloat16()
+        lens = torch.randint(max(1, L // 3), L + 1, (B,), device="cuda", generator=g)
+        mask = (torch.arange(L, device="cuda")[None, :] < lens[:, None]).long().contiguous()
+        ctx = torch.empty(B * L, H, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(B * heads * L, device="cuda")
+        dctx = (torch.randn(B * L, H, device="cuda", generator=g) * 0.1).bfloat16()
+        drop = (0.1, 99, 3)
+        ops.attention(qkv, mask, ctx, B, L, heads, drop=drop, lse=lse)
+        dq_ref = torch.zeros_like(qkv)
+        ops.attention_bwd(qkv, mask, ctx, dctx, dq_ref, B, L, heads, drop=drop, lse=lse)
+        dq = torch.zeros_like(qkv)
+        db = torch.full((3 * H,), 0.25, device="cuda")        # accumulated INTO
+        ops.attention_bwd(qkv, mask, ctx, dctx, dq, B, L, heads, drop=drop, lse=lse, dbias=db)
+        assert torch.equal(dq, dq_ref)
+        want = dq_ref.float().sum(0) + 0.25
+        assert torch.allclose(db, want, rtol=2e-2, atol=2e-2 * float(want.abs().max())), (B, L, float((db - want).abs().max()))
