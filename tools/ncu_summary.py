@@ -44,7 +44,7 @@ def launches(path, out_json=None):
     for k, (n, us, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| `{k[:70]}` | {n} | {us:.1f} | {100 * us / tot:.1f} % | {by / n / 1e6:.1f} |")
     if out_json:
-        gem = {k: v for k, v in agg.items() if "gemm" in k}
+        gem = {k: v for k, v in agg.items() if "gemm" in k or "conv64_halo" in k}   # the tcgen05 GEMM family of bench.py's roofline
         n = sum(v[0] for v in gem.values())
         doc = {"source": path, "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch, one eager train step "
                                        "(B=128, L=128), ncu --clock-control none",
