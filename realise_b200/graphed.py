@@ -23,7 +23,7 @@ What makes the capture replayable:
 """
 import torch
 
-from . import ops
+from . import hostio, ops
 from .batch import MAX_PHO_LEN
 
 
@@ -51,10 +51,7 @@ class GraphedTrainStep:
         for k in ("src_idx", "masks", "tgt_idx", "loss_masks"):
             out[k] = batch[k]
         if c.with_pho == "yes":
-            lens = batch["pho_lens"]
-            if not torch.is_tensor(lens):
-                lens = torch.tensor(lens, dtype=torch.int32)
-            out["pho_lens"] = lens
+            out["pho_lens"] = hostio.lens_to_device(batch["pho_lens"], dev)   # a Python list in the reference's batches
             pho = batch["pho_idx"]
             if pho.shape[1] < MAX_PHO_LEN:    # pad_sequence pads to the batch maximum (src/utils.py:92-96): fix T = 7 so that
                 pho = torch.nn.functional.pad(pho, (0, MAX_PHO_LEN - pho.shape[1]))   # every batch replays the same graph

@@ -14,7 +14,7 @@ from copy import deepcopy
 import torch
 from torch import nn
 
-from . import ops
+from . import hostio, ops
 from .synth import ArchConfig, PHO_VOCAB
 
 RES_CHANNELS = [None, 64, 128, 256, 512, 768]
@@ -621,7 +621,7 @@ class SpellBertPho2ResArch3Abla(nn.Module):
             if torch.is_tensor(lens):
                 inputs["pho_lens"] = lens.to(device=dev, dtype=torch.int32, non_blocking=True)
             else:
-                inputs["pho_lens"] = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+                inputs["pho_lens"] = hostio.lens_to_device(lens, dev)
             inputs["pho_idx"] = batch["pho_idx"].contiguous()
         if self.training:
             if "tgt_idx" not in batch:

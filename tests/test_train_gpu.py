@@ -693,3 +693,69 @@ def test_attention_bwd_fused_bias_gradient_equals_column_sums_of_dqkv():
         assert torch.equal(dq, dq_ref)
         want = dq_ref.float().sum(0) + 0.25
         assert torch.allclose(db, want, rtol=2e-2, atol=2e-2 * float(want.abs().max())), (B, L, float((db - want).abs().max()))
+
+
+def test_specialised_gemm_epilogues_match_the_generic_epilogue_bit_for_bit():
+    """Every compile-time specialised epilogue (SPEC_* in gemm.cu) against the generic, runtime-flag epilogue of the same
+    kernel family (tune_no_pair = 5): same arithmetic in the same order, so the results must be identical bits (split-K
+    sums meet in a different order: close, not identical)."""
+    from realise_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+
+    def rnd(*s, scale=1.0):
+        return torch.randn(*s, device="cuda", generator=g) * scale
+
+    M = 1024
+    cases = []
+    # (name, N, K, kwargs builder) — K = 768: short-K pair kernel; K = 3072: long-K variant (>= 24 k-blocks)
+    for K in (768, 3072):
+        cases.append((f"out16 K={K}", 512, K, lambda N: dict(bias=rnd(N)), torch.bfloat16))
+        cases.append((f"res32+drop K={K}", 768, K, lambda N: dict(bias=rnd(N), res=rnd(M, N), drop=(0.1, 77, 3)), torch.float32))
+        cases.append((f"res32 K={K}", 768, K, lambda N: dict(res=rnd(M, N)), torch.float32))
+    cases.append(("gelu_save", 512, 768, lambda N: dict(bias=rnd(N, scale=0.1), act=ops.ACT_GELU_SAVE,
+                                                        out2=torch.empty(M, N, device="cuda", dtype=torch.bfloat16)), torch.bfloat16))
+    cases.append(("gelu_grad", 512, 768, lambda N: dict(res=rnd(M, N).bfloat16(), act=ops.ACT_GELU_GRAD), torch.bfloat16))
+    cases.append(("gelu_grad+colsum", 512, 768, lambda N: dict(res=rnd(M, N).bfloat16(), act=ops.ACT_GELU_GRAD,
+                                                               colsum=torch.zeros(N, device="cuda")), torch.bfloat16))
+    cases.append(("stem 128x64 tiles", 64, 32, lambda N: dict(), torch.bfloat16))
+    for name, N, K, mk, odt in cases:
+        Mi = 4096 if N == 64 else M
+        a = (rnd(Mi, K) * 0.5).bfloat16()
+        b = (rnd(N, K) * 0.05).bfloat16()
+        kw = mk(N)
+        if "res" in kw and kw["res"].shape[0] != Mi:
+            continue
+        outs = []
+        for mode in (5, 0):
+            ops.TUNE_NO_PAIR = mode
+            try:
+                k2 = dict(kw)
+                if "out2" in k2:
+                    k2["out2"] = torch.empty_like(kw["out2"])
+                if "colsum" in k2:
+                    k2["colsum"] = torch.zeros_like(kw["colsum"])
+                out = torch.empty(Mi, N, device="cuda", dtype=odt)
+                ops.gemm(a, b, out, **k2)
+            finally:
+                ops.TUNE_NO_PAIR = 0
+            outs.append((out, k2.get("out2"), k2.get("colsum")))
+        assert torch.equal(outs[0][0], outs[1][0]), name
+        if outs[0][1] is not None:
+            assert torch.equal(outs[0][1], outs[1][1]), name
+        if outs[0][2] is not None:
+            assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-3), name
+    # split-K weight gradient (TMA reduce-add): specialised vs generic agree to rounding of the different summation order
+    a = (rnd(4096, 768) * 0.1).bfloat16()
+    b = (rnd(4096, 512) * 0.1).bfloat16()
+    outs = []
+    for mode in (5, 0):
+        ops.TUNE_NO_PAIR = mode
+        try:
+            out = torch.zeros(768, 512, device="cuda")
+            ops.gemm(a, b, out, a_t=True, b_t=True, split_k=-1)
+        finally:
+            ops.TUNE_NO_PAIR = 0
+        outs.append(out)
+    ref = a.float().t() @ b.float()
+    assert torch.allclose(outs[0], outs[1], rtol=1e-4, atol=1e-3 * float(ref.abs().max()))
+    assert torch.allclose(outs[1], ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
