@@ -79,19 +79,15 @@ constexpr uint32_t SPEC_GELU_SAVE = EF_VALID | EF_TMA_STORE | EF_TMA_OUT2 | EF_O
 constexpr uint32_t SPEC_GELU_GRAD = EF_VALID | EF_TMA_STORE | EF_DEEP | EF_TMA_RES | EF_RES_ALL | EF_RES | EF_VEC |
                                     ((uint32_t)RL_ACT_GELU_GRAD << EF_ACT_SHIFT);          // du = (dy W2) o gelu'(u) -> bf16
 constexpr uint32_t SPEC_GELU_GRAD_CS = SPEC_GELU_GRAD | EF_COLSUM;                          // ... and db1 = column sums of du
+// forward-only (eval) formats: fp16 operands and 16-bit results
+constexpr uint32_t SPEC_OUT16_F16 = SPEC_OUT16 | EF_O_F16;                                                      // QKV
+constexpr uint32_t SPEC_GELU16_F16 = SPEC_OUT16 | EF_O_F16 | ((uint32_t)RL_ACT_GELU << EF_ACT_SHIFT);            // FFN1 + GELU
 constexpr uint32_t SPEC_RES32_ND = EF_VALID | EF_TMA_STORE | EF_TMA_RES | EF_RES | EF_RES_F32 | EF_OUT_F32 | EF_VEC;   // f32 residual -> f32, no dropout (dgrads)
 constexpr uint32_t SPEC_SPLITK = EF_VALID | EF_TMA_STORE | EF_OUT_F32 | EF_ATOMIC | EF_VEC;     // split-K weight gradients (TMA reduce-add)
 constexpr uint32_t SPEC_RES32 = EF_VALID | EF_TMA_STORE | EF_TMA_RES | EF_RES | EF_RES_F32 | EF_OUT_F32 | EF_DROP | EF_VEC;  // bias + dropout + f32 residual -> f32
 
 using rl::fast_erf;
 using rl::gelu_grad;
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == RL_ACT_GELU) return x * 0.5f * (1.0f + fast_erf(x * 0.70710678118654752440f));
-  if (act == RL_ACT_RELU) return fmaxf(x, 0.0f);
-  if (act == RL_ACT_TANH) return tanhf(x);
-  return x;
-}
 
 __device__ __forceinline__ long long remap_row(const KParams& p, int row) {
   if (p.out_remap == 2) {  // data gradient of a stride-2 conv: this GEMM produces one parity plane of dX
@@ -1733,6 +1729,9 @@ extern "C" int rl_gemm_bf16(const rl_gemm_desc* d, void* stream) {
     if (p.eflags == SPEC_GELU_SAVE) return launch_gemm2<256, 4, false, 2, SPEC_GELU_SAVE>(tmA, tmB, tmC, tmC2, tmR, p, st);
     if (p.eflags == SPEC_RES32) return launch_gemm2<256, 4, false, 2, SPEC_RES32>(tmA, tmB, tmC, tmC2, tmR, p, st);
     if (p.eflags == SPEC_GELU_GRAD) return launch_gemm2<256, 4, false, 2, SPEC_GELU_GRAD>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (p.eflags == SPEC_RES32_ND) return launch_gemm2<256, 4, false, 2, SPEC_RES32_ND>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (p.eflags == SPEC_OUT16_F16) return launch_gemm2<256, 4, false, 2, SPEC_OUT16_F16>(tmA, tmB, tmC, tmC2, tmR, p, st);
+    if (p.eflags == SPEC_GELU16_F16) return launch_gemm2<256, 4, false, 2, SPEC_GELU16_F16>(tmA, tmB, tmC, tmC2, tmR, p, st);
   }
   if (pair && bn == 256 && cols && d->tune_no_pair != 5 && p.eflags == SPEC_GELU_GRAD_CS)
     return launch_gemm2<256, 4, true, 2, SPEC_GELU_GRAD_CS>(tmA, tmB, tmC, tmC2, tmR, p, st);

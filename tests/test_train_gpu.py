@@ -718,10 +718,14 @@ def test_specialised_gemm_epilogues_match_the_generic_epilogue_bit_for_bit():
     cases.append(("gelu_grad+colsum", 512, 768, lambda N: dict(res=rnd(M, N).bfloat16(), act=ops.ACT_GELU_GRAD,
                                                                colsum=torch.zeros(N, device="cuda")), torch.bfloat16))
     cases.append(("stem 128x64 tiles", 64, 32, lambda N: dict(), torch.bfloat16))
+    # forward-only formats (fp16 operands and results): QKV, FFN1 + GELU
+    cases.append(("fp16 out16", 512, 768, lambda N: dict(bias=rnd(N)), torch.float16))
+    cases.append(("fp16 gelu", 512, 768, lambda N: dict(bias=rnd(N, scale=0.1), act=ops.ACT_GELU), torch.float16))
     for name, N, K, mk, odt in cases:
         Mi = 4096 if N == 64 else M
-        a = (rnd(Mi, K) * 0.5).bfloat16()
-        b = (rnd(N, K) * 0.05).bfloat16()
+        h16 = torch.float16 if odt == torch.float16 else torch.bfloat16
+        a = (rnd(Mi, K) * 0.5).to(h16)
+        b = (rnd(N, K) * 0.05).to(h16)
         kw = mk(N)
         if "res" in kw and kw["res"].shape[0] != Mi:
             continue
