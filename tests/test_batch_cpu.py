@@ -36,3 +36,21 @@ def test_table_lookup_matches_per_batch_conversion():
 def test_pho_vocab_is_the_reference_symbol_table():
     v = pho_vocab()
     assert len(v) == 33 and v["P"] == 0 and v["1"] == 1 and v["5"] == 5 and v["a"] == 6 and v["z"] == 31 and v["U"] == 32
+
+
+def test_pho_lens_host_path_accepts_lists_tensors_and_empty_input():
+    """realise_b200.hostio.lens_to_device: batch['pho_lens'] arrives as a Python list (src/utils.py:92-98); the result is
+    an int32 tensor with the same values whichever container it came in (the CUDA branch adds a pinned staging ring)."""
+    import torch
+    from realise_b200 import hostio
+    lens = [1, 7, 3, 2, 6, 1]
+    a = hostio.lens_to_device(lens, "cpu")
+    assert a.dtype == torch.int32 and a.tolist() == lens
+    b = hostio.lens_to_device(torch.tensor(lens, dtype=torch.int64), "cpu")
+    assert b.dtype == torch.int32 and b.tolist() == lens
+    assert hostio.lens_to_device([], "cpu").numel() == 0
+    # the returned tensor owns its memory (the list's temporary buffer is gone)
+    lens2 = list(range(1, 2001))
+    c = hostio.lens_to_device(lens2, "cpu")
+    del lens2
+    assert int(c.sum()) == 2001 * 2000 // 2
