@@ -31,6 +31,7 @@ class _StepFn(torch.autograd.Function):
         ctx.saved = engine.saved          # the activations belong to THIS forward: a second forward before the backward
         engine.saved = None               # (e.g. a train-mode loss probe) neither overwrites nor leaks them
         ctx.mark_non_differentiable(logits)
+        ctx.set_materialize_grads(False)  # or autograd zero-fills a [B, L, 21128] gradient for the logits on every backward (0.18 ms)
         return loss, logits
 
     @staticmethod
@@ -39,6 +40,8 @@ class _StepFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError("realise_b200: backward through the same forward twice (activations already released)")
         eng.saved, ctx.saved = ctx.saved, None
+        if gloss is None:                 # only reachable by differentiating a function of the logits alone
+            raise RuntimeError("realise_b200: the training graph differentiates the loss; logits carry no gradient")
         eng.backward_and_sync(gloss)
         return (None, None) + (None,) * len(eng.params)
 
