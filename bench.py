@@ -479,7 +479,7 @@ def measure_train(args, dev, rank, world, dist, peaks):
                      # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, from the committed ncu pass over one
                      # train step (profiles/r02_train_traffic.json); null when that file is absent
                      "traffic": load_traffic(),
-                     "kernel": "gemm_bf16_kernel / gemm2_bf16_kernel (tcgen05 GEMM, implicit-GEMM conv, split-K wgrad): "
+                     "kernel": "gemm_bf16_kernel / gemm2_bf16_kernel / conv64_halo_kernel (tcgen05 GEMM, implicit-GEMM conv, split-K wgrad): "
                                f"executed 2*M*N*K over CUDA-event time of its {gn} launches in one train step",
                      "peak_source": peaks["source"] + " bf16 sustained"},
         "roofline_detail": {
